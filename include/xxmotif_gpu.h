@@ -1,0 +1,172 @@
+/*
+ * xxmotif_gpu.h -- C ABI of libxxmotif_gpu.so: the B200 (sm_100a) implementation of XXmotif's PWM-refinement
+ * hot path (window scan -> site p-value -> site selection -> PWM recount), one context per GPU.
+ *
+ * Every entry point replaces one reference call site (paths relative to soedinglab/xxmotif src/).  The reference
+ * has no FFI of its own: the seam is the set of member functions of the process-wide singletons StartPosUpdater,
+ * PVal_Calculator and Kmer_Generator_Reloaded<dna_hash_t>; INTEGRATION.md shows the
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are HOST pointers; the library owns every device buffer.
+ *   - every function returns 0 on success, non-zero on error; xxm_last_error() gives the message.  There is no
+ *     CPU fallback: without a CUDA device xxm_create() fails.
+ *   - one host thread per context (the reference is single-threaded and non-reentrant).
+ *   - sequences are numbered 1..nent and positions 1..n exactly like the reference (Alignment.h:23-41); with
+ *     revcomp the positions run over the doubled sequence fwd + N + revcomp (seqset.cpp:128-178).
+ *   - xxm_site is bit-identical to sorted_sites_type (refinementPhase/Sorted_Sites.h:6-10).
+ */
+#ifndef XXMOTIF_GPU_H
+#define XXMOTIF_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XXM_PWM_LENGTH 30 /* Globals.h:27; PWM arrays are double[31][5], row 0 and column 0 unused/counts */
+
+typedef struct xxm_ctx xxm_ctx;
+
+typedef struct {
+	float score;
+	int32_t startPos;
+	int32_t sequence;
+} xxm_site;
+
+/* The Global:: switches the path reads (Globals.h:113-537, Globals.cpp:36-124 defaults). */
+typedef struct {
+	int32_t mops;                 /* Global::multipleOccurrence   (--mops)          */
+	int32_t oops;                 /* Global::oneOccurrence        (--oops)          */
+	int32_t localization;         /* Global::usePositionalProbs   (--localization)  */
+	int32_t maxMotifsPerSequence; /* Global::maxMotifsPerSequence, default 1000     */
+	int32_t maxSeqCount;          /* Global::maxSeqCount, default 1000              */
+	double plusFrac;              /* Global::plusFrac, default 0                    */
+	double overrepCorrection;     /* Global::overrepCorrection, default 1.05        */
+	double bg[5];                 /* Global::negBg if a negSet exists else posBg    */
+	double bgLog[5];              /* matching *_log array                           */
+} xxm_options;
+
+/* which site list a call refers to (members of StartPosUpdater, StartPosUpdater.h:72-74) */
+enum { XXM_LIST_SORTED_SITES = 0, XXM_LIST_SORTED_SITES_ELONG = 1, XXM_LIST_BEST_STARTPOS = 2 };
+/* order in which xxm_get_sites() materialises a list */
+enum { XXM_ORDER_AS_IS = 0, XXM_ORDER_BY_SCORE = 1, XXM_ORDER_BY_STARTPOS = 2 };
+
+/* ---- life cycle ----------------------------------------------------------------------------------------------- */
+int xxm_create(int device, xxm_ctx** out);
+void xxm_destroy(xxm_ctx* ctx);
+const char* xxm_last_error(const xxm_ctx* ctx); /* ctx may be NULL: message of the last failed xxm_create */
+int xxm_set_options(xxm_ctx* ctx, const xxm_options* opt);
+
+/* ---- a1: the encoded sequence set ----------------------------------------------------------------------------------
+ * replaces: Global::posSet as filled by Alignment::getEntity (seqFormat/Alignment.cpp:149-195) + createRevcomp
+ * (seqset.cpp:128-178) + calculateSequenceFeatures (seqset.cpp:21-36).
+ * n[i], codes: the sequences BEFORE createRevcomp, codes 0=N,1=A,2=C,3=G,4=T concatenated without separators.
+ * The set is packed once (2-bit codes + 1-bit N mask) and stays resident in HBM; with revcomp != 0 the reverse
+ * strand is generated on the device.  total[]/avgLength[] follow the reference's arithmetic, quirks included. */
+int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp);
+int xxm_seqset_info(const xxm_ctx* ctx, int32_t* total /*[nent+1] or NULL*/, double* avgLength /*[nent+1] or NULL*/,
+                    int32_t* max_leng, int32_t* min_leng);
+
+/* ---- a5: background + p-value tables -------------------------------------------------------------------------------
+ * xxm_set_background replaces the NullModel statics read by calculate_kmer_probability (NullModel.cpp:42-54,
+ * NullModel.h:13): order and the two 2^(3(order+1)) float tables _rprobs/_rconds.
+ * xxm_reinitialize replaces Kmer_Generator_Reloaded<dna_hash_t>::reinitialize(pwm, cols, posSetSize, totalPositions)
+ * (branch_and_bound-inl.h:183-258); pwm is double[31][5] row-major (log probabilities), cols the match columns. */
+int xxm_set_background(xxm_ctx* ctx, int32_t order, const float* rprobs, const float* rconds);
+int xxm_reinitialize(xxm_ctx* ctx, const double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize,
+                     int32_t totalPositions);
+/* introspection of the tables of the last xxm_reinitialize (tests): nparts, match columns, MAX_KMER_SIZE, and per part
+ * the dense pValueHash (size 4^len), the score classes (descending) with their id lists; probabilityHash for part 0 */
+int xxm_tables_info(const xxm_ctx* ctx, int32_t* L, int32_t* maxk, int32_t* nparts, int64_t size[2], int32_t nclasses[2], int64_t nids[2]);
+int xxm_tables_get(const xxm_ctx* ctx, int32_t part, double* pvalues /*size*/, double* probs /*size, part 0 only, may be NULL*/,
+                   int32_t* classScore, int32_t* classCount, int64_t* classIds);
+
+/* ---- a3/a4/a13: site p-value of given windows -----------------------------------------------------------------------
+ * replaces PVal_Calculator::calculatePval(kmerHash, kmer, cols, seq, pos, len, delta_0, size, length, avgLength,
+ * pValScore, mops) (pValCalculation.h:106-114) for a batch of windows of the current model; used by
+ * StartPosUpdater::getProbabilitiesPerSite (StartPosUpdater.h:91-132).  firstMotifColumn/enr*: arguments of
+ * initPositionalProbs (pValCalculation.cpp:195) when localization is on. */
+int xxm_window_pvals(xxm_ctx* ctx, int32_t nwin, const int32_t* seq, const int32_t* pos, int32_t posSetSize, int32_t firstMotifColumn,
+                     int32_t enrStart, int32_t enrEnd, int32_t mops, double* finalPval, double* pValScore);
+
+/* ---- a2: full scan -------------------------------------------------------------------------------------------------
+ * replaces StartPosUpdater::fill_sites_with_possible_startPositions(kmerHash, keepPosSetSize=true, motif)
+ * (StartPosUpdater-inl.h:70-140) incl. updateMultOcc (StartPosUtils.h:12-65).  Results stay on the device:
+ * list BEST_STARTPOS (all windows with finalPval < 1) and list SORTED_SITES (after overlap removal). */
+int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t* nbSites, int32_t* nbBestSites,
+                  int32_t* maxSites);
+
+/* ---- a10: candidate re-score under the current (variant) model ------------------------------------------------------
+ * replaces fill_elongSites_with_possible_startPositions(kmerHash, motif, pwm, tmpColumns, palin)
+ * (StartPosUpdater-inl.h:143-221); re-scores list BEST_STARTPOS into list SORTED_SITES_ELONG. */
+int xxm_rescore(xxm_ctx* ctx, int32_t firstMotifColumn, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t palin,
+                int32_t* nbSites, int32_t* maxSites);
+
+/* ---- a11: final OOPS scan ------------------------------------------------------------------------------------------
+ * replaces fill_sites_with_possible_startPositions_oops (StartPosUpdater-inl.h:224-266): best site of EVERY sequence
+ * with mops=false into list SORTED_SITES (one slot per sequence, score 1 = none). */
+int xxm_scan_oops(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t* nbSites, int32_t* maxSites);
+
+/* ---- a12: re-score a motif's own site list -------------------------------------------------------------------------
+ * replaces fill_sites_with_startPosList(kmerHash, motif, instanceThreshold) (StartPosUpdater-inl.h:6-68);
+ * sitePos is relative to PWM column 1 like Motif::_sites. */
+int xxm_rescore_startposlist(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t nSites, const int32_t* siteSeq,
+                             const int32_t* sitePos, int32_t instanceThreshold, int32_t* nbSites, int32_t* maxSites);
+
+/* ---- a7/a8/a9: sort, optimal subset, PWM recount -------------------------------------------------------------------
+ * xxm_update_pwm_with_best_subset replaces update_PWM_with_bestSubset (which = SORTED_SITES) and
+ * update_elongPWM_with_bestSubset (which = SORTED_SITES_ELONG) (StartPosUpdater.cpp:78-112): stable sort by float
+ * score, getBestSubset (StartPosUpdater.h:135-238), Motif::updatePWM_OOL (Motif.cpp:617-651).  pwm31x5 is overwritten
+ * like the reference's pwm argument.  *updated = 0 when the reference would return early (no site / best score 1). */
+int xxm_update_pwm_with_best_subset(xxm_ctx* ctx, int32_t which, double* pwm31x5, int32_t firstColumn, int32_t posSetSize, int32_t plus,
+                                    double pseudo, int32_t* updated, int32_t* bestMotifNb, double* bestPval);
+/* replaces fill_startPosList_with_bestSubset (StartPosUpdater.cpp:52-63): outputs the chosen sites (relative to PWM
+ * column 1) sorted by start position; *nOut = -1 when the reference would return early */
+int xxm_startposlist_best_subset(xxm_ctx* ctx, int32_t firstColumn, int32_t posSetSize, int32_t* outSeq, int32_t* outPos, int32_t cap,
+                                 int32_t* nOut, int32_t* bestMotifNb, double* bestPval);
+/* replaces fill_startPosList_with_elongSites (StartPosUpdater.cpp:114-134) */
+int xxm_startposlist_from_elong(xxm_ctx* ctx, int32_t bestMotifNb, int32_t firstTmpColumn, int32_t* outSeq, int32_t* outPos, int32_t cap,
+                                int32_t* nOut, double* worstScore);
+/* replaces set_BindingSites (StartPosUpdater.cpp:65-76) with ThresholdChecker "<thr": sites sorted by start position */
+int xxm_set_binding_sites(xxm_ctx* ctx, double thr, xxm_site* out, int32_t cap, int32_t* nOut);
+/* replaces getBestStartPos()/getSortedSites() (StartPosUpdater.h:46-47) + sortSitesByScore/sortSitesByStartPos
+ * (StartPosUtils.h:68-78): copies a device-resident list to the host in the requested order */
+int xxm_get_sites(xxm_ctx* ctx, int32_t which, int32_t order, int32_t palin, xxm_site* out, int32_t cap, int32_t* nOut);
+
+/* ---- a14: forward / reverse-complement log-odds histogram ----------------------------------------------------------
+ * replaces the counting loops of Output::printScoreDistribution (output.cpp:1033-1078) with
+ * Motif::calculateMatrixScore_logOdds / getMaxMatrixScore / getPalindrome (Motif.h:584-612, Motif.cpp:1068-1079).
+ * fwd/bwd receive npos = max_leng - ncols + 1 counts. */
+int xxm_logodds_hist(xxm_ctx* ctx, const double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize, double* fwd, double* bwd,
+                     int32_t npos, double* maxScore, double* maxScore2);
+
+/* ---- host-side pieces of the path, callable without a device (unit tests of the host logic) -------------------------
+ * xxm_host_tables: the table construction xxm_reinitialize performs (branch_and_bound-inl.h:183-603), without staging.
+ *   info[9] = L, maxk, nparts, size0, size1, nclasses0, nclasses1, nids0, nids1; the arrays of `part` may be NULL.
+ * xxm_host_best_subset: getBestSubset (StartPosUpdater.h:135-238) over a score-sorted site array; logTotal is the
+ *   largest index of LogTable::LOG_sum_i that may be read (>= maxSites). */
+int xxm_host_tables(const double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions, const double* bgLog5,
+                    int32_t order, const float* rprobs, const float* rconds, int32_t part, int64_t* info, double* pvalues, double* probs,
+                    int32_t* classScore, int32_t* classCount, int64_t* classIds);
+int xxm_host_best_subset(const float* score, const int32_t* seq, int32_t nbSites, int32_t posSetSize, int32_t maxSeqCount, int32_t maxSites,
+                         int32_t nent, int32_t maxMotifsPerSequence, int32_t oneOccurrence, double plusFrac, int32_t* bestMotifNb,
+                         double* bestPval);
+
+/* ---- measurement ----------------------------------------------------------------------------------------------------
+ * device-side timing of the most recent call of each kernel (CUDA events on the context's stream), launch counts */
+typedef struct {
+	int64_t launches;        /* kernels launched by this context so far */
+	float last_scan_ms;      /* device time of the last full-scan kernel */
+	int64_t last_scan_bases; /* stored bases the last full scan covered */
+	int64_t last_scan_hits;  /* windows with finalPval < 1 it found */
+} xxm_stats;
+int xxm_get_stats(const xxm_ctx* ctx, xxm_stats* out);
+/* the CUDA stream the context launches on, as a cudaStream_t cast to void* (for external event timing) */
+void* xxm_stream(const xxm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,36 @@
+"""The C-ABI library loads and exports every symbol include/xxmotif_gpu.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "xxmotif_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(xxm_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    import __graft_entry__ as g
+    g.build()
+    import xxmotif_b200 as xb
+    lib = ctypes.CDLL(xb.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert sorted(xb.EXPORTS) == names
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import xxmotif_b200 as xb
+    with pytest.raises(xb.XxmError) as e:
+        xb.Context(0)
+    assert "no CUDA device" in str(e.value)

@@ -1,0 +1,313 @@
+"""ctypes binding of libxxmotif_gpu.so (include/xxmotif_gpu.h).
+
+This is the thin Python face of the C ABI used by the tests and by bench.py; the product is the shared library.
+There is no fallback of any kind: if the library is missing or no CUDA device is present, construction fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxxmotif_gpu.so")
+
+SITE_DTYPE = np.dtype([("score", np.float32), ("startPos", np.int32), ("sequence", np.int32)])
+
+LIST_SORTED_SITES, LIST_SORTED_SITES_ELONG, LIST_BEST_STARTPOS = 0, 1, 2
+ORDER_AS_IS, ORDER_BY_SCORE, ORDER_BY_STARTPOS = 0, 1, 2
+
+EXPORTS = [
+    "xxm_create", "xxm_destroy", "xxm_last_error", "xxm_set_options", "xxm_load_seqset", "xxm_seqset_info", "xxm_set_background",
+    "xxm_reinitialize", "xxm_tables_info", "xxm_tables_get", "xxm_window_pvals", "xxm_scan_full", "xxm_rescore", "xxm_scan_oops",
+    "xxm_rescore_startposlist", "xxm_update_pwm_with_best_subset", "xxm_startposlist_best_subset", "xxm_startposlist_from_elong",
+    "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset",
+]
+
+
+class XxmOptions(C.Structure):
+    _fields_ = [("mops", C.c_int32), ("oops", C.c_int32), ("localization", C.c_int32), ("maxMotifsPerSequence", C.c_int32),
+                ("maxSeqCount", C.c_int32), ("plusFrac", C.c_double), ("overrepCorrection", C.c_double), ("bg", C.c_double * 5),
+                ("bgLog", C.c_double * 5)]
+
+
+class XxmStats(C.Structure):
+    _fields_ = [("launches", C.c_int64), ("last_scan_ms", C.c_float), ("last_scan_bases", C.c_int64), ("last_scan_hits", C.c_int64)]
+
+
+class XxmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Load libxxmotif_gpu.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise XxmError("libxxmotif_gpu.so not built: run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C xxmotif_b200/csrc`")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, dbl = C.c_void_p, C.c_int32, C.c_double
+    P = C.POINTER
+    L.xxm_create.restype = i32
+    L.xxm_create.argtypes = [i32, P(vp)]
+    L.xxm_destroy.restype = None
+    L.xxm_destroy.argtypes = [vp]
+    L.xxm_last_error.restype = C.c_char_p
+    L.xxm_last_error.argtypes = [vp]
+    L.xxm_stream.restype = vp
+    L.xxm_stream.argtypes = [vp]
+    sig = {
+        "xxm_set_options": [vp, P(XxmOptions)],
+        "xxm_load_seqset": [vp, i32, vp, vp, i32],
+        "xxm_seqset_info": [vp, vp, vp, P(i32), P(i32)],
+        "xxm_set_background": [vp, i32, vp, vp],
+        "xxm_reinitialize": [vp, vp, vp, i32, i32, i32],
+        "xxm_tables_info": [vp, P(i32), P(i32), P(i32), vp, vp, vp],
+        "xxm_tables_get": [vp, i32, vp, vp, vp, vp, vp],
+        "xxm_window_pvals": [vp, i32, vp, vp, i32, i32, i32, i32, i32, vp, vp],
+        "xxm_scan_full": [vp, i32, i32, i32, P(i32), P(i32), P(i32)],
+        "xxm_rescore": [vp, i32, i32, i32, i32, i32, P(i32), P(i32)],
+        "xxm_scan_oops": [vp, i32, i32, i32, P(i32), P(i32)],
+        "xxm_rescore_startposlist": [vp, i32, i32, i32, i32, vp, vp, i32, P(i32), P(i32)],
+        "xxm_update_pwm_with_best_subset": [vp, i32, vp, i32, i32, i32, dbl, P(i32), P(i32), P(dbl)],
+        "xxm_startposlist_best_subset": [vp, i32, i32, vp, vp, i32, P(i32), P(i32), P(dbl)],
+        "xxm_startposlist_from_elong": [vp, i32, i32, vp, vp, i32, P(i32), P(dbl)],
+        "xxm_set_binding_sites": [vp, dbl, vp, i32, P(i32)],
+        "xxm_get_sites": [vp, i32, i32, i32, vp, i32, P(i32)],
+        "xxm_logodds_hist": [vp, vp, vp, i32, i32, vp, vp, i32, P(dbl), P(dbl)],
+        "xxm_get_stats": [vp, P(XxmStats)],
+        "xxm_host_tables": [vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp],
+        "xxm_host_best_subset": [vp, vp, i32, i32, i32, i32, i32, i32, i32, dbl, P(i32), P(dbl)],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.restype = i32
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One GPU context == the reference's StartPosUpdater + PVal_Calculator + Kmer_Generator_Reloaded singletons."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        if self.L.xxm_create(device, C.byref(h)):
+            raise XxmError(self.L.xxm_last_error(None).decode())
+        self.h = h
+        self.nent = 0
+        self.ncols = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.xxm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise XxmError(self.L.xxm_last_error(self.h).decode())
+
+    # ---- configuration / inputs
+    def set_options(self, mops=False, oops=False, localization=False, bg=None, bgLog=None, maxMotifsPerSequence=1000, maxSeqCount=1000,
+                    plusFrac=0.0, overrepCorrection=1.05):
+        o = XxmOptions()
+        o.mops, o.oops, o.localization = int(mops), int(oops), int(localization)
+        o.maxMotifsPerSequence, o.maxSeqCount = maxMotifsPerSequence, maxSeqCount
+        o.plusFrac, o.overrepCorrection = plusFrac, overrepCorrection
+        for i in range(5):
+            o.bg[i] = float(bg[i])
+            o.bgLog[i] = float(bgLog[i])
+        self._ck(self.L.xxm_set_options(self.h, C.byref(o)))
+
+    def load_seqset(self, n, codes, revcomp=False):
+        n = np.ascontiguousarray(n, dtype=np.int32)
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        assert int(n.astype(np.int64).sum()) == codes.size
+        self._ck(self.L.xxm_load_seqset(self.h, len(n), _p(n), _p(codes), int(revcomp)))
+        self.nent = len(n)
+
+    def seqset_info(self):
+        total = np.zeros(self.nent + 1, dtype=np.int32)
+        avg = np.zeros(self.nent + 1, dtype=np.float64)
+        mx, mn = C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.xxm_seqset_info(self.h, _p(total), _p(avg), C.byref(mx), C.byref(mn)))
+        return total, avg, mx.value, mn.value
+
+    def set_background(self, order, rprobs, rconds):
+        rp = np.ascontiguousarray(rprobs, dtype=np.float32)
+        rc = np.ascontiguousarray(rconds, dtype=np.float32)
+        assert rp.size == 1 << (3 * (order + 1)) and rc.size == rp.size
+        self._ck(self.L.xxm_set_background(self.h, order, _p(rp), _p(rc)))
+
+    def reinitialize(self, pwm, cols, posSetSize, totalPositions):
+        pwm = np.ascontiguousarray(pwm, dtype=np.float64).reshape(155)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        self._ck(self.L.xxm_reinitialize(self.h, _p(pwm), _p(cols), len(cols), posSetSize, totalPositions))
+        self.ncols = len(cols)
+
+    def tables(self):
+        Lc, mk, nparts = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        size = np.zeros(2, dtype=np.int64)
+        ncls = np.zeros(2, dtype=np.int32)
+        nids = np.zeros(2, dtype=np.int64)
+        self._ck(self.L.xxm_tables_info(self.h, C.byref(Lc), C.byref(mk), C.byref(nparts), _p(size), _p(ncls), _p(nids)))
+        out = {"L": Lc.value, "maxk": mk.value, "nparts": nparts.value, "pvalues": [], "classes": [], "probs": None}
+        for part in range(nparts.value):
+            pv = np.zeros(size[part], dtype=np.float64)
+            pr = np.zeros(size[part], dtype=np.float64) if (part == 0 and nparts.value == 2) else None
+            cs = np.zeros(ncls[part], dtype=np.int32)
+            cc = np.zeros(ncls[part], dtype=np.int32)
+            ci = np.zeros(nids[part], dtype=np.int64)
+            self._ck(self.L.xxm_tables_get(self.h, part, _p(pv), _p(pr) if pr is not None else None, _p(cs), _p(cc), _p(ci)))
+            out["pvalues"].append(pv)
+            out["classes"].append((cs, cc, ci))
+            if pr is not None:
+                out["probs"] = pr
+        return out
+
+    # ---- the hot path
+    def window_pvals(self, seq, pos, posSetSize, firstMotifColumn, enr, mops):
+        seq = np.ascontiguousarray(seq, dtype=np.int32)
+        pos = np.ascontiguousarray(pos, dtype=np.int32)
+        f = np.ones(len(seq), dtype=np.float64)
+        s = np.ones(len(seq), dtype=np.float64)
+        self._ck(self.L.xxm_window_pvals(self.h, len(seq), _p(seq), _p(pos), posSetSize, firstMotifColumn, enr[0], enr[1], int(mops), _p(f), _p(s)))
+        return f, s
+
+    def scan_full(self, posSetSize, enr):
+        a, b, c = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.xxm_scan_full(self.h, posSetSize, enr[0], enr[1], C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def rescore(self, firstMotifColumn, posSetSize, enr, palin=False):
+        a, c = C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.xxm_rescore(self.h, firstMotifColumn, posSetSize, enr[0], enr[1], int(palin), C.byref(a), C.byref(c)))
+        return a.value, c.value
+
+    def scan_oops(self, posSetSize, enr):
+        a, c = C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.xxm_scan_oops(self.h, posSetSize, enr[0], enr[1], C.byref(a), C.byref(c)))
+        return a.value, c.value
+
+    def rescore_startposlist(self, posSetSize, enr, siteSeq, sitePos, instanceThreshold=False):
+        ss = np.ascontiguousarray(siteSeq, dtype=np.int32)
+        sp = np.ascontiguousarray(sitePos, dtype=np.int32)
+        a, c = C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.xxm_rescore_startposlist(self.h, posSetSize, enr[0], enr[1], len(ss), _p(ss), _p(sp), int(instanceThreshold), C.byref(a),
+                                                 C.byref(c)))
+        return a.value, c.value
+
+    def update_pwm_with_best_subset(self, which, pwm, firstColumn, posSetSize, plus, pseudo):
+        pwm = np.ascontiguousarray(pwm, dtype=np.float64).reshape(155).copy()
+        upd, nb, bp = C.c_int32(0), C.c_int32(0), C.c_double(0.0)
+        self._ck(self.L.xxm_update_pwm_with_best_subset(self.h, which, _p(pwm), firstColumn, posSetSize, int(plus), pseudo, C.byref(upd), C.byref(nb),
+                                                        C.byref(bp)))
+        return upd.value, nb.value, bp.value, pwm
+
+    def startposlist_best_subset(self, firstColumn, posSetSize, cap):
+        os_ = np.zeros(max(1, cap), dtype=np.int32)
+        op = np.zeros(max(1, cap), dtype=np.int32)
+        n, nb, bp = C.c_int32(0), C.c_int32(0), C.c_double(0.0)
+        self._ck(self.L.xxm_startposlist_best_subset(self.h, firstColumn, posSetSize, _p(os_), _p(op), len(os_), C.byref(n), C.byref(nb), C.byref(bp)))
+        k = max(0, n.value)
+        return n.value, nb.value, bp.value, os_[:k], op[:k]
+
+    def startposlist_from_elong(self, bestMotifNb, firstTmpColumn):
+        os_ = np.zeros(max(1, bestMotifNb), dtype=np.int32)
+        op = np.zeros(max(1, bestMotifNb), dtype=np.int32)
+        n, w = C.c_int32(0), C.c_double(1.0)
+        self._ck(self.L.xxm_startposlist_from_elong(self.h, bestMotifNb, firstTmpColumn, _p(os_), _p(op), len(os_), C.byref(n), C.byref(w)))
+        return os_[:n.value], op[:n.value], w.value
+
+    def set_binding_sites(self, thr, cap):
+        out = np.zeros(max(1, cap), dtype=SITE_DTYPE)
+        n = C.c_int32(0)
+        self._ck(self.L.xxm_set_binding_sites(self.h, thr, _p(out), len(out), C.byref(n)))
+        return out[:n.value]
+
+    def get_sites(self, which, order=ORDER_AS_IS, cap=None):
+        if cap is None:
+            cap = 1 << 16
+        while True:
+            out = np.zeros(max(1, cap), dtype=SITE_DTYPE)
+            n = C.c_int32(0)
+            rc = self.L.xxm_get_sites(self.h, which, order, 0, _p(out), len(out), C.byref(n))
+            if rc and n.value > len(out):
+                cap = n.value
+                continue
+            self._ck(rc)
+            return out[:n.value]
+
+    def logodds_hist(self, pwm, cols, posSetSize, npos):
+        pwm = np.ascontiguousarray(pwm, dtype=np.float64).reshape(155)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        fw = np.zeros(max(1, npos), dtype=np.float64)
+        bw = np.zeros(max(1, npos), dtype=np.float64)
+        m1, m2 = C.c_double(0), C.c_double(0)
+        self._ck(self.L.xxm_logodds_hist(self.h, _p(pwm), _p(cols), len(cols), posSetSize, _p(fw), _p(bw), npos, C.byref(m1), C.byref(m2)))
+        return fw[:npos], bw[:npos], m1.value, m2.value
+
+    def stats(self):
+        s = XxmStats()
+        self._ck(self.L.xxm_get_stats(self.h, C.byref(s)))
+        return {"launches": s.launches, "last_scan_ms": s.last_scan_ms, "last_scan_bases": s.last_scan_bases, "last_scan_hits": s.last_scan_hits}
+
+    def stream(self):
+        return self.L.xxm_stream(self.h)
+
+
+def host_tables(pwm, cols, posSetSize, totalPositions, bgLog, order, rprobs, rconds):
+    """Device-free table construction (xxm_host_tables): returns the same dict as Context.tables()."""
+    L = load_library()
+    pwm = np.ascontiguousarray(pwm, dtype=np.float64).reshape(155)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    bgl = np.ascontiguousarray(bgLog, dtype=np.float64)
+    rp = np.ascontiguousarray(rprobs, dtype=np.float32)
+    rc = np.ascontiguousarray(rconds, dtype=np.float32)
+    info = np.zeros(9, dtype=np.int64)
+    rcode = L.xxm_host_tables(_p(pwm), _p(cols), len(cols), posSetSize, totalPositions, _p(bgl), order, _p(rp), _p(rc), -1, _p(info), None, None, None,
+                              None, None)
+    if rcode:
+        raise XxmError("xxm_host_tables failed with %d" % rcode)
+    out = {"L": int(info[0]), "maxk": int(info[1]), "nparts": int(info[2]), "pvalues": [], "classes": [], "probs": None}
+    for part in range(out["nparts"]):
+        pv = np.zeros(info[3 + part], dtype=np.float64)
+        pr = np.zeros(info[3 + part], dtype=np.float64) if (part == 0 and out["nparts"] == 2) else None
+        cs = np.zeros(info[5 + part], dtype=np.int32)
+        cc = np.zeros(info[5 + part], dtype=np.int32)
+        ci = np.zeros(info[7 + part], dtype=np.int64)
+        rcode = L.xxm_host_tables(_p(pwm), _p(cols), len(cols), posSetSize, totalPositions, _p(bgl), order, _p(rp), _p(rc), part, _p(info), _p(pv),
+                                  _p(pr) if pr is not None else None, _p(cs), _p(cc), _p(ci))
+        if rcode:
+            raise XxmError("xxm_host_tables failed with %d" % rcode)
+        out["pvalues"].append(pv)
+        out["classes"].append((cs, cc, ci))
+        if pr is not None:
+            out["probs"] = pr
+    return out
+
+
+def host_best_subset(score, seq, posSetSize, maxSites, nent, maxSeqCount=1000, maxMotifsPerSequence=1000, oneOccurrence=False, plusFrac=0.0):
+    L = load_library()
+    score = np.ascontiguousarray(score, dtype=np.float32)
+    seq = np.ascontiguousarray(seq, dtype=np.int32)
+    nb, bp = C.c_int32(0), C.c_double(0.0)
+    rcode = L.xxm_host_best_subset(_p(score), _p(seq), len(score), posSetSize, maxSeqCount, maxSites, nent, maxMotifsPerSequence, int(oneOccurrence),
+                                   plusFrac, C.byref(nb), C.byref(bp))
+    if rcode:
+        raise XxmError("xxm_host_best_subset failed with %d" % rcode)
+    return nb.value, bp.value

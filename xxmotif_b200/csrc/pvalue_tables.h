@@ -1,0 +1,48 @@
+// Host-side construction of the k-mer -> p-value tables for one (PWM, column set).
+//
+// Follows Kmer_Generator_Reloaded<DnaHash>::reinitialize / set_kmer_to_Pvalue_hash / create_similar_kmers_rec /
+// calculate_kmer_probability / recalculatePrefixProbabilities / getRightKmerConditional
+// (reference src/branch_and_bound-inl.h:54-100, :183-323, :462-603) -- SURVEY.md section 8 row a5 ("stays on the host in
+// the first slice; rows are staged H2D per iteration").  The result is kept in compact form (enumerated ids with their
+// class, classes with their cumulative p-value); the dense 4^k arrays of the reference are only materialised on the
+// device as rank tables.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace xxm {
+
+struct NullModelView {
+	int order = 0;
+	const float* rprobs = nullptr;  // 2^(3(order+1)) entries, index = 3 bits per char, first char most significant
+	const float* rconds = nullptr;
+};
+
+struct TablePart {
+	int len = 0;                      // number of match columns covered by this part
+	std::vector<uint32_t> ids;        // enumerated k-mer ids in class order (descending score, then enumeration order)
+	std::vector<uint32_t> cls;        // class index of ids[i]
+	std::vector<double> prob;         // background probability of ids[i] (the reference's probabilityHash, left part only)
+	std::vector<int32_t> classScore;  // integer score of every class, descending
+	std::vector<int32_t> classCount;  // ids per class
+	std::vector<double> classPval;    // cumulative p-value of the class == pValueHash[part][id] for all its ids
+};
+
+struct PvalueTables {
+	int error = 0;            // 1: reference behaviour undefined (int overflow for long gapped left parts), 2: PWM column not normalised
+	int L = 0;                // match columns
+	int maxk = 8;             // MAX_KMER_SIZE
+	int nparts = 1;
+	int span = 0;             // lastCol - firstCol + 1
+	int coloff[32] = {0};     // offset of match column k from the first match column
+	int gaps[32] = {0};
+	double logodds[32][5];    // PWM[i][a] = pwm[col_i][a] - bgLog[a], i = 1..L
+	double pruneThr = 0;      // posSetSize / (totalPositions * 2.0)
+	TablePart part[2];
+	std::vector<double> leftClassProb;  // per left class: sum of prob over its ids (list order)
+};
+
+void build_pvalue_tables(const double* pwm31x5, const int32_t* cols, int ncols, int posSetSize, int totalPositions,
+                         const double* bgLog5, const NullModelView& nm, PvalueTables& out);
+
+}  // namespace xxm

@@ -1,0 +1,755 @@
+// libxxmotif_gpu.so -- host side of the C ABI in include/xxmotif_gpu.h: owns the device buffers, stages the model of
+// every reinitialize(), launches the kernels of xxm_kernels.cuh and runs the sequential host statistics.
+// There is no CPU fallback: every entry point needs the CUDA device the context was created on.
+#include "../../include/xxmotif_gpu.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "host_stats.h"
+#include "pvalue_tables.h"
+#include "xxm_kernels.cuh"
+
+using namespace xxm;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename T>
+struct DevBuf {
+	T* p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t n) {
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 64;
+		cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// a device-resident site list (members of StartPosUpdater: bestStartPos / sortedSites / sortedSites_elong)
+enum ListKind { kListEmpty = 0, kListCompact, kListFlagged, kListSlots };
+struct SiteList {
+	ListKind kind = kListEmpty;
+	const uint32_t* seq = nullptr;  // entry arrays (may alias another list's arrays)
+	const uint32_t* pos = nullptr;
+	const uint32_t* vidx = nullptr; // only meaningful while the model that produced it is current
+	uint32_t n = 0;                 // entries
+	int shift = 0;                  // startPos = pos + shift
+	const float* score = nullptr;   // per entry (compact/flagged) or per slot (slots)
+	const uint8_t* keep = nullptr;  // flagged
+	const uint32_t* slotIdx = nullptr;
+	uint32_t nslots = 0;
+	uint32_t members = 0;           // sites with score < 1
+	uint32_t maxPerSeq = 0;
+	bool orderedBySeqPos = true;
+	bool tableValued = false;       // float score is a function of vidx under the current model
+	bool mopsValues = true;         // ... taken from the mops (true) or the mode (false) finalPval table
+	uint64_t modelSerial = 0;
+};
+
+}  // namespace
+
+struct xxm_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::string err;
+	xxm_options opt{};
+	bool haveOpt = false;
+	int numSMs = 148;
+	xxm_stats stats{};
+
+	// ---- sequence set
+	int nent = 0;
+	bool revcomp = false;
+	std::vector<int32_t> len, total;
+	std::vector<double> avgLength;
+	int max_leng = 0, min_leng = 0;
+	std::vector<uint32_t> wordOff;
+	uint32_t nwords = 0;
+	DevBuf<uint64_t> d_codes;
+	DevBuf<uint32_t> d_nmask, d_wordOff, d_blk2seq;
+	DevBuf<int32_t> d_len;
+	SeqStream S{};
+
+	// ---- background + model
+	NullModelView nm;
+	std::vector<float> rprobs, rconds;
+	PvalueTables tab;
+	bool haveModel = false;
+	uint64_t modelSerial = 0;
+	int modelPosSetSize = 0;
+	int modelFirstCol = 1;  // cols[0] of the current model
+	Model M{};
+	DevBuf<uint32_t> d_rank0, d_rank1, d_hit0, d_ids, d_cls;
+	DevBuf<uint8_t> d_clsOk;
+	DevBuf<double> d_cpval0, d_cpval1, d_leftProb;
+	DevBuf<int32_t> d_cscore0, d_cscore1;
+	DevBuf<int32_t> d_memoKey;
+	DevBuf<double> d_memoVal;
+	DevBuf<uint32_t> d_memoState, d_flags32;
+	// value tables
+	uint32_t nval = 0;
+	DevBuf<double> d_pS, d_finalMops, d_finalMode, d_posProb, d_perCand;
+	std::vector<double> h_pS, h_finalMops, h_finalMode;  // nparts == 1: per class; nparts == 2: per slot after a round trip
+	bool memoModeValid = false;
+	std::vector<double> posProb, sum_i;
+	bool posProbValid = false;
+
+	// ---- lists
+	DevBuf<uint32_t> b_seq, b_pos, b_vidx, t_seq, t_pos, t_vidx, u_seq, u_pos, u_vidx;
+	DevBuf<float> b_score, s_kscore, e_kscore, slotScore, e_slotScore, tmpScore, u_score;
+	DevBuf<uint8_t> s_keep, e_keep, flag8;
+	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
+	DevBuf<uint64_t> status, total64;
+	DevBuf<unsigned long long> d_counts;
+	DevBuf<SiteRec> d_sites;
+	DevBuf<unsigned int> d_hf, d_hb;
+	uint32_t nBest = 0;
+	SiteList L[3];
+	int nbSites = 0, maxSites = 0;
+
+	LogSum logsum;
+
+	int fail(const char* fmt, ...) {
+		char buf[512];
+		va_list ap;
+		va_start(ap, fmt);
+		vsnprintf(buf, sizeof buf, fmt, ap);
+		va_end(ap);
+		err = buf;
+		return 1;
+	}
+};
+
+#define CK(call)                                                                                              \
+	do {                                                                                                      \
+		cudaError_t e__ = (call);                                                                             \
+		if (e__ != cudaSuccess) return ctx->fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+#define CKK()                                                                                                 \
+	do {                                                                                                      \
+		ctx->stats.launches++;                                                                                \
+		cudaError_t e__ = cudaGetLastError();                                                                 \
+		if (e__ != cudaSuccess) return ctx->fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+#define TRY(expr)            \
+	do {                     \
+		int r__ = (expr);    \
+		if (r__) return r__; \
+	} while (0)
+
+static inline uint32_t cdiv(uint64_t a, uint32_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
+
+// =====================================================================================================================
+// life cycle
+// =====================================================================================================================
+extern "C" int xxm_create(int device, xxm_ctx** out) {
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libxxmotif_gpu has no CPU fallback)";
+		return 1;
+	}
+	if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return 1; }
+	e = cudaSetDevice(device);
+	if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return 1; }
+	xxm_ctx* ctx = new xxm_ctx();
+	ctx->device = device;
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->numSMs = prop.multiProcessorCount;
+	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
+	    cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+		g_create_error = "cannot create stream/events";
+		delete ctx;
+		return 1;
+	}
+	ctx->opt.maxMotifsPerSequence = 1000;
+	ctx->opt.maxSeqCount = 1000;
+	ctx->opt.overrepCorrection = 1.05;
+	*out = ctx;
+	return 0;
+}
+
+extern "C" void xxm_destroy(xxm_ctx* ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	// DevBuf members are released explicitly (no destructor: the struct is copied nowhere, but keep it trivial)
+	ctx->d_codes.release(); ctx->d_nmask.release(); ctx->d_wordOff.release(); ctx->d_blk2seq.release(); ctx->d_len.release();
+	ctx->d_rank0.release(); ctx->d_rank1.release(); ctx->d_hit0.release(); ctx->d_ids.release(); ctx->d_cls.release(); ctx->d_clsOk.release();
+	ctx->d_cpval0.release(); ctx->d_cpval1.release(); ctx->d_leftProb.release(); ctx->d_cscore0.release(); ctx->d_cscore1.release();
+	ctx->d_memoKey.release(); ctx->d_memoVal.release(); ctx->d_memoState.release(); ctx->d_flags32.release();
+	ctx->d_pS.release(); ctx->d_finalMops.release(); ctx->d_finalMode.release(); ctx->d_posProb.release(); ctx->d_perCand.release();
+	ctx->b_seq.release(); ctx->b_pos.release(); ctx->b_vidx.release(); ctx->t_seq.release(); ctx->t_pos.release(); ctx->t_vidx.release();
+	ctx->u_seq.release(); ctx->u_pos.release(); ctx->u_vidx.release(); ctx->b_score.release(); ctx->s_kscore.release(); ctx->e_kscore.release();
+	ctx->slotScore.release(); ctx->tmpScore.release(); ctx->s_keep.release(); ctx->e_keep.release(); ctx->flag8.release(); ctx->stk.release();
+	ctx->slotIdx.release(); ctx->e_slotIdx.release(); ctx->e_slotScore.release(); ctx->u_score.release(); ctx->counters.release(); ctx->hist.release(); ctx->idxA.release(); ctx->idxB.release(); ctx->keysA.release();
+	ctx->keysB.release(); ctx->rsHist.release(); ctx->status.release(); ctx->total64.release(); ctx->d_counts.release(); ctx->d_sites.release();
+	ctx->d_hf.release(); ctx->d_hb.release();
+	cudaEventDestroy(ctx->ev0);
+	cudaEventDestroy(ctx->ev1);
+	cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+extern "C" const char* xxm_last_error(const xxm_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int xxm_set_options(xxm_ctx* ctx, const xxm_options* opt) {
+	ctx->opt = *opt;
+	ctx->haveOpt = true;
+	ctx->haveModel = false;
+	return 0;
+}
+
+extern "C" void* xxm_stream(const xxm_ctx* ctx) { return reinterpret_cast<void*>(ctx->stream); }
+extern "C" int xxm_get_stats(const xxm_ctx* ctx, xxm_stats* out) { *out = ctx->stats; return 0; }
+
+// =====================================================================================================================
+// a1: sequence set
+// =====================================================================================================================
+extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp) {
+	CK(cudaSetDevice(ctx->device));
+	if (nent <= 0) return ctx->fail("empty sequence set");
+	ctx->nent = nent;
+	ctx->revcomp = revcomp != 0;
+	ctx->len.resize(nent);
+	ctx->total.assign(static_cast<size_t>(nent) + 1, 0);
+	ctx->avgLength.assign(static_cast<size_t>(nent) + 1, 0.0);
+	ctx->wordOff.resize(static_cast<size_t>(nent) + 1);
+	std::vector<uint64_t> rawOff(static_cast<size_t>(nent) + 1);
+	// calculateSequenceFeatures (seqset.cpp:21-36) on the raw set, then -- with revcomp -- the recount at the end of
+	// createRevcomp (seqset.cpp:165-177) which compares codes with the CHARACTER '0' and therefore counts every
+	// position of the doubled sequence.
+	uint64_t off = 0, words = 0;
+	double acc = 0;
+	int mx = 0, mn = 2147483647;
+	int64_t tot = 0;
+	for (int i = 0; i < nent; ++i) {
+		rawOff[i] = off;
+		const int n0 = n[i];
+		if (n0 < 1) return ctx->fail("sequence %d is empty", i + 1);
+		int notX = 0;
+		for (int j = 0; j < n0; ++j) {
+			if (codes[off + j] > 4) return ctx->fail("sequence %d: code %d out of range at %d", i + 1, codes[off + j], j + 1);
+			if (codes[off + j] != 0) notX++;
+		}
+		const int nstore = revcomp ? 2 * n0 + 1 : n0;
+		if (revcomp) notX = nstore;
+		if (notX != 0) acc += std::log(notX);
+		tot += notX;
+		if (tot > 2147483647LL) return ctx->fail("more than 2^31-1 residues: the reference's int totals overflow (Alignment.h:40-41)");
+		ctx->total[i + 1] = static_cast<int32_t>(tot);
+		ctx->avgLength[i + 1] = std::exp(acc / (i + 1));
+		ctx->len[i] = nstore;
+		mx = std::max(mx, nstore);
+		mn = std::min(mn, nstore);
+		ctx->wordOff[i] = static_cast<uint32_t>(words);
+		words += (static_cast<uint64_t>(nstore) + kPadBases + 31) / 32;
+		if (words > 0xFFFFFF00ull) return ctx->fail("sequence stream exceeds 2^32 words");
+		off += n0;
+	}
+	rawOff[nent] = off;
+	ctx->wordOff[nent] = static_cast<uint32_t>(words);
+	ctx->nwords = static_cast<uint32_t>(words);
+	ctx->max_leng = mx;
+	ctx->min_leng = mn;
+	// coarse word -> sequence index
+	const uint32_t nblk = ctx->nwords / kBlkWords + 1;
+	std::vector<uint32_t> blk(nblk);
+	{
+		uint32_t s = 0;
+		for (uint32_t b = 0; b < nblk; ++b) {
+			const uint32_t w = b * kBlkWords;
+			while (s + 1 < static_cast<uint32_t>(nent) && ctx->wordOff[s + 1] <= w) ++s;
+			blk[b] = s;
+		}
+	}
+	CK(ctx->d_codes.ensure(static_cast<size_t>(ctx->nwords) + 2));
+	CK(ctx->d_nmask.ensure(static_cast<size_t>(ctx->nwords) + 2));
+	CK(ctx->d_wordOff.ensure(static_cast<size_t>(nent) + 1));
+	CK(ctx->d_len.ensure(nent));
+	CK(ctx->d_blk2seq.ensure(nblk));
+	uint8_t* d_raw = nullptr;
+	uint64_t* d_rawOff = nullptr;
+	CK(cudaMalloc(reinterpret_cast<void**>(&d_raw), off ? off : 1));
+	CK(cudaMalloc(reinterpret_cast<void**>(&d_rawOff), (static_cast<size_t>(nent) + 1) * sizeof(uint64_t)));
+	CK(cudaMemcpyAsync(d_raw, codes, off, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(d_rawOff, rawOff.data(), rawOff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->d_wordOff.p, ctx->wordOff.data(), ctx->wordOff.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->d_len.p, ctx->len.data(), ctx->len.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->d_blk2seq.p, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	ctx->S.codes = ctx->d_codes.p;
+	ctx->S.nmask = ctx->d_nmask.p;
+	ctx->S.wordOff = ctx->d_wordOff.p;
+	ctx->S.len = ctx->d_len.p;
+	ctx->S.blk2seq = ctx->d_blk2seq.p;
+	ctx->S.nwords = ctx->nwords;
+	ctx->S.nent = nent;
+	k_encode<<<cdiv(static_cast<uint64_t>(ctx->nwords) + 2, 256), 256, 0, ctx->stream>>>(d_raw, d_rawOff, ctx->S, ctx->d_codes.p, ctx->d_nmask.p,
+	                                                                                   revcomp ? 1 : 0);
+	CKK();
+	CK(cudaStreamSynchronize(ctx->stream));
+	cudaFree(d_raw);
+	cudaFree(d_rawOff);
+	init_sum_i(ctx->sum_i, ctx->max_leng);
+	ctx->haveModel = false;
+	for (auto& l : ctx->L) l = SiteList();
+	ctx->nBest = 0;
+	return 0;
+}
+
+extern "C" int xxm_seqset_info(const xxm_ctx* ctx, int32_t* total, double* avgLength, int32_t* max_leng, int32_t* min_leng) {
+	if (total) std::memcpy(total, ctx->total.data(), ctx->total.size() * sizeof(int32_t));
+	if (avgLength) std::memcpy(avgLength, ctx->avgLength.data(), ctx->avgLength.size() * sizeof(double));
+	if (max_leng) *max_leng = ctx->max_leng;
+	if (min_leng) *min_leng = ctx->min_leng;
+	return 0;
+}
+
+// =====================================================================================================================
+// a5: background + model
+// =====================================================================================================================
+extern "C" int xxm_set_background(xxm_ctx* ctx, int32_t order, const float* rprobs, const float* rconds) {
+	if (order < 0 || order > 9) return ctx->fail("background order %d not supported", order);
+	const size_t n = static_cast<size_t>(1) << (3 * (order + 1));
+	ctx->rprobs.assign(rprobs, rprobs + n);
+	ctx->rconds.assign(rconds, rconds + n);
+	ctx->nm.order = order;
+	ctx->nm.rprobs = ctx->rprobs.data();
+	ctx->nm.rconds = ctx->rconds.data();
+	ctx->haveModel = false;
+	return 0;
+}
+
+template <typename T>
+static int upload(xxm_ctx* ctx, DevBuf<T>& d, const std::vector<T>& h) {
+	CK(d.ensure(std::max<size_t>(1, h.size())));
+	if (!h.empty()) CK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+	return 0;
+}
+
+static int stage_part(xxm_ctx* ctx, const TablePart& P, bool single, DevBuf<uint32_t>& rank, DevBuf<uint32_t>* bitmap) {
+	const size_t size = static_cast<size_t>(1) << (2 * P.len);
+	CK(rank.ensure(size));
+	CK(cudaMemsetAsync(rank.p, 0, size * 4, ctx->stream));
+	if (bitmap) {
+		CK(bitmap->ensure(std::max<size_t>(1, size / 32)));
+		CK(cudaMemsetAsync(bitmap->p, 0, std::max<size_t>(1, size / 32) * 4, ctx->stream));
+	}
+	std::vector<uint8_t> ok(P.classPval.size());
+	for (size_t c = 0; c < ok.size(); ++c) ok[c] = (P.classPval[c] != 0.0) && !(single && P.classPval[c] == 1.0);
+	TRY(upload(ctx, ctx->d_ids, P.ids));
+	TRY(upload(ctx, ctx->d_cls, P.cls));
+	TRY(upload(ctx, ctx->d_clsOk, ok));
+	const int n = static_cast<int>(P.ids.size());
+	if (n) {
+		k_fill_rank<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->d_ids.p, ctx->d_cls.p, ctx->d_clsOk.p, n, rank.p, bitmap ? bitmap->p : nullptr);
+		CKK();
+	}
+	return 0;
+}
+
+static double zoops_final(double pS, double exponent) { return 1 - std::pow(1 - pS, exponent); }  // pValCalculation.h:96
+
+extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions) {
+	CK(cudaSetDevice(ctx->device));
+	if (!ctx->nent) return ctx->fail("no sequence set loaded");
+	if (!ctx->nm.rprobs) return ctx->fail("no background model set");
+	if (ncols < 1 || ncols > 26) return ctx->fail("%d match columns not supported (reference maximum is 26)", ncols);
+	for (int i = 0; i < ncols; ++i)
+		if (cols[i] < 1 || cols[i] > XXM_PWM_LENGTH || (i && cols[i] <= cols[i - 1])) return ctx->fail("invalid match columns");
+	if (posSetSize < 1 || posSetSize > ctx->nent) return ctx->fail("posSetSize out of range");
+	build_pvalue_tables(pwm, cols, ncols, posSetSize, totalPositions, ctx->opt.bgLog, ctx->nm, ctx->tab);
+	const PvalueTables& T = ctx->tab;
+	if (T.error == 1) return ctx->fail("gapped motif with >8 match columns and a left part spanning >10 positions: reference behaviour undefined");
+	if (T.error == 2) return ctx->fail("PWM column not normalised (the reference asserts, branch_and_bound-inl.h:223)");
+	if (T.part[0].len > 13 || (T.nparts == 2 && T.part[1].len > 13)) return ctx->fail("table part too long");
+	ctx->modelSerial++;
+	ctx->modelPosSetSize = posSetSize;
+	ctx->modelFirstCol = cols[0];
+	Model& M = ctx->M;
+	std::memset(&M, 0, sizeof M);
+	M.L = T.L; M.maxk = T.maxk; M.nparts = T.nparts; M.span = T.span;
+	M.len0 = T.part[0].len; M.len1 = T.nparts == 2 ? T.part[1].len : 0;
+	M.contiguous = (T.span == T.L);
+	for (int k = 0; k < T.L; ++k) {
+		M.coloff[k] = T.coloff[k];
+		for (int a = 0; a < 4; ++a) M.logodds[k][a] = T.logodds[k + 1][a + 1];
+	}
+	M.pruneThr = T.pruneThr;
+	M.corr = std::pow(ctx->opt.overrepCorrection, T.L);  // pOverrepCorrection[i] = pow(overrepCorrection, i), pValCalculation.cpp:23-24
+	TRY(stage_part(ctx, T.part[0], T.nparts == 1, ctx->d_rank0, &ctx->d_hit0));
+	M.rank0 = ctx->d_rank0.p;
+	M.hit0 = ctx->d_hit0.p;
+	TRY(upload(ctx, ctx->d_cpval0, T.part[0].classPval));
+	TRY(upload(ctx, ctx->d_cscore0, T.part[0].classScore));
+	M.cpval0 = ctx->d_cpval0.p; M.cscore0 = ctx->d_cscore0.p; M.nclass0 = static_cast<int>(T.part[0].classPval.size());
+	const double exponent = ctx->avgLength[posSetSize] - T.span + 1;
+	ctx->memoModeValid = false;
+	ctx->posProbValid = false;
+	if (T.nparts == 1) {
+		const size_t nc = T.part[0].classPval.size();
+		ctx->nval = static_cast<uint32_t>(nc);
+		ctx->h_pS.resize(nc); ctx->h_finalMops.resize(nc); ctx->h_finalMode.resize(nc);
+		for (size_t c = 0; c < nc; ++c) {
+			const double v = T.part[0].classPval[c];
+			if (v == 0.0 || v == 1.0) { ctx->h_pS[c] = 1; ctx->h_finalMops[c] = 1; ctx->h_finalMode[c] = 1; continue; }
+			const double pS = v * M.corr;
+			ctx->h_pS[c] = pS;
+			ctx->h_finalMops[c] = pS;
+			ctx->h_finalMode[c] = ctx->opt.mops ? pS : zoops_final(pS, exponent);
+		}
+		TRY(upload(ctx, ctx->d_pS, ctx->h_pS));
+		TRY(upload(ctx, ctx->d_finalMops, ctx->h_finalMops));
+		TRY(upload(ctx, ctx->d_finalMode, ctx->h_finalMode));
+	} else {
+		TRY(stage_part(ctx, T.part[1], false, ctx->d_rank1, nullptr));
+		M.rank1 = ctx->d_rank1.p;
+		TRY(upload(ctx, ctx->d_cpval1, T.part[1].classPval));
+		TRY(upload(ctx, ctx->d_cscore1, T.part[1].classScore));
+		TRY(upload(ctx, ctx->d_leftProb, T.leftClassProb));
+		M.cpval1 = ctx->d_cpval1.p; M.cscore1 = ctx->d_cscore1.p; M.leftProb = ctx->d_leftProb.p;
+		M.nclass1 = static_cast<int>(T.part[1].classPval.size());
+		// memo capacity: distinct scores <= enumerated left ids x enumerated right ids
+		uint64_t want = 4ull * std::max<uint64_t>(1, T.part[0].ids.size()) * std::max<uint64_t>(1, T.part[1].ids.size());
+		uint32_t cap = 1u << 12;
+		while (cap < want && cap < (1u << 24)) cap <<= 1;
+		CK(ctx->d_memoKey.ensure(cap));
+		CK(ctx->d_memoVal.ensure(cap));
+		CK(ctx->d_memoState.ensure(cap));
+		CK(ctx->d_flags32.ensure(4));
+		k_fill_u32<<<cdiv(cap, 256), 256, 0, ctx->stream>>>(reinterpret_cast<uint32_t*>(ctx->d_memoKey.p), static_cast<uint32_t>(kMemoEmpty), cap);
+		CKK();
+		CK(cudaMemsetAsync(ctx->d_memoState.p, 0, static_cast<size_t>(cap) * 4, ctx->stream));
+		CK(cudaMemsetAsync(ctx->d_memoVal.p, 0, static_cast<size_t>(cap) * 8, ctx->stream));
+		CK(cudaMemsetAsync(ctx->d_flags32.p, 0, 16, ctx->stream));
+		M.memoKey = ctx->d_memoKey.p; M.memoVal = ctx->d_memoVal.p; M.memoState = ctx->d_memoState.p; M.memoCap = cap;
+		M.memoOverflow = ctx->d_flags32.p;
+		ctx->nval = cap;
+		CK(ctx->d_pS.ensure(cap));
+		CK(ctx->d_finalMops.ensure(cap));
+		CK(ctx->d_finalMode.ensure(cap));
+	}
+	ctx->haveModel = true;
+	return 0;
+}
+
+extern "C" int xxm_tables_info(const xxm_ctx* ctx, int32_t* L, int32_t* maxk, int32_t* nparts, int64_t size[2], int32_t nclasses[2], int64_t nids[2]) {
+	const PvalueTables& T = ctx->tab;
+	*L = T.L; *maxk = T.maxk; *nparts = T.nparts;
+	for (int p = 0; p < 2; ++p) {
+		size[p] = p < T.nparts ? (static_cast<int64_t>(1) << (2 * T.part[p].len)) : 0;
+		nclasses[p] = p < T.nparts ? static_cast<int32_t>(T.part[p].classScore.size()) : 0;
+		nids[p] = p < T.nparts ? static_cast<int64_t>(T.part[p].ids.size()) : 0;
+	}
+	return 0;
+}
+
+extern "C" int xxm_tables_get(const xxm_ctx* ctx, int32_t part, double* pvalues, double* probs, int32_t* classScore, int32_t* classCount,
+                              int64_t* classIds) {
+	const PvalueTables& T = ctx->tab;
+	if (part < 0 || part >= T.nparts) return 1;
+	const TablePart& P = T.part[part];
+	const size_t size = static_cast<size_t>(1) << (2 * P.len);
+	if (pvalues) std::fill(pvalues, pvalues + size, 0.0);
+	if (probs) std::fill(probs, probs + size, 0.0);
+	for (size_t i = 0; i < P.ids.size(); ++i) {
+		if (pvalues) pvalues[P.ids[i]] = P.classPval[P.cls[i]];
+		if (probs && !P.prob.empty()) probs[P.ids[i]] = P.prob[i];
+		if (classIds) classIds[i] = P.ids[i];
+	}
+	for (size_t c = 0; c < P.classScore.size(); ++c) {
+		if (classScore) classScore[c] = P.classScore[c];
+		if (classCount) classCount[c] = P.classCount[c];
+	}
+	return 0;
+}
+
+// =====================================================================================================================
+// value tables
+// =====================================================================================================================
+static int stage_pos_prob(xxm_ctx* ctx, int motifLength, int firstMotifColumn, int enrStart, int enrEnd, int offset) {
+	init_positional_probs(ctx->posProb, ctx->max_leng, ctx->revcomp, motifLength, firstMotifColumn, enrStart, enrEnd, offset);
+	TRY(upload(ctx, ctx->d_posProb, ctx->posProb));
+	ctx->posProbValid = true;
+	return 0;
+}
+
+// evaluate fresh memo slots; with needMode also fill the ZOOPS/OOPS finalPval of every occupied slot on the host
+// (1 - pow(1 - pS, avgLength - length + 1) needs the C library's pow to be bit-identical)
+static int finalize_memo(xxm_ctx* ctx, bool needMode) {
+	if (ctx->M.nparts != 2) return 0;
+	const uint32_t cap = ctx->M.memoCap;
+	k_memo_eval<<<cdiv(cap, 128), 128, 0, ctx->stream>>>(ctx->M);
+	CKK();
+	k_memo_values<<<cdiv(cap, 256), 256, 0, ctx->stream>>>(ctx->M, ctx->d_pS.p, ctx->d_finalMops.p);
+	CKK();
+	uint32_t ovf = 0;
+	CK(cudaMemcpyAsync(&ovf, ctx->M.memoOverflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	const bool roundTrip = needMode && !ctx->opt.mops;
+	std::vector<int32_t> keys;
+	if (roundTrip) {
+		keys.resize(cap);
+		ctx->h_pS.resize(cap);
+		CK(cudaMemcpyAsync(keys.data(), ctx->M.memoKey, static_cast<size_t>(cap) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaMemcpyAsync(ctx->h_pS.data(), ctx->d_pS.p, static_cast<size_t>(cap) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (ovf) return ctx->fail("memo table of the >8-column path overflowed (capacity %u)", cap);
+	if (roundTrip) {
+		const double exponent = ctx->avgLength[ctx->modelPosSetSize] - ctx->tab.span + 1;
+		ctx->h_finalMode.assign(cap, 1.0);
+		for (uint32_t h = 0; h < cap; ++h) {
+			if (keys[h] == kMemoEmpty) continue;
+			const double pS = ctx->h_pS[h];
+			ctx->h_finalMode[h] = (pS == 1.0) ? 1.0 : zoops_final(pS, exponent);
+		}
+		CK(cudaMemcpyAsync(ctx->d_finalMode.p, ctx->h_finalMode.data(), static_cast<size_t>(cap) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	} else if (needMode) {
+		CK(cudaMemcpyAsync(ctx->d_finalMode.p, ctx->d_finalMops.p, static_cast<size_t>(cap) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	}
+	return 0;
+}
+
+static Values make_values(xxm_ctx* ctx, bool mops) {
+	Values V{};
+	V.pS = ctx->d_pS.p;
+	V.posProb = ctx->d_posProb.p;
+	V.perCand = ctx->d_perCand.p;
+	if (!ctx->opt.localization) {
+		V.kind = kFinalTable;
+		V.finalTab = mops ? ctx->d_finalMops.p : ctx->d_finalMode.p;
+	} else if (mops) {
+		V.kind = kFinalLocMops;
+	} else {
+		V.kind = kFinalPerCand;
+	}
+	return V;
+}
+
+// ZOOPS/OOPS with localization: finalPval = calculateFinalPval(len, delta_0, pS * positionalProb[pos]) needs pow/exp
+// (pValCalculation.h:82, :116-120) -> per-candidate host evaluation (exact, rare: --localization without --mops)
+static int compute_per_candidate(xxm_ctx* ctx, const uint32_t* d_seq, const uint32_t* d_pos, const uint32_t* d_vidx, uint32_t n, int shift, int enrStart,
+                                 int enrEnd) {
+	CK(ctx->d_perCand.ensure(std::max<uint32_t>(1, n)));
+	if (!n) return 0;
+	std::vector<uint32_t> seq(n), pos(n), vidx(n);
+	std::vector<double> pS(ctx->nval);
+	CK(cudaMemcpyAsync(seq.data(), d_seq, n * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(pos.data(), d_pos, n * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(vidx.data(), d_vidx, n * 4ull, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(pS.data(), ctx->d_pS.p, ctx->nval * 8ull, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	std::vector<double> fin(n, 1.0);
+	const int region = enrEnd - enrStart + 1;
+	const int length = ctx->tab.span;
+	for (uint32_t i = 0; i < n; ++i) {
+		if (vidx[i] == kNone) continue;
+		const double p = pS[vidx[i]];
+		if (p == 1.0) continue;
+		const int len = ctx->len[seq[i] - 1] - length + 1;
+		const int delta_0 = std::min(len, region);
+		fin[i] = final_pval_localized(ctx->sum_i, len, delta_0, p * ctx->posProb[static_cast<int>(pos[i]) + shift]);
+	}
+	CK(cudaMemcpyAsync(ctx->d_perCand.p, fin.data(), n * 8ull, cudaMemcpyHostToDevice, ctx->stream));
+	return 0;
+}
+
+static void set_max_sites_mops(xxm_ctx* ctx, int posSetSize) {
+	const int length = ctx->tab.span;
+	ctx->maxSites = ctx->total[posSetSize] - posSetSize * (length - 1);
+	if (ctx->revcomp) ctx->maxSites = ctx->total[posSetSize] - 2 * posSetSize * (length - 1);
+}
+
+// =====================================================================================================================
+// scan machinery
+// =====================================================================================================================
+static int run_scan(xxm_ctx* ctx, int nseq, const Values& V, int checkFinal, DevBuf<uint32_t>& oseq, DevBuf<uint32_t>& opos, DevBuf<uint32_t>& ovidx,
+                    uint32_t* nOut, bool timeIt) {
+	const uint32_t scanWords = ctx->wordOff[nseq];
+	const uint32_t ntiles = cdiv(scanWords, kScanThreads);
+	size_t cap = std::max<size_t>(oseq.cap, static_cast<size_t>(scanWords) * 32 / 16 + 4096);
+	for (int attempt = 0; attempt < 3; ++attempt) {
+		CK(oseq.ensure(cap));
+		CK(opos.ensure(cap));
+		CK(ovidx.ensure(cap));
+		cap = std::min(oseq.cap, std::min(opos.cap, ovidx.cap));
+		CK(ctx->status.ensure(ntiles + 1));
+		CK(ctx->total64.ensure(2));
+		CK(ctx->counters.ensure(8));
+		CK(cudaMemsetAsync(ctx->status.p, 0, (static_cast<size_t>(ntiles) + 1) * 8, ctx->stream));
+		CK(cudaMemsetAsync(ctx->total64.p, 0, 16, ctx->stream));
+		CK(cudaMemsetAsync(ctx->counters.p, 0, 32, ctx->stream));
+		ScanOut O{};
+		O.seq = oseq.p; O.pos = opos.p; O.vidx = ovidx.p;
+		O.cap = static_cast<uint32_t>(std::min<size_t>(cap, 0xFFFFFFFFu));
+		O.status = ctx->status.p;
+		O.ticket = ctx->counters.p + 4;
+		O.total = ctx->total64.p;
+		const size_t bmBytes = (static_cast<size_t>(1) << (2 * ctx->M.len0)) / 8;
+		const bool smem = bmBytes <= 32 * 1024;
+		const int grid = std::max(1, std::min<int>(static_cast<int>(ntiles), ctx->numSMs * (smem && bmBytes > 8192 ? 4 : 8)));
+		if (timeIt) CK(cudaEventRecord(ctx->ev0, ctx->stream));
+		if (smem) k_scan<true><<<grid, kScanThreads, std::max<size_t>(bmBytes, 4), ctx->stream>>>(ctx->S, ctx->M, V, O, scanWords, ntiles, checkFinal);
+		else k_scan<false><<<grid, kScanThreads, 4, ctx->stream>>>(ctx->S, ctx->M, V, O, scanWords, ntiles, checkFinal);
+		CKK();
+		if (timeIt) CK(cudaEventRecord(ctx->ev1, ctx->stream));
+		uint64_t tot = 0;
+		CK(cudaMemcpyAsync(&tot, ctx->total64.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+		CK(cudaStreamSynchronize(ctx->stream));
+		if (timeIt) {
+			float ms = 0;
+			cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+			ctx->stats.last_scan_ms = ms;
+			ctx->stats.last_scan_bases = static_cast<int64_t>(scanWords) * 32;
+			ctx->stats.last_scan_hits = static_cast<int64_t>(tot);
+		}
+		if (tot <= cap) { *nOut = static_cast<uint32_t>(tot); return 0; }
+		cap = static_cast<size_t>(tot) + 1024;  // rerun with enough room
+	}
+	return ctx->fail("scan output does not fit");
+}
+
+static int compact_list(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, const uint8_t* flag, uint32_t n, uint32_t* oseq,
+                        uint32_t* opos, uint32_t* ovidx, uint32_t* oidx, uint32_t* nOut) {
+	*nOut = 0;
+	if (!n) return 0;
+	const uint32_t ntiles = cdiv(n, 256);
+	CK(ctx->status.ensure(ntiles + 1));
+	CK(ctx->total64.ensure(2));
+	CK(ctx->counters.ensure(8));
+	CK(cudaMemsetAsync(ctx->status.p, 0, (static_cast<size_t>(ntiles) + 1) * 8, ctx->stream));
+	CK(cudaMemsetAsync(ctx->total64.p, 0, 16, ctx->stream));
+	CK(cudaMemsetAsync(ctx->counters.p + 4, 0, 4, ctx->stream));
+	CompactIO io{};
+	io.seq = seq; io.pos = pos; io.vidx = vidx; io.flag = flag; io.n = n;
+	io.oseq = oseq; io.opos = opos; io.ovidx = ovidx; io.oidx = oidx;
+	io.status = ctx->status.p; io.ticket = ctx->counters.p + 4; io.total = ctx->total64.p;
+	k_compact<<<std::min<uint32_t>(ntiles, ctx->numSMs * 8), 256, 0, ctx->stream>>>(io, ntiles);
+	CKK();
+	uint64_t tot = 0;
+	CK(cudaMemcpyAsync(&tot, ctx->total64.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	*nOut = static_cast<uint32_t>(tot);
+	return 0;
+}
+
+// updateMultOcc over an entry list -> keep flags + float scores
+static int select_mops(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, uint32_t n, int shift, bool ordered,
+                       DevBuf<uint8_t>& keep, DevBuf<float>& kscore, uint32_t* nKept, uint32_t* maxPerSeq) {
+	CK(keep.ensure(std::max<uint32_t>(1, n)));
+	CK(kscore.ensure(std::max<uint32_t>(1, n)));
+	CK(ctx->stk.ensure(std::max<uint32_t>(1, n)));
+	CK(ctx->counters.ensure(8));
+	CK(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
+	*nKept = 0; *maxPerSeq = 0;
+	if (!n) return 0;
+	CK(cudaMemsetAsync(keep.p, 0, n, ctx->stream));
+	SelectIO io{};
+	io.seq = seq; io.pos = pos; io.vidx = vidx; io.n = n; io.shift = shift; io.length = ctx->tab.span; io.revcomp = ctx->revcomp;
+	io.stk = ctx->stk.p; io.kscore = kscore.p; io.keep = keep.p; io.counters = ctx->counters.p;
+	if (ordered) k_select_mops<<<cdiv(n, 128), 128, 0, ctx->stream>>>(ctx->S, V, io);
+	else k_select_mops_serial<<<1, 32, 0, ctx->stream>>>(ctx->S, V, io);
+	CKK();
+	uint32_t c[2] = {0, 0};
+	CK(cudaMemcpyAsync(c, ctx->counters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	*nKept = c[0]; *maxPerSeq = c[1];
+	return 0;
+}
+
+static int select_slots(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, uint32_t n, int shift, bool ordered,
+                        uint32_t nslots, DevBuf<uint32_t>& sIdx, DevBuf<float>& sScore, uint32_t* nFilled) {
+	CK(sIdx.ensure(std::max<uint32_t>(1, nslots)));
+	CK(sScore.ensure(std::max<uint32_t>(1, nslots)));
+	CK(ctx->counters.ensure(8));
+	CK(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
+	k_fill_u32<<<cdiv(nslots, 256), 256, 0, ctx->stream>>>(sIdx.p, kNone, nslots);
+	CKK();
+	k_fill_f32<<<cdiv(nslots, 256), 256, 0, ctx->stream>>>(sScore.p, 1.0f, nslots);
+	CKK();
+	*nFilled = 0;
+	if (n) {
+		SlotIO io{};
+		io.seq = seq; io.pos = pos; io.vidx = vidx; io.n = n; io.shift = shift;
+		io.slotIdx = sIdx.p; io.slotScore = sScore.p; io.counters = ctx->counters.p;
+		if (ordered) k_select_zoops<<<cdiv(n, 128), 128, 0, ctx->stream>>>(V, io);
+		else k_select_zoops_serial<<<1, 32, 0, ctx->stream>>>(V, io);
+		CKK();
+		CK(cudaMemcpyAsync(nFilled, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	}
+	CK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+// =====================================================================================================================
+// a2: full scan
+// =====================================================================================================================
+extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t* nbSites, int32_t* nbBestSites, int32_t* maxSites) {
+	CK(cudaSetDevice(ctx->device));
+	if (!ctx->haveModel) return ctx->fail("xxm_scan_full: no model (call xxm_reinitialize)");
+	if (posSetSize < 1 || posSetSize > ctx->nent) return ctx->fail("posSetSize out of range");
+	const PvalueTables& T = ctx->tab;
+	if (ctx->opt.localization) TRY(stage_pos_prob(ctx, T.span, ctx->modelFirstCol, enrStart, enrEnd, 0));
+	const Values V = make_values(ctx, true);  // the full scan always uses mops = true (StartPosUpdater-inl.h:99)
+	uint32_t n = 0;
+	if (T.nparts == 1) {
+		TRY(run_scan(ctx, posSetSize, V, 1, ctx->b_seq, ctx->b_pos, ctx->b_vidx, &n, true));
+	} else {
+		// candidates first; the p-value of a >8-column window is known only after the memo slots are evaluated
+		uint32_t nc = 0;
+		TRY(run_scan(ctx, posSetSize, V, 0, ctx->t_seq, ctx->t_pos, ctx->t_vidx, &nc, true));
+		TRY(finalize_memo(ctx, false));
+		CK(ctx->flag8.ensure(std::max<uint32_t>(1, nc)));
+		CK(ctx->counters.ensure(8));
+		CK(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
+		if (nc) {
+			k_flag_hits<<<cdiv(nc, 256), 256, 0, ctx->stream>>>(V, ctx->t_vidx.p, ctx->t_pos.p, nc, ctx->flag8.p, ctx->counters.p);
+			CKK();
+		}
+		CK(ctx->b_seq.ensure(std::max<uint32_t>(1, nc)));
+		CK(ctx->b_pos.ensure(std::max<uint32_t>(1, nc)));
+		CK(ctx->b_vidx.ensure(std::max<uint32_t>(1, nc)));
+		TRY(compact_list(ctx, ctx->t_seq.p, ctx->t_pos.p, ctx->t_vidx.p, ctx->flag8.p, nc, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, nullptr, &n));
+	}
+	ctx->nBest = n;
+	// bestStartPos[].score = float(pValScore) (StartPosUpdater-inl.h:105)
+	CK(ctx->b_score.ensure(std::max<uint32_t>(1, n)));
+	if (n) {
+		k_entry_scores<<<cdiv(n, 256), 256, 0, ctx->stream>>>(V, ctx->b_vidx.p, ctx->b_pos.p, n, 0, 0, ctx->b_score.p);
+		CKK();
+	}
+	SiteList& B = ctx->L[XXM_LIST_BEST_STARTPOS];
+	B = SiteList();
+	B.kind = kListCompact; B.seq = ctx->b_seq.p; B.pos = ctx->b_pos.p; B.vidx = ctx->b_vidx.p; B.n = n; B.score = ctx->b_score.p; B.members = n;
+	B.modelSerial = ctx->modelSerial;
+	// updateMultOcc -> sortedSites
+	uint32_t kept = 0, mps = 0;
+	TRY(select_mops(ctx, V, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, n, 0, true, ctx->s_keep, ctx->s_kscore, &kept, &mps));
+	SiteList& Sd = ctx->L[XXM_LIST_SORTED_SITES];
+	Sd = SiteList();
+	Sd.kind = kListFlagged; Sd.seq = ctx->b_seq.p; Sd.pos = ctx->b_pos.p; Sd.vidx = ctx->b_vidx.p; Sd.n = n; Sd.score = ctx->s_kscore.p;
+	Sd.keep = ctx->s_keep.p; Sd.members = kept; Sd.maxPerSeq = mps; Sd.tableValued = (V.kind == kFinalTable); Sd.modelSerial = ctx->modelSerial;
+	ctx->nbSites = static_cast<int>(kept);
+	set_max_sites_mops(ctx, posSetSize);
+	*nbSites = ctx->nbSites;
+	*nbBestSites = static_cast<int32_t>(n);
+	*maxSites = ctx->maxSites;
+	return 0;
+}
+
+#include "xxm_gpu_part2.inc"

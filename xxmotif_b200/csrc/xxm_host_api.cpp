@@ -1,0 +1,67 @@
+// Device-free entry points of the C ABI (include/xxmotif_gpu.h, "host-side pieces"): the same host code the GPU path
+// uses, exposed so that the host logic can be unit-tested on a machine without a GPU.
+#include "../../include/xxmotif_gpu.h"
+
+#include <algorithm>
+#include <vector>
+
+#include "host_stats.h"
+#include "pvalue_tables.h"
+
+using namespace xxm;
+
+extern "C" int xxm_host_tables(const double* pwm, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions, const double* bgLog,
+                               int32_t order, const float* rprobs, const float* rconds, int32_t part, int64_t* info, double* pvalues, double* probs,
+                               int32_t* classScore, int32_t* classCount, int64_t* classIds) {
+	NullModelView nm;
+	nm.order = order;
+	nm.rprobs = rprobs;
+	nm.rconds = rconds;
+	PvalueTables T;
+	build_pvalue_tables(pwm, cols, ncols, posSetSize, totalPositions, bgLog, nm, T);
+	if (T.error) return T.error;
+	info[0] = T.L; info[1] = T.maxk; info[2] = T.nparts;
+	for (int p = 0; p < 2; ++p) {
+		const bool have = p < T.nparts;
+		info[3 + p] = have ? (static_cast<int64_t>(1) << (2 * T.part[p].len)) : 0;
+		info[5 + p] = have ? static_cast<int64_t>(T.part[p].classScore.size()) : 0;
+		info[7 + p] = have ? static_cast<int64_t>(T.part[p].ids.size()) : 0;
+	}
+	if (part < 0 || part >= T.nparts) return 0;
+	const TablePart& P = T.part[part];
+	const size_t size = static_cast<size_t>(1) << (2 * P.len);
+	if (pvalues) std::fill(pvalues, pvalues + size, 0.0);
+	if (probs) std::fill(probs, probs + size, 0.0);
+	for (size_t i = 0; i < P.ids.size(); ++i) {
+		if (pvalues) pvalues[P.ids[i]] = P.classPval[P.cls[i]];
+		if (probs && !P.prob.empty()) probs[P.ids[i]] = P.prob[i];
+		if (classIds) classIds[i] = P.ids[i];
+	}
+	for (size_t c = 0; c < P.classScore.size(); ++c) {
+		if (classScore) classScore[c] = P.classScore[c];
+		if (classCount) classCount[c] = P.classCount[c];
+	}
+	return 0;
+}
+
+extern "C" int xxm_host_best_subset(const float* score, const int32_t* seq, int32_t nbSites, int32_t posSetSize, int32_t maxSeqCount, int32_t maxSites,
+                                    int32_t nent, int32_t maxMotifsPerSequence, int32_t oneOccurrence, double plusFrac, int32_t* bestMotifNb,
+                                    double* bestPval) {
+	LogSum ls;
+	const int64_t limit = static_cast<int64_t>(posSetSize) * maxSeqCount;
+	SubsetChoice c = best_subset_from_sorted(ls, score, seq, nbSites, limit, maxSites, nent, maxMotifsPerSequence, oneOccurrence != 0, plusFrac);
+	// cross-check with the run-length formulation used by the histogram fast path
+	std::vector<ScoreRun> runs;
+	for (int32_t i = 0; i < nbSites; ++i) {
+		if (!runs.empty() && runs.back().score == score[i]) runs.back().count++;
+		else runs.push_back(ScoreRun{score[i], 1});
+	}
+	SubsetChoice r = best_subset_from_runs(ls, runs, nbSites, limit, maxSites, oneOccurrence != 0, plusFrac);
+	*bestMotifNb = c.bestMotifNb;
+	*bestPval = c.bestPval;
+	std::vector<int32_t> per(static_cast<size_t>(nent) + 1, 0);
+	bool caps = false;
+	for (int32_t i = 0; i < nbSites; ++i) if (++per[seq[i]] > maxMotifsPerSequence) caps = true;
+	if (!caps && plusFrac == 0.0 && (r.bestMotifNb != c.bestMotifNb || r.bestPval != c.bestPval)) return 3;
+	return 0;
+}

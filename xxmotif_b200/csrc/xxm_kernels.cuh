@@ -1,0 +1,705 @@
+// Hand-written sm_100a kernels of the PWM-refinement hot path.  No tensor cores: the path is an HBM-bound
+// integer gather/compaction.  All kernels run on the context's stream.
+#pragma once
+#include "xxm_device.cuh"
+
+namespace xxm {
+
+constexpr int kScanThreads = 256;
+constexpr uint64_t kFlagAgg = 1ull << 62;   // decoupled look-back: tile aggregate available
+constexpr uint64_t kFlagIncl = 2ull << 62;  // inclusive prefix available
+constexpr uint64_t kValMask = (1ull << 62) - 1;
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1  encode: raw codes (0=N,1..4) -> packed stream, generating the reverse strand on the fly
+//     (createRevcomp, seqset.cpp:128-178: S[n+1] = N, S[n+1+k] = complement(S[n+1-k])).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_encode(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rawOff, SeqStream S, uint64_t* __restrict__ codes,
+                         uint32_t* __restrict__ nmask, int revcomp) {
+	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= S.nwords + 2) return;
+	if (w >= S.nwords) { codes[w] = 0; nmask[w] = 0xFFFFFFFFu; return; }
+	const uint32_t s = find_seq(S, w);
+	const int n = S.len[s];
+	const int n0 = revcomp ? (n - 1) / 2 : n;
+	const uint8_t* r = raw + rawOff[s];
+	uint64_t c = 0;
+	uint32_t m = 0;
+	const int q0 = static_cast<int>(w - S.wordOff[s]) * 32 + 1;
+	for (int j = 0; j < 32; ++j) {
+		const int q = q0 + j;
+		int code = 0;
+		if (q <= n0) code = r[q - 1];
+		else if (revcomp && q > n0 + 1 && q <= n) { const int f = r[2 * n0 + 2 - q - 1]; code = f ? 5 - f : 0; }
+		if (code == 0) m |= 1u << j;
+		else c |= static_cast<uint64_t>(code - 1) << (2 * j);
+	}
+	codes[w] = c;
+	nmask[w] = m;
+}
+
+// scatter compact (id, class) lists into the dense rank table and the "can be a site" bitmap
+__global__ void k_fill_rank(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ cls, const uint8_t* __restrict__ clsOk, int n,
+                            uint32_t* __restrict__ rank, uint32_t* __restrict__ bitmap) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t id = ids[i], c = cls[i];
+	if (!clsOk[c]) return;  // pValueHash value 0 ("not in table", branch_and_bound-inl.h:392) or exactly 1
+	rank[id] = c + 1;
+	if (bitmap) atomicOr(&bitmap[id >> 5], 1u << (id & 31));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// window evaluation shared by the scan and the re-score kernels: get_kmer_probability_all_positions +
+// get_kmer_probability_matched_only (branch_and_bound-inl.h:361-457).  Returns the value index or kNone.
+// For > maxk match columns the value is a memo slot keyed by the integer score s (the convolution at :425-449
+// depends on the window only through s); slots are evaluated afterwards by k_memo_eval.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t memo_slot(const Model& M, int32_t s) {
+	uint32_t h = (static_cast<uint32_t>(s) * 2654435761u) & (M.memoCap - 1);
+	for (uint32_t probe = 0; probe < M.memoCap; ++probe) {
+		const int32_t old = atomicCAS(&M.memoKey[h], kMemoEmpty, s);
+		if (old == kMemoEmpty || old == s) return h;
+		h = (h + 1) & (M.memoCap - 1);
+	}
+	atomicExch(M.memoOverflow, 1u);
+	return kNone;
+}
+
+__device__ __forceinline__ uint32_t eval_window(const Model& M, uint64_t c0, uint64_t c1, uint32_t m0, uint32_t m1, int j) {
+	// N in a match column -> 1.0 (:388,:397,:407); gap columns may hold N
+	uint32_t id0 = 0, id1 = 0;
+	if (M.contiguous) {
+		const uint64_t mm = (static_cast<uint64_t>(m1) << 32 | m0) >> j;
+		if (mm & ((M.span >= 32) ? 0xFFFFFFFFull : ((1ull << M.span) - 1))) return kNone;
+		id0 = kmer_at(c0, c1, j, M.len0);
+		if (M.nparts == 2) {
+			for (int k = 0; k < M.len1; ++k) id1 |= base_at(c0, c1, j + M.len0 + k) << (2 * k);
+		}
+	} else {
+		const uint64_t mm = (static_cast<uint64_t>(m1) << 32 | m0);
+		for (int k = 0; k < M.L; ++k) {
+			const int o = j + M.coloff[k];
+			if ((mm >> o) & 1ull) return kNone;
+			const uint32_t b = base_at(c0, c1, o);
+			if (k < M.len0) id0 |= b << (2 * k);
+			else id1 |= b << (2 * (k - M.len0));
+		}
+	}
+	const uint32_t r0 = M.rank0[id0];
+	if (r0 == 0) return kNone;
+	if (M.nparts == 1) return r0 - 1;
+	const uint32_t r1 = M.rank1[id1];
+	if (r1 == 0) return kNone;
+	if (__dmul_rn(M.cpval0[r0 - 1], M.cpval1[r1 - 1]) > M.pruneThr) return kNone;  // :417
+	double score = 0;  // get_Kmer_score :42-50, natural column order, no contraction
+	for (int k = 0; k < M.L; ++k) score = __dadd_rn(score, M.logodds[k][base_at(c0, c1, j + M.coloff[k])]);
+	const int32_t s = static_cast<int32_t>(__dsub_rn(__dmul_rn(score, 1e6), 1.0));
+	return memo_slot(M, s);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2  full scan (fill_sites_with_possible_startPositions, StartPosUpdater-inl.h:90-113, the `for i / for j` body).
+//     One thread owns one 32-base word = 32 window starts.  Persistent CTAs take tiles by ticket; hits are written
+//     in global (sequence, position) order through a single-pass decoupled look-back prefix over tiles, so no sort
+//     is needed downstream (the reference's scan order IS (seq,pos) order).
+// ---------------------------------------------------------------------------------------------------------------
+struct ScanOut {
+	uint32_t* seq;     // 1-based sequence number
+	uint32_t* pos;     // 1-based start position
+	uint32_t* vidx;    // value index
+	uint32_t cap;
+	uint64_t* status;  // [ntiles] look-back words (zeroed before launch)
+	uint32_t* ticket;  // zeroed before launch
+	uint64_t* total;   // out: number of hits
+};
+
+template <bool kSmemBitmap>
+__global__ void __launch_bounds__(kScanThreads) k_scan(SeqStream S, Model M, Values V, ScanOut O, uint32_t scanWords, uint32_t ntiles,
+                                                       int checkFinal) {
+	extern __shared__ uint32_t s_bm[];
+	__shared__ uint32_t s_tile;
+	__shared__ uint32_t s_warp[kScanThreads / 32];
+	__shared__ uint64_t s_base;
+	const uint32_t* bm = M.hit0;
+	if (kSmemBitmap) {
+		const uint32_t nw = (1u << (2 * M.len0)) / 32u;
+		for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) s_bm[i] = M.hit0[i];
+		bm = s_bm;
+	}
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0) s_tile = atomicAdd(O.ticket, 1u);
+		__syncthreads();
+		const uint32_t tile = s_tile;
+		if (tile >= ntiles) break;
+		const uint32_t w = tile * kScanThreads + threadIdx.x;
+		uint64_t c0 = 0, c1 = 0;
+		uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
+		if (w < scanWords) {
+			c0 = S.codes[w]; c1 = S.codes[w + 1];
+			m0 = S.nmask[w]; m1 = S.nmask[w + 1];
+		}
+		// pass 1: bitmap pre-filter on the left k-mer (exact when there is a single table and no localization)
+		uint32_t cand = 0;
+		if (m0 != 0xFFFFFFFFu) {
+			if (M.contiguous) {
+#pragma unroll 8
+				for (int j = 0; j < 32; ++j) {
+					const uint32_t id = kmer_at(c0, c1, j, M.len0);
+					cand |= ((bm[id >> 5] >> (id & 31)) & 1u) << j;
+				}
+			} else {
+				for (int j = 0; j < 32; ++j) {
+					uint32_t id = 0;
+					for (int k = 0; k < M.len0; ++k) id |= base_at(c0, c1, j + M.coloff[k]) << (2 * k);
+					cand |= ((bm[id >> 5] >> (id & 31)) & 1u) << j;
+				}
+			}
+			cand &= ~m0;  // the first match column is the window start
+		}
+		// pass 2: exact evaluation of the survivors
+		uint32_t seq0 = 0, wo = 0;
+		uint32_t hits = 0;
+		if (cand) {
+			seq0 = find_seq(S, w);
+			wo = S.wordOff[seq0];
+			uint32_t rem = cand;
+			while (rem) {
+				const int j = __ffs(rem) - 1;
+				rem &= rem - 1;
+				const uint32_t v = eval_window(M, c0, c1, m0, m1, j);
+				if (v == kNone) continue;
+				if (checkFinal) {
+					const int pos = static_cast<int>(w - wo) * 32 + j + 1;
+					if (!(final_of(V, v, 0, pos) < 1.0)) continue;  // finalPval >= 1 -> continue, :101
+				}
+				hits |= 1u << j;
+			}
+		}
+		// ordered output offset: warp scan -> block scan -> look-back over tiles
+		const uint32_t cnt = __popc(hits);
+		uint32_t incl = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+			if (lane >= d) incl += t;
+		}
+		if (lane == 31) s_warp[wid] = incl;
+		__syncthreads();
+		uint32_t woff = 0, btotal = 0;
+#pragma unroll
+		for (int k = 0; k < kScanThreads / 32; ++k) {
+			if (k < wid) woff += s_warp[k];
+			btotal += s_warp[k];
+		}
+		if (threadIdx.x == 0) {
+			volatile uint64_t* st = O.status;
+			uint64_t excl = 0;
+			if (tile == 0) {
+				st[0] = kFlagIncl | btotal;
+			} else {
+				st[tile] = kFlagAgg | btotal;
+				for (uint32_t t = tile - 1;; --t) {
+					uint64_t v;
+					do { v = st[t]; } while ((v >> 62) == 0);
+					excl += v & kValMask;
+					if ((v >> 62) == 2) break;
+				}
+				st[tile] = kFlagIncl | (excl + btotal);
+			}
+			if (tile == ntiles - 1) *O.total = excl + btotal;
+			s_base = excl;
+		}
+		__syncthreads();
+		if (hits) {
+			uint64_t o = s_base + woff + (incl - cnt);
+			uint32_t rem = hits;
+			while (rem) {
+				const int j = __ffs(rem) - 1;
+				rem &= rem - 1;
+				if (o < O.cap) {
+					O.seq[o] = seq0 + 1;
+					O.pos[o] = (w - wo) * 32 + j + 1;
+					O.vidx[o] = eval_window(M, c0, c1, m0, m1, j);
+				}
+				++o;
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// memo evaluation for > maxk columns: the convolution of branch_and_bound-inl.h:419-449 for one integer score s.
+// One thread per occupied, not yet evaluated slot; strictly the reference's loop and summation order.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int class_search(const int32_t* score, int n, int S) {  // binarySearch :339-357
+	int low = 0, high = n;
+	while (low < high) {
+		const int mid = low + ((high - low) / 2);
+		if (score[mid] > S) low = mid + 1;
+		else high = mid;
+	}
+	if (low < n && score[low] == S) return low;
+	return low - 1;
+}
+
+__global__ void k_memo_eval(Model M) {
+	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+	if (h >= M.memoCap) return;
+	const int32_t s = M.memoKey[h];
+	if (s == kMemoEmpty || M.memoState[h]) return;
+	const int s1_max = M.cscore0[0], s2_max = M.cscore1[0];
+	int it = class_search(M.cscore1, M.nclass1, s - s1_max);
+	double pValue = 0;
+	for (int i = 0; i < M.nclass0; ++i) {
+		const int s1 = M.cscore0[i];
+		if (s - s2_max > s1) break;
+		while (it != 0 && M.cscore1[it] < s - s1) --it;
+		pValue = __dadd_rn(pValue, __dmul_rn(M.leftProb[i], M.cpval1[it]));
+	}
+	M.memoVal[h] = pValue;
+	M.memoState[h] = 1;
+}
+
+// pS / finalPval(mops) of memo slots: pValScore == 1 stays 1 (pValCalculation.h:70), otherwise * 1.05^L (:72)
+__global__ void k_memo_values(Model M, double* __restrict__ pS, double* __restrict__ finalMops) {
+	const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+	if (h >= M.memoCap) return;
+	double v = 1.0;
+	if (M.memoKey[h] != kMemoEmpty) {
+		const double p = M.memoVal[h];
+		v = (p == 1.0) ? 1.0 : __dmul_rn(p, M.corr);
+	}
+	pS[h] = v;
+	finalMops[h] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// evaluation of explicit windows (re-score of a candidate list, a motif's own sites, per-site p-values):
+// the calculatePval part of fill_elongSites_with_possible_startPositions (StartPosUpdater-inl.h:167-190).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_eval_list(SeqStream S, Model M, const uint32_t* __restrict__ seq, const uint32_t* __restrict__ pos, uint32_t n, int shift,
+                            uint32_t* __restrict__ vidx) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t s = seq[i] - 1;
+	const int p = static_cast<int>(pos[i]) + shift;
+	uint32_t v = kNone;
+	if (p >= 1 && p + M.span - 1 <= S.len[s]) {  // :181
+		const uint32_t g = static_cast<uint32_t>(p - 1);
+		const uint32_t w = S.wordOff[s] + (g >> 5);
+		v = eval_window(M, S.codes[w], S.codes[w + 1], S.nmask[w], S.nmask[w + 1], g & 31);
+	}
+	vidx[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3  updateMultOcc (StartPosUtils.h:12-65): greedy non-overlap in scan order incl. the reverse-strand look-back.
+//     Sequential inside a sequence, independent across sequences: the thread of the first entry of every run of
+//     equal sequence numbers walks its run.  `stk` holds the kept entries of the run in place ([a, a+cnt)).
+// ---------------------------------------------------------------------------------------------------------------
+struct SelectIO {
+	const uint32_t* seq;
+	const uint32_t* pos;
+	const uint32_t* vidx;
+	uint32_t n;
+	int shift;           // added to pos (column-variant offset of the re-score, StartPosUpdater-inl.h:170)
+	int length;          // motif span
+	int revcomp;
+	uint32_t* stk;       // [n] scratch
+	float* kscore;       // [n] float(finalPval) of kept entries
+	uint8_t* keep;       // [n] out (zeroed before launch)
+	uint32_t* counters;  // [0] nbSites, [1] max kept per sequence
+};
+
+__device__ __forceinline__ void mops_walk(const SeqStream& S, const Values& V, const SelectIO& io, uint32_t a, uint32_t b) {
+	uint32_t cnt = 0;
+	uint32_t* stk = io.stk + a;
+	for (uint32_t i = a; i < b; ++i) {
+		const uint32_t v = io.vidx[i];
+		if (v == kNone) continue;
+		const int seq = static_cast<int>(io.seq[i]);
+		const int pos = static_cast<int>(io.pos[i]) + io.shift;
+		const double pVal = final_of(V, v, i, pos);
+		if (!(pVal < 1.0)) continue;
+		bool reject = false;
+		if (cnt > 0) {
+			const uint32_t t = stk[cnt - 1];
+			if (static_cast<int>(io.seq[t]) == seq && static_cast<int>(io.pos[t]) + io.shift + io.length >= pos) {
+				if (static_cast<double>(io.kscore[t]) <= pVal) reject = true;
+				else --cnt;
+			}
+		}
+		if (!reject && io.revcomp && pos > io.length / 2) {
+			int back = 1;
+			const int revPos = S.len[seq - 1] - io.length + 2 - pos;
+			while (static_cast<int>(cnt) - back >= 0 && static_cast<int>(io.seq[stk[cnt - back]]) == seq &&
+			       static_cast<int>(io.pos[stk[cnt - back]]) + io.shift > revPos + io.length - 1)
+				++back;
+			if (static_cast<int>(cnt) - back >= 0 && static_cast<int>(io.seq[stk[cnt - back]]) == seq &&
+			    static_cast<int>(io.pos[stk[cnt - back]]) + io.shift >= revPos - io.length + 1) {
+				if (static_cast<double>(io.kscore[stk[cnt - back]]) <= pVal) reject = true;
+				else {
+					while (back > 1) { stk[cnt - back] = stk[cnt - back + 1]; --back; }
+					--cnt;
+				}
+			}
+		}
+		if (reject) continue;
+		stk[cnt++] = i;
+		io.kscore[i] = static_cast<float>(pVal);
+	}
+	for (uint32_t k = 0; k < cnt; ++k) io.keep[stk[k]] = 1;
+	if (cnt) { atomicAdd(&io.counters[0], cnt); atomicMax(&io.counters[1], cnt); }
+}
+
+__global__ void k_select_mops(SeqStream S, Values V, SelectIO io) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= io.n) return;
+	if (i > 0 && io.seq[i - 1] == io.seq[i]) return;  // not a run head
+	uint32_t b = i + 1;
+	while (b < io.n && io.seq[b] == io.seq[i]) ++b;
+	mops_walk(S, V, io, i, b);
+}
+__global__ void k_select_mops_serial(SeqStream S, Values V, SelectIO io) {
+	if (blockIdx.x == 0 && threadIdx.x == 0) mops_walk(S, V, io, 0, io.n);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ZOOPS / OOPS: best site per sequence with the reference's comparison `finalPval(double) < slot.score(float)`
+// in list order (StartPosUpdater-inl.h:196-203, :253-257, :47-53).  slotIdx[seq-1] = entry index or kNone.
+// ---------------------------------------------------------------------------------------------------------------
+struct SlotIO {
+	const uint32_t* seq;
+	const uint32_t* pos;
+	const uint32_t* vidx;
+	uint32_t n;
+	int shift;
+	uint32_t* slotIdx;   // [nslots] (filled with kNone before launch)
+	float* slotScore;    // [nslots] (filled with 1.0f before launch)
+	uint32_t* counters;  // [0] number of sequences that received a site
+};
+
+__device__ __forceinline__ void zoops_walk(const Values& V, const SlotIO& io, uint32_t a, uint32_t b) {
+	for (uint32_t i = a; i < b; ++i) {
+		const uint32_t v = io.vidx[i];
+		if (v == kNone) continue;
+		const int pos = static_cast<int>(io.pos[i]) + io.shift;
+		const double f = final_of(V, v, i, pos);
+		const uint32_t s = io.seq[i] - 1;
+		if (f < static_cast<double>(io.slotScore[s])) {
+			if (io.slotIdx[s] == kNone) atomicAdd(&io.counters[0], 1u);
+			io.slotIdx[s] = i;
+			io.slotScore[s] = static_cast<float>(f);
+		}
+	}
+}
+__global__ void k_select_zoops(Values V, SlotIO io) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= io.n) return;
+	if (i > 0 && io.seq[i - 1] == io.seq[i]) return;
+	uint32_t b = i + 1;
+	while (b < io.n && io.seq[b] == io.seq[i]) ++b;
+	zoops_walk(V, io, i, b);
+}
+__global__ void k_select_zoops_serial(Values V, SlotIO io) {
+	if (blockIdx.x == 0 && threadIdx.x == 0) zoops_walk(V, io, 0, io.n);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, uint32_t n) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) p[i] = v;
+}
+__global__ void k_fill_f32(float* p, float v, uint32_t n) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) p[i] = v;
+}
+
+// flags of entries that are sites of their list (finalPval < 1 under the values of the evaluation that made it)
+__global__ void k_flag_hits(Values V, const uint32_t* __restrict__ vidx, const uint32_t* __restrict__ pos, uint32_t n, uint8_t* __restrict__ flag,
+                            uint32_t* __restrict__ count) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t v = vidx[i];
+	const bool ok = (v != kNone) && (final_of(V, v, i, static_cast<int>(pos[i])) < 1.0);
+	flag[i] = ok;
+	if (ok) atomicAdd(count, 1u);
+}
+
+// ordered compaction of a (seq,pos,vidx) list by flag; single CTA-chain look-back like k_scan
+struct CompactIO {
+	const uint32_t *seq, *pos, *vidx;
+	const uint8_t* flag;
+	uint32_t n;
+	uint32_t *oseq, *opos, *ovidx, *oidx;  // any may be null
+	uint64_t* status;                       // zeroed
+	uint32_t* ticket;                       // zeroed
+	uint64_t* total;
+};
+__global__ void __launch_bounds__(256) k_compact(CompactIO io, uint32_t ntiles) {
+	__shared__ uint32_t s_tile;
+	__shared__ uint32_t s_warp[8];
+	__shared__ uint64_t s_base;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	for (;;) {
+		__syncthreads();
+		if (threadIdx.x == 0) s_tile = atomicAdd(io.ticket, 1u);
+		__syncthreads();
+		const uint32_t tile = s_tile;
+		if (tile >= ntiles) break;
+		const uint32_t i = tile * 256 + threadIdx.x;
+		const uint32_t f = (i < io.n) ? io.flag[i] : 0u;
+		const uint32_t ball = __ballot_sync(0xFFFFFFFFu, f);
+		const uint32_t excl_w = __popc(ball & ((1u << lane) - 1));
+		if (lane == 0) s_warp[wid] = __popc(ball);
+		__syncthreads();
+		uint32_t woff = 0, btotal = 0;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) { if (k < wid) woff += s_warp[k]; btotal += s_warp[k]; }
+		if (threadIdx.x == 0) {
+			volatile uint64_t* st = io.status;
+			uint64_t excl = 0;
+			if (tile == 0) st[0] = kFlagIncl | btotal;
+			else {
+				st[tile] = kFlagAgg | btotal;
+				for (uint32_t t = tile - 1;; --t) {
+					uint64_t v;
+					do { v = st[t]; } while ((v >> 62) == 0);
+					excl += v & kValMask;
+					if ((v >> 62) == 2) break;
+				}
+				st[tile] = kFlagIncl | (excl + btotal);
+			}
+			if (tile == ntiles - 1) *io.total = excl + btotal;
+			s_base = excl;
+		}
+		__syncthreads();
+		if (f) {
+			const uint64_t o = s_base + woff + excl_w;
+			if (io.oseq) io.oseq[o] = io.seq[i];
+			if (io.opos) io.opos[o] = io.pos[i];
+			if (io.ovidx) io.ovidx[o] = io.vidx[i];
+			if (io.oidx) io.oidx[o] = i;
+		}
+	}
+}
+
+// histogram of kept entries over value indices (table-valued finalPval: the float score is a function of vidx)
+__global__ void k_hist_vidx(const uint32_t* __restrict__ vidx, const uint8_t* __restrict__ keep, uint32_t n, uint32_t* __restrict__ hist) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || !keep[i]) return;
+	atomicAdd(&hist[vidx[i]], 1u);
+}
+__global__ void k_hist_slots(const uint32_t* __restrict__ slotIdx, const uint32_t* __restrict__ vidx, uint32_t nslots, uint32_t* __restrict__ hist) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= nslots) return;
+	const uint32_t i = slotIdx[s];
+	if (i != kNone) atomicAdd(&hist[vidx[i]], 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K5  PWM recount (Motif::updateCounts, Motif.cpp:653-672): 30-column context of every chosen site.
+//     chosen = kept entry whose float score is <= thr (the optimal subset always ends at the end of a run of equal
+//     scores, StartPosUpdater.h:184), or an explicit index list.
+// ---------------------------------------------------------------------------------------------------------------
+struct CountIO {
+	const uint32_t *seq, *pos;
+	int shift;
+	const uint8_t* keep;        // null with idx
+	const float* kscore;        // float score per entry (null with idx)
+	const uint32_t* idx;        // explicit entries (null with keep)
+	const uint32_t* slotIdx;    // per-sequence slots: entry of slot t (kNone: empty), chosen if slotScore[t] <= thr
+	const float* slotScore;
+	uint32_t n;
+	float thr;
+	int firstColumn;            // motifColumns.front(): pos - firstColumn + 1 is the position of PWM column 1
+	unsigned long long* counts; // [31*5] zeroed
+};
+__global__ void __launch_bounds__(256) k_count_pwm(SeqStream S, CountIO io) {
+	__shared__ unsigned int s_cnt[31 * 5];
+	for (int k = threadIdx.x; k < 31 * 5; k += blockDim.x) s_cnt[k] = 0;
+	__syncthreads();
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < io.n) {
+		uint32_t i = t;
+		bool use = true;
+		if (io.idx) i = io.idx[t];
+		else if (io.slotIdx) { i = io.slotIdx[t]; use = (i != kNone) && io.slotScore[t] <= io.thr; }
+		else use = io.keep[i] && io.kscore[i] <= io.thr;
+		if (use) {
+			const uint32_t s = io.seq[i] - 1;
+			const int n = S.len[s];
+			const int p0 = static_cast<int>(io.pos[i]) + io.shift - io.firstColumn + 1;
+			const uint32_t wo = S.wordOff[s];
+			for (int j = 1; j <= 30; ++j) {
+				const int p = p0 + j - 1;
+				if (p < 1 || p > n) continue;
+				const uint32_t g = static_cast<uint32_t>(p - 1);
+				const uint32_t w = wo + (g >> 5);
+				if ((S.nmask[w] >> (g & 31)) & 1u) continue;
+				const uint32_t b = static_cast<uint32_t>(S.codes[w] >> (2 * (g & 31))) & 3u;
+				atomicAdd(&s_cnt[j * 5 + b + 1], 1u);
+				atomicAdd(&s_cnt[j * 5], 1u);
+			}
+		}
+	}
+	__syncthreads();
+	for (int k = threadIdx.x; k < 31 * 5; k += blockDim.x)
+		if (s_cnt[k]) atomicAdd(&io.counts[k], static_cast<unsigned long long>(s_cnt[k]));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// stable LSD radix sort on 32-bit keys with an index payload (sortSitesByScore, StartPosUtils.h:68-70: positive
+// float scores order like their bit patterns; stability == glibc's merge-sort qsort).
+// One warp sorts one chunk per pass: digit histogram per chunk -> global scan -> stable scatter with match_any.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSortChunk = 2048;
+__global__ void k_rs_hist(const uint32_t* __restrict__ keys, uint32_t n, int shift, uint32_t* __restrict__ hist /*[256][nchunks]*/, uint32_t nchunks) {
+	__shared__ uint32_t s_h[256];
+	for (int k = threadIdx.x; k < 256; k += blockDim.x) s_h[k] = 0;
+	__syncthreads();
+	const uint32_t base = blockIdx.x * kSortChunk;
+	for (uint32_t k = threadIdx.x; k < kSortChunk; k += blockDim.x) {
+		const uint32_t i = base + k;
+		if (i < n) atomicAdd(&s_h[(keys[i] >> shift) & 255u], 1u);
+	}
+	__syncthreads();
+	for (int k = threadIdx.x; k < 256; k += blockDim.x) hist[static_cast<size_t>(k) * nchunks + blockIdx.x] = s_h[k];
+}
+// exclusive scan of hist in (digit, chunk) order, single CTA
+__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* __restrict__ hist, uint32_t total) {
+	__shared__ uint32_t s_w[32];
+	__shared__ uint32_t s_carry;
+	if (threadIdx.x == 0) s_carry = 0;
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	for (uint32_t base = 0; base < total; base += 1024) {
+		const uint32_t i = base + threadIdx.x;
+		const uint32_t v = (i < total) ? hist[i] : 0u;
+		uint32_t incl = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+		if (lane == 31) s_w[wid] = incl;
+		__syncthreads();
+		uint32_t woff = 0, tot = 0;
+		for (int k = 0; k < 32; ++k) { if (k < wid) woff += s_w[k]; tot += s_w[k]; }
+		const uint32_t carry = s_carry;
+		if (i < total) hist[i] = carry + woff + incl - v;
+		__syncthreads();
+		if (threadIdx.x == 0) s_carry = carry + tot;
+		__syncthreads();
+	}
+}
+__global__ void __launch_bounds__(32) k_rs_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n, int shift,
+                                                    const uint32_t* __restrict__ hist, uint32_t nchunks, uint32_t* __restrict__ okeys,
+                                                    uint32_t* __restrict__ ovals) {
+	__shared__ uint32_t s_off[256];
+	const int lane = threadIdx.x;
+	for (int k = lane; k < 256; k += 32) s_off[k] = hist[static_cast<size_t>(k) * nchunks + blockIdx.x];
+	__syncwarp();
+	const uint32_t base = blockIdx.x * kSortChunk;
+	for (uint32_t k = 0; k < kSortChunk; k += 32) {
+		const uint32_t i = base + k + lane;
+		const bool ok = i < n;
+		const uint32_t key = ok ? keys[i] : 0u;
+		const uint32_t d = ok ? ((key >> shift) & 255u) : 256u + lane;  // inactive lanes get unique pseudo digits
+		const uint32_t peers = __match_any_sync(0xFFFFFFFFu, d);
+		const uint32_t rank = __popc(peers & ((1u << lane) - 1));
+		uint32_t off = 0;
+		if (ok) off = s_off[d];
+		__syncwarp();
+		if (ok) {
+			okeys[off + rank] = key;
+			ovals[off + rank] = vals[i];
+			if (rank == static_cast<uint32_t>(__popc(peers)) - 1) s_off[d] = off + rank + 1;
+		}
+		__syncwarp();
+	}
+}
+
+// gather float-score keys (bit patterns) of the members of a list
+__global__ void k_gather_keys(const float* __restrict__ score, const uint32_t* __restrict__ idx, uint32_t n, uint32_t* __restrict__ keys,
+                              uint32_t* __restrict__ vals) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	keys[i] = __float_as_uint(score[idx[i]]);
+	vals[i] = idx[i];
+}
+// materialise xxm_site records: (score from kscore/float table, pos + shift, seq) for entries idx[0..n)
+struct SiteRec { float score; int32_t startPos; int32_t sequence; };
+__global__ void k_emit_sites(const uint32_t* __restrict__ seq, const uint32_t* __restrict__ pos, const float* __restrict__ score, const uint32_t* __restrict__ idx,
+                             uint32_t n, int shift, SiteRec* __restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t e = idx ? idx[i] : i;
+	SiteRec r;
+	r.score = score[e];
+	r.startPos = static_cast<int32_t>(pos[e]) + shift;
+	r.sequence = static_cast<int32_t>(seq[e]);
+	out[i] = r;
+}
+// float(pS) of list entries (bestStartPos[].score, StartPosUpdater-inl.h:105) or float(finalPval)
+__global__ void k_entry_scores(Values V, const uint32_t* __restrict__ vidx, const uint32_t* __restrict__ pos, uint32_t n, int shift, int wantFinal,
+                               float* __restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t v = vidx[i];
+	float r = 1.0f;
+	if (v != kNone) r = static_cast<float>(wantFinal ? final_of(V, v, i, static_cast<int>(pos[i]) + shift) : V.pS[v]);
+	out[i] = r;
+}
+// doubles for xxm_window_pvals
+__global__ void k_entry_doubles(Values V, const uint32_t* __restrict__ vidx, const uint32_t* __restrict__ pos, uint32_t n, double* __restrict__ fin,
+                                double* __restrict__ ps) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t v = vidx[i];
+	double f = 1.0, p = 1.0;
+	if (v != kNone) {
+		p = V.pS[v];
+		f = (p == 1.0) ? 1.0 : final_of(V, v, i, static_cast<int>(pos[i]));
+	}
+	fin[i] = f;
+	ps[i] = p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K6  forward / reverse-complement log-odds histogram (Output::printScoreDistribution, output.cpp:1050-1064;
+//     calculateMatrixScore_logOdds, Motif.h:584-599).  One thread per 32-base word; double sums in column order.
+// ---------------------------------------------------------------------------------------------------------------
+struct HistModel {
+	int ncols, span;
+	int coloff[32];
+	double lodF[32][5];  // [k][0] = N penalty, [k][1+code]
+	double lodB[32][5];
+	double thrF, thrB;
+};
+__global__ void k_logodds_hist(SeqStream S, HistModel H, uint32_t scanWords, unsigned int* __restrict__ fwd, unsigned int* __restrict__ bwd, int npos) {
+	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= scanWords) return;
+	const uint64_t c0 = S.codes[w], c1 = S.codes[w + 1];
+	const uint64_t mm = (static_cast<uint64_t>(S.nmask[w + 1]) << 32) | S.nmask[w];
+	const uint32_t s = find_seq(S, w);
+	const int n = S.len[s];
+	const int p0 = static_cast<int>(w - S.wordOff[s]) * 32 + 1;
+	for (int j = 0; j < 32; ++j) {
+		const int pos = p0 + j;
+		if (pos > n - H.span + 1 || pos > npos) break;
+		double f = 0, b = 0;
+		for (int k = 0; k < H.ncols; ++k) {
+			const int o = j + H.coloff[k];
+			const int a = ((mm >> o) & 1ull) ? 0 : 1 + static_cast<int>(base_at(c0, c1, o));
+			f = __dadd_rn(f, H.lodF[k][a]);
+			b = __dadd_rn(b, H.lodB[k][a]);
+		}
+		if (f > H.thrF) atomicAdd(&fwd[pos - 1], 1u);
+		if (b > H.thrB) atomicAdd(&bwd[pos - 1], 1u);
+	}
+}
+
+}  // namespace xxm
