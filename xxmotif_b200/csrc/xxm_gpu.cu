@@ -411,7 +411,7 @@ extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* 
 			const double pS = v * M.corr;
 			ctx->h_pS[c] = pS;
 			ctx->h_finalMops[c] = pS;
-			ctx->h_finalMode[c] = ctx->opt.mops ? pS : zoops_final(pS, exponent);
+			ctx->h_finalMode[c] = zoops_final(pS, exponent);
 		}
 		TRY(upload(ctx, ctx->d_pS, ctx->h_pS));
 		TRY(upload(ctx, ctx->d_finalMops, ctx->h_finalMops));
@@ -500,7 +500,7 @@ static int finalize_memo(xxm_ctx* ctx, bool needMode) {
 	CKK();
 	uint32_t ovf = 0;
 	CK(cudaMemcpyAsync(&ovf, ctx->M.memoOverflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
-	const bool roundTrip = needMode && !ctx->opt.mops;
+	const bool roundTrip = needMode;
 	std::vector<int32_t> keys;
 	if (roundTrip) {
 		keys.resize(cap);
