@@ -142,6 +142,18 @@ int xxm_get_sites(xxm_ctx* ctx, int32_t which, int32_t order, int32_t palin, xxm
 int xxm_logodds_hist(xxm_ctx* ctx, const double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize, double* fwd, double* bwd,
                      int32_t npos, double* maxScore, double* maxScore2);
 
+/* ---- a8/a9 split in phases, for a sequence set sharded over several GPUs (one context per GPU) ---------
+ * The reference chooses the optimal subset over ALL sites (getBestSubset) and recounts the PWM from them.  With shards,
+ * each context reports the run-length histogram of its float site scores (xxm_score_runs, ascending, score 1 excluded);
+ * the caller merges the histograms of all ranks (NCCL all-gather), chooses the subset once (xxm_host_choose_subset),
+ * every context counts its sites with score <= the subset's last score (xxm_count_sites), the 31x5 count matrices are
+ * summed (NCCL all-reduce) and turned into the new PWM (xxm_host_build_pwm = Motif::buildPWM, Motif.cpp:584-591). */
+int xxm_score_runs(xxm_ctx* ctx, int32_t which, float* scores, int64_t* counts, int32_t cap, int32_t* nruns);
+int xxm_count_sites(xxm_ctx* ctx, int32_t which, float thr, int32_t firstColumn, double* counts31x5, int64_t* nsites);
+int xxm_host_choose_subset(const float* scores, const int64_t* counts, int32_t nruns, int64_t nbSites, int64_t limit, int64_t maxSites,
+                           int32_t oneOccurrence, double plusFrac, int64_t* bestMotifNb, double* bestPval, float* lastScore);
+int xxm_host_build_pwm(const double* counts31x5, double pseudoTimesK, const double* bg5, double* pwm31x5);
+
 /* ---- host-side pieces of the path, callable without a device (unit tests of the host logic) -------------------------
  * xxm_host_tables: the table construction xxm_reinitialize performs (branch_and_bound-inl.h:183-603), without staging.
  *   info[9] = L, maxk, nparts, size0, size1, nclasses0, nclasses1, nids0, nids1; the arrays of `part` may be NULL.
@@ -150,6 +162,13 @@ int xxm_logodds_hist(xxm_ctx* ctx, const double* pwm31x5, const int32_t* cols, i
 int xxm_host_tables(const double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions, const double* bgLog5,
                     int32_t order, const float* rprobs, const float* rconds, int32_t part, int64_t* info, double* pvalues, double* probs,
                     int32_t* classScore, int32_t* classCount, int64_t* classIds);
+/* xxm_host_null_model: NullModel::init(sequences, alpha = pseudocountsFactor, beta = countsOffset, order, gaps = true,
+ *   freqs = NULL) (NullModel.cpp:64-201) -> the two 2^(3(order+1)) float tables xxm_set_background takes.  n/codes are the
+ *   sequences as the reference holds them when the model is trained (AFTER createRevcomp if --revcomp).
+ * xxm_host_background: posBg/negBg and their logs (checkSequenceSet, backgroundDistribution.cpp:50-95). */
+int xxm_host_null_model(int32_t nent, const int32_t* n, const uint8_t* codes, int32_t order, float alpha, float beta, float* rprobs,
+                        float* rconds);
+int xxm_host_background(int32_t nent, const int32_t* n, const uint8_t* codes, double* bg5, double* bgLog5);
 int xxm_host_best_subset(const float* score, const int32_t* seq, int32_t nbSites, int32_t posSetSize, int32_t maxSeqCount, int32_t maxSites,
                          int32_t nent, int32_t maxMotifsPerSequence, int32_t oneOccurrence, double plusFrac, int32_t* bestMotifNb,
                          double* bestPval);

@@ -24,7 +24,7 @@ void LogSum::extend(int64_t upTo) {
 		const int64_t cnt = std::min<int64_t>(kBlock, end - i + 1);
 		logs.resize(static_cast<size_t>(cnt));
 		if (cnt < (1 << 16) || nt == 1) {
-			for (int64_t k = 0; k < cnt; ++k) logs[k] = std::log(static_cast<double>(static_cast<int>(i + k)));
+			for (int64_t k = 0; k < cnt; ++k) logs[k] = std::log(static_cast<double>(i + k));
 		} else {
 			std::vector<std::thread> th;
 			const int64_t per = (cnt + nt - 1) / nt;
@@ -32,7 +32,7 @@ void LogSum::extend(int64_t upTo) {
 				const int64_t a = t * per, b = std::min<int64_t>(cnt, a + per);
 				if (a >= b) break;
 				th.emplace_back([&logs, a, b, i]() {
-					for (int64_t k = a; k < b; ++k) logs[k] = std::log(static_cast<double>(static_cast<int>(i + k)));
+					for (int64_t k = a; k < b; ++k) logs[k] = std::log(static_cast<double>(i + k));
 				});
 			}
 			for (auto& x : th) x.join();
@@ -52,14 +52,14 @@ double LogSum::at(int64_t i) {
 	const int64_t c = i / kStride;
 	if (c >= static_cast<int64_t>(ckpt_.size())) extend(i);
 	double acc = ckpt_[static_cast<size_t>(c)];
-	for (int64_t k = c * kStride + 1; k <= i; ++k) acc = std::log(static_cast<double>(static_cast<int>(k))) + acc;
+	for (int64_t k = c * kStride + 1; k <= i; ++k) acc = std::log(static_cast<double>(k)) + acc;
 	return acc;
 }
 
-double order_statistics_pvalue(LogSum& ls, int motifNb, int N, double p) {
+double order_statistics_pvalue(LogSum& ls, int64_t motifNb, int64_t N, double p) {
 	if (N * p > motifNb || p == 1) return 0;
 	double sum_K_1, delta_K_1;
-	int K = 0;
+	int64_t K = 0;
 	// log_binomial(N, motifNb, p): LOG_sum_i[N] - LOG_sum_i[k] - LOG_sum_i[N-k] + k*log(prob) + (N-k)*log(1-prob)
 	double logN = (ls.at(N) - ls.at(motifNb) - ls.at(N - motifNb) + motifNb * std::log(p) + (N - motifNb) * std::log(1 - p));
 	double alpha_K_1, sum_K = 0;
@@ -161,7 +161,7 @@ double final_pval_localized(const std::vector<double>& sum_i, int len, int delta
 namespace {
 struct Sweep {
 	LogSum& ls;
-	int maxSites;
+	int64_t maxSites;
 	bool oneOccurrence;
 	double plusFrac;  // 1 + Global::plusFrac
 	SubsetChoice c;
@@ -189,7 +189,7 @@ struct Sweep {
 };
 }  // namespace
 
-SubsetChoice best_subset_from_runs(LogSum& ls, const std::vector<ScoreRun>& runs, int64_t nbSites, int64_t limit, int maxSites, bool oneOccurrence,
+SubsetChoice best_subset_from_runs(LogSum& ls, const std::vector<ScoreRun>& runs, int64_t nbSites, int64_t limit, int64_t maxSites, bool oneOccurrence,
                                    double plusFracGlobal) {
 	Sweep sw{ls, maxSites, oneOccurrence, 1 + plusFracGlobal, SubsetChoice(), 1, false};
 	if (nbSites == 0) return sw.c;
@@ -209,7 +209,7 @@ SubsetChoice best_subset_from_runs(LogSum& ls, const std::vector<ScoreRun>& runs
 	return sw.c;
 }
 
-SubsetChoice best_subset_from_sorted(LogSum& ls, const float* score, const int32_t* seq, int64_t nbSites, int64_t limit, int maxSites, int nent,
+SubsetChoice best_subset_from_sorted(LogSum& ls, const float* score, const int32_t* seq, int64_t nbSites, int64_t limit, int64_t maxSites, int nent,
                                      int maxMotifsPerSequence, bool oneOccurrence, double plusFracGlobal) {
 	Sweep sw{ls, maxSites, oneOccurrence, 1 + plusFracGlobal, SubsetChoice(), 1, false};
 	if (nbSites == 0) return sw.c;

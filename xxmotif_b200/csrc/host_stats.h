@@ -22,7 +22,7 @@ private:
 };
 
 // calculateOrderStatisticsPvalue (utils.h:80-102) with log_binomial (utils.h:61-64)
-double order_statistics_pvalue(LogSum& ls, int motifNb, int N, double p);
+double order_statistics_pvalue(LogSum& ls, int64_t motifNb, int64_t N, double p);
 
 // fast_log (utils.h:138-162)
 float fast_log(float x);
@@ -53,10 +53,10 @@ struct SubsetChoice {
 	float lastScore = 0.f;
 	int bestMotifNbPlus = 0;
 };
-SubsetChoice best_subset_from_runs(LogSum& ls, const std::vector<ScoreRun>& runs, int64_t nbSites, int64_t limit, int maxSites, bool oneOccurrence,
+SubsetChoice best_subset_from_runs(LogSum& ls, const std::vector<ScoreRun>& runs, int64_t nbSites, int64_t limit, int64_t maxSites, bool oneOccurrence,
                                    double plusFracGlobal);
 // the literal loop over a sorted site array (scores + 1-based sequence numbers) with per-sequence caps
-SubsetChoice best_subset_from_sorted(LogSum& ls, const float* score, const int32_t* seq, int64_t nbSites, int64_t limit, int maxSites, int nent,
+SubsetChoice best_subset_from_sorted(LogSum& ls, const float* score, const int32_t* seq, int64_t nbSites, int64_t limit, int64_t maxSites, int nent,
                                      int maxMotifsPerSequence, bool oneOccurrence, double plusFracGlobal);
 
 }  // namespace xxm

@@ -23,6 +23,7 @@ struct SeqStream {
 	const uint32_t* blk2seq;   // [nwords / kBlkWords + 1] sequence that owns word (b * kBlkWords)
 	uint32_t nwords;
 	int32_t nent;
+	uint32_t uniformWps;       // words per sequence when all sequences have the same stored length, else 0
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -41,7 +42,9 @@ struct Model {
 	int coloff[32];        // offset of match column k from the window start
 	const uint32_t* rank0; // [4^len0] class index + 1 of the left k-mer (0: not enumerated)
 	const uint32_t* rank1; // [4^len1]
-	const uint32_t* hit0;  // bitmap over 4^len0: left k-mer can produce finalPval < 1
+	const uint32_t* hit0;  // bitmap over 4^len0: left k-mer is in the table
+	const uint8_t* t8;     // [65536] stage-1 byte table of the scan (xxm_scan2.cuh)
+	uint32_t exactBits;    // windows (bit j of a word) whose stage-1 bit already is the exact left-k-mer test
 	const double* cpval0;  // [nclass0] cumulative p-value of left classes  (pValueHash[0])
 	const double* cpval1;  // [nclass1]
 	const int32_t* cscore0;// [nclass0] descending

@@ -14,6 +14,7 @@
 #include "host_stats.h"
 #include "pvalue_tables.h"
 #include "xxm_kernels.cuh"
+#include "xxm_scan2.cuh"
 
 using namespace xxm;
 
@@ -114,6 +115,8 @@ struct xxm_ctx {
 	DevBuf<uint8_t> s_keep, e_keep, flag8;
 	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
 	DevBuf<uint64_t> status, total64;
+	DevBuf<uint32_t> r_seq, r_pos, r_vidx, r_count, r_off, d_pbits;
+	DevBuf<uint8_t> d_t8;
 	DevBuf<unsigned long long> d_counts;
 	DevBuf<SiteRec> d_sites;
 	DevBuf<unsigned int> d_hf, d_hb;
@@ -152,6 +155,7 @@ struct xxm_ctx {
 	} while (0)
 
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
+static int stage_t8(xxm_ctx* ctx);  // xxm_gpu_scan2.inc
 
 // =====================================================================================================================
 // life cycle
@@ -200,6 +204,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	ctx->slotIdx.release(); ctx->e_slotIdx.release(); ctx->e_slotScore.release(); ctx->u_score.release(); ctx->counters.release(); ctx->hist.release(); ctx->idxA.release(); ctx->idxB.release(); ctx->keysA.release();
 	ctx->keysB.release(); ctx->rsHist.release(); ctx->status.release(); ctx->total64.release(); ctx->d_counts.release(); ctx->d_sites.release();
 	ctx->d_hf.release(); ctx->d_hb.release();
+	ctx->r_seq.release(); ctx->r_pos.release(); ctx->r_vidx.release(); ctx->r_count.release(); ctx->r_off.release(); ctx->d_pbits.release(); ctx->d_t8.release();
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
 	cudaStreamDestroy(ctx->stream);
@@ -299,6 +304,7 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	ctx->S.blk2seq = ctx->d_blk2seq.p;
 	ctx->S.nwords = ctx->nwords;
 	ctx->S.nent = nent;
+	ctx->S.uniformWps = (mx == mn) ? static_cast<uint32_t>((static_cast<uint64_t>(mx) + kPadBases + 31) / 32) : 0u;
 	k_encode<<<cdiv(static_cast<uint64_t>(ctx->nwords) + 2, 256), 256, 0, ctx->stream>>>(d_raw, d_rawOff, ctx->S, ctx->d_codes.p, ctx->d_nmask.p,
 	                                                                                   revcomp ? 1 : 0);
 	CKK();
@@ -444,6 +450,7 @@ extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* 
 		CK(ctx->d_finalMops.ensure(cap));
 		CK(ctx->d_finalMode.ensure(cap));
 	}
+	TRY(stage_t8(ctx));
 	ctx->haveModel = true;
 	return 0;
 }
@@ -578,50 +585,11 @@ static void set_max_sites_mops(xxm_ctx* ctx, int posSetSize) {
 // =====================================================================================================================
 // scan machinery
 // =====================================================================================================================
+#include "xxm_gpu_scan2.inc"
+
 static int run_scan(xxm_ctx* ctx, int nseq, const Values& V, int checkFinal, DevBuf<uint32_t>& oseq, DevBuf<uint32_t>& opos, DevBuf<uint32_t>& ovidx,
-                    uint32_t* nOut, bool timeIt) {
-	const uint32_t scanWords = ctx->wordOff[nseq];
-	const uint32_t ntiles = cdiv(scanWords, kScanThreads);
-	size_t cap = std::max<size_t>(oseq.cap, static_cast<size_t>(scanWords) * 32 / 16 + 4096);
-	for (int attempt = 0; attempt < 3; ++attempt) {
-		CK(oseq.ensure(cap));
-		CK(opos.ensure(cap));
-		CK(ovidx.ensure(cap));
-		cap = std::min(oseq.cap, std::min(opos.cap, ovidx.cap));
-		CK(ctx->status.ensure(ntiles + 1));
-		CK(ctx->total64.ensure(2));
-		CK(ctx->counters.ensure(8));
-		CK(cudaMemsetAsync(ctx->status.p, 0, (static_cast<size_t>(ntiles) + 1) * 8, ctx->stream));
-		CK(cudaMemsetAsync(ctx->total64.p, 0, 16, ctx->stream));
-		CK(cudaMemsetAsync(ctx->counters.p, 0, 32, ctx->stream));
-		ScanOut O{};
-		O.seq = oseq.p; O.pos = opos.p; O.vidx = ovidx.p;
-		O.cap = static_cast<uint32_t>(std::min<size_t>(cap, 0xFFFFFFFFu));
-		O.status = ctx->status.p;
-		O.ticket = ctx->counters.p + 4;
-		O.total = ctx->total64.p;
-		const size_t bmBytes = (static_cast<size_t>(1) << (2 * ctx->M.len0)) / 8;
-		const bool smem = bmBytes <= 32 * 1024;
-		const int grid = std::max(1, std::min<int>(static_cast<int>(ntiles), ctx->numSMs * (smem && bmBytes > 8192 ? 4 : 8)));
-		if (timeIt) CK(cudaEventRecord(ctx->ev0, ctx->stream));
-		if (smem) k_scan<true><<<grid, kScanThreads, std::max<size_t>(bmBytes, 4), ctx->stream>>>(ctx->S, ctx->M, V, O, scanWords, ntiles, checkFinal);
-		else k_scan<false><<<grid, kScanThreads, 4, ctx->stream>>>(ctx->S, ctx->M, V, O, scanWords, ntiles, checkFinal);
-		CKK();
-		if (timeIt) CK(cudaEventRecord(ctx->ev1, ctx->stream));
-		uint64_t tot = 0;
-		CK(cudaMemcpyAsync(&tot, ctx->total64.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaStreamSynchronize(ctx->stream));
-		if (timeIt) {
-			float ms = 0;
-			cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-			ctx->stats.last_scan_ms = ms;
-			ctx->stats.last_scan_bases = static_cast<int64_t>(scanWords) * 32;
-			ctx->stats.last_scan_hits = static_cast<int64_t>(tot);
-		}
-		if (tot <= cap) { *nOut = static_cast<uint32_t>(tot); return 0; }
-		cap = static_cast<size_t>(tot) + 1024;  // rerun with enough room
-	}
-	return ctx->fail("scan output does not fit");
+                    DevBuf<float>* oscore, uint32_t* nOut, bool timeIt) {
+	return run_scan2(ctx, nseq, V, checkFinal, oseq, opos, ovidx, oscore, nOut, timeIt);
 }
 
 static int compact_list(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, const uint8_t* flag, uint32_t n, uint32_t* oseq,
@@ -708,11 +676,11 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 	const Values V = make_values(ctx, true);  // the full scan always uses mops = true (StartPosUpdater-inl.h:99)
 	uint32_t n = 0;
 	if (T.nparts == 1) {
-		TRY(run_scan(ctx, posSetSize, V, 1, ctx->b_seq, ctx->b_pos, ctx->b_vidx, &n, true));
+		TRY(run_scan(ctx, posSetSize, V, 1, ctx->b_seq, ctx->b_pos, ctx->b_vidx, &ctx->b_score, &n, true));
 	} else {
 		// candidates first; the p-value of a >8-column window is known only after the memo slots are evaluated
 		uint32_t nc = 0;
-		TRY(run_scan(ctx, posSetSize, V, 0, ctx->t_seq, ctx->t_pos, ctx->t_vidx, &nc, true));
+		TRY(run_scan(ctx, posSetSize, V, 0, ctx->t_seq, ctx->t_pos, ctx->t_vidx, nullptr, &nc, true));
 		TRY(finalize_memo(ctx, false));
 		CK(ctx->flag8.ensure(std::max<uint32_t>(1, nc)));
 		CK(ctx->counters.ensure(8));
@@ -729,7 +697,7 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 	ctx->nBest = n;
 	// bestStartPos[].score = float(pValScore) (StartPosUpdater-inl.h:105)
 	CK(ctx->b_score.ensure(std::max<uint32_t>(1, n)));
-	if (n) {
+	if (n && T.nparts == 2) {
 		k_entry_scores<<<cdiv(n, 256), 256, 0, ctx->stream>>>(V, ctx->b_vidx.p, ctx->b_pos.p, n, 0, 0, ctx->b_score.p);
 		CKK();
 	}
@@ -753,3 +721,4 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 }
 
 #include "xxm_gpu_part2.inc"
+#include "xxm_gpu_part3.inc"

@@ -65,3 +65,27 @@ extern "C" int xxm_host_best_subset(const float* score, const int32_t* seq, int3
 	if (!caps && plusFrac == 0.0 && (r.bestMotifNb != c.bestMotifNb || r.bestPval != c.bestPval)) return 3;
 	return 0;
 }
+
+// ---- split-phase subset choice for sharded sequence sets (see xxm_gpu_part3.inc) ------------------------------------
+static LogSum g_logsum;
+
+extern "C" int xxm_host_choose_subset(const float* scores, const int64_t* counts, int32_t nruns, int64_t nbSites, int64_t limit, int64_t maxSites,
+                                      int32_t oneOccurrence, double plusFrac, int64_t* bestMotifNb, double* bestPval, float* lastScore) {
+	*bestMotifNb = 0;
+	*bestPval = 1.0;
+	*lastScore = 0.f;
+	std::vector<ScoreRun> runs(static_cast<size_t>(std::max(0, nruns)));
+	for (int i = 0; i < nruns; ++i) runs[i] = ScoreRun{scores[i], counts[i]};
+	if (runs.empty() || runs[0].score == 1.0f) return 0;
+	g_logsum.reserve(std::max<int64_t>(1, maxSites));
+	SubsetChoice c = best_subset_from_runs(g_logsum, runs, nbSites, limit, maxSites, oneOccurrence != 0, plusFrac);
+	*bestMotifNb = c.bestMotifNb;
+	*bestPval = c.bestPval;
+	*lastScore = c.lastScore;
+	return 0;
+}
+
+extern "C" int xxm_host_build_pwm(const double* counts31x5, double pseudoTimesK, const double* bg5, double* pwm31x5) {
+	build_pwm_from_counts(counts31x5, pseudoTimesK, bg5, pwm31x5);
+	return 0;
+}

@@ -1,0 +1,121 @@
+"""Host-side input preparation for the hot path: reverse-complement doubling, mono-nucleotide background and the
+order-k NullModel tables (device-free entry points of the C ABI), plus synthetic planted-motif sequence sets.
+
+Used by bench.py, the tests and the refinement driver; never touches oracle/.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+EXTRA_EXPORTS = ["xxm_host_null_model", "xxm_host_background"]
+
+
+def _lib():
+    L = capi.load_library()
+    if not getattr(L, "_hostprep_ready", False):
+        vp, i32, flt = C.c_void_p, C.c_int32, C.c_float
+        L.xxm_host_null_model.restype = i32
+        L.xxm_host_null_model.argtypes = [i32, vp, vp, i32, flt, flt, vp, vp]
+        L.xxm_host_background.restype = i32
+        L.xxm_host_background.argtypes = [i32, vp, vp, vp, vp]
+        L._hostprep_ready = True
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def revcomp_double(n, codes):
+    """createRevcomp (seqset.cpp:128-178): every sequence becomes fwd + N + reverse complement. Vectorised."""
+    n = np.asarray(n, dtype=np.int64)
+    codes = np.asarray(codes, dtype=np.uint8)
+    n2 = 2 * n + 1
+    out = np.zeros(int(n2.sum()), dtype=np.uint8)
+    src_off = np.concatenate(([0], np.cumsum(n)))[:-1]
+    dst_off = np.concatenate(([0], np.cumsum(n2)))[:-1]
+    comp = np.array([0, 4, 3, 2, 1], dtype=np.uint8)
+    if len(set(n.tolist())) == 1:  # uniform length: pure reshape
+        L = int(n[0])
+        a = codes.reshape(len(n), L)
+        o = out.reshape(len(n), 2 * L + 1)
+        o[:, :L] = a
+        o[:, L + 1:] = comp[a[:, ::-1]]
+        return n2.astype(np.int32), out
+    for s, d, L in zip(src_off, dst_off, n):
+        s, d, L = int(s), int(d), int(L)
+        out[d:d + L] = codes[s:s + L]
+        out[d + L + 1:d + 2 * L + 1] = comp[codes[s:s + L][::-1]]
+    return n2.astype(np.int32), out
+
+
+def background(n, codes):
+    """posBg / negBg and logs over the sequences as stored (after revcomp doubling)."""
+    n = np.ascontiguousarray(n, dtype=np.int32)
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    bg = np.zeros(5)
+    bgl = np.zeros(5)
+    if _lib().xxm_host_background(len(n), _p(n), _p(codes), _p(bg), _p(bgl)):
+        raise capi.XxmError("xxm_host_background failed")
+    return bg, bgl
+
+
+def null_model(n, codes, order=2, alpha=10.0, beta=0.0):
+    """NullModel::init over the sequences as stored -> (rprobs, rconds) float32 tables of size 2^(3(order+1))."""
+    n = np.ascontiguousarray(n, dtype=np.int32)
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    size = 1 << (3 * (order + 1))
+    rp = np.zeros(size, dtype=np.float32)
+    rc = np.zeros(size, dtype=np.float32)
+    if _lib().xxm_host_null_model(len(n), _p(n), _p(codes), order, alpha, beta, _p(rp), _p(rc)):
+        raise capi.XxmError("xxm_host_null_model failed")
+    return rp, rc
+
+
+IUPAC = {"A": [1], "C": [2], "G": [3], "T": [4], "W": [1, 4], "R": [1, 3], "Y": [2, 4], "S": [2, 3], "K": [3, 4], "M": [1, 2], "N": [1, 2, 3, 4]}
+
+
+def synthetic_set(nseq, length, motif="TATAWAWR", frac=0.5, seed=4, chunk=1 << 16):
+    """i.i.d. uniform ACGT sequences of one length with one planted IUPAC instance in a fraction of them
+    (SURVEY.md 8(d) cfg4 shape). Returns (n int32[nseq], codes uint8[nseq*length]) with codes 1..4."""
+    rng = np.random.default_rng(seed)
+    codes = np.empty(nseq * length, dtype=np.uint8)
+    m = len(motif)
+    for a in range(0, nseq, chunk):
+        b = min(nseq, a + chunk)
+        blk = rng.integers(1, 5, size=(b - a, length), dtype=np.uint8)
+        has = rng.random(b - a) < frac
+        pos = rng.integers(0, length - m + 1, size=b - a)
+        rows = np.flatnonzero(has)
+        for j, ch in enumerate(motif):
+            alts = np.array(IUPAC[ch], dtype=np.uint8)
+            blk[rows, pos[rows] + j] = alts[rng.integers(0, len(alts), size=len(rows))]
+        codes[a * length:b * length] = blk.reshape(-1)
+    return np.full(nseq, length, dtype=np.int32), codes
+
+
+TATA_PROFILE = np.array([  # the README's 4 x 8 TATA profile shape (rows A, C, G, T), values in percent
+    [5, 90, 5, 90, 45, 90, 50, 45],
+    [5, 3, 5, 3, 5, 3, 5, 5],
+    [5, 3, 5, 3, 5, 3, 5, 45],
+    [85, 4, 85, 4, 45, 4, 40, 5]], dtype=np.float64)
+
+
+def profile_pwm(profile=TATA_PROFILE):
+    """Motif::InitProfMotif (Motif.cpp:720-799): a 4 x L profile -> the 31 x 5 log PWM centred in 30 columns and its
+    match columns. Values are divided by 100 and renormalised per column; other columns are uniform."""
+    L = profile.shape[1]
+    pwm = np.zeros((31, 5))
+    first = (30 - L) // 2 + 1
+    pwm[1:, 1:] = np.log(1.0 / 4)
+    for i in range(L):
+        col = profile[:, i] / 100.0
+        tot = 0.0
+        for v in col:
+            tot += v
+        pwm[first + i, 0] = tot
+        for a in range(4):
+            pwm[first + i, a + 1] = np.log((col[a] + 0.0 / 1000) / (tot + 4 * 0.0 / 1000))
+    return pwm.reshape(-1), np.arange(first, first + L, dtype=np.int32)
