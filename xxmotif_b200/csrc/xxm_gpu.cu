@@ -15,6 +15,7 @@
 #include "pvalue_tables.h"
 #include "xxm_kernels.cuh"
 #include "xxm_scan2.cuh"
+#include "xxm_select2.cuh"
 
 using namespace xxm;
 
@@ -58,6 +59,7 @@ struct SiteList {
 	bool tableValued = false;       // float score is a function of vidx under the current model
 	bool mopsValues = true;         // ... taken from the mops (true) or the mode (false) finalPval table
 	uint64_t modelSerial = 0;
+	uint64_t histSerial = 0;        // != 0: ctx->hist already holds this list's value-index histogram (fused into the select kernel)
 };
 
 }  // namespace
@@ -121,6 +123,8 @@ struct xxm_ctx {
 	DevBuf<SiteRec> d_sites;
 	DevBuf<unsigned int> d_hf, d_hb;
 	uint32_t nBest = 0;
+	bool histValid = false;      // ctx->hist holds the value-index histogram of the list made by the last select_mops
+	uint64_t histSerial = 0, histCounter = 0;
 	SiteList L[3];
 	int nbSites = 0, maxSites = 0;
 
@@ -630,13 +634,34 @@ static int select_mops(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const
 	SelectIO io{};
 	io.seq = seq; io.pos = pos; io.vidx = vidx; io.n = n; io.shift = shift; io.length = ctx->tab.span; io.revcomp = ctx->revcomp;
 	io.stk = ctx->stk.p; io.kscore = kscore.p; io.keep = keep.p; io.counters = ctx->counters.p;
-	if (ordered) k_select_mops<<<cdiv(n, 128), 128, 0, ctx->stream>>>(ctx->S, V, io);
-	else k_select_mops_serial<<<1, 32, 0, ctx->stream>>>(ctx->S, V, io);
-	CKK();
+	ctx->histValid = false;
+	// forward-only sets whose per-sequence site count cannot reach the cap: cluster walk with the class histogram fused in
+	const bool capSafe = ctx->max_leng / (ctx->tab.span + 1) + 1 <= ctx->opt.maxMotifsPerSequence;
+	if (ordered && !ctx->revcomp && capSafe) {
+		SelectFwdIO f{};
+		f.seq = seq; f.pos = pos; f.vidx = vidx; f.n = n; f.length = ctx->tab.span; f.kscore = kscore.p; f.keep = keep.p; f.counters = ctx->counters.p;
+		const bool wantHist = (V.kind == kFinalTable);
+		if (wantHist) {
+			CK(ctx->hist.ensure(std::max<uint32_t>(1, ctx->nval)));
+			CK(cudaMemsetAsync(ctx->hist.p, 0, ctx->nval * 4ull, ctx->stream));
+			f.hist = ctx->hist.p; f.nval = ctx->nval; f.smemHist = ctx->nval <= 8192;
+		}
+		const size_t sm = (wantHist && f.smemHist) ? ctx->nval * 4ull : 0;
+		const uint32_t grid = std::min<uint32_t>(cdiv(n, 256), static_cast<uint32_t>(ctx->numSMs) * 8);
+		k_select_mops_fwd<<<grid, 256, sm, ctx->stream>>>(V, f);
+		CKK();
+		ctx->histValid = wantHist;
+		ctx->histSerial = ++ctx->histCounter;
+	} else {
+		if (ordered) k_select_mops<<<cdiv(n, 128), 128, 0, ctx->stream>>>(ctx->S, V, io);
+		else k_select_mops_serial<<<1, 32, 0, ctx->stream>>>(ctx->S, V, io);
+		CKK();
+	}
 	uint32_t c[2] = {0, 0};
 	CK(cudaMemcpyAsync(c, ctx->counters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	*nKept = c[0]; *maxPerSeq = c[1];
+	if (ordered && !ctx->revcomp && capSafe) *maxPerSeq = std::min<uint32_t>(c[0], static_cast<uint32_t>(ctx->max_leng / (ctx->tab.span + 1) + 1));
 	return 0;
 }
 
@@ -712,6 +737,7 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 	Sd = SiteList();
 	Sd.kind = kListFlagged; Sd.seq = ctx->b_seq.p; Sd.pos = ctx->b_pos.p; Sd.vidx = ctx->b_vidx.p; Sd.n = n; Sd.score = ctx->s_kscore.p;
 	Sd.keep = ctx->s_keep.p; Sd.members = kept; Sd.maxPerSeq = mps; Sd.tableValued = (V.kind == kFinalTable); Sd.modelSerial = ctx->modelSerial;
+	Sd.histSerial = ctx->histValid ? ctx->histSerial : 0;
 	ctx->nbSites = static_cast<int>(kept);
 	set_max_sites_mops(ctx, posSetSize);
 	*nbSites = ctx->nbSites;
