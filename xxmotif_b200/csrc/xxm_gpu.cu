@@ -16,6 +16,7 @@
 #include "xxm_kernels.cuh"
 #include "xxm_scan2.cuh"
 #include "xxm_select2.cuh"
+#include "xxm_scan3.cuh"
 
 using namespace xxm;
 
@@ -123,6 +124,7 @@ struct xxm_ctx {
 	DevBuf<SiteRec> d_sites;
 	DevBuf<unsigned int> d_hf, d_hb;
 	uint32_t nBest = 0;
+	bool scanFindsOnlySites = false;  // single table, no localization: every window the scan finds has finalPval < 1
 	bool histValid = false;      // ctx->hist holds the value-index histogram of the list made by the last select_mops
 	uint64_t histSerial = 0, histCounter = 0;
 	SiteList L[3];
@@ -590,10 +592,14 @@ static void set_max_sites_mops(xxm_ctx* ctx, int posSetSize) {
 // scan machinery
 // =====================================================================================================================
 #include "xxm_gpu_scan2.inc"
+#include "xxm_gpu_scan3.inc"
 
+// the scan finds the windows whose left k-mer is in the table; unless ctx->scanFindsOnlySites the caller still has to
+// drop the entries whose finalPval turns out to be >= 1 (or whose right part / product test fails)
 static int run_scan(xxm_ctx* ctx, int nseq, const Values& V, int checkFinal, DevBuf<uint32_t>& oseq, DevBuf<uint32_t>& opos, DevBuf<uint32_t>& ovidx,
                     DevBuf<float>* oscore, uint32_t* nOut, bool timeIt) {
-	return run_scan2(ctx, nseq, V, checkFinal, oseq, opos, ovidx, oscore, nOut, timeIt);
+	(void) checkFinal;
+	return run_scan3(ctx, nseq, V, oseq, opos, ovidx, oscore, nOut, timeIt);
 }
 
 static int compact_list(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, const uint8_t* flag, uint32_t n, uint32_t* oseq,
@@ -700,7 +706,7 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 	if (ctx->opt.localization) TRY(stage_pos_prob(ctx, T.span, ctx->modelFirstCol, enrStart, enrEnd, 0));
 	const Values V = make_values(ctx, true);  // the full scan always uses mops = true (StartPosUpdater-inl.h:99)
 	uint32_t n = 0;
-	if (T.nparts == 1) {
+	if (ctx->scanFindsOnlySites) {
 		TRY(run_scan(ctx, posSetSize, V, 1, ctx->b_seq, ctx->b_pos, ctx->b_vidx, &ctx->b_score, &n, true));
 	} else {
 		// candidates first; the p-value of a >8-column window is known only after the memo slots are evaluated
@@ -722,7 +728,7 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 	ctx->nBest = n;
 	// bestStartPos[].score = float(pValScore) (StartPosUpdater-inl.h:105)
 	CK(ctx->b_score.ensure(std::max<uint32_t>(1, n)));
-	if (n && T.nparts == 2) {
+	if (n && !ctx->scanFindsOnlySites) {
 		k_entry_scores<<<cdiv(n, 256), 256, 0, ctx->stream>>>(V, ctx->b_vidx.p, ctx->b_pos.p, n, 0, 0, ctx->b_score.p);
 		CKK();
 	}
