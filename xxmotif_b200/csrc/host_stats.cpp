@@ -49,10 +49,14 @@ void LogSum::reserve(int64_t upTo) { extend(upTo); }
 
 double LogSum::at(int64_t i) {
 	if (i <= 0) return 0.0;  // LOG_sum_i[0] = 0
+	for (int k = 0; k < 4; ++k) if (lastIdx_[k] == i) return lastVal_[k];
 	const int64_t c = i / kStride;
 	if (c >= static_cast<int64_t>(ckpt_.size())) extend(i);
 	double acc = ckpt_[static_cast<size_t>(c)];
 	for (int64_t k = c * kStride + 1; k <= i; ++k) acc = std::log(static_cast<double>(k)) + acc;
+	lastIdx_[lastSlot_] = i;
+	lastVal_[lastSlot_] = acc;
+	lastSlot_ = (lastSlot_ + 1) & 3;
 	return acc;
 }
 

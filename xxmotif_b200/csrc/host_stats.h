@@ -16,8 +16,11 @@ public:
 	void reserve(int64_t upTo);  // extend the checkpoints (multi-threaded log(), sequential accumulation)
 
 private:
-	static constexpr int64_t kStride = 1024;
+	static constexpr int64_t kStride = 128;
 	std::vector<double> ckpt_{0.0};  // ckpt_[c] = LOG_sum_i[c * kStride]
+	int64_t lastIdx_[4] = {-1, -1, -1, -1};
+	double lastVal_[4] = {0, 0, 0, 0};
+	int lastSlot_ = 0;
 	void extend(int64_t upTo);
 };
 

@@ -119,7 +119,9 @@ struct xxm_ctx {
 	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
 	DevBuf<uint64_t> status, total64;
 	DevBuf<uint32_t> r_seq, r_pos, r_vidx, r_count, r_off, d_pbits;
-	DevBuf<uint8_t> d_t8;
+	DevBuf<uint8_t> d_t8, d_raw;
+	DevBuf<uint64_t> d_rawOff;
+	DevBuf<int32_t> d_notX;
 	DevBuf<unsigned long long> d_counts;
 	DevBuf<SiteRec> d_sites;
 	DevBuf<unsigned int> d_hf, d_hb;
@@ -232,6 +234,50 @@ extern "C" int xxm_get_stats(const xxm_ctx* ctx, xxm_stats* out) { *out = ctx->s
 // =====================================================================================================================
 // a1: sequence set
 // =====================================================================================================================
+namespace xxm {
+// per sequence: number of residues that are not N (code 0); any code > 4 raises the flag.  One warp per sequence.
+__global__ void k_seq_stats(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rawOff, int nent, int32_t* __restrict__ notX,
+                            uint32_t* __restrict__ bad) {
+	const int lane = threadIdx.x & 31;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t s = warp; s < static_cast<uint32_t>(nent); s += nwarps) {
+		const uint64_t a = rawOff[s], b = rawOff[s + 1];
+		uint32_t cnt = 0, err = 0;
+		for (uint64_t i = a + lane; i < b; i += 32) {
+			const uint8_t c = raw[i];
+			cnt += (c != 0);
+			err |= (c > 4);
+		}
+		for (int d = 16; d; d >>= 1) { cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d); err |= __shfl_xor_sync(0xFFFFFFFFu, err, d); }
+		if (lane == 0) { notX[s] = static_cast<int32_t>(cnt); if (err) atomicExch(bad, s + 1); }
+	}
+}
+}  // namespace xxm
+
+static int upload_raw_and_count(xxm_ctx* ctx, int nent, const uint8_t* codes, const std::vector<uint64_t>& rawOff, uint8_t** d_rawOut, uint64_t** d_rawOffOut,
+                                std::vector<int32_t>& notX) {
+	const uint64_t bytes = rawOff[nent];
+	CK(ctx->d_raw.ensure(std::max<uint64_t>(1, bytes)));
+	CK(ctx->d_rawOff.ensure(static_cast<size_t>(nent) + 1));
+	CK(ctx->d_notX.ensure(nent));
+	CK(ctx->counters.ensure(8));
+	CK(cudaMemsetAsync(ctx->counters.p, 0, 32, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->d_raw.p, codes, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->d_rawOff.p, rawOff.data(), rawOff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+	k_seq_stats<<<ctx->numSMs * 8, 256, 0, ctx->stream>>>(ctx->d_raw.p, ctx->d_rawOff.p, nent, ctx->d_notX.p, ctx->counters.p);
+	CKK();
+	notX.resize(nent);
+	uint32_t bad = 0;
+	CK(cudaMemcpyAsync(notX.data(), ctx->d_notX.p, static_cast<size_t>(nent) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaMemcpyAsync(&bad, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	if (bad) return ctx->fail("sequence %u holds a code outside 0..4", bad);
+	*d_rawOut = ctx->d_raw.p;
+	*d_rawOffOut = ctx->d_rawOff.p;
+	return 0;
+}
+
 extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp) {
 	CK(cudaSetDevice(ctx->device));
 	if (nent <= 0) return ctx->fail("empty sequence set");
@@ -249,15 +295,25 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	double acc = 0;
 	int mx = 0, mn = 2147483647;
 	int64_t tot = 0;
+	// the raw codes go to the device first; the per-sequence count of non-N residues and the range check of the codes
+	// are done there (one coalesced pass) instead of a serial host loop over every base
+	std::vector<int32_t> notXv;
+	uint8_t* d_raw = nullptr;
+	uint64_t* d_rawOff = nullptr;
+	{
+		uint64_t o = 0;
+		for (int i = 0; i < nent; ++i) {
+			if (n[i] < 1) return ctx->fail("sequence %d is empty", i + 1);
+			rawOff[i] = o;
+			o += static_cast<uint64_t>(n[i]);
+		}
+		rawOff[nent] = o;
+		TRY(upload_raw_and_count(ctx, nent, codes, rawOff, &d_raw, &d_rawOff, notXv));
+	}
 	for (int i = 0; i < nent; ++i) {
 		rawOff[i] = off;
 		const int n0 = n[i];
-		if (n0 < 1) return ctx->fail("sequence %d is empty", i + 1);
-		int notX = 0;
-		for (int j = 0; j < n0; ++j) {
-			if (codes[off + j] > 4) return ctx->fail("sequence %d: code %d out of range at %d", i + 1, codes[off + j], j + 1);
-			if (codes[off + j] != 0) notX++;
-		}
+		int notX = notXv[i];
 		const int nstore = revcomp ? 2 * n0 + 1 : n0;
 		if (revcomp) notX = nstore;
 		if (notX != 0) acc += std::log(notX);
@@ -294,12 +350,6 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	CK(ctx->d_wordOff.ensure(static_cast<size_t>(nent) + 1));
 	CK(ctx->d_len.ensure(nent));
 	CK(ctx->d_blk2seq.ensure(nblk));
-	uint8_t* d_raw = nullptr;
-	uint64_t* d_rawOff = nullptr;
-	CK(cudaMalloc(reinterpret_cast<void**>(&d_raw), off ? off : 1));
-	CK(cudaMalloc(reinterpret_cast<void**>(&d_rawOff), (static_cast<size_t>(nent) + 1) * sizeof(uint64_t)));
-	CK(cudaMemcpyAsync(d_raw, codes, off, cudaMemcpyHostToDevice, ctx->stream));
-	CK(cudaMemcpyAsync(d_rawOff, rawOff.data(), rawOff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemcpyAsync(ctx->d_wordOff.p, ctx->wordOff.data(), ctx->wordOff.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemcpyAsync(ctx->d_len.p, ctx->len.data(), ctx->len.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemcpyAsync(ctx->d_blk2seq.p, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -315,8 +365,9 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	                                                                                   revcomp ? 1 : 0);
 	CKK();
 	CK(cudaStreamSynchronize(ctx->stream));
-	cudaFree(d_raw);
-	cudaFree(d_rawOff);
+	if (ctx->d_raw.cap > (8ull << 30)) ctx->d_raw.release();  // the raw codes are only needed for packing
+	(void) d_raw;
+	(void) d_rawOff;
 	init_sum_i(ctx->sum_i, ctx->max_leng);
 	ctx->haveModel = false;
 	for (auto& l : ctx->L) l = SiteList();

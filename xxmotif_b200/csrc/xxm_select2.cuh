@@ -71,34 +71,44 @@ __global__ void __launch_bounds__(256) k_select_mops_fwd(Values V, SelectFwdIO i
 			if (s_hist[k]) atomicAdd(&io.hist[k], s_hist[k]);
 }
 
+// Warp-cooperative: every warp walks 32 entries at a time, finds the chosen ones by ballot and then spends one lane per
+// PWM column on each chosen site (30 lanes busy, two shared-memory atomics per lane on distinct counters).
 __global__ void __launch_bounds__(256) k_count_pwm2(SeqStream S, CountIO io) {
 	__shared__ unsigned int s_cnt[31 * 5];
 	for (int k = threadIdx.x; k < 31 * 5; k += blockDim.x) s_cnt[k] = 0;
 	__syncthreads();
-	for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < io.n; t += gridDim.x * blockDim.x) {
+	const int lane = threadIdx.x & 31;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t t0 = warp * 32; t0 < io.n; t0 += nwarps * 32) {
+		const uint32_t t = t0 + lane;
 		uint32_t i = t;
-		bool use = true;
-		if (io.idx) i = io.idx[t];
-		else if (io.slotIdx) { i = io.slotIdx[t]; use = (i != kNone) && io.slotScore[t] <= io.thr; }
-		else use = io.keep[i] && io.kscore[i] <= io.thr;
-		if (!use) continue;
-		const uint32_t s = io.seq[i] - 1;
-		const int n = S.len[s];
-		const int p0 = static_cast<int>(io.pos[i]) + io.shift - io.firstColumn + 1;
-		const uint32_t wo = S.uniformWps ? s * S.uniformWps : S.wordOff[s];
-		// the 30-column context spans at most two 32-base words: load them once
-		const int pa = max(p0, 1), pb = min(p0 + 29, n);
-		if (pa > pb) continue;
-		const uint32_t w0 = wo + (static_cast<uint32_t>(pa - 1) >> 5);
-		const uint64_t c0 = S.codes[w0], c1 = S.codes[w0 + 1];
-		const uint64_t mm = (static_cast<uint64_t>(S.nmask[w0 + 1]) << 32) | S.nmask[w0];
-		const int o0 = (pa - 1) & 31;
-		for (int p = pa; p <= pb; ++p) {
-			const int o = o0 + (p - pa);
-			if ((mm >> o) & 1ull) continue;
-			const int j = p - p0 + 1;
-			atomicAdd(&s_cnt[j * 5 + base_at(c0, c1, o) + 1], 1u);
-			atomicAdd(&s_cnt[j * 5], 1u);
+		bool use = t < io.n;
+		if (use) {
+			if (io.idx) i = io.idx[t];
+			else if (io.slotIdx) { i = io.slotIdx[t]; use = (i != kNone) && io.slotScore[t] <= io.thr; }
+			else use = io.keep[i] && io.kscore[i] <= io.thr;
+		}
+		uint32_t sq = 0, ps = 0;
+		if (use) { sq = io.seq[i]; ps = io.pos[i]; }
+		uint32_t chosen = __ballot_sync(0xFFFFFFFFu, use);
+		while (chosen) {
+			const int src = __ffs(chosen) - 1;
+			chosen &= chosen - 1;
+			const uint32_t s = __shfl_sync(0xFFFFFFFFu, sq, src) - 1;
+			const int p0 = static_cast<int>(__shfl_sync(0xFFFFFFFFu, ps, src)) + io.shift - io.firstColumn + 1;
+			const int j = lane + 1;  // PWM column of this lane
+			const int p = p0 + lane;
+			if (j <= 30 && p >= 1 && p <= S.len[s]) {
+				const uint32_t wo = S.uniformWps ? s * S.uniformWps : S.wordOff[s];
+				const uint32_t g = static_cast<uint32_t>(p - 1);
+				const uint32_t w = wo + (g >> 5);
+				if (!((S.nmask[w] >> (g & 31)) & 1u)) {
+					const uint32_t b = static_cast<uint32_t>(S.codes[w] >> (2 * (g & 31))) & 3u;
+					atomicAdd(&s_cnt[j * 5 + b + 1], 1u);
+					atomicAdd(&s_cnt[j * 5], 1u);
+				}
+			}
 		}
 	}
 	__syncthreads();
