@@ -35,8 +35,8 @@ PROFILE_TXT = """0.05 0.90 0.05 0.90 0.45 0.90 0.50 0.45
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nseq", type=int, default=1000000)
     ap.add_argument("--seqlen", type=int, default=1000)
@@ -137,7 +137,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -220,13 +220,16 @@ def ours(a):
     pwm = pwm0.copy()
     for _ in range(max(a.warmup, 3)):
         pwm, info = step(pwm)
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(3):  # keep the GPU busy while nvidia-smi starts sampling
+        pwm, info = step(pwm)
     # ---- timed region: K steps, barrier + synchronize on both sides, CUDA events on the library's stream
     scan_ms, scan_bytes = [], []
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.rows.clear()
     launches0 = ctx.stats()["launches"]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)

@@ -1,0 +1,188 @@
+"""GPU parity, part 2: the CUDA path against the oracle (the pinned C restatement) on larger seeded sets, and
+size-independent properties at BASELINE.json's full size (1M x 1 kb)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(nseq, length, seed, revcomp, mops, localization, order=2):
+    import oracle_lib as ol
+    import xxmotif_b200 as xb
+    from xxmotif_b200 import hostprep
+    n, codes = hostprep.synthetic_set(nseq, length, seed=seed, frac=0.6)
+    rng = np.random.default_rng(seed + 99)
+    if nseq <= 5000:  # sprinkle some N runs
+        for _ in range(nseq // 3):
+            p = int(rng.integers(0, codes.size - 6))
+            codes[p:p + int(rng.integers(1, 6))] = 0
+    if revcomp:
+        n2, c2 = hostprep.revcomp_double(n, codes)
+    else:
+        n2, c2 = n, codes
+    bg, bgl = hostprep.background(n2, c2)
+    rp, rc = hostprep.null_model(n2, c2, order=order)
+    ctx = xb.Context(0)
+    ctx.set_options(mops=mops, localization=localization, bg=bg, bgLog=bgl)
+    ctx.set_background(order, rp, rc)
+    ctx.load_seqset(n, codes, revcomp=revcomp)
+    oset = ol.SeqSet(n, codes, revcomp=revcomp)
+    onm = ol.NullModel(order=order, rprobs=rp, rconds=rc)
+    octx = ol.Ctx(oset, revcomp, mops, False, localization, bg, bgl)
+    return ctx, octx, oset, onm, bg, bgl, n, codes
+
+
+def _site_eq(name, got, want):
+    assert len(got) == len(want), "%s: %d != %d entries" % (name, len(got), len(want))
+    for f in ("score", "startPos", "sequence"):
+        bad = np.flatnonzero(got[f] != want[f])
+        assert bad.size == 0, "%s.%s: %d mismatches, first at %d: %s vs %s" % (name, f, bad.size, bad[0], got[f][bad[0]], want[f][bad[0]])
+
+
+@pytest.mark.parametrize("revcomp,mops,localization,length", [(False, False, False, 400), (True, True, False, 300), (False, True, True, 300),
+                                                              (True, False, False, 250)])
+def test_refinement_steps_vs_oracle(revcomp, mops, localization, length):
+    import oracle_lib as ol
+    import xxmotif_b200 as xb
+    from xxmotif_b200 import hostprep
+    ctx, octx, oset, onm, bg, bgl, n, codes = _setup(3000, length, 11, revcomp, mops, localization)
+    try:
+        total, avg, mxl, mnl = ctx.seqset_info()
+        assert (total == oset.total).all() and (avg[1:] == oset.avgLength[1:]).all()
+        pwm, cols = hostprep.profile_pwm()
+        nent = len(n)
+        enr = (1 - int(cols[0]) + 1, mxl - int(cols[0]) + 1)
+        for it in range(3):
+            ctx.reinitialize(pwm, cols, nent, int(total[nent]))
+            tab = ol.Tables(pwm, cols, nent, int(total[nent]), bgl, onm)
+            nb, nbest, mx = ctx.scan_full(nent, enr)
+            octx.scan_full(tab, cols, nent, enr, True)
+            assert (nb, nbest, mx) == (octx.nbSites, octx.nbBestSites, octx.maxSites)
+            _site_eq("best", ctx.get_sites(xb.LIST_BEST_STARTPOS, xb.ORDER_BY_SCORE), octx.best())
+            _site_eq("sites", ctx.get_sites(xb.LIST_SORTED_SITES, xb.ORDER_AS_IS), octx.sites())
+            ok, nbm, bp, new = ctx.update_pwm_with_best_subset(xb.LIST_SORTED_SITES, pwm, int(cols[0]), nent, False, 0.1)
+            ook, onbm, obp, onew = octx.update_pwm_with_best_subset(0, pwm, cols, nent, 0, False, 0.1)
+            assert (ok, nbm, bp) == (ook, onbm, obp)
+            assert (new[5:] == onew[5:]).all()
+            # candidate re-score under column variants (one longer, one shorter, one shifted)
+            for tmp in (np.arange(cols[0] - 2, cols[-1] + 1), np.arange(cols[0] + 1, cols[-1] + 1), np.arange(cols[0] + 1, cols[-1] + 2)):
+                tmp = tmp.astype(np.int32)
+                ctx.reinitialize(new, tmp, nent, int(total[nent]))
+                ttab = ol.Tables(new, tmp, nent, int(total[nent]), bgl, onm)
+                nb2, mx2 = ctx.rescore(int(cols[0]), nent, enr)
+                octx.rescore(ttab, int(cols[0]), tmp, nent, enr, False)
+                assert (nb2, mx2) == (octx.nbSites, octx.maxSites)
+                got = ctx.get_sites(xb.LIST_SORTED_SITES_ELONG, xb.ORDER_AS_IS)
+                want = octx.elong(nb2)
+                m = want["score"] != 1
+                assert (got["score"][:nb2] == want["score"]).all()
+                assert (got["startPos"][:nb2][m] == want["startPos"][m]).all() and (got["sequence"][:nb2][m] == want["sequence"][m]).all()
+                ok, nbm, bp, e1 = ctx.update_pwm_with_best_subset(xb.LIST_SORTED_SITES_ELONG, new, int(tmp[0]), nent, True, 0.1)
+                ook, onbm, obp, oe1 = octx.update_pwm_with_best_subset(1, new, tmp, nent, 0, True, 0.1)
+                assert (ok, nbm, bp) == (ook, onbm, obp)
+                if ok:
+                    assert (e1[5:] == oe1[5:]).all()
+            pwm = new
+    finally:
+        ctx.close()
+
+
+def test_full_size_properties():
+    """1M x 1 kb (BASELINE cfg4 shape): ordering, consistency of the fused histogram, idempotence, and a bit-exact
+    comparison of the first 2000 sequences with the oracle."""
+    import torch
+    import oracle_lib as ol
+    import xxmotif_b200 as xb
+    from xxmotif_b200 import hostprep, sharded
+    if torch.cuda.get_device_properties(0).total_memory < 40e9:
+        pytest.skip("needs a large GPU")
+    nseq, length = 1000000, 1000
+    n, codes = hostprep.synthetic_set(nseq, length, seed=4)
+    bg, bgl = hostprep.background(n[:50000], codes[:50000 * length])  # any fixed background is a valid input of the path
+    rp, rc = hostprep.null_model(n[:50000], codes[:50000 * length], order=2)
+    ctx = xb.Context(0)
+    try:
+        ctx.set_options(mops=False, bg=bg, bgLog=bgl)
+        ctx.set_background(2, rp, rc)
+        ctx.load_seqset(n, codes, revcomp=False)
+        total, avg, mxl, mnl = ctx.seqset_info()
+        assert int(total[nseq]) == nseq * length
+        pwm, cols = hostprep.profile_pwm()
+        enr = (1 - int(cols[0]) + 1, mxl - int(cols[0]) + 1)
+        job = sharded.ShardedRefinement(ctx, None, nent_local=nseq, total_local=int(total[nseq]), pseudo=0.1, bg=bg)
+        pwm1, info1 = job.optimize_step(pwm, cols, enr)
+        pwm2, info2 = job.optimize_step(pwm1, cols, enr)
+        # the candidate list is strictly increasing in (sequence, position) -- the reference's scan order
+        best = ctx.get_sites(xb.LIST_BEST_STARTPOS, xb.ORDER_AS_IS, cap=info2["nbBestSites"] + 8)
+        assert len(best) == info2["nbBestSites"]
+        key = best["sequence"].astype(np.int64) * 4096 + best["startPos"]
+        assert (np.diff(key) > 0).all()
+        assert best["startPos"].min() >= 1 and best["startPos"].max() <= length - 8 + 1
+        # fused class histogram == number of kept sites; kept sites never overlap
+        sc, cn = sharded.score_runs(ctx, xb.LIST_SORTED_SITES)
+        assert int(cn.sum()) == info2["nbSites"] and (np.diff(sc) > 0).all()
+        kept = ctx.get_sites(xb.LIST_SORTED_SITES, xb.ORDER_AS_IS, cap=info2["nbSites"] + 8)
+        same = kept["sequence"][1:] == kept["sequence"][:-1]
+        assert ((kept["startPos"][1:] - kept["startPos"][:-1])[same] > 8).all()
+        # idempotence: the same PWM gives the same step
+        pwm2b, info2b = job.optimize_step(pwm1, cols, enr)
+        assert info2b == info2 and (pwm2b == pwm2).all()
+        # bit-exact against the oracle on the first 2000 sequences
+        m = 2000
+        oset = ol.SeqSet(n[:m], codes[:m * length])
+        onm = ol.NullModel(order=2, rprobs=rp, rconds=rc)
+        octx = ol.Ctx(oset, False, False, False, False, bg, bgl)
+        tab = ol.Tables(pwm1, cols, m, m * length, bgl, onm)
+        octx.scan_full(tab, cols, m, enr, True)
+        want = ol.sort_by_startpos(octx.best())
+        got = best[best["sequence"] <= m]
+        assert len(got) == len(want)
+        for f in ("score", "startPos", "sequence"):
+            assert (got[f] == want[f]).all()
+        wk = octx.sites()
+        gk = kept[kept["sequence"] <= m]
+        assert len(gk) == len(wk) and (gk["startPos"] == wk["startPos"]).all() and (gk["score"] == wk["score"]).all()
+    finally:
+        ctx.close()
+
+
+def test_shard_invariance():
+    """Two half shards combined through the split-phase API give exactly the step of the whole set."""
+    import xxmotif_b200 as xb
+    from xxmotif_b200 import hostprep, sharded
+    nseq, length = 40000, 500
+    n, codes = hostprep.synthetic_set(nseq, length, seed=21)
+    bg, bgl = hostprep.background(n, codes)
+    rp, rc = hostprep.null_model(n, codes, order=2)
+    pwm, cols = hostprep.profile_pwm()
+
+    def make(lo, hi):
+        c = xb.Context(0)
+        c.set_options(mops=True, bg=bg, bgLog=bgl)
+        c.set_background(2, rp, rc)
+        c.load_seqset(n[lo:hi], codes[lo * length:hi * length])
+        return c
+
+    whole, a, b = make(0, nseq), make(0, nseq // 2), make(nseq // 2, nseq)
+    try:
+        enr = (1 - int(cols[0]) + 1, length - int(cols[0]) + 1)
+        p = pwm
+        for it in range(2):
+            job = sharded.ShardedRefinement(whole, None, nent_local=nseq, total_local=nseq * length, pseudo=0.1, bg=bg)
+            pw, iw = job.optimize_step(p, cols, enr)
+            runs, counts, nb = [], [], 0
+            for c in (a, b):
+                c.reinitialize(p, cols, nseq // 2, nseq // 2 * length)
+                k, _, _ = c.scan_full(nseq // 2, enr)
+                nb += k
+                runs.append(sharded.score_runs(c, xb.LIST_SORTED_SITES))
+            gsc, gcn = sharded.merge_runs([r[0] for r in runs], [r[1] for r in runs])
+            maxSites = nseq * length - nseq * 7
+            K, bp, thr = sharded.choose_subset(gsc, gcn, nb, nseq * 1000, maxSites)
+            cnt = sum(sharded.count_sites(c, xb.LIST_SORTED_SITES, thr, int(cols[0])) for c in (a, b))
+            ps = sharded.build_pwm(cnt, 0.1 * K, bg)
+            assert nb == iw["nbSites"] and K == iw["bestMotifNb"] and bp == iw["bestPval"]
+            assert (ps == pw).all()
+            p = pw
+    finally:
+        whole.close(); a.close(); b.close()

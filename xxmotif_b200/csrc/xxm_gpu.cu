@@ -696,7 +696,7 @@ static int select_mops(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const
 	const bool capSafe = ctx->max_leng / (ctx->tab.span + 1) + 1 <= ctx->opt.maxMotifsPerSequence;
 	if (ordered && !ctx->revcomp && capSafe) {
 		SelectFwdIO f{};
-		f.seq = seq; f.pos = pos; f.vidx = vidx; f.n = n; f.length = ctx->tab.span; f.kscore = kscore.p; f.keep = keep.p; f.counters = ctx->counters.p;
+		f.seq = seq; f.pos = pos; f.vidx = vidx; f.n = n; f.length = ctx->tab.span; f.shift = shift; f.kscore = kscore.p; f.keep = keep.p; f.counters = ctx->counters.p;
 		const bool wantHist = (V.kind == kFinalTable);
 		if (wantHist) {
 			CK(ctx->hist.ensure(std::max<uint32_t>(1, ctx->nval)));

@@ -20,6 +20,7 @@ struct SelectFwdIO {
 	const uint32_t* vidx;
 	uint32_t n;
 	int length;
+	int shift;           // startPos = pos + shift (only matters for the positional prior)
 	float* kscore;       // [n]
 	uint8_t* keep;       // [n] zeroed
 	uint32_t* counters;  // [0] += kept sites
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(256) k_select_mops_fwd(Values V, SelectFwdIO i
 			prevPos = pj;
 			const uint32_t v = io.vidx[j];
 			if (v == kNone) continue;
-			const double pVal = final_of(V, v, j, static_cast<int>(pj));
+			const double pVal = final_of(V, v, j, static_cast<int>(pj) + io.shift);
 			if (!(pVal < 1.0)) continue;
 			if (last != kNone && lastPos + io.length >= pj) {
 				if (static_cast<double>(lastScore) <= pVal) continue;  // the kept site is at least as good: drop the new one
