@@ -17,6 +17,7 @@
 #include "xxm_scan2.cuh"
 #include "xxm_select2.cuh"
 #include "xxm_scan3.cuh"
+#include "xxm_scan4.cuh"
 
 using namespace xxm;
 
@@ -644,13 +645,14 @@ static void set_max_sites_mops(xxm_ctx* ctx, int posSetSize) {
 // =====================================================================================================================
 #include "xxm_gpu_scan2.inc"
 #include "xxm_gpu_scan3.inc"
+#include "xxm_gpu_scan4.inc"
 
 // the scan finds the windows whose left k-mer is in the table; unless ctx->scanFindsOnlySites the caller still has to
 // drop the entries whose finalPval turns out to be >= 1 (or whose right part / product test fails)
 static int run_scan(xxm_ctx* ctx, int nseq, const Values& V, int checkFinal, DevBuf<uint32_t>& oseq, DevBuf<uint32_t>& opos, DevBuf<uint32_t>& ovidx,
                     DevBuf<float>* oscore, uint32_t* nOut, bool timeIt) {
 	(void) checkFinal;
-	return run_scan3(ctx, nseq, V, oseq, opos, ovidx, oscore, nOut, timeIt);
+	return run_scan4(ctx, nseq, V, oseq, opos, ovidx, oscore, nOut, timeIt);
 }
 
 static int compact_list(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, const uint8_t* flag, uint32_t n, uint32_t* oseq,
