@@ -706,7 +706,7 @@ static int select_mops(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const
 			f.hist = ctx->hist.p; f.nval = ctx->nval; f.smemHist = ctx->nval <= 8192;
 		}
 		const size_t sm = (wantHist && f.smemHist) ? ctx->nval * 4ull : 0;
-		const uint32_t grid = std::min<uint32_t>(cdiv(n, 256), static_cast<uint32_t>(ctx->numSMs) * 8);
+		const uint32_t grid = std::min<uint32_t>(cdiv(n, 256), static_cast<uint32_t>(ctx->numSMs) * 64);
 		k_select_mops_fwd<<<grid, 256, sm, ctx->stream>>>(V, f);
 		CKK();
 		ctx->histValid = wantHist;

@@ -48,7 +48,7 @@ __global__ void k_build_t9(T9Build B, uint8_t* __restrict__ t9) {
 }
 
 template <bool kSmemBitmap>
-__global__ void __launch_bounds__(kScan4Threads, 2) k_scan4(SeqStream S, Model M, uint32_t* __restrict__ hitmask, uint32_t* __restrict__ tileCount,
+__global__ void __launch_bounds__(kScan4Threads, 3) k_scan4(SeqStream S, Model M, uint32_t* __restrict__ hitmask, uint32_t* __restrict__ tileCount,
                                                             uint32_t scanWords, uint32_t wordsPerWarp) {
 	extern __shared__ __align__(16) uint8_t smem4[];
 	uint8_t* s_t9 = smem4;  // 64 KB
@@ -126,10 +126,11 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand4(SeqStream S, Model M
 	const uint32_t wbase = tile * kTileWords;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
 	uint32_t h[4];
-#pragma unroll
-	for (int k = 0; k < 4; ++k) {
-		const uint32_t w = wbase + 4 * tid + k;
-		h[k] = (w < scanWords) ? hitmask[w] : 0u;
+	{
+		const uint4 hv = (wbase + 4 * tid + 3 < scanWords) ? reinterpret_cast<const uint4*>(hitmask + wbase)[tid] : make_uint4(0, 0, 0, 0);
+		h[0] = hv.x; h[1] = hv.y; h[2] = hv.z; h[3] = hv.w;
+		if (!(wbase + 4 * tid + 3 < scanWords))
+			for (int k = 0; k < 4; ++k) { const uint32_t w = wbase + 4 * tid + k; h[k] = (w < scanWords) ? hitmask[w] : 0u; }
 	}
 	const uint32_t cnt = __popc(h[0]) + __popc(h[1]) + __popc(h[2]) + __popc(h[3]);
 	uint32_t incl = cnt;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand4(SeqStream S, Model M
 	uint32_t woff = 0, total = 0;
 #pragma unroll
 	for (int k = 0; k < kExpandThreads / 32; ++k) { if (k < wid) woff += s_warp[k]; total += s_warp[k]; }
+	if (total == 0) return;
 	const uint32_t myOff = woff + incl - cnt;
 	const uint32_t dst = tileOff[tile];
 	for (uint32_t qbase = 0; qbase < total; qbase += kExpandQueue) {
@@ -164,7 +166,8 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand4(SeqStream S, Model M
 		const uint32_t nq = min(static_cast<uint32_t>(kExpandQueue), total - qbase);
 		for (uint32_t q = tid; q < nq; q += kExpandThreads) {
 			const uint32_t e = s_q[q];
-			const uint32_t w = wbase + (e >> 5);
+			const uint32_t wi = e >> 5;
+			const uint32_t w = wbase + wi;
 			const int j = static_cast<int>(e & 31u);
 			const uint32_t v = eval_window(M, S.codes[w], S.codes[w + 1], S.nmask[w], S.nmask[w + 1], j);
 			uint32_t sq, wo;
@@ -179,6 +182,37 @@ __global__ void __launch_bounds__(kExpandThreads) k_expand4(SeqStream S, Model M
 			}
 		}
 	}
+}
+
+// exclusive prefix over the tile counts, three small kernels (block sums -> scan of block sums -> add back)
+__global__ void __launch_bounds__(1024) k_tile_blocksum(const uint32_t* __restrict__ cnt, uint32_t n, uint32_t* __restrict__ bsum) {
+	__shared__ uint32_t s_w[32];
+	const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+	uint32_t v = (i < n) ? cnt[i] : 0u;
+#pragma unroll
+	for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+	if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		uint32_t t = s_w[threadIdx.x];
+#pragma unroll
+		for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, d);
+		if (threadIdx.x == 0) bsum[blockIdx.x] = t;
+	}
+}
+__global__ void __launch_bounds__(1024) k_tile_offsets(const uint32_t* __restrict__ cnt, uint32_t n, const uint32_t* __restrict__ boff, uint32_t* __restrict__ off) {
+	__shared__ uint32_t s_w[32];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
+	const uint32_t v = (i < n) ? cnt[i] : 0u;
+	uint32_t incl = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+	if (lane == 31) s_w[wid] = incl;
+	__syncthreads();
+	uint32_t woff = 0;
+	for (int k = 0; k < wid; ++k) woff += s_w[k];
+	if (i < n) off[i] = boff[blockIdx.x] + woff + incl - v;
 }
 
 }  // namespace xxm
