@@ -142,6 +142,17 @@ int xxm_get_sites(xxm_ctx* ctx, int32_t which, int32_t order, int32_t palin, xxm
 int xxm_logodds_hist(xxm_ctx* ctx, const double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize, double* fwd, double* bwd,
                      int32_t npos, double* maxScore, double* maxScore2);
 
+/* ---- a15: localization statistics ------------------------------------------------------------------------------------
+ * xxm_update_enriched_region replaces Motif::updateEnrichedRegion(StartPosUpdater::getBestStartPos()) (Motif.cpp:968-1019,
+ * called from MotifContainer::iterate, MotifContainer.cpp:241) incl. MotifRegion::getRegion (motifRegion.cpp:67-188):
+ * histogram of the start positions of the candidates with score < 1e-3 on the device, region search on the host.
+ * enr = {max, startRegion, endRegion} of Motif::_enrichment (relative to PWM column 1), updated in place.
+ * xxm_host_positional_pval replaces StartPosUpdater::setPositionalPval (StartPosUpdater.cpp:207-274) for a site list
+ * (positions relative to PWM column 1); returns 2 where the reference prints "In no man's land" and exits. */
+int xxm_update_enriched_region(xxm_ctx* ctx, int32_t firstMotifColumn, int32_t motifLength, int32_t* enr);
+int xxm_host_positional_pval(int32_t max_leng, int32_t revcomp, int32_t enrMax, int32_t firstMotifColumn, int32_t motifLength, const int32_t* sitePos,
+                             int32_t nSites, double* out);
+
 /* ---- a8/a9 split in phases, for a sequence set sharded over several GPUs (one context per GPU) ---------
  * The reference chooses the optimal subset over ALL sites (getBestSubset) and recounts the PWM from them.  With shards,
  * each context reports the run-length histogram of its float site scores (xxm_score_runs, ascending, score 1 excluded);

@@ -144,6 +144,13 @@ void xo_logodds_hist(const xo_ctx*, const double* pwm31x5, const int32_t* cols, 
 double xo_positional_pval(const xo_ctx*, int32_t enrMax, int32_t firstMotifColumn, int32_t motifLength,
                           const int32_t* sitePos, int32_t nSites);
 
+/* MotifRegion::getRegion, nucleotides/motifRegion.cpp:67-188 ; out = {set, max, startRegion, endRegion} */
+void xo_motif_region(const xo_ctx*, const int32_t* startPosCounts, int32_t counts, int32_t startRange, int32_t endRange, int32_t* out);
+/* Motif::updateEnrichedRegion(bestStartPos), Motif.cpp:968-1019 ; best = score-sorted candidates terminated by score 1;
+ * enr = {max, startRegion, endRegion} relative to PWM column 1 (in/out) */
+void xo_update_enriched_region(const xo_ctx*, const xo_site* best, int32_t revcomp, int32_t max_leng, int32_t firstMotifColumn, int32_t motifLength,
+                               int32_t* enr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -807,3 +807,4 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 
 #include "xxm_gpu_part2.inc"
 #include "xxm_gpu_part3.inc"
+#include "xxm_gpu_part4.inc"
