@@ -153,6 +153,40 @@ int xxm_update_enriched_region(xxm_ctx* ctx, int32_t firstMotifColumn, int32_t m
 int xxm_host_positional_pval(int32_t max_leng, int32_t revcomp, int32_t enrMax, int32_t firstMotifColumn, int32_t motifLength, const int32_t* sitePos,
                              int32_t nSites, double* out);
 
+/* ---- the callers of the path, re-stated above this ABI -----------------------------------
+ * xxm_motif mirrors the part of class Motif (refinementPhase/Motif.h) that the refinement loop reads and writes.
+ * xxm_optimize_motif        = IterateMotif::optimizeMotif(motif, true, false)      (Iterate_Motif.cpp:23-37)
+ * xxm_maximize_motif_length = IterateMotif::maximizeMotifLength(motif, lengthCorrection, false)  (Iterate_Motif.cpp:40-149)
+ * xxm_iterate_motif         = the per-motif loop of MotifContainer::iterate        (MotifContainer.cpp:231-264)      */
+typedef struct {
+	double pwm[31 * 5];   /* Motif::_pwm, log probabilities, row-major [column 0..30][0..4] */
+	int32_t ncols;
+	int32_t cols[30];     /* Motif::_motifColumns */
+	int32_t posSetSize;   /* Motif::_posSetSize */
+	int32_t enr[3];       /* Motif::_enrichment: max, startRegion, endRegion */
+	double pval;          /* Motif::_pVal (log) */
+	double posPval;       /* Motif::_posPVal (log) */
+	double worstScore;    /* Motif::_worstScore */
+	int32_t nsites;       /* Motif::_sites: sequence and position relative to PWM column 1 */
+	int32_t siteCap;
+	int32_t* siteSeq;
+	int32_t* sitePos;
+} xxm_motif;
+typedef struct {
+	int32_t totalPositions;      /* Global::posSet->total[posSetSize] */
+	int32_t revcomp;             /* Global::revcomp */
+	int32_t localization;        /* Global::usePositionalProbs */
+	int32_t maximizeMotifLength; /* Global::maximizeMotifLength (false with --no-pwm-length-optimization) */
+	int32_t minMatchPositions;   /* Global::minMatchPositions, default 5 */
+	int32_t maxMatchPositions;   /* Global::maxMatchPositions, default 17 */
+	double pseudo;               /* Global::pseudo, default 0.1 */
+	double neff_pwm;             /* Global::neff_pwm, default 10 */
+	double* elongPWM;            /* optional double[31*5]: IterateMotif::elongPWM carried between calls (NULL: zeros) */
+} xxm_refine_params;
+int xxm_optimize_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* p);
+int xxm_maximize_motif_length(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* p, int32_t lengthCorrection, int32_t* noChange);
+int xxm_iterate_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* p, int32_t* rounds);
+
 /* ---- a8/a9 split in phases, for a sequence set sharded over several GPUs (one context per GPU) ---------
  * The reference chooses the optimal subset over ALL sites (getBestSubset) and recounts the PWM from them.  With shards,
  * each context reports the run-length histogram of its float site scores (xxm_score_runs, ascending, score 1 excluded);

@@ -23,8 +23,8 @@ def test_header_symbols_exported():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), "missing export " + n
-    from xxmotif_b200 import hostprep, localization, sharded
-    assert sorted(xb.EXPORTS + hostprep.EXTRA_EXPORTS + sharded.EXTRA_EXPORTS + localization.EXTRA_EXPORTS) == names
+    from xxmotif_b200 import hostprep, localization, refine, sharded
+    assert sorted(xb.EXPORTS + hostprep.EXTRA_EXPORTS + sharded.EXTRA_EXPORTS + localization.EXTRA_EXPORTS + refine.EXTRA_EXPORTS) == names
 
 
 def test_create_fails_loudly_without_gpu():

@@ -1,0 +1,189 @@
+// The callers of the hot path, re-stated above the C ABI ("next" rows of section 8):
+//   IterateMotif::optimizeMotif        refinementPhase/Iterate_Motif.cpp:23-37
+//   IterateMotif::maximizeMotifLength  refinementPhase/Iterate_Motif.cpp:40-149  (+ fillTmpColumn_noGaps, Iterate_Motif.h:46-99)
+//   the per-motif loop of MotifContainer::iterate   refinementPhase/MotifContainer.cpp:216-270
+//   Motif::offset                      refinementPhase/Motif.h:648-673
+// Everything data-sized happens behind xxm_* calls; this file only sequences them and keeps the motif state.
+#include "../../include/xxmotif_gpu.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace {
+
+struct Cols {
+	std::vector<int32_t> c;
+	int front() const { return c.front(); }
+	int back() const { return c.back(); }
+	int span() const { return c.back() - c.front() + 1; }
+};
+
+// fillTmpColumn_noGaps (Iterate_Motif.h:46-99): false = skip this (front, back) combination
+bool variant_columns(const Cols& motif, int front, int back, int minMatch, int maxMatch, Cols& tmp) {
+	tmp = motif;
+	const int first = motif.front(), last = motif.back();
+	if (front == 0 && back == 0) {
+	} else if (front != 0 && back == 0) {
+		if (front < 0) { for (int i = first - 1; i > first - 1 + front; --i) tmp.c.insert(tmp.c.begin(), i); }
+		else { for (int i = 0; i < front && !tmp.c.empty(); ++i) tmp.c.erase(tmp.c.begin()); }
+	} else if (front == 0 && back != 0) {
+		if (back < 0) { for (int i = 0; i > back && !tmp.c.empty(); --i) tmp.c.pop_back(); }
+		else { for (int i = last + 1; i < last + 1 + back; ++i) tmp.c.push_back(i); }
+	} else if (front == -1 && back == -1) {
+		tmp.c.insert(tmp.c.begin(), first - 1);
+		tmp.c.pop_back();
+	} else if (front == 1 && back == 1) {
+		tmp.c.erase(tmp.c.begin());
+		tmp.c.push_back(last + 1);
+	} else {
+		return false;
+	}
+	if (static_cast<int>(tmp.c.size()) < minMatch) return false;
+	if (static_cast<int>(tmp.c.size()) > maxMatch) return false;
+	if (tmp.c.empty() || tmp.front() < 1 || tmp.back() > XXM_PWM_LENGTH) return false;  // would leave the 30-column PWM (undefined in the reference)
+	return true;
+}
+
+Cols cols_of(const xxm_motif* m) {
+	Cols c;
+	c.c.assign(m->cols, m->cols + m->ncols);
+	return c;
+}
+void set_cols(xxm_motif* m, const Cols& c) {
+	m->ncols = static_cast<int32_t>(c.c.size());
+	std::copy(c.c.begin(), c.c.end(), m->cols);
+}
+
+int set_positional_pval(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* P) {
+	int32_t mx = 0, mn = 0;
+	if (xxm_seqset_info(ctx, nullptr, nullptr, &mx, &mn)) return 1;
+	const Cols c = cols_of(m);
+	double p = 0;
+	const int rc = xxm_host_positional_pval(mx, P->revcomp, m->enr[0], c.front(), c.span(), m->sitePos, m->nsites, &p);
+	if (rc) return rc;
+	m->posPval = p;
+	return 0;
+}
+
+}  // namespace
+
+extern "C" int xxm_optimize_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* P) {
+	for (int iter = 0; iter < 2; ++iter) {
+		if (xxm_reinitialize(ctx, m->pwm, m->cols, m->ncols, m->posSetSize, P->totalPositions)) return 1;
+		int32_t nb = 0, nbest = 0, mx = 0;
+		if (xxm_scan_full(ctx, m->posSetSize, m->enr[1], m->enr[2], &nb, &nbest, &mx)) return 1;
+		int32_t upd = 0, bestNb = 0;
+		double bestPval = 0;
+		if (xxm_update_pwm_with_best_subset(ctx, XXM_LIST_SORTED_SITES, m->pwm, m->cols[0], m->posSetSize, 0, P->pseudo, &upd, &bestNb, &bestPval)) return 1;
+	}
+	return set_positional_pval(ctx, m, P);
+}
+
+extern "C" int xxm_maximize_motif_length(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* P, int32_t lengthCorrection, int32_t* noChangeOut) {
+	const Cols motifCols = cols_of(m);
+	int bestMotifNb = 0;
+	bool noChange = false;
+	double bestPval = DBL_MAX;
+	Cols bestElongation = motifCols;
+	std::vector<double> elong(31 * 5, 0.0), bestElong(31 * 5, 0.0);
+	if (P->elongPWM) std::memcpy(elong.data(), P->elongPWM, sizeof(double) * 31 * 5);
+	std::vector<int32_t> realSeq, realPos;
+	const int lo = lengthCorrection ? -2 : 0, hi = lengthCorrection ? 2 : 0;
+	for (int front = lo; front <= hi; ++front) {
+		for (int back = lo; back <= hi; ++back) {
+			Cols tmp;
+			if (!variant_columns(motifCols, front, back, P->minMatchPositions, P->maxMatchPositions, tmp)) continue;
+			int32_t motifNb = 0;
+			double overrepPval = 1e100;
+			for (int iter = 0; iter < 3; ++iter) {
+				const double* pwm = (iter == 0) ? m->pwm : elong.data();
+				if (xxm_reinitialize(ctx, pwm, tmp.c.data(), static_cast<int32_t>(tmp.c.size()), m->posSetSize, P->totalPositions)) return 1;
+				int32_t nb = 0, mx = 0;
+				if (xxm_rescore(ctx, motifCols.front(), m->posSetSize, m->enr[1], m->enr[2], 0, &nb, &mx)) return 1;
+				int32_t upd = 0, nbOut = 0;
+				double pvOut = 0;
+				std::vector<double> work(elong);
+				if (xxm_update_pwm_with_best_subset(ctx, XXM_LIST_SORTED_SITES_ELONG, work.data(), tmp.front(), m->posSetSize, iter == 0, P->pseudo, &upd, &nbOut,
+				                                    &pvOut))
+					return 1;
+				if (upd) { elong = work; motifNb = nbOut; overrepPval = pvOut; }
+				if (motifNb == 0) break;
+			}
+			if (motifNb == 0) continue;
+			const double newPval = overrepPval + tmp.span() * std::log(P->neff_pwm);  // calculate_log_bonferonni, utils.h:39-56
+			if (newPval < bestPval) {
+				bestPval = newPval;
+				bestElongation = tmp;
+				bestMotifNb = motifNb;
+				noChange = (front == 0 && back == 0);
+				for (int32_t col : tmp.c)
+					for (int a = 1; a <= 4; ++a) bestElong[col * 5 + a] = elong[col * 5 + a];
+				realSeq.assign(static_cast<size_t>(bestMotifNb), 0);
+				realPos.assign(static_cast<size_t>(bestMotifNb), 0);
+				int32_t n = 0;
+				double worst = 1;
+				if (xxm_startposlist_from_elong(ctx, bestMotifNb, tmp.front(), realSeq.data(), realPos.data(), bestMotifNb, &n, &worst)) return 1;
+				realSeq.resize(static_cast<size_t>(n));
+				realPos.resize(static_cast<size_t>(n));
+				m->worstScore = worst;
+			}
+		}
+	}
+	if (P->elongPWM) std::memcpy(P->elongPWM, elong.data(), sizeof(double) * 31 * 5);
+	*noChangeOut = noChange;
+	if (bestMotifNb == 0) return 0;
+	m->pval = bestPval;
+	set_cols(m, bestElongation);
+	const int newFirst = (XXM_PWM_LENGTH - bestElongation.span()) / 2 + 1;
+	const int offset = newFirst - bestElongation.front();
+	if (static_cast<int32_t>(realSeq.size()) > m->siteCap) return 2;
+	m->nsites = static_cast<int32_t>(realSeq.size());
+	for (int32_t i = 0; i < m->nsites; ++i) { m->siteSeq[i] = realSeq[i]; m->sitePos[i] = realPos[i] - offset; }
+	for (int32_t col : bestElongation.c)
+		for (int a = 1; a <= 4; ++a) m->pwm[col * 5 + a] = bestElong[col * 5 + a];
+	if (offset != 0) {  // Motif::offset, Motif.h:648-673
+		m->enr[0] -= offset; m->enr[1] -= offset; m->enr[2] -= offset;
+		if (offset > 0) {
+			for (auto it = bestElongation.c.rbegin(); it != bestElongation.c.rend(); ++it)
+				for (int a = 1; a <= 4; ++a) m->pwm[(*it + offset) * 5 + a] = m->pwm[*it * 5 + a];
+		} else {
+			for (int32_t col : bestElongation.c)
+				for (int a = 1; a <= 4; ++a) m->pwm[(col + offset) * 5 + a] = m->pwm[col * 5 + a];
+		}
+		for (int32_t i = 0; i < m->ncols; ++i) m->cols[i] += offset;
+	}
+	return set_positional_pval(ctx, m, P);
+}
+
+extern "C" int xxm_iterate_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* P, int32_t* rounds) {
+	double oldPval = 1000, bestPval = 1000;
+	int loop = 1;
+	*rounds = 0;
+	std::vector<double> elong(31 * 5, 0.0);  // IterateMotif::elongPWM lives for the whole iterate() call
+	xxm_refine_params Q = *P;
+	Q.elongPWM = elong.data();
+	do {
+		oldPval = bestPval;
+		int rc = xxm_optimize_motif(ctx, m, &Q);
+		if (rc) return rc;
+		if (P->localization) {
+			const Cols c = cols_of(m);
+			if (xxm_update_enriched_region(ctx, c.front(), c.span(), m->enr)) return 1;
+		}
+		int32_t noChange = 0;
+		rc = xxm_maximize_motif_length(ctx, m, &Q, P->maximizeMotifLength, &noChange);
+		if (rc) return rc;
+		bestPval = m->pval;
+		++*rounds;
+		if (loop > 0 && bestPval >= oldPval) loop = 0;
+	} while (loop > 0);
+	// m->getStartPosList().sort(StartPos::cmpStartPos), MotifContainer.cpp:262
+	std::vector<std::pair<int32_t, int32_t>> s(static_cast<size_t>(m->nsites));
+	for (int32_t i = 0; i < m->nsites; ++i) s[i] = {m->siteSeq[i], m->sitePos[i]};
+	std::stable_sort(s.begin(), s.end());
+	for (int32_t i = 0; i < m->nsites; ++i) { m->siteSeq[i] = s[i].first; m->sitePos[i] = s[i].second; }
+	return 0;
+}

@@ -1,0 +1,98 @@
+"""ctypes face of the callers of the hot path (csrc/refine.cpp): IterateMotif::optimizeMotif, ::maximizeMotifLength and the
+per-motif loop of MotifContainer::iterate, re-stated in C++ above the C ABI (include/xxmotif_gpu.h)."""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+EXTRA_EXPORTS = ["xxm_optimize_motif", "xxm_maximize_motif_length", "xxm_iterate_motif"]
+
+
+class XxmMotif(C.Structure):
+    _fields_ = [("pwm", C.c_double * (31 * 5)), ("ncols", C.c_int32), ("cols", C.c_int32 * 30), ("posSetSize", C.c_int32), ("enr", C.c_int32 * 3),
+                ("pval", C.c_double), ("posPval", C.c_double), ("worstScore", C.c_double), ("nsites", C.c_int32), ("siteCap", C.c_int32),
+                ("siteSeq", C.c_void_p), ("sitePos", C.c_void_p)]
+
+
+class XxmRefineParams(C.Structure):
+    _fields_ = [("totalPositions", C.c_int32), ("revcomp", C.c_int32), ("localization", C.c_int32), ("maximizeMotifLength", C.c_int32),
+                ("minMatchPositions", C.c_int32), ("maxMatchPositions", C.c_int32), ("pseudo", C.c_double), ("neff_pwm", C.c_double),
+                ("elongPWM", C.c_void_p)]
+
+
+def _lib():
+    L = capi.load_library()
+    if not getattr(L, "_refine_ready", False):
+        vp, i32 = C.c_void_p, C.c_int32
+        P = C.POINTER
+        L.xxm_optimize_motif.restype = i32
+        L.xxm_optimize_motif.argtypes = [vp, P(XxmMotif), P(XxmRefineParams)]
+        L.xxm_maximize_motif_length.restype = i32
+        L.xxm_maximize_motif_length.argtypes = [vp, P(XxmMotif), P(XxmRefineParams), i32, P(i32)]
+        L.xxm_iterate_motif.restype = i32
+        L.xxm_iterate_motif.argtypes = [vp, P(XxmMotif), P(XxmRefineParams), P(i32)]
+        L._refine_ready = True
+    return L
+
+
+class Motif:
+    """The part of class Motif (refinementPhase/Motif.h) the refinement loop reads and writes; sites are (sequence, position
+    relative to PWM column 1) like Motif::_sites."""
+
+    def __init__(self, pwm, cols, posSetSize, enr=(0, 0, 0), siteSeq=(), sitePos=(), siteCap=1 << 20, pval=0.0, posPval=0.0):
+        self.m = XxmMotif()
+        pwm = np.ascontiguousarray(pwm, dtype=np.float64).reshape(-1)
+        assert pwm.size == 31 * 5
+        C.memmove(self.m.pwm, pwm.ctypes.data, pwm.nbytes)
+        cols = [int(c) for c in cols]
+        self.m.ncols = len(cols)
+        for i, c in enumerate(cols):
+            self.m.cols[i] = c
+        self.m.posSetSize = int(posSetSize)
+        for i in range(3):
+            self.m.enr[i] = int(enr[i])
+        self.m.pval, self.m.posPval, self.m.worstScore = float(pval), float(posPval), 1.0
+        self._seq = np.zeros(siteCap, dtype=np.int32)
+        self._pos = np.zeros(siteCap, dtype=np.int32)
+        n = len(siteSeq)
+        self._seq[:n] = siteSeq
+        self._pos[:n] = sitePos
+        self.m.nsites, self.m.siteCap = n, siteCap
+        self.m.siteSeq = self._seq.ctypes.data
+        self.m.sitePos = self._pos.ctypes.data
+
+    pwm = property(lambda s: np.array(s.m.pwm[:], dtype=np.float64))
+    cols = property(lambda s: np.array(s.m.cols[:s.m.ncols], dtype=np.int32))
+    enr = property(lambda s: np.array(s.m.enr[:], dtype=np.int32))
+    pval = property(lambda s: s.m.pval)
+    posPval = property(lambda s: s.m.posPval)
+    worstScore = property(lambda s: s.m.worstScore)
+    siteSeq = property(lambda s: s._seq[:s.m.nsites].copy())
+    sitePos = property(lambda s: s._pos[:s.m.nsites].copy())
+
+
+class Refiner:
+    """IterateMotif + the Global:: switches it reads, bound to one context."""
+
+    def __init__(self, ctx, totalPositions, revcomp, localization, maximizeMotifLength=True, minMatchPositions=5, maxMatchPositions=17,
+                 pseudo=0.1, neff_pwm=10.0):
+        self.ctx = ctx
+        self.p = XxmRefineParams(int(totalPositions), int(revcomp), int(localization), int(maximizeMotifLength), int(minMatchPositions),
+                                 int(maxMatchPositions), float(pseudo), float(neff_pwm), None)
+        self._elong = np.zeros(31 * 5, dtype=np.float64)  # IterateMotif::elongPWM
+        self.p.elongPWM = self._elong.ctypes.data
+
+    def optimize_motif(self, motif):
+        self.ctx._ck(_lib().xxm_optimize_motif(self.ctx.h, C.byref(motif.m), C.byref(self.p)))
+
+    def maximize_motif_length(self, motif, lengthCorrection=None):
+        nc = C.c_int32(0)
+        lc = self.p.maximizeMotifLength if lengthCorrection is None else int(lengthCorrection)
+        self.ctx._ck(_lib().xxm_maximize_motif_length(self.ctx.h, C.byref(motif.m), C.byref(self.p), lc, C.byref(nc)))
+        return bool(nc.value)
+
+    def iterate_motif(self, motif):
+        r = C.c_int32(0)
+        self.ctx._ck(_lib().xxm_iterate_motif(self.ctx.h, C.byref(motif.m), C.byref(self.p), C.byref(r)))
+        return r.value
