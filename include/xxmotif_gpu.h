@@ -218,6 +218,13 @@ int xxm_host_best_subset(const float* score, const int32_t* seq, int32_t nbSites
                          int32_t nent, int32_t maxMotifsPerSequence, int32_t oneOccurrence, double plusFrac, int32_t* bestMotifNb,
                          double* bestPval);
 
+/* xxm_host_pair_table: the table of the full-scan find kernel (csrc/pair_table.h).  ids = the enumerated left k-mers that
+ *   count as scan hits (column c in bits [2c+1:2c]), coloff = base offset of each of the len0 left match columns.
+ *   table1024[q] describes the two windows starting at bases 0 and 1 of the 5-base group q: a window whose bases 0..3 are
+ *   the 4-mer x and bases 4..7 the 4-mer y is a hit iff a[x] + b[y] >= 128.  Returns 1 when the k-mer set is not
+ *   representable that way (the scan then uses its generic kernel). */
+int xxm_host_pair_table(const uint32_t* ids, int64_t nids, const int32_t* coloff, int32_t len0, uint32_t* table1024, int32_t* levels);
+
 /* ---- measurement ----------------------------------------------------------------------------------------------------
  * device-side timing of the most recent call of each kernel (CUDA events on the context's stream), launch counts */
 typedef struct {

@@ -54,3 +54,76 @@ def test_host_best_subset_vs_reference(golden, name):
         _eq(p + ".bestPval", bp, float(t[bp_key][0]))
         checked += 1
     assert checked >= 2
+
+
+def _pair_flags(tab, codes):
+    """numpy model of k_scan5: hit flag of every window of a base sequence (codes 0..3) from the 5-base pair table."""
+    n = len(codes)
+    c = np.concatenate([codes, np.zeros(16, dtype=np.int64)])
+    four = c[:n + 8] | (c[1:n + 9] << 2) | (c[2:n + 10] << 4) | (c[3:n + 11] << 6)  # 4-mer starting at every base
+    # entries are fetched per even base p through the 5-base index; a/b of base p and p+1 sit in bytes 3,2 / 1,0
+    q = c[:n + 8] | (c[1:n + 9] << 2) | (c[2:n + 10] << 4) | (c[3:n + 11] << 6) | (c[4:n + 12] << 8)
+    E = tab[q[0::2]].astype(np.int64)
+    a = np.empty(len(q), dtype=np.int64)
+    b = np.empty(len(q), dtype=np.int64)
+    a[0::2], b[0::2] = (E >> 24) & 255, (E >> 16) & 255
+    a[1::2], b[1::2] = ((E >> 8) & 255)[:len(a[1::2])], (E & 255)[:len(b[1::2])]
+    del four
+    return (a[:n] + b[4:n + 4]) >= 128
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_pair_table_exact(golden, name):
+    """The pair table of the scan (csrc/pair_table.h) is an EXACT restatement of 'left k-mer is in the p-value table' for
+    every table of the golden traces whose left match columns span at most 8 bases; longer spans are declined."""
+    t = golden(name)
+    if "nm.rprobs" not in t:
+        pytest.skip("order-8 NullModel tables are not in the fixture")
+    ti = TraceInputs(t)
+    rng = np.random.default_rng(7)
+    seq = rng.integers(0, 4, size=20000).astype(np.int64)
+    checked = 0
+    for p in _table_prefixes(t):
+        if p.startswith("opt"):
+            pwm, cols, pss = t[p + ".in.pwm"], t[p + ".in.cols"], int(t[p + ".in.posSetSize"][0])
+        elif p.startswith("el"):
+            pwm, cols, pss = t[p + ".pwm_in"], t[p + ".cols"], int(t["opt1.in.posSetSize"][0])
+        else:
+            pwm, cols, pss = t["converged.pwm"], t["converged.cols"], int(t["converged.posSetSize"][0])
+        d = capi.host_tables(pwm, cols, pss, int(ti.total[pss]), ti.bgLog, ti.order, t["nm.rprobs"], t["nm.rconds"])
+        pv = d["pvalues"][0]
+        len0 = int(round(np.log2(len(pv)) / 2))
+        coloff = (np.asarray(cols[:len0]) - int(cols[0])).astype(np.int32)
+        member = pv != 0
+        ids = np.nonzero(member)[0].astype(np.uint32)
+        ok, tab, levels = capi.host_pair_table(ids, coloff)
+        if coloff[-1] > 7:
+            assert not ok
+            continue
+        assert ok and levels <= 127, (p, levels)
+        # brute force over a random sequence: flag == membership of the gathered k-mer id
+        flags = _pair_flags(tab, seq)
+        c = np.concatenate([seq, np.zeros(16, dtype=np.int64)])
+        kid = np.zeros(len(seq), dtype=np.int64)
+        for k, o in enumerate(coloff):
+            kid |= c[o:o + len(seq)] << (2 * k)
+        assert np.array_equal(flags, member[kid]), p
+        # and over all 4^8 windows
+        w = np.arange(65536, dtype=np.int64)
+        kid = np.zeros(65536, dtype=np.int64)
+        for k, o in enumerate(coloff):
+            kid |= ((w >> (2 * o)) & 3) << (2 * k)
+        x0, y0 = w & 255, w >> 8
+        a = (tab[x0 | ((0) << 8)] >> 24) & 255  # entry q with bases 0..3 = x0 (base 4 irrelevant for a[x0])
+        bb = (tab[y0] >> 16) & 255
+        assert np.array_equal((a.astype(np.int64) + bb.astype(np.int64)) >= 128, member[kid]), p
+        checked += 1
+    assert checked >= 1 or name in ("c5_loc_gap",)
+
+
+def test_pair_table_declines_non_threshold_sets():
+    ids = np.array([0b00000000_00000001, 0b00000001_00000000], dtype=np.uint32)  # rows {x=1: y=0}, {x=0: y=1}: not nested
+    ok, _, _ = capi.host_pair_table(ids, np.arange(8, dtype=np.int32))
+    assert not ok
+    ok, tab, lv = capi.host_pair_table(np.zeros(0, dtype=np.uint32), np.arange(8, dtype=np.int32))
+    assert ok and lv == 0 and not tab.any()

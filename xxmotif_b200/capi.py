@@ -20,7 +20,7 @@ EXPORTS = [
     "xxm_create", "xxm_destroy", "xxm_last_error", "xxm_set_options", "xxm_load_seqset", "xxm_seqset_info", "xxm_set_background",
     "xxm_reinitialize", "xxm_tables_info", "xxm_tables_get", "xxm_window_pvals", "xxm_scan_full", "xxm_rescore", "xxm_scan_oops",
     "xxm_rescore_startposlist", "xxm_update_pwm_with_best_subset", "xxm_startposlist_best_subset", "xxm_startposlist_from_elong",
-    "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset",
+    "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset", "xxm_host_pair_table",
 ]
 
 
@@ -81,6 +81,7 @@ def load_library():
         "xxm_get_stats": [vp, P(XxmStats)],
         "xxm_host_tables": [vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp],
         "xxm_host_best_subset": [vp, vp, i32, i32, i32, i32, i32, i32, i32, dbl, P(i32), P(dbl)],
+        "xxm_host_pair_table": [vp, C.c_int64, vp, i32, vp, P(i32)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -311,3 +312,16 @@ def host_best_subset(score, seq, posSetSize, maxSites, nent, maxSeqCount=1000, m
     if rcode:
         raise XxmError("xxm_host_best_subset failed with %d" % rcode)
     return nb.value, bp.value
+
+
+def host_pair_table(ids, coloff):
+    """Device-free pair-table construction (xxm_host_pair_table): (representable, table[1024], levels)."""
+    L = load_library()
+    ids = np.ascontiguousarray(ids, dtype=np.uint32)
+    co = np.ascontiguousarray(coloff, dtype=np.int32)
+    tab = np.zeros(1024, dtype=np.uint32)
+    lv = C.c_int32(0)
+    rcode = L.xxm_host_pair_table(_p(ids), len(ids), _p(co), len(co), _p(tab), C.byref(lv))
+    if rcode not in (0, 1):
+        raise XxmError("xxm_host_pair_table failed with %d" % rcode)
+    return rcode == 0, tab, lv.value

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -14,10 +15,10 @@
 #include "host_stats.h"
 #include "pvalue_tables.h"
 #include "xxm_kernels.cuh"
-#include "xxm_scan2.cuh"
 #include "xxm_select2.cuh"
-#include "xxm_scan3.cuh"
 #include "xxm_scan4.cuh"
+#include "xxm_scan5.cuh"
+#include "pair_table.h"
 
 using namespace xxm;
 
@@ -119,8 +120,12 @@ struct xxm_ctx {
 	DevBuf<uint8_t> s_keep, e_keep, flag8;
 	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
 	DevBuf<uint64_t> status, total64;
-	DevBuf<uint32_t> r_seq, r_pos, r_vidx, r_count, r_off, d_pbits;
+	DevBuf<uint32_t> r_seq, d_pbits;
 	DevBuf<uint8_t> d_t8, d_raw;
+	DevBuf<uint32_t> d_pairTab;
+	std::vector<uint32_t> h_pairIds, h_pairTab;
+	bool pairOK = false;           // the pair table represents the left table exactly: k_scan5, else k_scan4
+	bool forceGenericScan = false; // tests: always take the generic find kernel
 	DevBuf<uint64_t> d_rawOff;
 	DevBuf<int32_t> d_notX;
 	DevBuf<unsigned long long> d_counts;
@@ -164,7 +169,7 @@ struct xxm_ctx {
 	} while (0)
 
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
-static int stage_t8(xxm_ctx* ctx);  // xxm_gpu_scan2.inc
+static int stage_scan(xxm_ctx* ctx);  // xxm_gpu_scan5.inc
 
 // =====================================================================================================================
 // life cycle
@@ -193,6 +198,7 @@ extern "C" int xxm_create(int device, xxm_ctx** out) {
 	ctx->opt.maxMotifsPerSequence = 1000;
 	ctx->opt.maxSeqCount = 1000;
 	ctx->opt.overrepCorrection = 1.05;
+	ctx->forceGenericScan = std::getenv("XXM_FORCE_GENERIC_SCAN") != nullptr;  // tests: exercise k_scan4 on every model
 	*out = ctx;
 	return 0;
 }
@@ -213,7 +219,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	ctx->slotIdx.release(); ctx->e_slotIdx.release(); ctx->e_slotScore.release(); ctx->u_score.release(); ctx->counters.release(); ctx->hist.release(); ctx->idxA.release(); ctx->idxB.release(); ctx->keysA.release();
 	ctx->keysB.release(); ctx->rsHist.release(); ctx->status.release(); ctx->total64.release(); ctx->d_counts.release(); ctx->d_sites.release();
 	ctx->d_hf.release(); ctx->d_hb.release();
-	ctx->r_seq.release(); ctx->r_pos.release(); ctx->r_vidx.release(); ctx->r_count.release(); ctx->r_off.release(); ctx->d_pbits.release(); ctx->d_t8.release();
+	ctx->r_seq.release(); ctx->d_pbits.release(); ctx->d_t8.release(); ctx->d_pairTab.release();
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
 	cudaStreamDestroy(ctx->stream);
@@ -508,7 +514,7 @@ extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* 
 		CK(ctx->d_finalMops.ensure(cap));
 		CK(ctx->d_finalMode.ensure(cap));
 	}
-	TRY(stage_t8(ctx));
+	TRY(stage_scan(ctx));
 	ctx->haveModel = true;
 	return 0;
 }
@@ -643,16 +649,15 @@ static void set_max_sites_mops(xxm_ctx* ctx, int posSetSize) {
 // =====================================================================================================================
 // scan machinery
 // =====================================================================================================================
-#include "xxm_gpu_scan2.inc"
-#include "xxm_gpu_scan3.inc"
 #include "xxm_gpu_scan4.inc"
+#include "xxm_gpu_scan5.inc"
 
 // the scan finds the windows whose left k-mer is in the table; unless ctx->scanFindsOnlySites the caller still has to
 // drop the entries whose finalPval turns out to be >= 1 (or whose right part / product test fails)
 static int run_scan(xxm_ctx* ctx, int nseq, const Values& V, int checkFinal, DevBuf<uint32_t>& oseq, DevBuf<uint32_t>& opos, DevBuf<uint32_t>& ovidx,
                     DevBuf<float>* oscore, uint32_t* nOut, bool timeIt) {
 	(void) checkFinal;
-	return run_scan4(ctx, nseq, V, oseq, opos, ovidx, oscore, nOut, timeIt);
+	return run_scan5(ctx, nseq, V, oseq, opos, ovidx, oscore, nOut, timeIt);
 }
 
 static int compact_list(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, const uint8_t* flag, uint32_t n, uint32_t* oseq,

@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "host_stats.h"
+#include "pair_table.h"
 #include "pvalue_tables.h"
 
 using namespace xxm;
@@ -88,4 +89,14 @@ extern "C" int xxm_host_choose_subset(const float* scores, const int64_t* counts
 extern "C" int xxm_host_build_pwm(const double* counts31x5, double pseudoTimesK, const double* bg5, double* pwm31x5) {
 	build_pwm_from_counts(counts31x5, pseudoTimesK, bg5, pwm31x5);
 	return 0;
+}
+
+extern "C" int xxm_host_pair_table(const uint32_t* ids, int64_t nids, const int32_t* coloff, int32_t len0, uint32_t* table1024, int32_t* levels) {
+	int off[32];
+	if (len0 < 1 || len0 > 13) return 2;
+	for (int i = 0; i < len0; ++i) off[i] = coloff[i];
+	int lv = 0;
+	const bool ok = build_pair_table(ids, static_cast<size_t>(nids), off, len0, table1024, &lv);
+	*levels = lv;
+	return ok ? 0 : 1;
 }

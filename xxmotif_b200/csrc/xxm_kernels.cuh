@@ -99,138 +99,6 @@ __device__ __forceinline__ uint32_t eval_window(const Model& M, uint64_t c0, uin
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2  full scan (fill_sites_with_possible_startPositions, StartPosUpdater-inl.h:90-113, the `for i / for j` body).
-//     One thread owns one 32-base word = 32 window starts.  Persistent CTAs take tiles by ticket; hits are written
-//     in global (sequence, position) order through a single-pass decoupled look-back prefix over tiles, so no sort
-//     is needed downstream (the reference's scan order IS (seq,pos) order).
-// ---------------------------------------------------------------------------------------------------------------
-struct ScanOut {
-	uint32_t* seq;     // 1-based sequence number
-	uint32_t* pos;     // 1-based start position
-	uint32_t* vidx;    // value index
-	uint32_t cap;
-	uint64_t* status;  // [ntiles] look-back words (zeroed before launch)
-	uint32_t* ticket;  // zeroed before launch
-	uint64_t* total;   // out: number of hits
-};
-
-template <bool kSmemBitmap>
-__global__ void __launch_bounds__(kScanThreads) k_scan(SeqStream S, Model M, Values V, ScanOut O, uint32_t scanWords, uint32_t ntiles,
-                                                       int checkFinal) {
-	extern __shared__ uint32_t s_bm[];
-	__shared__ uint32_t s_tile;
-	__shared__ uint32_t s_warp[kScanThreads / 32];
-	__shared__ uint64_t s_base;
-	const uint32_t* bm = M.hit0;
-	if (kSmemBitmap) {
-		const uint32_t nw = (1u << (2 * M.len0)) / 32u;
-		for (uint32_t i = threadIdx.x; i < nw; i += blockDim.x) s_bm[i] = M.hit0[i];
-		bm = s_bm;
-	}
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	for (;;) {
-		__syncthreads();
-		if (threadIdx.x == 0) s_tile = atomicAdd(O.ticket, 1u);
-		__syncthreads();
-		const uint32_t tile = s_tile;
-		if (tile >= ntiles) break;
-		const uint32_t w = tile * kScanThreads + threadIdx.x;
-		uint64_t c0 = 0, c1 = 0;
-		uint32_t m0 = 0xFFFFFFFFu, m1 = 0xFFFFFFFFu;
-		if (w < scanWords) {
-			c0 = S.codes[w]; c1 = S.codes[w + 1];
-			m0 = S.nmask[w]; m1 = S.nmask[w + 1];
-		}
-		// pass 1: bitmap pre-filter on the left k-mer (exact when there is a single table and no localization)
-		uint32_t cand = 0;
-		if (m0 != 0xFFFFFFFFu) {
-			if (M.contiguous) {
-#pragma unroll 8
-				for (int j = 0; j < 32; ++j) {
-					const uint32_t id = kmer_at(c0, c1, j, M.len0);
-					cand |= ((bm[id >> 5] >> (id & 31)) & 1u) << j;
-				}
-			} else {
-				for (int j = 0; j < 32; ++j) {
-					uint32_t id = 0;
-					for (int k = 0; k < M.len0; ++k) id |= base_at(c0, c1, j + M.coloff[k]) << (2 * k);
-					cand |= ((bm[id >> 5] >> (id & 31)) & 1u) << j;
-				}
-			}
-			cand &= ~m0;  // the first match column is the window start
-		}
-		// pass 2: exact evaluation of the survivors
-		uint32_t seq0 = 0, wo = 0;
-		uint32_t hits = 0;
-		if (cand) {
-			seq0 = find_seq(S, w);
-			wo = S.wordOff[seq0];
-			uint32_t rem = cand;
-			while (rem) {
-				const int j = __ffs(rem) - 1;
-				rem &= rem - 1;
-				const uint32_t v = eval_window(M, c0, c1, m0, m1, j);
-				if (v == kNone) continue;
-				if (checkFinal) {
-					const int pos = static_cast<int>(w - wo) * 32 + j + 1;
-					if (!(final_of(V, v, 0, pos) < 1.0)) continue;  // finalPval >= 1 -> continue, :101
-				}
-				hits |= 1u << j;
-			}
-		}
-		// ordered output offset: warp scan -> block scan -> look-back over tiles
-		const uint32_t cnt = __popc(hits);
-		uint32_t incl = cnt;
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-			if (lane >= d) incl += t;
-		}
-		if (lane == 31) s_warp[wid] = incl;
-		__syncthreads();
-		uint32_t woff = 0, btotal = 0;
-#pragma unroll
-		for (int k = 0; k < kScanThreads / 32; ++k) {
-			if (k < wid) woff += s_warp[k];
-			btotal += s_warp[k];
-		}
-		if (threadIdx.x == 0) {
-			volatile uint64_t* st = O.status;
-			uint64_t excl = 0;
-			if (tile == 0) {
-				st[0] = kFlagIncl | btotal;
-			} else {
-				st[tile] = kFlagAgg | btotal;
-				for (uint32_t t = tile - 1;; --t) {
-					uint64_t v;
-					do { v = st[t]; } while ((v >> 62) == 0);
-					excl += v & kValMask;
-					if ((v >> 62) == 2) break;
-				}
-				st[tile] = kFlagIncl | (excl + btotal);
-			}
-			if (tile == ntiles - 1) *O.total = excl + btotal;
-			s_base = excl;
-		}
-		__syncthreads();
-		if (hits) {
-			uint64_t o = s_base + woff + (incl - cnt);
-			uint32_t rem = hits;
-			while (rem) {
-				const int j = __ffs(rem) - 1;
-				rem &= rem - 1;
-				if (o < O.cap) {
-					O.seq[o] = seq0 + 1;
-					O.pos[o] = (w - wo) * 32 + j + 1;
-					O.vidx[o] = eval_window(M, c0, c1, m0, m1, j);
-				}
-				++o;
-			}
-		}
-	}
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // memo evaluation for > maxk columns: the convolution of branch_and_bound-inl.h:419-449 for one integer score s.
 // One thread per occupied, not yet evaluated slot; strictly the reference's loop and summation order.
 // ---------------------------------------------------------------------------------------------------------------

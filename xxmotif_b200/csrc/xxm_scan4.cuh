@@ -1,17 +1,14 @@
-// K2 (fourth generation): branch-free "find" kernel with a dense hit bitmap as output, and a balanced "expand" kernel.
+// K2, generic find kernel: used when the pair table of xxm_scan5.cuh cannot represent the left table exactly (match
+// columns of the left part spanning more than 8 bases, i.e. long gapped motifs; tables that are not threshold-shaped).
 //
 // find   (k_scan4):  one thread per 32-base word.  16 LDS.U8 per word into the 64 KB shared-memory table T9, indexed by
 //                    9 consecutive bases (18 bits; the byte is addressed by bases 0..7, base 8 selects one of its four
 //                    2-bit entries).  An entry holds the EXACT answers for the two windows that start at base 0 and at
 //                    base 1 of the group (left k-mer in the table) whenever all left match columns fit into the 9
-//                    bases -- true for every ungapped motif; otherwise the bits are projections and the word takes one
-//                    exact bitmap test per flagged window.  No compaction, no divergent loops in the common case: the
-//                    thread ORs its 16 x 2 bits into a 32-bit mask (bit j = window starting at base j of the word is a
-//                    site candidate), clears windows that touch an N, and stores the mask (4 B per 32 windows).  Each
-//                    warp also sums the hits of a 1024-word tile.
-// expand (k_expand4): one CTA per tile: prefix over the masks, hit offsets into a shared-memory queue in (word, bit)
-//                    order, then all threads resolve queue entries into records (value index, sequence, position, float
-//                    score) at the tile's global offset -- coalesced, balanced, and globally ordered by construction.
+//                    bases; otherwise the bits are projections and the word takes one exact bitmap test per flagged
+//                    window.  The thread ORs its 16 x 2 bits into a 32-bit mask in window order (bit j = window starting at
+//                    base j of the word is a site candidate) and stores it (4 B per 32 windows).  N handling, counting and
+//                    record generation are k_expand5's.
 #pragma once
 #include "xxm_kernels.cuh"
 
@@ -48,8 +45,7 @@ __global__ void k_build_t9(T9Build B, uint8_t* __restrict__ t9) {
 }
 
 template <bool kSmemBitmap>
-__global__ void __launch_bounds__(kScan4Threads, 3) k_scan4(SeqStream S, Model M, uint32_t* __restrict__ hitmask, uint32_t* __restrict__ tileCount,
-                                                            uint32_t scanWords, uint32_t wordsPerWarp) {
+__global__ void __launch_bounds__(kScan4Threads, 3) k_scan4(SeqStream S, Model M, uint32_t* __restrict__ hitmask, uint32_t scanWords, uint32_t wordsPerWarp) {
 	extern __shared__ __align__(16) uint8_t smem4[];
 	uint8_t* s_t9 = smem4;  // 64 KB
 	uint32_t* s_bm = reinterpret_cast<uint32_t*>(smem4 + 65536);
@@ -67,10 +63,9 @@ __global__ void __launch_bounds__(kScan4Threads, 3) k_scan4(SeqStream S, Model M
 	__syncthreads();
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t gw = blockIdx.x * kScan4Warps + wid;
-	const uint32_t wBeg = gw * wordsPerWarp;  // multiple of kTileWords
+	const uint32_t wBeg = gw * wordsPerWarp;
 	const uint32_t wEnd = min(scanWords, wBeg + wordsPerWarp);
 	const uint32_t inexact = ((M.exactBits & 1u) ? 0u : 0x55555555u) | ((M.exactBits & 2u) ? 0u : 0xAAAAAAAAu);
-	uint32_t tileHits = 0;
 	for (uint32_t base = wBeg; base < wEnd; base += 32) {
 		const uint32_t w = base + lane;
 		uint32_t hits = 0;
@@ -103,116 +98,7 @@ __global__ void __launch_bounds__(kScan4Threads, 3) k_scan4(SeqStream S, Model M
 			}
 			hitmask[w] = hits;
 		}
-		tileHits += __popc(hits);
-		if (((base + 32 - wBeg) & (kTileWords - 1)) == 0 || base + 32 >= wEnd) {  // end of a tile (or of the range)
-			uint32_t tsum = tileHits;
-#pragma unroll
-			for (int d = 16; d; d >>= 1) tsum += __shfl_xor_sync(0xFFFFFFFFu, tsum, d);
-			if (lane == 0) tileCount[base / kTileWords] = tsum;
-			tileHits = 0;
-		}
 	}
-}
-
-constexpr int kExpandThreads = 256;
-constexpr int kExpandQueue = 8192;
-
-__global__ void __launch_bounds__(kExpandThreads) k_expand4(SeqStream S, Model M, Values V, const uint32_t* __restrict__ hitmask, const uint32_t* __restrict__ tileOff,
-                                                            uint32_t scanWords, int wantScore, uint32_t* __restrict__ oseq, uint32_t* __restrict__ opos,
-                                                            uint32_t* __restrict__ ovidx, float* __restrict__ oscore, uint32_t cap) {
-	__shared__ uint16_t s_q[kExpandQueue];
-	__shared__ uint32_t s_warp[kExpandThreads / 32];
-	const uint32_t tile = blockIdx.x;
-	const uint32_t wbase = tile * kTileWords;
-	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	uint32_t h[4];
-	{
-		const uint4 hv = (wbase + 4 * tid + 3 < scanWords) ? reinterpret_cast<const uint4*>(hitmask + wbase)[tid] : make_uint4(0, 0, 0, 0);
-		h[0] = hv.x; h[1] = hv.y; h[2] = hv.z; h[3] = hv.w;
-		if (!(wbase + 4 * tid + 3 < scanWords))
-			for (int k = 0; k < 4; ++k) { const uint32_t w = wbase + 4 * tid + k; h[k] = (w < scanWords) ? hitmask[w] : 0u; }
-	}
-	const uint32_t cnt = __popc(h[0]) + __popc(h[1]) + __popc(h[2]) + __popc(h[3]);
-	uint32_t incl = cnt;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
-		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-		if (lane >= d) incl += t;
-	}
-	if (lane == 31) s_warp[wid] = incl;
-	__syncthreads();
-	uint32_t woff = 0, total = 0;
-#pragma unroll
-	for (int k = 0; k < kExpandThreads / 32; ++k) { if (k < wid) woff += s_warp[k]; total += s_warp[k]; }
-	if (total == 0) return;
-	const uint32_t myOff = woff + incl - cnt;
-	const uint32_t dst = tileOff[tile];
-	for (uint32_t qbase = 0; qbase < total; qbase += kExpandQueue) {
-		__syncthreads();
-		{  // queue the hits whose rank falls into [qbase, qbase + kExpandQueue)
-			uint32_t o = myOff;
-#pragma unroll
-			for (int k = 0; k < 4; ++k) {
-				uint32_t rem = h[k];
-				while (rem) {
-					const int j = __ffs(rem) - 1;
-					rem &= rem - 1;
-					if (o >= qbase && o < qbase + kExpandQueue) s_q[o - qbase] = static_cast<uint16_t>(((4 * tid + k) << 5) | j);
-					++o;
-				}
-			}
-		}
-		__syncthreads();
-		const uint32_t nq = min(static_cast<uint32_t>(kExpandQueue), total - qbase);
-		for (uint32_t q = tid; q < nq; q += kExpandThreads) {
-			const uint32_t e = s_q[q];
-			const uint32_t wi = e >> 5;
-			const uint32_t w = wbase + wi;
-			const int j = static_cast<int>(e & 31u);
-			const uint32_t v = eval_window(M, S.codes[w], S.codes[w + 1], S.nmask[w], S.nmask[w + 1], j);
-			uint32_t sq, wo;
-			if (S.uniformWps) { sq = w / S.uniformWps; wo = sq * S.uniformWps; }
-			else { sq = find_seq(S, w); wo = S.wordOff[sq]; }
-			const uint32_t o = dst + qbase + q;
-			if (o < cap) {
-				oseq[o] = sq + 1;
-				opos[o] = (w - wo) * 32 + static_cast<uint32_t>(j) + 1;
-				ovidx[o] = v;
-				if (wantScore) oscore[o] = (v == kNone) ? 1.0f : static_cast<float>(V.pS[v]);
-			}
-		}
-	}
-}
-
-// exclusive prefix over the tile counts, three small kernels (block sums -> scan of block sums -> add back)
-__global__ void __launch_bounds__(1024) k_tile_blocksum(const uint32_t* __restrict__ cnt, uint32_t n, uint32_t* __restrict__ bsum) {
-	__shared__ uint32_t s_w[32];
-	const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
-	uint32_t v = (i < n) ? cnt[i] : 0u;
-#pragma unroll
-	for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
-	if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
-	__syncthreads();
-	if (threadIdx.x < 32) {
-		uint32_t t = s_w[threadIdx.x];
-#pragma unroll
-		for (int d = 16; d; d >>= 1) t += __shfl_xor_sync(0xFFFFFFFFu, t, d);
-		if (threadIdx.x == 0) bsum[blockIdx.x] = t;
-	}
-}
-__global__ void __launch_bounds__(1024) k_tile_offsets(const uint32_t* __restrict__ cnt, uint32_t n, const uint32_t* __restrict__ boff, uint32_t* __restrict__ off) {
-	__shared__ uint32_t s_w[32];
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const uint32_t i = blockIdx.x * 1024 + threadIdx.x;
-	const uint32_t v = (i < n) ? cnt[i] : 0u;
-	uint32_t incl = v;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
-	if (lane == 31) s_w[wid] = incl;
-	__syncthreads();
-	uint32_t woff = 0;
-	for (int k = 0; k < wid; ++k) woff += s_w[k];
-	if (i < n) off[i] = boff[blockIdx.x] + woff + incl - v;
 }
 
 }  // namespace xxm

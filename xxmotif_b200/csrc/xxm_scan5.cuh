@@ -1,0 +1,326 @@
+// K2 (fifth generation): the full scan as a pure streaming "find" kernel plus a single-pass "expand" kernel.
+//
+// find   (k_scan5):  one thread per 64 consecutive window starts (two 64-bit code words, one 128-bit load).  The test "is
+//                    the left k-mer of this window in the p-value table" is the exact identity  a[x] + b[y] >= 128  over the
+//                    two 4-mers x (bases 0..3) and y (bases 4..7) of the window (pair_table.h).  One LDS.32 fetches
+//                    (a, b) for the two 4-mers starting at an even base and at the following odd base: the table is indexed
+//                    by 5 bases (1024 entries) and replicated once per lane (entry q of lane l at word q * 32 + l, 128 KB),
+//                    so every lookup is bank-conflict free.  Per pair of windows: 1 shift + 1 mask-or (address), 1 LDS,
+//                    1 multiply-add (E[j] + (E[j+2] << 8): the two byte sums of the pair; bit 7 of a byte sum is the hit
+//                    flag) and 1.5 instructions to gather the flags.  The kernel does not look at N masks and does not
+//                    count; it writes one 32-bit mask per 32 windows in "even/odd" order: bit 16 + t = window 2t,
+//                    bit t = window 2t + 1.
+// expand (k_expand5): one CTA per tile of 1024 words, tiles handed out by ticket.  Stages the tile's codes and N masks in
+//                    shared memory (coalesced), brings the masks into window order, clears windows with an N in a match
+//                    column (branch_and_bound-inl.h:388) and words outside the scanned range, counts, obtains the tile's
+//                    global offset by a decoupled look-back over the tile status words (warp-parallel), and resolves the
+//                    hits into records (value index, sequence, position, float score) in (sequence, position) order --
+//                    the reference's scan order, so nothing downstream needs a sort by position.
+#pragma once
+#include "xxm_kernels.cuh"
+
+namespace xxm {
+
+constexpr int kScan5Threads = 1024;
+constexpr int kPairTabWords = 1024 * 32;  // 128 KB of shared memory
+
+template <int J>
+__device__ __forceinline__ uint32_t pair_lookup(const uint32_t (&r)[5], const uint8_t* tab) {
+	constexpr int bit = 4 * J, k = bit / 32, o = bit % 32;  // the 10-bit field of pair J starts at bit o of r[k]; wanted at bits [7, 17)
+	uint32_t t;
+	if constexpr (o == 0) t = r[k] << 7;
+	else if constexpr (o == 4) t = r[k] << 3;
+	else if constexpr (o + 10 <= 32) t = r[k] >> (o - 7);
+	else t = __funnelshift_r(r[k], r[k + 1], o - 7);
+	return *reinterpret_cast<const uint32_t*>(tab + (t & 0x1FF80u));  // tab already points at this lane's column
+}
+
+template <int S>
+__device__ __forceinline__ uint32_t gather_flags(uint32_t acc, uint32_t tLo, uint32_t tHi) {
+	// bytes 3 / 1 of a T word hold the sums of its even / odd window; U = [odd(lo), odd(hi), even(lo), even(hi)]
+	const uint32_t u = __byte_perm(tLo, tHi, 0x7351);
+	const uint32_t x = (S == 7) ? u : (u >> (7 - S));
+	return acc | (x & (0x01010101u << S));
+}
+
+template <int G>
+__device__ __forceinline__ uint32_t scan5_word(const uint32_t (&e)[34]) {
+	uint32_t acc = 0;
+#define XXM_T(j) (e[(j)] + (e[(j) + 2] << 8))
+	acc = gather_flags<0>(acc, XXM_T(G + 0), XXM_T(G + 8));
+	acc = gather_flags<1>(acc, XXM_T(G + 1), XXM_T(G + 9));
+	acc = gather_flags<2>(acc, XXM_T(G + 2), XXM_T(G + 10));
+	acc = gather_flags<3>(acc, XXM_T(G + 3), XXM_T(G + 11));
+	acc = gather_flags<4>(acc, XXM_T(G + 4), XXM_T(G + 12));
+	acc = gather_flags<5>(acc, XXM_T(G + 5), XXM_T(G + 13));
+	acc = gather_flags<6>(acc, XXM_T(G + 6), XXM_T(G + 14));
+	acc = gather_flags<7>(acc, XXM_T(G + 7), XXM_T(G + 15));
+#undef XXM_T
+	return acc;
+}
+
+__global__ void __launch_bounds__(kScan5Threads, 1) k_scan5(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ pairTab,
+                                                           uint32_t* __restrict__ hitmask, uint32_t scanWords) {
+	extern __shared__ __align__(16) uint8_t smem5[];
+	{
+		uint32_t* s = reinterpret_cast<uint32_t*>(smem5);
+		for (uint32_t i = threadIdx.x; i < kPairTabWords; i += kScan5Threads) s[i] = pairTab[i >> 5];
+	}
+	__syncthreads();
+	const int lane = threadIdx.x & 31;
+	const uint8_t* tab = smem5 + 4 * lane;
+	const uint32_t warp = (blockIdx.x * kScan5Threads + threadIdx.x) >> 5;
+	const uint32_t nwarps = (gridDim.x * kScan5Threads) >> 5;
+	const uint32_t nchunks = (scanWords + 63) / 64;
+	for (uint32_t c = warp; c < nchunks; c += nwarps) {
+		const uint32_t w = c * 64 + 2 * lane;
+		uint32_t r[5] = {0, 0, 0, 0, 0};
+		if (w < scanWords) {
+			const uint4 v = *reinterpret_cast<const uint4*>(codes + w);
+			r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
+		}
+		r[4] = __shfl_down_sync(0xFFFFFFFFu, r[0], 1);
+		if (lane == 31) r[4] = (w + 2 <= scanWords) ? static_cast<uint32_t>(codes[w + 2]) : 0u;
+		uint32_t e[34];
+		e[0] = pair_lookup<0>(r, tab);   e[1] = pair_lookup<1>(r, tab);   e[2] = pair_lookup<2>(r, tab);   e[3] = pair_lookup<3>(r, tab);
+		e[4] = pair_lookup<4>(r, tab);   e[5] = pair_lookup<5>(r, tab);   e[6] = pair_lookup<6>(r, tab);   e[7] = pair_lookup<7>(r, tab);
+		e[8] = pair_lookup<8>(r, tab);   e[9] = pair_lookup<9>(r, tab);   e[10] = pair_lookup<10>(r, tab); e[11] = pair_lookup<11>(r, tab);
+		e[12] = pair_lookup<12>(r, tab); e[13] = pair_lookup<13>(r, tab); e[14] = pair_lookup<14>(r, tab); e[15] = pair_lookup<15>(r, tab);
+		e[16] = pair_lookup<16>(r, tab); e[17] = pair_lookup<17>(r, tab); e[18] = pair_lookup<18>(r, tab); e[19] = pair_lookup<19>(r, tab);
+		e[20] = pair_lookup<20>(r, tab); e[21] = pair_lookup<21>(r, tab); e[22] = pair_lookup<22>(r, tab); e[23] = pair_lookup<23>(r, tab);
+		e[24] = pair_lookup<24>(r, tab); e[25] = pair_lookup<25>(r, tab); e[26] = pair_lookup<26>(r, tab); e[27] = pair_lookup<27>(r, tab);
+		e[28] = pair_lookup<28>(r, tab); e[29] = pair_lookup<29>(r, tab); e[30] = pair_lookup<30>(r, tab); e[31] = pair_lookup<31>(r, tab);
+		e[32] = pair_lookup<32>(r, tab); e[33] = pair_lookup<33>(r, tab);
+		const uint32_t h0 = scan5_word<0>(e), h1 = scan5_word<16>(e);
+		if (w < scanWords) *reinterpret_cast<uint2*>(hitmask + w) = make_uint2(h0, h1);
+	}
+}
+
+// even/odd mask (bit 16 + t = window 2t, bit t = window 2t + 1) -> window order
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+	x = (x | (x << 8)) & 0x00FF00FFu;
+	x = (x | (x << 4)) & 0x0F0F0F0Fu;
+	x = (x | (x << 2)) & 0x33333333u;
+	x = (x | (x << 1)) & 0x55555555u;
+	return x;
+}
+__device__ __forceinline__ uint32_t eo_to_natural(uint32_t m) { return spread16(m >> 16) | (spread16(m & 0xFFFFu) << 1); }
+
+constexpr int kExpand5Threads = 256;
+constexpr int kExpand5Queue = 4096;
+
+struct Expand5IO {
+	const uint32_t* hitmask;
+	uint32_t scanWords;
+	int eoFormat;       // 1: masks in even/odd order (k_scan5), 0: window order (k_scan4)
+	int wantScore;
+	uint32_t *oseq, *opos, *ovidx;
+	float* oscore;
+	uint32_t cap;
+	uint64_t* status;   // [ntiles] zeroed: per-tile count
+	uint64_t* gstatus;  // [ntiles / 32 + 1] zeroed: per-group sum / inclusive prefix
+	uint32_t* ticket;   // zeroed
+	uint64_t* total;    // out
+	uint32_t ntiles;
+	uint32_t wpsMagic;  // floor(2^32 / uniformWps), 0 for ragged sets
+};
+
+struct HitRec { uint32_t seq, pos, v; };
+
+// kFast: one table, no gap columns -- the value index is rank0[k-mer] - 1 and the k-mer is one funnel shift away
+template <bool kFast>
+__device__ __forceinline__ HitRec expand_hit(const SeqStream& S, const Model& M, const Expand5IO& io, const uint64_t* s_codes, uint32_t wbase, uint32_t e) {
+	const uint32_t wi = e >> 5;
+	const uint32_t w = wbase + wi;
+	const int j = static_cast<int>(e & 31u);
+	HitRec r;
+	if (kFast) {
+		const uint2 c0 = *reinterpret_cast<const uint2*>(s_codes + wi);
+		const uint32_t c1 = static_cast<uint32_t>(s_codes[wi + 1]);
+		const uint32_t k = (j < 16) ? __funnelshift_r(c0.x, c0.y, 2 * j) : __funnelshift_r(c0.y, c1, 2 * j - 32);
+		r.v = M.rank0[k & ((1u << (2 * M.len0)) - 1u)] - 1u;  // the window is in the table: the find kernel is exact
+	} else {
+		r.v = eval_window(M, s_codes[wi], s_codes[wi + 1], 0u, 0u, j);  // N windows are already gone
+	}
+	uint32_t sq, wo;
+	if (io.wpsMagic) {
+		sq = __umulhi(w, io.wpsMagic);
+		wo = sq * S.uniformWps;
+		if (w - wo >= S.uniformWps) { ++sq; wo += S.uniformWps; }
+	} else {
+		sq = find_seq(S, w);
+		wo = S.wordOff[sq];
+	}
+	r.seq = sq + 1;
+	r.pos = (w - wo) * 32 + static_cast<uint32_t>(j) + 1;
+	return r;
+}
+
+template <bool kFast>
+__global__ void __launch_bounds__(kExpand5Threads) k_expand5(SeqStream S, Model M, Values V, Expand5IO io) {
+	__shared__ __align__(16) uint64_t s_codes[kTileWords + 4];
+	__shared__ uint16_t s_q[kExpand5Queue];
+	__shared__ uint32_t s_warp[kExpand5Threads / 32];
+	__shared__ uint32_t s_tile;
+	__shared__ uint64_t s_base;
+	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+	if (tid == 0) s_tile = atomicAdd(io.ticket, 1u);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	const uint32_t wbase = tile * kTileWords;
+	const uint32_t w0 = wbase + 4 * tid;
+	// ---- all loads of the thread up front: its four hit masks, five N masks, four code words (staged for the expansion)
+	uint32_t h[4], nm[5];
+	if (w0 + 4 < S.nwords + 2 && w0 + 3 < io.scanWords) {
+		const uint4 hv = *reinterpret_cast<const uint4*>(io.hitmask + w0);
+		const uint4 nv = *reinterpret_cast<const uint4*>(S.nmask + w0);
+		nm[4] = S.nmask[w0 + 4];
+		const uint4 ca = *reinterpret_cast<const uint4*>(S.codes + w0);
+		const uint4 cb = *reinterpret_cast<const uint4*>(S.codes + w0 + 2);
+		h[0] = hv.x; h[1] = hv.y; h[2] = hv.z; h[3] = hv.w;
+		nm[0] = nv.x; nm[1] = nv.y; nm[2] = nv.z; nm[3] = nv.w;
+		*reinterpret_cast<uint4*>(s_codes + 4 * tid) = ca;
+		*reinterpret_cast<uint4*>(s_codes + 4 * tid + 2) = cb;
+	} else {
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			const uint32_t w = w0 + k;
+			const bool in = w < S.nwords + 2;
+			h[k] = (w < io.scanWords) ? io.hitmask[w] : 0u;
+			nm[k] = in ? S.nmask[w] : 0xFFFFFFFFu;
+			s_codes[4 * tid + k] = in ? S.codes[w] : 0ull;
+		}
+		nm[4] = (w0 + 4 < S.nwords + 2) ? S.nmask[w0 + 4] : 0xFFFFFFFFu;
+	}
+	if (tid == 0) s_codes[kTileWords] = (wbase + kTileWords < S.nwords + 2) ? S.codes[wbase + kTileWords] : 0ull;
+	// ---- window order, N windows out (a window dies if any match column holds an N, branch_and_bound-inl.h:388)
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		if (!h[k]) continue;
+		if (io.eoFormat) h[k] = eo_to_natural(h[k]);
+		const uint64_t mm = (static_cast<uint64_t>(nm[k + 1]) << 32) | nm[k];
+		if (mm) {
+			uint32_t inv = 0;
+			if (M.contiguous) {  // OR of mm >> 0 .. mm >> (L - 1) by doubling
+				uint64_t x = mm;
+				int have = 1;
+				while (2 * have <= M.L) { x |= x >> have; have *= 2; }
+				if (have < M.L) x |= x >> (M.L - have);
+				inv = static_cast<uint32_t>(x);
+			} else {
+				for (int c = 0; c < M.L; ++c) inv |= static_cast<uint32_t>(mm >> M.coloff[c]);
+			}
+			h[k] &= ~inv;
+		}
+	}
+	const uint32_t c0 = __popc(h[0]), c1 = __popc(h[1]), c2 = __popc(h[2]);
+	const uint32_t cnt = c0 + c1 + c2 + __popc(h[3]);
+	uint32_t incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+		if (lane >= d) incl += t;
+	}
+	if (lane == 31) s_warp[wid] = incl;
+	__syncthreads();
+	uint32_t woff = 0, total = 0;
+#pragma unroll
+	for (int k = 0; k < kExpand5Threads / 32; ++k) { if (k < wid) woff += s_warp[k]; total += s_warp[k]; }
+	if (tid == 0) reinterpret_cast<volatile uint64_t*>(io.status)[tile] = kFlagAgg | total;  // as early as possible
+	const uint32_t myOff = woff + incl - cnt;
+	const bool fits = total <= static_cast<uint32_t>(kExpand5Queue);
+	if (fits) {  // the common case: the whole tile fits the queue
+		uint32_t o = myOff;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			uint32_t rem = h[k];
+			const uint32_t tag = static_cast<uint32_t>(4 * tid + k) << 5;
+			while (rem) {
+				s_q[o++] = static_cast<uint16_t>(tag | (__ffs(rem) - 1));
+				rem &= rem - 1;
+			}
+		}
+	}
+	__syncthreads();
+	HitRec first{0, 0, 0};
+	if (wid != 0 && fits && static_cast<uint32_t>(tid) < total) first = expand_hit<kFast>(S, M, io, s_codes, wbase, s_q[tid]);
+	if (wid == 0) {
+		// Two-level decoupled look-back.  A plain look-back advances its frontier by at most 32 tiles per L2 round trip,
+		// which is slower than the tiles can be expanded.  Tiles are therefore grouped by 32: a tile sums the counts of
+		// the tiles before it in its group (they hold earlier tickets, so they are running and will publish), the last
+		// tile of a group publishes the group sum, and the running prefix is carried group to group (32 groups =
+		// 1024 tiles per round trip).  Warps 1..7 expand their first hit meanwhile.
+		volatile uint64_t* st = io.status;
+		volatile uint64_t* gst = io.gstatus;
+		const uint32_t g = tile >> 5, r = tile & 31u;
+		const bool lastOfGroup = (r == 31u) || (tile == io.ntiles - 1);
+		uint64_t v = 0;
+		if (static_cast<uint32_t>(lane) < r) {
+			do { v = st[(g << 5) + lane]; } while ((v >> 62) == 0);
+			v &= kValMask;
+		}
+#pragma unroll
+		for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, d);
+		const uint64_t local = v;  // hits of the tiles before this one in its group
+		if (lastOfGroup && lane == 0 && g != 0) gst[g] = kFlagAgg | (local + total);
+		uint64_t gprefix = 0;
+		int64_t t = static_cast<int64_t>(g) - 1 - lane;
+		while (g != 0) {
+			uint64_t x = 2ull << 62;  // before the first group: inclusive prefix 0
+			if (t >= 0) x = gst[t];
+			while (__any_sync(0xFFFFFFFFu, (x >> 62) == 0)) {
+				if ((x >> 62) == 0) x = gst[t];
+			}
+			const uint32_t inclMask = __ballot_sync(0xFFFFFFFFu, (x >> 62) == 2);
+			const int firstIncl = inclMask ? (__ffs(inclMask) - 1) : 32;
+			uint64_t c = (lane <= firstIncl) ? (x & kValMask) : 0ull;
+#pragma unroll
+			for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+			gprefix += c;
+			if (inclMask) break;
+			t -= 32;
+		}
+		if (lastOfGroup && lane == 0) gst[g] = kFlagIncl | (gprefix + local + total);
+		if (lane == 0) {
+			s_base = gprefix + local;
+			if (tile == io.ntiles - 1) *io.total = gprefix + local + total;
+		}
+		if (fits && static_cast<uint32_t>(tid) < total) first = expand_hit<kFast>(S, M, io, s_codes, wbase, s_q[tid]);
+	}
+	__syncthreads();
+	if (total == 0) return;
+	const uint64_t base = s_base;
+	auto emit = [&](const HitRec& rec, uint64_t o) {
+		if (o < io.cap) {
+			io.oseq[o] = rec.seq;
+			io.opos[o] = rec.pos;
+			io.ovidx[o] = rec.v;
+			if (io.wantScore) io.oscore[o] = (rec.v == kNone) ? 1.0f : static_cast<float>(V.pS[rec.v]);
+		}
+	};
+	if (fits) {
+		if (static_cast<uint32_t>(tid) < total) emit(first, base + tid);
+		for (uint32_t q = tid + kExpand5Threads; q < total; q += kExpand5Threads) emit(expand_hit<kFast>(S, M, io, s_codes, wbase, s_q[q]), base + q);
+		return;
+	}
+	// dense tile: queue the hits in rounds
+	for (uint32_t qbase = 0; qbase < total; qbase += kExpand5Queue) {
+		__syncthreads();
+		uint32_t o = myOff;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			uint32_t rem = h[k];
+			while (rem) {
+				const int j = __ffs(rem) - 1;
+				rem &= rem - 1;
+				if (o >= qbase && o < qbase + kExpand5Queue) s_q[o - qbase] = static_cast<uint16_t>(((4 * tid + k) << 5) | j);
+				++o;
+			}
+		}
+		__syncthreads();
+		const uint32_t nq = min(static_cast<uint32_t>(kExpand5Queue), total - qbase);
+		for (uint32_t q = tid; q < nq; q += kExpand5Threads) emit(expand_hit<kFast>(S, M, io, s_codes, wbase, s_q[q]), base + qbase + q);
+	}
+}
+
+}  // namespace xxm
