@@ -229,9 +229,10 @@ int xxm_host_pair_table(const uint32_t* ids, int64_t nids, const int32_t* coloff
  * device-side timing of the most recent call of each kernel (CUDA events on the context's stream), launch counts */
 typedef struct {
 	int64_t launches;        /* kernels launched by this context so far */
-	float last_scan_ms;      /* device time of the last full-scan kernel */
+	float last_scan_ms;      /* device time of the kernels of the last full scan: find + expand */
 	int64_t last_scan_bases; /* stored bases the last full scan covered */
 	int64_t last_scan_hits;  /* windows with finalPval < 1 it found */
+	float last_find_ms;      /* device time of the find kernel alone (the rest of last_scan_ms is the expand kernel) */
 } xxm_stats;
 int xxm_get_stats(const xxm_ctx* ctx, xxm_stats* out);
 /* the CUDA stream the context launches on, as a cudaStream_t cast to void* (for external event timing) */

@@ -31,7 +31,8 @@ class XxmOptions(C.Structure):
 
 
 class XxmStats(C.Structure):
-    _fields_ = [("launches", C.c_int64), ("last_scan_ms", C.c_float), ("last_scan_bases", C.c_int64), ("last_scan_hits", C.c_int64)]
+    _fields_ = [("launches", C.c_int64), ("last_scan_ms", C.c_float), ("last_scan_bases", C.c_int64), ("last_scan_hits", C.c_int64),
+                ("last_find_ms", C.c_float)]
 
 
 class XxmError(RuntimeError):
@@ -265,7 +266,8 @@ class Context:
     def stats(self):
         s = XxmStats()
         self._ck(self.L.xxm_get_stats(self.h, C.byref(s)))
-        return {"launches": s.launches, "last_scan_ms": s.last_scan_ms, "last_scan_bases": s.last_scan_bases, "last_scan_hits": s.last_scan_hits}
+        return {"launches": s.launches, "last_scan_ms": s.last_scan_ms, "last_scan_bases": s.last_scan_bases, "last_scan_hits": s.last_scan_hits,
+                "last_find_ms": s.last_find_ms}
 
     def stream(self):
         return self.L.xxm_stream(self.h)

@@ -70,7 +70,7 @@ struct SiteList {
 struct xxm_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, evMid = nullptr;
 	std::string err;
 	xxm_options opt{};
 	bool haveOpt = false;
@@ -81,7 +81,8 @@ struct xxm_ctx {
 	int nent = 0;
 	bool revcomp = false;
 	std::vector<int32_t> len, total;
-	std::vector<double> avgLength;
+	std::vector<double> logAcc;  // running sum of log(non-N residues): avgLength[i] = exp(logAcc[i] / i), evaluated on demand
+	double avg_length(int i) const { return i ? std::exp(logAcc[i] / i) : 0.0; }  // calculateSequenceFeatures, seqset.cpp:31-34
 	int max_leng = 0, min_leng = 0;
 	std::vector<uint32_t> wordOff;
 	uint32_t nwords = 0;
@@ -190,7 +191,7 @@ extern "C" int xxm_create(int device, xxm_ctx** out) {
 	cudaDeviceProp prop;
 	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->numSMs = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
-	    cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+	    cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->evMid) != cudaSuccess) {
 		g_create_error = "cannot create stream/events";
 		delete ctx;
 		return 1;
@@ -222,6 +223,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	ctx->r_seq.release(); ctx->d_pbits.release(); ctx->d_t8.release(); ctx->d_pairTab.release();
 	cudaEventDestroy(ctx->ev0);
 	cudaEventDestroy(ctx->ev1);
+	cudaEventDestroy(ctx->evMid);
 	cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -292,14 +294,15 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	ctx->revcomp = revcomp != 0;
 	ctx->len.resize(nent);
 	ctx->total.assign(static_cast<size_t>(nent) + 1, 0);
-	ctx->avgLength.assign(static_cast<size_t>(nent) + 1, 0.0);
+	ctx->logAcc.assign(static_cast<size_t>(nent) + 1, 0.0);
 	ctx->wordOff.resize(static_cast<size_t>(nent) + 1);
 	std::vector<uint64_t> rawOff(static_cast<size_t>(nent) + 1);
 	// calculateSequenceFeatures (seqset.cpp:21-36) on the raw set, then -- with revcomp -- the recount at the end of
 	// createRevcomp (seqset.cpp:165-177) which compares codes with the CHARACTER '0' and therefore counts every
 	// position of the doubled sequence.
 	uint64_t off = 0, words = 0;
-	double acc = 0;
+	double acc = 0, lastLog = 0;
+	int lastNotX = 0;
 	int mx = 0, mn = 2147483647;
 	int64_t tot = 0;
 	// the raw codes go to the device first; the per-sequence count of non-N residues and the range check of the codes
@@ -323,11 +326,14 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 		int notX = notXv[i];
 		const int nstore = revcomp ? 2 * n0 + 1 : n0;
 		if (revcomp) notX = nstore;
-		if (notX != 0) acc += std::log(notX);
+		if (notX != 0) {
+			if (notX != lastNotX) { lastNotX = notX; lastLog = std::log(notX); }  // same argument, same glibc result
+			acc += lastLog;
+		}
 		tot += notX;
 		if (tot > 2147483647LL) return ctx->fail("more than 2^31-1 residues: the reference's int totals overflow (Alignment.h:40-41)");
 		ctx->total[i + 1] = static_cast<int32_t>(tot);
-		ctx->avgLength[i + 1] = std::exp(acc / (i + 1));
+		ctx->logAcc[i + 1] = acc;
 		ctx->len[i] = nstore;
 		mx = std::max(mx, nstore);
 		mn = std::min(mn, nstore);
@@ -384,7 +390,8 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 
 extern "C" int xxm_seqset_info(const xxm_ctx* ctx, int32_t* total, double* avgLength, int32_t* max_leng, int32_t* min_leng) {
 	if (total) std::memcpy(total, ctx->total.data(), ctx->total.size() * sizeof(int32_t));
-	if (avgLength) std::memcpy(avgLength, ctx->avgLength.data(), ctx->avgLength.size() * sizeof(double));
+	if (avgLength)
+		for (size_t i = 0; i < ctx->logAcc.size(); ++i) avgLength[i] = ctx->avg_length(static_cast<int>(i));
 	if (max_leng) *max_leng = ctx->max_leng;
 	if (min_leng) *min_leng = ctx->min_leng;
 	return 0;
@@ -468,7 +475,7 @@ extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* 
 	TRY(upload(ctx, ctx->d_cpval0, T.part[0].classPval));
 	TRY(upload(ctx, ctx->d_cscore0, T.part[0].classScore));
 	M.cpval0 = ctx->d_cpval0.p; M.cscore0 = ctx->d_cscore0.p; M.nclass0 = static_cast<int>(T.part[0].classPval.size());
-	const double exponent = ctx->avgLength[posSetSize] - T.span + 1;
+	const double exponent = ctx->avg_length(posSetSize) - T.span + 1;
 	ctx->memoModeValid = false;
 	ctx->posProbValid = false;
 	if (T.nparts == 1) {
@@ -582,7 +589,7 @@ static int finalize_memo(xxm_ctx* ctx, bool needMode) {
 	CK(cudaStreamSynchronize(ctx->stream));
 	if (ovf) return ctx->fail("memo table of the >8-column path overflowed (capacity %u)", cap);
 	if (roundTrip) {
-		const double exponent = ctx->avgLength[ctx->modelPosSetSize] - ctx->tab.span + 1;
+		const double exponent = ctx->avg_length(ctx->modelPosSetSize) - ctx->tab.span + 1;
 		ctx->h_finalMode.assign(cap, 1.0);
 		for (uint32_t h = 0; h < cap; ++h) {
 			if (keys[h] == kMemoEmpty) continue;
@@ -694,7 +701,6 @@ static int select_mops(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const
 	CK(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
 	*nKept = 0; *maxPerSeq = 0;
 	if (!n) return 0;
-	CK(cudaMemsetAsync(keep.p, 0, n, ctx->stream));
 	SelectIO io{};
 	io.seq = seq; io.pos = pos; io.vidx = vidx; io.n = n; io.shift = shift; io.length = ctx->tab.span; io.revcomp = ctx->revcomp;
 	io.stk = ctx->stk.p; io.kscore = kscore.p; io.keep = keep.p; io.counters = ctx->counters.p;
@@ -711,12 +717,13 @@ static int select_mops(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const
 			f.hist = ctx->hist.p; f.nval = ctx->nval; f.smemHist = ctx->nval <= 8192;
 		}
 		const size_t sm = (wantHist && f.smemHist) ? ctx->nval * 4ull : 0;
-		const uint32_t grid = std::min<uint32_t>(cdiv(n, 256), static_cast<uint32_t>(ctx->numSMs) * 64);
+		const uint32_t grid = std::min<uint32_t>(cdiv(n, 256 * kSelChunk), static_cast<uint32_t>(ctx->numSMs) * 16);  // a thread owns kSelChunk entries per pass
 		k_select_mops_fwd<<<grid, 256, sm, ctx->stream>>>(V, f);
 		CKK();
 		ctx->histValid = wantHist;
 		ctx->histSerial = ++ctx->histCounter;
 	} else {
+		CK(cudaMemsetAsync(keep.p, 0, n, ctx->stream));
 		if (ordered) k_select_mops<<<cdiv(n, 128), 128, 0, ctx->stream>>>(ctx->S, V, io);
 		else k_select_mops_serial<<<1, 32, 0, ctx->stream>>>(ctx->S, V, io);
 		CKK();

@@ -194,27 +194,34 @@ __global__ void __launch_bounds__(kExpand5Threads) k_expand5(SeqStream S, Model 
 	}
 	if (tid == 0) s_codes[kTileWords] = (wbase + kTileWords < S.nwords + 2) ? S.codes[wbase + kTileWords] : 0ull;
 	// ---- window order, N windows out (a window dies if any match column holds an N, branch_and_bound-inl.h:388)
+	if (io.eoFormat) {
 #pragma unroll
-	for (int k = 0; k < 4; ++k) {
-		if (!h[k]) continue;
-		if (io.eoFormat) h[k] = eo_to_natural(h[k]);
-		const uint64_t mm = (static_cast<uint64_t>(nm[k + 1]) << 32) | nm[k];
-		if (mm) {
-			uint32_t inv = 0;
-			if (M.contiguous) {  // OR of mm >> 0 .. mm >> (L - 1) by doubling
-				uint64_t x = mm;
-				int have = 1;
-				while (2 * have <= M.L) { x |= x >> have; have *= 2; }
-				if (have < M.L) x |= x >> (M.L - have);
-				inv = static_cast<uint32_t>(x);
-			} else {
-				for (int c = 0; c < M.L; ++c) inv |= static_cast<uint32_t>(mm >> M.coloff[c]);
+		for (int k = 0; k < 4; ++k) h[k] = eo_to_natural(h[k]);
+	}
+	if (__any_sync(0xFFFFFFFFu, (nm[0] | nm[1] | nm[2] | nm[3] | nm[4]) != 0u)) {  // a sequence end or an N within reach of this warp
+		if (M.contiguous) {  // OR of (mask >> 0) .. (mask >> (L - 1)) by doubling, all four words at once
+			uint32_t x[5] = {nm[0], nm[1], nm[2], nm[3], nm[4]};
+			int have = 1;
+			while (have < M.L) {
+				const int sh = min(have, M.L - have);
+#pragma unroll
+				for (int k = 0; k < 4; ++k) x[k] |= __funnelshift_r(x[k], x[k + 1], sh);
+				x[4] |= x[4] >> sh;
+				have += sh;
 			}
-			h[k] &= ~inv;
+#pragma unroll
+			for (int k = 0; k < 4; ++k) h[k] &= ~x[k];
+		} else {
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const uint64_t mm = (static_cast<uint64_t>(nm[k + 1]) << 32) | nm[k];
+				uint32_t inv = 0;
+				for (int c = 0; c < M.L; ++c) inv |= static_cast<uint32_t>(mm >> M.coloff[c]);
+				h[k] &= ~inv;
+			}
 		}
 	}
-	const uint32_t c0 = __popc(h[0]), c1 = __popc(h[1]), c2 = __popc(h[2]);
-	const uint32_t cnt = c0 + c1 + c2 + __popc(h[3]);
+	const uint32_t cnt = __popc(h[0]) + __popc(h[1]) + __popc(h[2]) + __popc(h[3]);
 	uint32_t incl = cnt;
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {

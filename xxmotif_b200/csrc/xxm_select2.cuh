@@ -3,12 +3,11 @@
 // k_select_mops_fwd: updateMultOcc (StartPosUtils.h:12-28) for sets WITHOUT --revcomp.  Only the forward-overlap rule
 //   applies there, and it can only ever replace the LAST kept site, so the greedy decomposes into independent
 //   "clusters": maximal runs of list entries of one sequence whose consecutive start positions are at most `length`
-//   apart (if pos[i-1] + length < pos[i] no kept site at or before pos[i-1] can overlap entry i).  The thread of the
-//   first entry of a cluster walks it with the state (last kept entry, its float score) in registers.  Kept sites are
-//   final when the next site is accepted or the cluster ends; at that moment their value index is added to a
-//   shared-memory histogram, which replaces the sort by score (the float score is a function of the value index).
-// k_count_pwm2: Motif::updateCounts (Motif.cpp:653-672) with a persistent grid so that the 31x5 counters are flushed
-//   once per CTA.
+//   apart (if pos[i-1] + length < pos[i] no kept site at or before pos[i-1] can overlap entry i).  Every thread owns 8
+//   consecutive entries and runs the greedy over them in registers, after replaying the entries of the same cluster that
+//   precede its chunk.  Kept sites are added to a shared-memory histogram over value indices, which replaces the sort by
+//   score (the float score is a function of the value index).
+// k_count_pwm2: Motif::updateCounts (Motif.cpp:653-672), persistent grid, one lane per chosen site, ballot counting.
 #pragma once
 #include "xxm_kernels.cuh"
 
@@ -22,12 +21,33 @@ struct SelectFwdIO {
 	int length;
 	int shift;           // startPos = pos + shift (only matters for the positional prior)
 	float* kscore;       // [n]
-	uint8_t* keep;       // [n] zeroed
+	uint8_t* keep;       // [n] (every entry is written)
 	uint32_t* counters;  // [0] += kept sites
 	uint32_t* hist;      // [nval] zeroed, or null
 	uint32_t nval;
 	int smemHist;        // histogram privatised in shared memory (nval * 4 bytes of dynamic smem)
 };
+
+constexpr int kSelChunk = 8;
+
+// state of the greedy: the kept site that a later entry can still replace
+struct SelState {
+	int64_t last = -1;
+	float lastScore = 0.f;
+	uint32_t lastPos = 0;
+};
+// one entry of updateMultOcc's forward rule (StartPosUtils.h:14-27).  Returns true when the entry becomes the kept site;
+// *replaced says whether it pushed out the previous kept site (false: that one is final).
+__device__ __forceinline__ bool sel_step(SelState& st, int64_t j, uint32_t pj, double finj, uint32_t length, bool* replaced) {
+	*replaced = false;
+	if (!(finj < 1.0)) return false;  // not a site (entries without a value carry p-value 1)
+	if (st.last >= 0 && st.lastPos + length >= pj) {
+		if (static_cast<double>(st.lastScore) <= finj) return false;  // the kept site is at least as good: drop the new one
+		*replaced = true;
+	}
+	st.last = j; st.lastScore = static_cast<float>(finj); st.lastPos = pj;
+	return true;
+}
 
 __global__ void __launch_bounds__(256) k_select_mops_fwd(Values V, SelectFwdIO io) {
 	extern __shared__ uint32_t s_hist[];
@@ -37,32 +57,111 @@ __global__ void __launch_bounds__(256) k_select_mops_fwd(Values V, SelectFwdIO i
 	if (threadIdx.x == 0) s_cnt = 0;
 	__syncthreads();
 	uint32_t* hist = io.smemHist ? s_hist : io.hist;
+	const uint32_t L = static_cast<uint32_t>(io.length);
+	const int lane = threadIdx.x & 31;
+	const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+	const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
+	const uint64_t nchunks = (static_cast<uint64_t>(io.n) + kSelChunk - 1) / kSelChunk;
 	uint32_t kept = 0;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < io.n; i += gridDim.x * blockDim.x) {
-		const uint32_t sq = io.seq[i];
-		if (i > 0 && io.seq[i - 1] == sq && io.pos[i - 1] + io.length >= io.pos[i]) continue;  // not a cluster head
-		uint32_t last = kNone, lastV = 0;
-		float lastScore = 0.f;
-		uint32_t lastPos = 0, prevPos = 0;
-		for (uint32_t j = i; j < io.n; ++j) {
-			const uint32_t pj = io.pos[j];
-			if (j > i && (io.seq[j] != sq || prevPos + io.length < pj)) break;
-			prevPos = pj;
-			const uint32_t v = io.vidx[j];
-			if (v == kNone) continue;
-			const double pVal = final_of(V, v, j, static_cast<int>(pj) + io.shift);
-			if (!(pVal < 1.0)) continue;
-			if (last != kNone && lastPos + io.length >= pj) {
-				if (static_cast<double>(lastScore) <= pVal) continue;  // the kept site is at least as good: drop the new one
-				io.keep[last] = 0;                                        // the new site replaces the last kept one
-				last = kNone;
+	auto fin_at = [&](int64_t j, uint32_t pj) -> double {
+		const uint32_t v = io.vidx[j];
+		return (v == kNone) ? 1.0 : final_of(V, v, static_cast<uint32_t>(j), static_cast<int>(pj) + io.shift);
+	};
+	// Every thread owns kSelChunk consecutive entries (vector loads, all in registers).  It replays the entries of its first
+	// entry's cluster that lie before the chunk (read only), decides its own entries, and then looks ahead while a later
+	// entry could still replace its last kept site.  Every keep flag is written by the owner of the entry.
+	for (uint64_t c0 = warp * 32; c0 < nchunks; c0 += nwarps * 32) {
+		const uint64_t c = c0 + lane;
+		const int64_t j0 = static_cast<int64_t>(c) * kSelChunk;
+		const int m = (c < nchunks) ? static_cast<int>(min(static_cast<uint64_t>(kSelChunk), static_cast<uint64_t>(io.n) - j0)) : 0;
+		uint32_t sq[kSelChunk], ps[kSelChunk], vi[kSelChunk];
+		if (m == kSelChunk) {
+			const uint4 a0 = *reinterpret_cast<const uint4*>(io.seq + j0), a1 = *reinterpret_cast<const uint4*>(io.seq + j0 + 4);
+			const uint4 b0 = *reinterpret_cast<const uint4*>(io.pos + j0), b1 = *reinterpret_cast<const uint4*>(io.pos + j0 + 4);
+			const uint4 v0 = *reinterpret_cast<const uint4*>(io.vidx + j0), v1 = *reinterpret_cast<const uint4*>(io.vidx + j0 + 4);
+			sq[0] = a0.x; sq[1] = a0.y; sq[2] = a0.z; sq[3] = a0.w; sq[4] = a1.x; sq[5] = a1.y; sq[6] = a1.z; sq[7] = a1.w;
+			ps[0] = b0.x; ps[1] = b0.y; ps[2] = b0.z; ps[3] = b0.w; ps[4] = b1.x; ps[5] = b1.y; ps[6] = b1.z; ps[7] = b1.w;
+			vi[0] = v0.x; vi[1] = v0.y; vi[2] = v0.z; vi[3] = v0.w; vi[4] = v1.x; vi[5] = v1.y; vi[6] = v1.z; vi[7] = v1.w;
+		} else {
+#pragma unroll
+			for (int k = 0; k < kSelChunk; ++k) {
+				const bool in = k < m;
+				sq[k] = in ? io.seq[j0 + k] : 0u;
+				ps[k] = in ? io.pos[j0 + k] : 0u;
+				vi[k] = in ? io.vidx[j0 + k] : kNone;
 			}
-			if (last != kNone) { ++kept; if (hist) atomicAdd(&hist[lastV], 1u); }
-			last = j; lastV = v; lastPos = pj; lastScore = static_cast<float>(pVal);
-			io.keep[j] = 1;
-			io.kscore[j] = lastScore;
 		}
-		if (last != kNone) { ++kept; if (hist) atomicAdd(&hist[lastV], 1u); }
+		double fin[kSelChunk];
+#pragma unroll
+		for (int k = 0; k < kSelChunk; ++k)
+			fin[k] = (k < m && vi[k] != kNone) ? final_of(V, vi[k], static_cast<uint32_t>(j0 + k), static_cast<int>(ps[k]) + io.shift) : 1.0;
+		SelState st;
+		bool rep;
+		uint32_t keepBits = 0;
+		if (m > 0) {
+			// ---- the part of the cluster before the chunk: back to its head, then forward again
+			if (j0 > 0) {
+				uint32_t pp = io.pos[j0 - 1];
+				if (io.seq[j0 - 1] == sq[0] && pp + L >= ps[0]) {
+					int64_t h = j0 - 1;
+					while (h > 0) {
+						const uint32_t p2 = io.pos[h - 1];
+						if (io.seq[h - 1] != sq[0] || p2 + L < pp) break;
+						pp = p2;
+						--h;
+					}
+					for (int64_t j = h; j < j0; ++j) {
+						const uint32_t pj = io.pos[j];
+						sel_step(st, j, pj, fin_at(j, pj), L, &rep);
+					}
+				}
+			}
+			// ---- own entries
+#pragma unroll
+			for (int k = 0; k < kSelChunk; ++k) {
+				if (k < m) {
+					if (k > 0 && sq[k] != sq[k - 1]) st.last = -1;  // a new sequence starts inside the chunk
+					const int64_t old = st.last;
+					if (sel_step(st, j0 + k, ps[k], fin[k], L, &rep)) {
+						keepBits |= 1u << k;
+						if (rep && old >= j0) keepBits &= ~(1u << static_cast<int>(old - j0));
+					}
+				}
+			}
+			// ---- can a later entry still replace my last kept site?
+			if (st.last >= j0) {
+				const uint32_t mySeq = sq[static_cast<int>(st.last - j0) & (kSelChunk - 1)];
+				for (int64_t j = j0 + m; j < static_cast<int64_t>(io.n); ++j) {
+					const uint32_t pj = io.pos[j];
+					if (io.seq[j] != mySeq || pj > st.lastPos + L) break;
+					const double fj = fin_at(j, pj);
+					if (!(fj < 1.0) || static_cast<double>(st.lastScore) <= fj) continue;
+					keepBits &= ~(1u << static_cast<int>(st.last - j0));
+					break;
+				}
+			}
+			// ---- flags and float scores of the chunk
+			if (m == kSelChunk) {
+				uint2 kb;
+				kb.x = (keepBits & 1u) | ((keepBits & 2u) << 7) | ((keepBits & 4u) << 14) | ((keepBits & 8u) << 21);
+				kb.y = ((keepBits >> 4) & 1u) | ((keepBits & 32u) << 3) | ((keepBits & 64u) << 10) | ((keepBits & 128u) << 17);
+				*reinterpret_cast<uint2*>(io.keep + j0) = kb;
+				*reinterpret_cast<float4*>(io.kscore + j0) = make_float4(static_cast<float>(fin[0]), static_cast<float>(fin[1]), static_cast<float>(fin[2]), static_cast<float>(fin[3]));
+				*reinterpret_cast<float4*>(io.kscore + j0 + 4) = make_float4(static_cast<float>(fin[4]), static_cast<float>(fin[5]), static_cast<float>(fin[6]), static_cast<float>(fin[7]));
+			} else {
+				for (int k = 0; k < m; ++k) { io.keep[j0 + k] = (keepBits >> k) & 1u; io.kscore[j0 + k] = static_cast<float>(fin[k]); }
+			}
+			kept += __popc(keepBits);
+		}
+		if (hist) {  // one shared-memory atomic per distinct value index of the warp and chunk slot
+#pragma unroll
+			for (int k = 0; k < kSelChunk; ++k) {
+				const bool add = (keepBits >> k) & 1u;
+				const uint32_t key = add ? vi[k] : (0x80000000u | static_cast<uint32_t>(lane));
+				const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+				if (add && lane == __ffs(peers) - 1) atomicAdd(&hist[vi[k]], static_cast<uint32_t>(__popc(peers)));
+			}
+		}
 	}
 	if (kept) atomicAdd(&s_cnt, kept);
 	__syncthreads();
@@ -72,15 +171,64 @@ __global__ void __launch_bounds__(256) k_select_mops_fwd(Values V, SelectFwdIO i
 			if (s_hist[k]) atomicAdd(&io.hist[k], s_hist[k]);
 }
 
-// Warp-cooperative: every warp walks 32 entries at a time, finds the chosen ones by ballot and then spends one lane per
-// PWM column on each chosen site (30 lanes busy, two shared-memory atomics per lane on distinct counters).
+// Motif::updateCounts over the chosen sites.  A warp scans 32 entries at a time and parks the chosen ones in a small
+// shared-memory buffer; whenever 32 are pending, every lane takes ONE site: it loads the two code words and N masks
+// that cover the 30-column context (all 32 sites' loads in flight together), aligns them to PWM column 1, and the warp
+// then counts column by column with three ballots (valid, base bit 0, base bit 1).  Lane j keeps the five counters of
+// PWM column j in registers, so there are no atomics until the warp is done.
+__device__ __forceinline__ void count_batch(const SeqStream& S, const CountIO& io, const uint32_t* buf, int m, int lane, uint32_t (&c)[5]) {
+	uint64_t bases = 0;          // 2 bits per PWM column, column 1 in bits [1:0]
+	uint32_t bad = 0xFFFFFFFFu;  // bit j: PWM column j + 1 is outside the sequence or holds an N
+	if (lane < m) {
+		const uint32_t i = buf[lane];
+		const uint32_t s = io.seq[i] - 1;
+		const int g0 = static_cast<int>(io.pos[i]) + io.shift - io.firstColumn;  // 0-based stream offset of PWM column 1 inside the sequence
+		const uint32_t wo = S.uniformWps ? s * S.uniformWps : S.wordOff[s];
+		const int len = S.len[s];
+		const int skip = g0 < 0 ? -g0 : 0;  // columns before the start of the sequence
+		if (skip < 30 && g0 + skip < len) {
+			const int gs = g0 + skip;
+			const uint32_t w = wo + (static_cast<uint32_t>(gs) >> 5);
+			const int off = gs & 31;
+			const uint64_t ca = S.codes[w], cb = S.codes[w + 1];
+			const uint64_t na = S.nmask[w], nb = S.nmask[w + 1];
+			uint64_t b = ca >> (2 * off);
+			if (off) b |= cb << (64 - 2 * off);
+			uint64_t nmv = ((nb << 32) | na) >> off;  // the >= 32 padding positions after every sequence are flagged: no length test needed
+			b <<= 2 * skip;
+			nmv = (nmv << skip) | ((1ull << skip) - 1ull);
+			const int over = g0 + 30 - len;  // columns past the end of the sequence (they are flagged N anyway while over <= 32)
+			if (over > 0) nmv |= ~0ull << (30 - over);
+			bases = b;
+			bad = static_cast<uint32_t>(nmv);
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < 30; ++j) {
+		const uint32_t mv = __ballot_sync(0xFFFFFFFFu, !((bad >> j) & 1u));
+		const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, (bases >> (2 * j)) & 1ull);
+		const uint32_t m1 = __ballot_sync(0xFFFFFFFFu, (bases >> (2 * j + 1)) & 1ull);
+		if (lane == j + 1) {
+			c[0] += __popc(mv);
+			c[1] += __popc(mv & ~m1 & ~m0);
+			c[2] += __popc(mv & ~m1 & m0);
+			c[3] += __popc(mv & m1 & ~m0);
+			c[4] += __popc(mv & m1 & m0);
+		}
+	}
+}
+
 __global__ void __launch_bounds__(256) k_count_pwm2(SeqStream S, CountIO io) {
 	__shared__ unsigned int s_cnt[31 * 5];
+	__shared__ uint32_t s_buf[8][64];
 	for (int k = threadIdx.x; k < 31 * 5; k += blockDim.x) s_cnt[k] = 0;
 	__syncthreads();
-	const int lane = threadIdx.x & 31;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+	uint32_t* buf = s_buf[wid];
+	uint32_t c[5] = {0, 0, 0, 0, 0};
+	int npend = 0;
 	for (uint32_t t0 = warp * 32; t0 < io.n; t0 += nwarps * 32) {
 		const uint32_t t = t0 + lane;
 		uint32_t i = t;
@@ -90,27 +238,25 @@ __global__ void __launch_bounds__(256) k_count_pwm2(SeqStream S, CountIO io) {
 			else if (io.slotIdx) { i = io.slotIdx[t]; use = (i != kNone) && io.slotScore[t] <= io.thr; }
 			else use = io.keep[i] && io.kscore[i] <= io.thr;
 		}
-		uint32_t sq = 0, ps = 0;
-		if (use) { sq = io.seq[i]; ps = io.pos[i]; }
-		uint32_t chosen = __ballot_sync(0xFFFFFFFFu, use);
-		while (chosen) {
-			const int src = __ffs(chosen) - 1;
-			chosen &= chosen - 1;
-			const uint32_t s = __shfl_sync(0xFFFFFFFFu, sq, src) - 1;
-			const int p0 = static_cast<int>(__shfl_sync(0xFFFFFFFFu, ps, src)) + io.shift - io.firstColumn + 1;
-			const int j = lane + 1;  // PWM column of this lane
-			const int p = p0 + lane;
-			if (j <= 30 && p >= 1 && p <= S.len[s]) {
-				const uint32_t wo = S.uniformWps ? s * S.uniformWps : S.wordOff[s];
-				const uint32_t g = static_cast<uint32_t>(p - 1);
-				const uint32_t w = wo + (g >> 5);
-				if (!((S.nmask[w] >> (g & 31)) & 1u)) {
-					const uint32_t b = static_cast<uint32_t>(S.codes[w] >> (2 * (g & 31))) & 3u;
-					atomicAdd(&s_cnt[j * 5 + b + 1], 1u);
-					atomicAdd(&s_cnt[j * 5], 1u);
-				}
-			}
+		const uint32_t chosen = __ballot_sync(0xFFFFFFFFu, use);
+		if (use) buf[npend + __popc(chosen & ((1u << lane) - 1u))] = i;
+		npend += __popc(chosen);
+		__syncwarp();
+		if (npend >= 32) {
+			count_batch(S, io, buf, 32, lane, c);
+			__syncwarp();
+			const uint32_t rest = (lane < npend - 32) ? buf[32 + lane] : 0u;
+			__syncwarp();
+			buf[lane] = rest;
+			npend -= 32;
+			__syncwarp();
 		}
+	}
+	if (npend) count_batch(S, io, buf, npend, lane, c);
+	if (lane >= 1 && lane <= 30) {
+#pragma unroll
+		for (int k = 0; k < 5; ++k)
+			if (c[k]) atomicAdd(&s_cnt[lane * 5 + k], c[k]);
 	}
 	__syncthreads();
 	for (int k = threadIdx.x; k < 31 * 5; k += blockDim.x)
