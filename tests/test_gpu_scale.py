@@ -186,3 +186,72 @@ def test_shard_invariance():
             p = pw
     finally:
         whole.close(); a.close(); b.close()
+
+
+@pytest.mark.parametrize("revcomp,mops", [(False, False), (False, True), (True, True)])
+def test_low_complexity_ragged_vs_oracle(revcomp, mops):
+    """Stress case for the scan machinery: ragged lengths, long TA repeats and poly-A runs (hit clusters hundreds of entries
+    long, tiles with more hits than the expand queue holds), N runs at sequence ends -- bit-exact against the oracle."""
+    import oracle_lib as ol
+    import xxmotif_b200 as xb
+    from xxmotif_b200 import hostprep
+    rng = np.random.default_rng(5)
+    nseq = 1500
+    lens = rng.integers(40, 900, size=nseq).astype(np.int32)
+    parts = []
+    for L in lens:
+        kind = rng.integers(0, 4)
+        if kind == 0:
+            s = np.tile(np.array([4, 1], dtype=np.uint8), L // 2 + 1)[:L]  # TATATA...
+        elif kind == 1:
+            s = np.full(L, 1, dtype=np.uint8)  # poly-A
+            s[rng.integers(0, L, size=max(1, L // 50))] = 4
+        else:
+            s = rng.integers(1, 5, size=L).astype(np.uint8)
+            if L > 60:
+                a = int(rng.integers(0, L - 50))
+                s[a:a + 40] = np.tile(np.array([4, 1, 4, 1, 1, 1], dtype=np.uint8), 7)[:40]
+        if rng.random() < 0.3:
+            k = int(rng.integers(1, 12))
+            s[-k:] = 0
+        if rng.random() < 0.2:
+            a = int(rng.integers(0, L - 3))
+            s[a:a + 3] = 0
+        parts.append(s)
+    codes = np.concatenate(parts)
+    n = lens
+    if revcomp:
+        n2, c2 = hostprep.revcomp_double(n, codes)
+    else:
+        n2, c2 = n, codes
+    bg, bgl = hostprep.background(n2, c2)
+    rp, rc = hostprep.null_model(n2, c2, order=2)
+    ctx = xb.Context(0)
+    try:
+        ctx.set_options(mops=mops, bg=bg, bgLog=bgl)
+        ctx.set_background(2, rp, rc)
+        ctx.load_seqset(n, codes, revcomp=revcomp)
+        oset = ol.SeqSet(n, codes, revcomp=revcomp)
+        onm = ol.NullModel(order=2, rprobs=rp, rconds=rc)
+        octx = ol.Ctx(oset, revcomp, mops, False, False, bg, bgl)
+        total, avg, mxl, mnl = ctx.seqset_info()
+        assert (total == oset.total).all()
+        pwm, cols = hostprep.profile_pwm()
+        nent = len(n)
+        enr = (1 - int(cols[0]) + 1, mxl - int(cols[0]) + 1)
+        for it in range(2):
+            ctx.reinitialize(pwm, cols, nent, int(total[nent]))
+            tab = ol.Tables(pwm, cols, nent, int(total[nent]), bgl, onm)
+            nb, nbest, mx = ctx.scan_full(nent, enr)
+            octx.scan_full(tab, cols, nent, enr, True)
+            assert (nb, nbest, mx) == (octx.nbSites, octx.nbBestSites, octx.maxSites)
+            assert nbest > (1000 if revcomp else 50000)  # the forward cases are dense on purpose (tiles overflow the expand queue)
+            _site_eq("best", ctx.get_sites(xb.LIST_BEST_STARTPOS, xb.ORDER_BY_SCORE, cap=nbest + 8), octx.best())
+            _site_eq("sites", ctx.get_sites(xb.LIST_SORTED_SITES, xb.ORDER_AS_IS, cap=nb + 8), octx.sites())
+            ok, nbm, bp, new = ctx.update_pwm_with_best_subset(xb.LIST_SORTED_SITES, pwm, int(cols[0]), nent, False, 0.1)
+            ook, onbm, obp, onew = octx.update_pwm_with_best_subset(0, pwm, cols, nent, 0, False, 0.1)
+            assert (ok, nbm, bp) == (ook, onbm, obp)
+            assert (new[5:] == onew[5:]).all()
+            pwm = new
+    finally:
+        ctx.close()

@@ -33,7 +33,7 @@ public:
 		leaves_.clear();
 		enumerate(1, 0.0);
 		// classes by descending integer score; inside a class the enumeration order is kept (std::map + list::push_back)
-		std::stable_sort(leaves_.begin(), leaves_.end(), [](const Leaf& a, const Leaf& b) { return a.score > b.score; });
+		sort_leaves_by_score_desc();
 		TablePart& P = t_.part[part];
 		P.len = len_;
 		const size_t n = leaves_.size();
@@ -95,6 +95,25 @@ public:
 	double t_lin_[32][5];
 
 private:
+	// stable LSD radix sort (3 x 11 bits) on the key "larger score first": same order as a stable sort by descending score,
+	// which is what the reference's std::map<int, list> + push_back produce, at a fraction of std::stable_sort's cost
+	void sort_leaves_by_score_desc() {
+		const size_t n = leaves_.size();
+		tmp_.resize(n);
+		Leaf* src = leaves_.data();
+		Leaf* dst = tmp_.data();
+		for (int pass = 0; pass < 3; ++pass) {
+			uint32_t cnt[2049];
+			std::memset(cnt, 0, sizeof cnt);
+			const int sh = 11 * pass;
+			for (size_t i = 0; i < n; ++i) cnt[((~(static_cast<uint32_t>(src[i].score) ^ 0x80000000u) >> sh) & 2047u) + 1]++;
+			for (int b = 0; b < 2048; ++b) cnt[b + 1] += cnt[b];
+			for (size_t i = 0; i < n; ++i) dst[cnt[(~(static_cast<uint32_t>(src[i].score) ^ 0x80000000u) >> sh) & 2047u]++] = src[i];
+			std::swap(src, dst);
+		}
+		if (src != leaves_.data()) std::memcpy(leaves_.data(), src, n * sizeof(Leaf));
+	}
+
 	// rowSwap / colSwap / swappedPWM / S_max (branch_and_bound-inl.h:470-536).  The column comparison indexes the
 	// log-odds matrix with the part-relative column number on its left side, as the reference does.
 	void order_columns() {
@@ -125,7 +144,7 @@ private:
 	void enumerate(int j, double sj) {
 		for (int a = 1; a <= 4; ++a) {
 			const double s1 = sj + sw_[j][a];
-			if (static_cast<int>((s1 + smax_[j + 1]) * 1e6) < T_) continue;
+			if (static_cast<int>((s1 + smax_[j + 1]) * 1e6) < T_) break;  // the reference says `continue`; sw_[j][] is sorted descending, so every later base fails too
 			pick_[col_[j] - 1] = static_cast<uint8_t>(row_[col_[j]][a]);
 			if (j + 1 <= len_) {
 				enumerate(j + 1, s1);
@@ -204,7 +223,7 @@ private:
 	double sw_[34][5];
 	double smax_[36];
 	uint8_t pick_[34];
-	std::vector<Leaf> leaves_;
+	std::vector<Leaf> leaves_, tmp_;
 	std::vector<int> prefixes_;
 	std::vector<int> prefixLen_;
 	std::unordered_map<int, float> rightCond_;

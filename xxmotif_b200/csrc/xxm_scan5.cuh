@@ -237,15 +237,19 @@ __global__ void __launch_bounds__(kExpand5Threads) k_expand5(SeqStream S, Model 
 	const uint32_t myOff = woff + incl - cnt;
 	const bool fits = total <= static_cast<uint32_t>(kExpand5Queue);
 	if (fits) {  // the common case: the whole tile fits the queue
-		uint32_t o = myOff;
-#pragma unroll
-		for (int k = 0; k < 4; ++k) {
-			uint32_t rem = h[k];
-			const uint32_t tag = static_cast<uint32_t>(4 * tid + k) << 5;
-			while (rem) {
-				s_q[o++] = static_cast<uint16_t>(tag | (__ffs(rem) - 1));
-				rem &= rem - 1;
-			}
+		// one loop over the 128 windows of the thread (two 64-bit halves): the trip count of a warp is the largest hit
+		// count of a lane, not the sum over the four words of the largest per-word counts
+		uint16_t* q = s_q + myOff;
+		const uint32_t tag = static_cast<uint32_t>(4 * tid) << 5;
+		uint64_t rem = (static_cast<uint64_t>(h[1]) << 32) | h[0];
+		while (rem) {
+			*q++ = static_cast<uint16_t>(tag + (__ffsll(static_cast<long long>(rem)) - 1));
+			rem &= rem - 1;
+		}
+		rem = (static_cast<uint64_t>(h[3]) << 32) | h[2];
+		while (rem) {
+			*q++ = static_cast<uint16_t>(tag + 64 + (__ffsll(static_cast<long long>(rem)) - 1));
+			rem &= rem - 1;
 		}
 	}
 	__syncthreads();

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) k_select_mops_fwd(Values V, SelectFwdIO i
 			fin[k] = (k < m && vi[k] != kNone) ? final_of(V, vi[k], static_cast<uint32_t>(j0 + k), static_cast<int>(ps[k]) + io.shift) : 1.0;
 		SelState st;
 		bool rep;
-		uint32_t keepBits = 0;
+		uint32_t keepBits = 0, lastSeq = 0;
 		if (m > 0) {
 			// ---- the part of the cluster before the chunk: back to its head, then forward again
 			if (j0 > 0) {
@@ -125,12 +125,13 @@ __global__ void __launch_bounds__(256) k_select_mops_fwd(Values V, SelectFwdIO i
 					if (sel_step(st, j0 + k, ps[k], fin[k], L, &rep)) {
 						keepBits |= 1u << k;
 						if (rep && old >= j0) keepBits &= ~(1u << static_cast<int>(old - j0));
+						lastSeq = sq[k];
 					}
 				}
 			}
 			// ---- can a later entry still replace my last kept site?
 			if (st.last >= j0) {
-				const uint32_t mySeq = sq[static_cast<int>(st.last - j0) & (kSelChunk - 1)];
+				const uint32_t mySeq = lastSeq;
 				for (int64_t j = j0 + m; j < static_cast<int64_t>(io.n); ++j) {
 					const uint32_t pj = io.pos[j];
 					if (io.seq[j] != mySeq || pj > st.lastPos + L) break;
@@ -149,17 +150,16 @@ __global__ void __launch_bounds__(256) k_select_mops_fwd(Values V, SelectFwdIO i
 				*reinterpret_cast<float4*>(io.kscore + j0) = make_float4(static_cast<float>(fin[0]), static_cast<float>(fin[1]), static_cast<float>(fin[2]), static_cast<float>(fin[3]));
 				*reinterpret_cast<float4*>(io.kscore + j0 + 4) = make_float4(static_cast<float>(fin[4]), static_cast<float>(fin[5]), static_cast<float>(fin[6]), static_cast<float>(fin[7]));
 			} else {
-				for (int k = 0; k < m; ++k) { io.keep[j0 + k] = (keepBits >> k) & 1u; io.kscore[j0 + k] = static_cast<float>(fin[k]); }
+#pragma unroll
+				for (int k = 0; k < kSelChunk; ++k)
+					if (k < m) { io.keep[j0 + k] = (keepBits >> k) & 1u; io.kscore[j0 + k] = static_cast<float>(fin[k]); }
 			}
 			kept += __popc(keepBits);
 		}
-		if (hist) {  // one shared-memory atomic per distinct value index of the warp and chunk slot
+		if (hist) {
 #pragma unroll
 			for (int k = 0; k < kSelChunk; ++k) {
-				const bool add = (keepBits >> k) & 1u;
-				const uint32_t key = add ? vi[k] : (0x80000000u | static_cast<uint32_t>(lane));
-				const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
-				if (add && lane == __ffs(peers) - 1) atomicAdd(&hist[vi[k]], static_cast<uint32_t>(__popc(peers)));
+				if ((keepBits >> k) & 1u) atomicAdd(&hist[vi[k]], 1u);
 			}
 		}
 	}
