@@ -183,6 +183,7 @@ def ours(a):
     import xxmotif_b200 as xb
     from xxmotif_b200 import hostprep, sharded
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("XXM_NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -201,6 +202,11 @@ def ours(a):
     codes = pinned.numpy()
     bg, bgl = hostprep.background(n, codes)
     rp, rc = hostprep.null_model(n, codes, order=2)
+    if dist:  # one background model for the whole set (rank 0's shard stands in for it): every rank must build the same tables
+        for arr in (bg, bgl, rp, rc):
+            t = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+            dist.broadcast(t, src=0)
+            arr[...] = t.cpu().numpy()
     ctx = xb.Context(local)
     ctx.set_options(mops=False, oops=False, localization=False, bg=bg, bgLog=bgl)
     ctx.set_background(2, rp, rc)

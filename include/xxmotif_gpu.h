@@ -199,6 +199,28 @@ int xxm_host_choose_subset(const float* scores, const int64_t* counts, int32_t n
                            int32_t oneOccurrence, double plusFrac, int64_t* bestMotifNb, double* bestPval, float* lastScore);
 int xxm_host_build_pwm(const double* counts31x5, double pseudoTimesK, const double* bg5, double* pwm31x5);
 
+/* ---- one optimizeMotif iteration as one call, over a possibly sharded set --------------------------------------------
+ * xxm_optimize_step = one pass of the loop body of IterateMotif::optimizeMotif (Iterate_Motif.cpp:26-32): reinitialize,
+ * full scan + updateMultOcc, getBestSubset over ALL sites, Motif::updatePWM_OOL; pwm31x5 is overwritten with the new PWM.
+ * With a communicator attached (xxm_comm_init; one process and one context per GPU, every rank holding its own block of
+ * sequences) the value-index histogram of the kept sites and the 31x5 counts are summed over NCCL on the device before the
+ * host sees them; posSetSize / totalPositions are the rank's own, the global ones are their sums.
+ * xxm_comm_unique_id: ncclGetUniqueId on rank 0; the caller distributes the 128 bytes (MPI, torch.distributed, a file). */
+typedef struct {
+	int64_t nbSites;       /* kept sites of this rank after updateMultOcc */
+	int64_t nbBestSites;   /* windows with finalPval < 1 of this rank */
+	int64_t nbSitesGlobal; /* kept sites of all ranks */
+	int64_t maxSites;      /* StartPosUpdater::maxSites over all ranks */
+	int64_t bestMotifNb;
+	double bestPval;
+	int32_t updated;       /* 0: the reference returns early (no site) and the PWM is unchanged */
+} xxm_step_info;
+int xxm_comm_unique_id(uint8_t* id128);
+int xxm_comm_init(xxm_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t* id128);
+int xxm_comm_destroy(xxm_ctx* ctx);
+int xxm_optimize_step(xxm_ctx* ctx, double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions, int32_t enrStart,
+                      int32_t enrEnd, double pseudo, xxm_step_info* info);
+
 /* ---- host-side pieces of the path, callable without a device (unit tests of the host logic) -------------------------
  * xxm_host_tables: the table construction xxm_reinitialize performs (branch_and_bound-inl.h:183-603), without staging.
  *   info[9] = L, maxk, nparts, size0, size1, nclasses0, nclasses1, nids0, nids1; the arrays of `part` may be NULL.

@@ -21,6 +21,7 @@ EXPORTS = [
     "xxm_reinitialize", "xxm_tables_info", "xxm_tables_get", "xxm_window_pvals", "xxm_scan_full", "xxm_rescore", "xxm_scan_oops",
     "xxm_rescore_startposlist", "xxm_update_pwm_with_best_subset", "xxm_startposlist_best_subset", "xxm_startposlist_from_elong",
     "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset", "xxm_host_pair_table",
+    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step",
 ]
 
 
@@ -33,6 +34,11 @@ class XxmOptions(C.Structure):
 class XxmStats(C.Structure):
     _fields_ = [("launches", C.c_int64), ("last_scan_ms", C.c_float), ("last_scan_bases", C.c_int64), ("last_scan_hits", C.c_int64),
                 ("last_find_ms", C.c_float)]
+
+
+class XxmStepInfo(C.Structure):
+    _fields_ = [("nbSites", C.c_int64), ("nbBestSites", C.c_int64), ("nbSitesGlobal", C.c_int64), ("maxSites", C.c_int64), ("bestMotifNb", C.c_int64),
+                ("bestPval", C.c_double), ("updated", C.c_int32)]
 
 
 class XxmError(RuntimeError):
@@ -83,6 +89,10 @@ def load_library():
         "xxm_host_tables": [vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp],
         "xxm_host_best_subset": [vp, vp, i32, i32, i32, i32, i32, i32, i32, dbl, P(i32), P(dbl)],
         "xxm_host_pair_table": [vp, C.c_int64, vp, i32, vp, P(i32)],
+        "xxm_comm_unique_id": [vp],
+        "xxm_comm_init": [vp, i32, i32, vp],
+        "xxm_comm_destroy": [vp],
+        "xxm_optimize_step": [vp, vp, vp, i32, i32, i32, i32, i32, dbl, P(XxmStepInfo)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -263,6 +273,31 @@ class Context:
         self._ck(self.L.xxm_logodds_hist(self.h, _p(pwm), _p(cols), len(cols), posSetSize, _p(fw), _p(bw), npos, C.byref(m1), C.byref(m2)))
         return fw[:npos], bw[:npos], m1.value, m2.value
 
+    def comm_init(self, rank, nranks, id128):
+        """attach an NCCL communicator (one process and one context per GPU); id128 = comm_unique_id() of rank 0"""
+        idb = np.ascontiguousarray(id128, dtype=np.uint8)
+        assert idb.size == 128
+        self._ck(self.L.xxm_comm_init(self.h, int(rank), int(nranks), _p(idb)))
+
+    def optimize_step(self, pwm, cols, posSetSize, totalPositions, enr, pseudo):
+        """one optimizeMotif iteration as one native call (xxm_optimize_step): returns (new pwm, info dict)"""
+        pw = np.ascontiguousarray(pwm, dtype=np.float64).reshape(155).copy()
+        cl = np.ascontiguousarray(cols, dtype=np.int32)
+        info = XxmStepInfo()
+        self._ck(self.L.xxm_optimize_step(self.h, _p(pw), _p(cl), len(cl), int(posSetSize), int(totalPositions), int(enr[0]), int(enr[1]), float(pseudo),
+                                          C.byref(info)))
+        return pw, {"nbSites": info.nbSites, "nbBestSites": info.nbBestSites, "nbSites_global": info.nbSitesGlobal, "maxSites": info.maxSites,
+                    "bestMotifNb": info.bestMotifNb, "bestPval": info.bestPval, "updated": bool(info.updated)}
+
+    def nval_hint(self):
+        """number of value indices of the current model (size of the histogram a step reads back)"""
+        L_, mk, npart = C.c_int32(), C.c_int32(), C.c_int32()
+        size = (C.c_int64 * 2)()
+        ncl = (C.c_int32 * 2)()
+        nid = (C.c_int64 * 2)()
+        self.L.xxm_tables_info(self.h, C.byref(L_), C.byref(mk), C.byref(npart), size, ncl, nid)
+        return int(ncl[0])
+
     def stats(self):
         s = XxmStats()
         self._ck(self.L.xxm_get_stats(self.h, C.byref(s)))
@@ -327,3 +362,12 @@ def host_pair_table(ids, coloff):
     if rcode not in (0, 1):
         raise XxmError("xxm_host_pair_table failed with %d" % rcode)
     return rcode == 0, tab, lv.value
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0); distribute the 128 bytes to the other ranks"""
+    L = load_library()
+    idb = np.zeros(128, dtype=np.uint8)
+    if L.xxm_comm_unique_id(_p(idb)):
+        raise XxmError(L.xxm_last_error(None).decode())
+    return idb

@@ -8,6 +8,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <csignal>
+#include <execinfo.h>
+#include <unistd.h>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -19,6 +22,7 @@
 #include "xxm_scan4.cuh"
 #include "xxm_scan5.cuh"
 #include "pair_table.h"
+#include "nccl_dyn.h"
 
 using namespace xxm;
 
@@ -124,6 +128,11 @@ struct xxm_ctx {
 	DevBuf<uint32_t> r_seq, d_pbits;
 	DevBuf<uint8_t> d_t8, d_raw;
 	DevBuf<uint32_t> d_pairTab;
+	DevBuf<unsigned long long> d_xchg;  // value-index histogram + scalars on their way through NCCL
+	std::vector<unsigned long long> h_xchg;
+	std::vector<ScoreRun> h_runs;
+	void* comm = nullptr;               // ncclComm_t of a sharded set (xxm_comm_init), else null
+	int commRank = 0, commSize = 1;
 	std::vector<uint32_t> h_pairIds, h_pairTab;
 	bool pairOK = false;           // the pair table represents the left table exactly: k_scan5, else k_scan4
 	bool forceGenericScan = false; // tests: always take the generic find kernel
@@ -175,8 +184,19 @@ static int stage_scan(xxm_ctx* ctx);  // xxm_gpu_scan5.inc
 // =====================================================================================================================
 // life cycle
 // =====================================================================================================================
+static void xxm_segv_handler(int sig) {
+	void* frames[64];
+	const int n = backtrace(frames, 64);
+	const char msg[] = "libxxmotif_gpu: fatal signal, native backtrace:\n";
+	if (write(2, msg, sizeof msg - 1) < 0) {}
+	backtrace_symbols_fd(frames, n, 2);
+	signal(sig, SIG_DFL);
+	raise(sig);
+}
+
 extern "C" int xxm_create(int device, xxm_ctx** out) {
 	*out = nullptr;
+	if (std::getenv("XXM_DEBUG_SEGV")) { signal(SIGSEGV, xxm_segv_handler); signal(SIGABRT, xxm_segv_handler); }  // debugging aid: native backtrace on a crash
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
 	if (e != cudaSuccess || ndev == 0) {
@@ -204,10 +224,12 @@ extern "C" int xxm_create(int device, xxm_ctx** out) {
 	return 0;
 }
 
+extern "C" int xxm_comm_destroy(xxm_ctx* ctx);
 extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	xxm_comm_destroy(ctx);
 	// DevBuf members are released explicitly (no destructor: the struct is copied nowhere, but keep it trivial)
 	ctx->d_codes.release(); ctx->d_nmask.release(); ctx->d_wordOff.release(); ctx->d_blk2seq.release(); ctx->d_len.release();
 	ctx->d_rank0.release(); ctx->d_rank1.release(); ctx->d_hit0.release(); ctx->d_ids.release(); ctx->d_cls.release(); ctx->d_clsOk.release();
@@ -820,3 +842,4 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 #include "xxm_gpu_part2.inc"
 #include "xxm_gpu_part3.inc"
 #include "xxm_gpu_part4.inc"
+#include "xxm_gpu_part5.inc"

@@ -94,26 +94,79 @@ def build_pwm(counts, pseudoTimesK, bg):
 
 
 class Exchange:
-    """The two small collectives of a step over torch.distributed (NCCL on GPUs, gloo in the CPU tests)."""
+    """The two small collectives of a step over torch.distributed (NCCL on GPUs, gloo in the CPU tests).
+
+    Both are latency bound (a few KB), so each is ONE collective on preallocated buffers: the runs of a rank travel as one
+    fixed-size int64 row [n, scalars..., scores as int32 bit patterns..., counts...] through all_gather_into_tensor, the
+    31x5 counts through one all_reduce; host <-> device staging goes through pinned memory."""
+
+    CAP_RUNS = 4096
+    NSCAL = 3
 
     def __init__(self, dist=None, device=None):
         self.dist = dist
         self.device = device
         self.world = dist.get_world_size() if dist else 1
+        self._ready = False
+
+    def _setup(self):
+        import torch
+        cuda = self.device is not None and self.device.type == "cuda"
+        W = 1 + self.NSCAL + 2 * self.CAP_RUNS
+        self._W = W
+        self._h_in = torch.zeros(W, dtype=torch.int64, pin_memory=cuda)
+        self._h_out = torch.zeros(self.world * W, dtype=torch.int64, pin_memory=cuda)
+        self._d_in = torch.zeros(W, dtype=torch.int64, device=self.device)
+        self._d_out = torch.zeros(self.world * W, dtype=torch.int64, device=self.device)
+        self._h_cnt = torch.zeros(155, dtype=torch.float64, pin_memory=cuda)
+        self._d_cnt = torch.zeros(155, dtype=torch.float64, device=self.device)
+        self._cuda = cuda
+        self._ready = True
 
     def gather_runs(self, sc, cn, scalars):
-        """all-gather of (scores, counts) runs + all-reduce(sum) of a few int64 scalars."""
+        """all-gather of (scores, counts) runs + sum of a few int64 scalars."""
         if not self.dist:
             return [sc], [cn], list(scalars)
         import torch
+        if not self._ready:
+            self._setup()
+        k = len(sc)
+        assert len(scalars) == self.NSCAL
+        if k > self.CAP_RUNS:
+            return self._gather_runs_any_size(sc, cn, scalars)
+        W, C0 = self._W, 1 + self.NSCAL
+        h = self._h_in.numpy()
+        h[0] = k
+        h[1:C0] = scalars
+        h[C0:C0 + k] = sc.view(np.int32)
+        h[C0 + self.CAP_RUNS:C0 + self.CAP_RUNS + k] = cn
+        self._d_in.copy_(self._h_in, non_blocking=True)
+        self.dist.all_gather_into_tensor(self._d_out, self._d_in)
+        self._h_out.copy_(self._d_out, non_blocking=True)
+        if self._cuda:
+            torch.cuda.current_stream().synchronize()
+        o = self._h_out.numpy().reshape(self.world, W)
+        if (o[:, 0] < 0).any():  # some rank had more runs than a row holds: everybody takes the general path
+            return self._gather_runs_any_size(sc, cn, scalars)
+        scs = [o[r, C0:C0 + int(o[r, 0])].astype(np.int32).view(np.float32) for r in range(self.world)]
+        cns = [o[r, C0 + self.CAP_RUNS:C0 + self.CAP_RUNS + int(o[r, 0])].copy() for r in range(self.world)]
+        tot = [int(o[:, 1 + j].sum()) for j in range(self.NSCAL)]
+        return scs, cns, tot
+
+    def _gather_runs_any_size(self, sc, cn, scalars):
+        import torch
         dist = self.dist
+        if len(sc) > self.CAP_RUNS:  # tell the ranks that took the fixed-size path
+            self._h_in.numpy()[0] = -1
+            self._d_in.copy_(self._h_in)
+            dist.all_gather_into_tensor(self._d_out, self._d_in)
         lens = torch.tensor([len(sc)] + [int(x) for x in scalars], dtype=torch.int64, device=self.device)
         all_lens = [torch.zeros_like(lens) for _ in range(self.world)]
         dist.all_gather(all_lens, lens)
-        mx = max(int(t[0]) for t in all_lens)
-        buf = torch.zeros(2 * max(mx, 1), dtype=torch.int64, device=self.device)
+        mx = max(1, max(int(t[0]) for t in all_lens))
+        buf = torch.zeros(2 * mx, dtype=torch.int64, device=self.device)
         buf[:len(sc)] = torch.from_numpy(sc.view(np.int32).astype(np.int64)).to(self.device)
-        buf[max(mx, 1):max(mx, 1) + len(cn)] = torch.from_numpy(cn).to(self.device)
+        buf[mx:mx + len(cn)] = torch.from_numpy(cn).to(self.device)
         bufs = [torch.zeros_like(buf) for _ in range(self.world)]
         dist.all_gather(bufs, buf)
         scs, cns = [], []
@@ -121,7 +174,7 @@ class Exchange:
             k = int(t[0])
             b = b.cpu().numpy()
             scs.append(b[:k].astype(np.int32).view(np.float32))
-            cns.append(b[max(mx, 1):max(mx, 1) + k].copy())
+            cns.append(b[mx:mx + k].copy())
         tot = [sum(int(t[1 + j]) for t in all_lens) for j in range(len(scalars))]
         return scs, cns, tot
 
@@ -129,30 +182,53 @@ class Exchange:
         if not self.dist:
             return counts
         import torch
-        t = torch.from_numpy(counts).to(self.device)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-        return t.cpu().numpy()
+        if not self._ready:
+            self._setup()
+        self._h_cnt.numpy()[:] = counts
+        self._d_cnt.copy_(self._h_cnt, non_blocking=True)
+        self.dist.all_reduce(self._d_cnt, op=self.dist.ReduceOp.SUM)
+        self._h_cnt.copy_(self._d_cnt, non_blocking=True)
+        if self._cuda:
+            torch.cuda.current_stream().synchronize()
+        return self._h_cnt.numpy().copy()
 
 
 class ShardedRefinement:
     """optimizeMotif iterations (Iterate_Motif.cpp:26-32) over a sharded set; `ctx` is the rank's xxmotif_b200.Context."""
 
     def __init__(self, ctx, dist, nent_local, total_local, pseudo=0.1, revcomp=False, oneOccurrence=False, maxSeqCount=1000, plusFrac=0.0,
-                 bg=None):
+                 bg=None, native=True):
+        """native=True: the whole step is one C-ABI call (xxm_optimize_step) and the two small reductions run over NCCL on
+        the library's stream, device to device.  native=False: the split-phase entry points with the exchange in Python
+        (any torch.distributed backend; this is also what the CPU/gloo test drives)."""
         self.ctx = ctx
         device = None
+        self.native = native
         if dist is not None:
             import torch
             device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+            if dist.get_backend() != "nccl":
+                self.native = False
         self.ex = Exchange(dist, device)
         self.nent_local, self.total_local = nent_local, total_local
         self.pseudo, self.revcomp = pseudo, revcomp
         self.oneOccurrence, self.maxSeqCount, self.plusFrac = oneOccurrence, maxSeqCount, plusFrac
         self.bg = bg
         self.last_d2h_bytes = 0
+        if self.native and dist is not None and dist.get_world_size() > 1:
+            import torch
+            idt = torch.zeros(128, dtype=torch.uint8, device=device)
+            if dist.get_rank() == 0:
+                idt.copy_(torch.from_numpy(capi.comm_unique_id()))
+            dist.broadcast(idt, src=0)
+            ctx.comm_init(dist.get_rank(), dist.get_world_size(), idt.cpu().numpy())
 
     def optimize_step(self, pwm, cols, enr):
         ctx = self.ctx
+        if self.native:
+            new, info = ctx.optimize_step(pwm, cols, self.nent_local, self.total_local, enr, self.pseudo)
+            self.last_d2h_bytes = 8 * (ctx.nval_hint() + 3) + 155 * 8 + 64
+            return new, info
         ctx.reinitialize(pwm, cols, self.nent_local, self.total_local)
         nbSites, nbBest, _ = ctx.scan_full(self.nent_local, enr)
         sc, cn = score_runs(ctx, capi.LIST_SORTED_SITES)
