@@ -67,6 +67,7 @@ struct SiteList {
 	bool mopsValues = true;         // ... taken from the mops (true) or the mode (false) finalPval table
 	uint64_t modelSerial = 0;
 	uint64_t histSerial = 0;        // != 0: ctx->hist already holds this list's value-index histogram (fused into the select kernel)
+	const double* lazyPS = nullptr; // score == nullptr: float(lazyPS[vidx]) on demand (snapshot of the pS table of the scan's model)
 };
 
 }  // namespace
@@ -121,6 +122,7 @@ struct xxm_ctx {
 
 	// ---- lists
 	DevBuf<uint32_t> b_seq, b_pos, b_vidx, t_seq, t_pos, t_vidx, u_seq, u_pos, u_vidx;
+	DevBuf<double> b_pSsnap;
 	DevBuf<float> b_score, s_kscore, e_kscore, slotScore, e_slotScore, tmpScore, u_score;
 	DevBuf<uint8_t> s_keep, e_keep, flag8;
 	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
@@ -237,7 +239,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	ctx->d_memoKey.release(); ctx->d_memoVal.release(); ctx->d_memoState.release(); ctx->d_flags32.release();
 	ctx->d_pS.release(); ctx->d_finalMops.release(); ctx->d_finalMode.release(); ctx->d_posProb.release(); ctx->d_perCand.release();
 	ctx->b_seq.release(); ctx->b_pos.release(); ctx->b_vidx.release(); ctx->t_seq.release(); ctx->t_pos.release(); ctx->t_vidx.release();
-	ctx->u_seq.release(); ctx->u_pos.release(); ctx->u_vidx.release(); ctx->b_score.release(); ctx->s_kscore.release(); ctx->e_kscore.release();
+	ctx->u_seq.release(); ctx->u_pos.release(); ctx->u_vidx.release(); ctx->b_score.release(); ctx->b_pSsnap.release(); ctx->s_kscore.release(); ctx->e_kscore.release();
 	ctx->slotScore.release(); ctx->tmpScore.release(); ctx->s_keep.release(); ctx->e_keep.release(); ctx->flag8.release(); ctx->stk.release();
 	ctx->slotIdx.release(); ctx->e_slotIdx.release(); ctx->e_slotScore.release(); ctx->u_score.release(); ctx->counters.release(); ctx->hist.release(); ctx->idxA.release(); ctx->idxB.release(); ctx->keysA.release();
 	ctx->keysB.release(); ctx->rsHist.release(); ctx->status.release(); ctx->total64.release(); ctx->d_counts.release(); ctx->d_sites.release();
@@ -793,8 +795,11 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 	if (ctx->opt.localization) TRY(stage_pos_prob(ctx, T.span, ctx->modelFirstCol, enrStart, enrEnd, 0));
 	const Values V = make_values(ctx, true);  // the full scan always uses mops = true (StartPosUpdater-inl.h:99)
 	uint32_t n = 0;
+	const bool lazyScores = ctx->scanFindsOnlySites;  // bestStartPos[].score = float(pS[value index]): materialised only if somebody reads it
 	if (ctx->scanFindsOnlySites) {
-		TRY(run_scan(ctx, posSetSize, V, 1, ctx->b_seq, ctx->b_pos, ctx->b_vidx, &ctx->b_score, &n, true));
+		TRY(run_scan(ctx, posSetSize, V, 1, ctx->b_seq, ctx->b_pos, ctx->b_vidx, nullptr, &n, true));
+		CK(ctx->b_pSsnap.ensure(std::max<uint32_t>(1, ctx->nval)));
+		CK(cudaMemcpyAsync(ctx->b_pSsnap.p, ctx->d_pS.p, ctx->nval * 8ull, cudaMemcpyDeviceToDevice, ctx->stream));
 	} else {
 		// candidates first; the p-value of a >8-column window is known only after the memo slots are evaluated
 		uint32_t nc = 0;
@@ -814,14 +819,14 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 	}
 	ctx->nBest = n;
 	// bestStartPos[].score = float(pValScore) (StartPosUpdater-inl.h:105)
-	CK(ctx->b_score.ensure(std::max<uint32_t>(1, n)));
+	if (!lazyScores) CK(ctx->b_score.ensure(std::max<uint32_t>(1, n)));
 	if (n && !ctx->scanFindsOnlySites) {
 		k_entry_scores<<<cdiv(n, 256), 256, 0, ctx->stream>>>(V, ctx->b_vidx.p, ctx->b_pos.p, n, 0, 0, ctx->b_score.p);
 		CKK();
 	}
 	SiteList& B = ctx->L[XXM_LIST_BEST_STARTPOS];
 	B = SiteList();
-	B.kind = kListCompact; B.seq = ctx->b_seq.p; B.pos = ctx->b_pos.p; B.vidx = ctx->b_vidx.p; B.n = n; B.score = ctx->b_score.p; B.members = n;
+	B.kind = kListCompact; B.seq = ctx->b_seq.p; B.pos = ctx->b_pos.p; B.vidx = ctx->b_vidx.p; B.n = n; B.score = lazyScores ? nullptr : ctx->b_score.p; B.lazyPS = lazyScores ? ctx->b_pSsnap.p : nullptr; B.members = n;
 	B.modelSerial = ctx->modelSerial;
 	// updateMultOcc -> sortedSites
 	uint32_t kept = 0, mps = 0;

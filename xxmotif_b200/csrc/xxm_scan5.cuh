@@ -161,12 +161,11 @@ __global__ void __launch_bounds__(kExpand5Threads) k_expand5(SeqStream S, Model 
 	__shared__ __align__(16) uint64_t s_codes[kTileWords + 4];
 	__shared__ uint16_t s_q[kExpand5Queue];
 	__shared__ uint32_t s_warp[kExpand5Threads / 32];
-	__shared__ uint32_t s_tile;
 	__shared__ uint64_t s_base;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	if (tid == 0) s_tile = atomicAdd(io.ticket, 1u);
-	__syncthreads();
-	const uint32_t tile = s_tile;
+	// tile = block index: like CUB's decoupled look-back this relies on blocks being dispatched in index order (a tile only
+	// ever waits for tiles with smaller indices, which then are resident or done)
+	const uint32_t tile = blockIdx.x;
 	const uint32_t wbase = tile * kTileWords;
 	const uint32_t w0 = wbase + 4 * tid;
 	// ---- all loads of the thread up front: its four hit masks, five N masks, four code words (staged for the expansion)

@@ -49,7 +49,7 @@ __device__ __forceinline__ bool sel_step(SelState& st, int64_t j, uint32_t pj, d
 	return true;
 }
 
-__global__ void __launch_bounds__(256) k_select_mops_fwd(Values V, SelectFwdIO io) {
+__global__ void __launch_bounds__(256, 4) k_select_mops_fwd(Values V, SelectFwdIO io) {
 	extern __shared__ uint32_t s_hist[];
 	__shared__ uint32_t s_cnt;
 	if (io.smemHist)
