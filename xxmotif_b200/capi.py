@@ -148,7 +148,7 @@ class Context:
     def load_seqset(self, n, codes, revcomp=False):
         n = np.ascontiguousarray(n, dtype=np.int32)
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
-        assert int(n.astype(np.int64).sum()) == codes.size
+        assert int(n.sum(dtype=np.int64)) == codes.size
         self._ck(self.L.xxm_load_seqset(self.h, len(n), _p(n), _p(codes), int(revcomp)))
         self.nent = len(n)
 

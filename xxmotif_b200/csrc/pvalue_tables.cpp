@@ -29,9 +29,11 @@ public:
 	// one call of set_kmer_to_Pvalue_hash (branch_and_bound-inl.h:462-577) for match columns [start, stop] (1-based)
 	void build_part(int part, int start, int stop, int threshold, bool collectPrefixes, int gapOffset) {
 		part_ = part; start_ = start; len_ = stop - start + 1; T_ = threshold; collect_ = collectPrefixes; gapOffset_ = gapOffset;
+		ungapped_ = true;
+		for (int m = 0; m + 1 < len_; ++m) ungapped_ = ungapped_ && t_.gaps[m + gapOffset_] == 0;
 		order_columns();
 		leaves_.clear();
-		enumerate(1, 0.0);
+		enumerate(1, 0.0, 0u);
 		// classes by descending integer score; inside a class the enumeration order is kept (std::map + list::push_back)
 		sort_leaves_by_score_desc();
 		TablePart& P = t_.part[part];
@@ -99,7 +101,39 @@ private:
 	// which is what the reference's std::map<int, list> + push_back produce, at a fraction of std::stable_sort's cost
 	void sort_leaves_by_score_desc() {
 		const size_t n = leaves_.size();
+		if (n < 2) return;
 		tmp_.resize(n);
+		if (n <= 16384) {
+			// small tables (the usual case: a few thousand leaves): one stable counting pass into 2048 score-range buckets,
+			// then a stable insertion sort that only ever moves elements inside their bucket
+			int32_t mn = leaves_[0].score, mx = mn;
+			for (size_t i = 1; i < n; ++i) { mn = std::min(mn, leaves_[i].score); mx = std::max(mx, leaves_[i].score); }
+			const uint64_t range = static_cast<uint64_t>(static_cast<int64_t>(mx) - mn) + 1;
+			const uint64_t scale = (2048ull << 32) / range;
+			uint32_t cnt[2049];
+			std::memset(cnt, 0, sizeof cnt);
+			auto bucket = [&](int32_t sc) { return static_cast<uint32_t>((static_cast<uint64_t>(static_cast<int64_t>(mx) - sc) * scale) >> 32); };
+			for (size_t i = 0; i < n; ++i) cnt[bucket(leaves_[i].score) + 1]++;
+			for (int b = 0; b < 2048; ++b) cnt[b + 1] += cnt[b];
+			for (size_t i = 0; i < n; ++i) tmp_[cnt[bucket(leaves_[i].score)]++] = leaves_[i];
+			size_t lo = 0;
+			for (int b = 0; b < 2048; ++b) {  // after the scatter cnt[b] is the end of bucket b
+				const size_t hi = cnt[b];
+				if (hi - lo > 24) {
+					std::stable_sort(tmp_.begin() + lo, tmp_.begin() + hi, [](const Leaf& x, const Leaf& y) { return x.score > y.score; });
+				} else {
+					for (size_t i = lo + 1; i < hi; ++i) {
+						const Leaf x = tmp_[i];
+						size_t j = i;
+						while (j > lo && tmp_[j - 1].score < x.score) { tmp_[j] = tmp_[j - 1]; --j; }
+						tmp_[j] = x;
+					}
+				}
+				lo = hi;
+			}
+			leaves_.swap(tmp_);
+			return;
+		}
 		Leaf* src = leaves_.data();
 		Leaf* dst = tmp_.data();
 		for (int pass = 0; pass < 3; ++pass) {
@@ -141,24 +175,37 @@ private:
 	}
 
 	// create_similar_kmers_rec (branch_and_bound-inl.h:586-603)
-	void enumerate(int j, double sj) {
+	// (the k-mer id -- 2 bits per match column, first column least significant -- is accumulated on the way down)
+	void enumerate(int j, double sj, uint32_t idj) {
+		const int sh = 2 * (col_[j] - 1);
+		const int* rw = row_[col_[j]];
 		for (int a = 1; a <= 4; ++a) {
 			const double s1 = sj + sw_[j][a];
 			if (static_cast<int>((s1 + smax_[j + 1]) * 1e6) < T_) break;  // the reference says `continue`; sw_[j][] is sorted descending, so every later base fails too
-			pick_[col_[j] - 1] = static_cast<uint8_t>(row_[col_[j]][a]);
-			if (j + 1 <= len_) {
-				enumerate(j + 1, s1);
-			} else {
-				uint32_t id = 0;
-				for (int p = len_ - 1; p >= 0; --p) id = (id << 2) + pick_[p] - 1;
-				leaves_.push_back(Leaf{static_cast<int32_t>(s1 * 1e6), id});
-			}
+			const uint32_t id = idj | (static_cast<uint32_t>(rw[a] - 1) << sh);
+			if (j + 1 <= len_) enumerate(j + 1, s1, id);
+			else leaves_.push_back(Leaf{static_cast<int32_t>(s1 * 1e6), id});
 		}
 	}
 
 	// calculate_kmer_probability (branch_and_bound-inl.h:54-100)
 	double background_probability(uint32_t kmerId) {
+		if (part_ == 0 && !collect_ && ungapped_ && len_ > nm_.order + 1) {
+			// same table entries multiplied in the same order as below; the (order+1)-character index is rolled along
+			const int o1 = nm_.order + 1;
+			const uint32_t mask = (1u << (3 * o1)) - 1u;
+			uint32_t id = kmerId, k = 0;
+			for (int m = 0; m < o1; ++m) { k = (k << 3) + (id & 3u) + 1u; id >>= 2; }
+			double p = nm_.rprobs[k];
+			for (int m = o1; m < len_; ++m) {
+				k = ((k << 3) + (id & 3u) + 1u) & mask;
+				id >>= 2;
+				p *= nm_.rconds[k];
+			}
+			return p;
+		}
 		uint8_t ex[128];
+		ex[0] = 0;
 		uint32_t id = kmerId;
 		int n = 0;
 		for (int m = 0; m < len_; ++m) {
@@ -217,12 +264,11 @@ private:
 	PvalueTables& t_;
 	const NullModelView& nm_;
 	int part_ = 0, start_ = 1, len_ = 0, T_ = 0, gapOffset_ = 0;
-	bool collect_ = false;
+	bool collect_ = false, ungapped_ = false;
 	int row_[34][5];
 	int col_[34];
 	double sw_[34][5];
 	double smax_[36];
-	uint8_t pick_[34];
 	std::vector<Leaf> leaves_, tmp_;
 	std::vector<int> prefixes_;
 	std::vector<int> prefixLen_;

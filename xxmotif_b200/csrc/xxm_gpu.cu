@@ -4,6 +4,7 @@
 #include "../../include/xxmotif_gpu.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -105,8 +106,23 @@ struct xxm_ctx {
 	int modelPosSetSize = 0;
 	int modelFirstCol = 1;  // cols[0] of the current model
 	Model M{};
-	DevBuf<uint32_t> d_rank0, d_rank1, d_hit0, d_ids, d_cls;
-	DevBuf<uint8_t> d_clsOk;
+	DevBuf<uint32_t> d_rank0, d_rank1, d_hit0, d_ids[2], d_cls[2];
+	DevBuf<uint8_t> d_clsOk[2];
+	// batched staging of the small per-model tables (xxm_reinitialize): everything goes through one pinned buffer, one
+	// H2D copy and one scatter kernel instead of a dozen pageable copies
+	struct UpSeg { void* dst; uint32_t off, bytes; };
+	struct FillJob { int k; int n; uint32_t* rank; uint32_t* bitmap; };
+	bool batching = false, stageInFlight = false;
+	std::vector<UpSeg> upSegs;
+	std::vector<FillJob> fillJobs;
+	uint8_t* h_stage = nullptr;
+	size_t h_stageCap = 0, stageUsed = 0;
+	DevBuf<uint8_t> d_stage;
+	cudaEvent_t evStage = nullptr;
+	// a full scan whose launches are queued but whose counts have not been read yet (xxm_optimize_step)
+	struct PendingScan { bool active = false; size_t cap = 0; int posSetSize = 0; uint32_t scanWords = 0; };
+	PendingScan pend;
+	unsigned long long* h_pin = nullptr;  // pinned: [0] hits of the pending scan, [1] its select counters (2 x u32)
 	DevBuf<double> d_cpval0, d_cpval1, d_leftProb;
 	DevBuf<int32_t> d_cscore0, d_cscore1;
 	DevBuf<int32_t> d_memoKey;
@@ -132,6 +148,8 @@ struct xxm_ctx {
 	DevBuf<uint32_t> d_pairTab;
 	DevBuf<unsigned long long> d_xchg;  // value-index histogram + scalars on their way through NCCL
 	std::vector<unsigned long long> h_xchg;
+	unsigned long long* h_pinXchg = nullptr;  // pinned landing buffer of the exchange vector / the count matrix
+	size_t h_pinXchgCap = 0;
 	std::vector<ScoreRun> h_runs;
 	void* comm = nullptr;               // ncclComm_t of a sharded set (xxm_comm_init), else null
 	int commRank = 0, commSize = 1;
@@ -139,7 +157,11 @@ struct xxm_ctx {
 	bool pairOK = false;           // the pair table represents the left table exactly: k_scan5, else k_scan4
 	bool forceGenericScan = false; // tests: always take the generic find kernel
 	DevBuf<uint64_t> d_rawOff;
-	DevBuf<int32_t> d_notX;
+	DevBuf<int32_t> d_notX, d_n;
+	int32_t* h_notX = nullptr;  // pinned
+	size_t h_notXCap = 0;
+	cudaStream_t copyStream = nullptr;
+	std::vector<cudaEvent_t> evPool;
 	DevBuf<unsigned long long> d_counts;
 	DevBuf<SiteRec> d_sites;
 	DevBuf<unsigned int> d_hf, d_hb;
@@ -213,8 +235,14 @@ extern "C" int xxm_create(int device, xxm_ctx** out) {
 	cudaDeviceProp prop;
 	if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->numSMs = prop.multiProcessorCount;
 	if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ctx->ev0) != cudaSuccess ||
-	    cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->evMid) != cudaSuccess) {
+	    cudaEventCreate(&ctx->ev1) != cudaSuccess || cudaEventCreate(&ctx->evMid) != cudaSuccess ||
+	    cudaEventCreateWithFlags(&ctx->evStage, cudaEventDisableTiming) != cudaSuccess) {
 		g_create_error = "cannot create stream/events";
+		delete ctx;
+		return 1;
+	}
+	if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_pin), 64, cudaHostAllocDefault) != cudaSuccess) {
+		g_create_error = "cannot allocate pinned memory";
 		delete ctx;
 		return 1;
 	}
@@ -234,7 +262,10 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	xxm_comm_destroy(ctx);
 	// DevBuf members are released explicitly (no destructor: the struct is copied nowhere, but keep it trivial)
 	ctx->d_codes.release(); ctx->d_nmask.release(); ctx->d_wordOff.release(); ctx->d_blk2seq.release(); ctx->d_len.release();
-	ctx->d_rank0.release(); ctx->d_rank1.release(); ctx->d_hit0.release(); ctx->d_ids.release(); ctx->d_cls.release(); ctx->d_clsOk.release();
+	ctx->d_rank0.release(); ctx->d_rank1.release(); ctx->d_hit0.release(); for (int k = 0; k < 2; ++k) { ctx->d_ids[k].release(); ctx->d_cls[k].release(); ctx->d_clsOk[k].release(); }
+	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_n.release();
+	for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
+	if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream); if (ctx->h_pinXchg) cudaFreeHost(ctx->h_pinXchg); if (ctx->evStage) cudaEventDestroy(ctx->evStage);
 	ctx->d_cpval0.release(); ctx->d_cpval1.release(); ctx->d_leftProb.release(); ctx->d_cscore0.release(); ctx->d_cscore1.release();
 	ctx->d_memoKey.release(); ctx->d_memoVal.release(); ctx->d_memoState.release(); ctx->d_flags32.release();
 	ctx->d_pS.release(); ctx->d_finalMops.release(); ctx->d_finalMode.release(); ctx->d_posProb.release(); ctx->d_perCand.release();
@@ -268,128 +299,149 @@ extern "C" int xxm_get_stats(const xxm_ctx* ctx, xxm_stats* out) { *out = ctx->s
 // a1: sequence set
 // =====================================================================================================================
 namespace xxm {
-// per sequence: number of residues that are not N (code 0); any code > 4 raises the flag.  One warp per sequence.
-__global__ void k_seq_stats(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rawOff, int nent, int32_t* __restrict__ notX,
+// per sequence: number of residues that are not N (code 0); any code > 4 raises the flag.  One warp per sequence of [s0, s1).
+__global__ void k_seq_stats(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rawOff, uint32_t s0, uint32_t s1, int32_t* __restrict__ notX,
                             uint32_t* __restrict__ bad) {
 	const int lane = threadIdx.x & 31;
 	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
-	for (uint32_t s = warp; s < static_cast<uint32_t>(nent); s += nwarps) {
+	for (uint32_t s = s0 + warp; s < s1; s += nwarps) {
 		const uint64_t a = rawOff[s], b = rawOff[s + 1];
 		uint32_t cnt = 0, err = 0;
-		for (uint64_t i = a + lane; i < b; i += 32) {
-			const uint8_t c = raw[i];
-			cnt += (c != 0);
-			err |= (c > 4);
+		// 16 bytes per lane once the pointer is aligned
+		uint64_t i = a;
+		const uint64_t aUp = min(b, (a + 15) & ~static_cast<uint64_t>(15));
+		for (uint64_t k = i + lane; k < aUp; k += 32) { const uint8_t c = raw[k]; cnt += (c != 0); err |= (c > 4); }
+		i = aUp;
+		const uint64_t nv = (b - i) / 16;
+		for (uint64_t v = lane; v < nv; v += 32) {
+			const uint4 q = *reinterpret_cast<const uint4*>(raw + i + 16 * v);
+			const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+			for (int t = 0; t < 4; ++t) {
+				const uint32_t x = w4[t];
+				// bytes != 0 (for codes 0..7): bit 0 | bit 1 | bit 2; codes > 4: bit 2 and (bit 0 or bit 1), or any higher bit (then the count is moot)
+				const uint32_t nz = (x | (x >> 1) | (x >> 2)) & 0x01010101u;
+				cnt += __popc(nz);
+				err |= (x & 0xF8F8F8F8u) | ((x >> 2) & (x | (x >> 1)) & 0x01010101u);
+			}
 		}
+		for (uint64_t k = i + 16 * nv + lane; k < b; k += 32) { const uint8_t c = raw[k]; cnt += (c != 0); err |= (c > 4); }
 		for (int d = 16; d; d >>= 1) { cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d); err |= __shfl_xor_sync(0xFFFFFFFFu, err, d); }
 		if (lane == 0) { notX[s] = static_cast<int32_t>(cnt); if (err) atomicExch(bad, s + 1); }
 	}
 }
-}  // namespace xxm
 
-static int upload_raw_and_count(xxm_ctx* ctx, int nent, const uint8_t* codes, const std::vector<uint64_t>& rawOff, uint8_t** d_rawOut, uint64_t** d_rawOffOut,
-                                std::vector<int32_t>& notX) {
-	const uint64_t bytes = rawOff[nent];
-	CK(ctx->d_raw.ensure(std::max<uint64_t>(1, bytes)));
-	CK(ctx->d_rawOff.ensure(static_cast<size_t>(nent) + 1));
-	CK(ctx->d_notX.ensure(nent));
-	CK(ctx->counters.ensure(8));
-	CK(cudaMemsetAsync(ctx->counters.p, 0, 32, ctx->stream));
-	CK(cudaMemcpyAsync(ctx->d_raw.p, codes, bytes, cudaMemcpyHostToDevice, ctx->stream));
-	CK(cudaMemcpyAsync(ctx->d_rawOff.p, rawOff.data(), rawOff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-	k_seq_stats<<<ctx->numSMs * 8, 256, 0, ctx->stream>>>(ctx->d_raw.p, ctx->d_rawOff.p, nent, ctx->d_notX.p, ctx->counters.p);
-	CKK();
-	notX.resize(nent);
-	uint32_t bad = 0;
-	CK(cudaMemcpyAsync(notX.data(), ctx->d_notX.p, static_cast<size_t>(nent) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-	CK(cudaMemcpyAsync(&bad, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-	CK(cudaStreamSynchronize(ctx->stream));
-	if (bad) return ctx->fail("sequence %u holds a code outside 0..4", bad);
-	*d_rawOut = ctx->d_raw.p;
-	*d_rawOffOut = ctx->d_rawOff.p;
-	return 0;
+// layout of the stream from the raw lengths alone (one block): rawOff (bytes), wordOff (words), len (stored length)
+__global__ void __launch_bounds__(1024) k_seq_layout(const int32_t* __restrict__ n, uint32_t nent, int revcomp, uint64_t* __restrict__ rawOff,
+                                                     uint32_t* __restrict__ wordOff, int32_t* __restrict__ len) {
+	__shared__ uint64_t s_raw[1024];
+	__shared__ uint64_t s_wrd[1024];
+	const uint32_t per = (nent + 1023) / 1024;
+	const uint32_t a = min(nent, threadIdx.x * per), b = min(nent, a + per);
+	uint64_t r = 0, w = 0;
+	for (uint32_t i = a; i < b; ++i) {
+		const uint64_t n0 = static_cast<uint64_t>(n[i]);
+		const uint64_t ns = revcomp ? 2 * n0 + 1 : n0;
+		r += n0;
+		w += (ns + kPadBases + 31) / 32;
+	}
+	s_raw[threadIdx.x] = r;
+	s_wrd[threadIdx.x] = w;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint64_t ar = 0, aw = 0;
+		for (int t = 0; t < 1024; ++t) { const uint64_t x = s_raw[t], y = s_wrd[t]; s_raw[t] = ar; s_wrd[t] = aw; ar += x; aw += y; }
+		rawOff[nent] = ar;
+		wordOff[nent] = static_cast<uint32_t>(aw);
+	}
+	__syncthreads();
+	r = s_raw[threadIdx.x];
+	w = s_wrd[threadIdx.x];
+	for (uint32_t i = a; i < b; ++i) {
+		const uint64_t n0 = static_cast<uint64_t>(n[i]);
+		const uint64_t ns = revcomp ? 2 * n0 + 1 : n0;
+		rawOff[i] = r;
+		wordOff[i] = static_cast<uint32_t>(w);
+		len[i] = static_cast<int32_t>(ns);
+		r += n0;
+		w += (ns + kPadBases + 31) / 32;
+	}
 }
 
+// coarse word -> sequence index: blk2seq[b] = the sequence that owns word b * kBlkWords
+__global__ void k_blk2seq(const uint32_t* __restrict__ wordOff, uint32_t nent, uint32_t nblk, uint32_t* __restrict__ blk2seq) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= nent) return;
+	const uint32_t w0 = wordOff[s], w1 = wordOff[s + 1];
+	for (uint32_t b = (w0 + kBlkWords - 1) / kBlkWords; b < nblk && (b * kBlkWords < w1 || s + 1 == nent); ++b) blk2seq[b] = s;
+}
+}  // namespace xxm
+
+// a1.  The raw codes travel in chunks of whole sequences on a copy stream; behind every chunk the per-sequence statistics
+// (non-N residues, range check) and the packing kernel run on the compute stream, and the host folds the statistics of a
+// chunk into total[] / avgLength[] while the next chunks are still on the bus.
 extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp) {
 	CK(cudaSetDevice(ctx->device));
 	if (nent <= 0) return ctx->fail("empty sequence set");
+	static const bool trace = std::getenv("XXM_TRACE") != nullptr;
+	const auto tStart = std::chrono::steady_clock::now();
 	ctx->nent = nent;
 	ctx->revcomp = revcomp != 0;
 	ctx->len.resize(nent);
-	ctx->total.assign(static_cast<size_t>(nent) + 1, 0);
-	ctx->logAcc.assign(static_cast<size_t>(nent) + 1, 0.0);
+	ctx->total.resize(static_cast<size_t>(nent) + 1);
+	ctx->logAcc.resize(static_cast<size_t>(nent) + 1);
+	ctx->total[0] = 0;
+	ctx->logAcc[0] = 0.0;
 	ctx->wordOff.resize(static_cast<size_t>(nent) + 1);
-	std::vector<uint64_t> rawOff(static_cast<size_t>(nent) + 1);
-	// calculateSequenceFeatures (seqset.cpp:21-36) on the raw set, then -- with revcomp -- the recount at the end of
-	// createRevcomp (seqset.cpp:165-177) which compares codes with the CHARACTER '0' and therefore counts every
-	// position of the doubled sequence (SURVEY.md A.4).
+	if (!ctx->copyStream) CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+	// ---- layout on the device from the lengths alone
+	CK(ctx->d_n.ensure(nent));
+	CK(ctx->d_rawOff.ensure(static_cast<size_t>(nent) + 1));
+	CK(ctx->d_wordOff.ensure(static_cast<size_t>(nent) + 1));
+	CK(ctx->d_len.ensure(nent));
+	CK(ctx->d_notX.ensure(nent));
+	CK(ctx->counters.ensure(8));
+	CK(cudaMemsetAsync(ctx->counters.p, 0, 32, ctx->stream));
+	CK(cudaMemcpyAsync(ctx->d_n.p, n, static_cast<size_t>(nent) * 4, cudaMemcpyHostToDevice, ctx->stream));
+	k_seq_layout<<<1, 1024, 0, ctx->stream>>>(ctx->d_n.p, static_cast<uint32_t>(nent), revcomp ? 1 : 0, ctx->d_rawOff.p, ctx->d_wordOff.p, ctx->d_len.p);
+	CKK();
+	// ---- sizes first (no stores: a fraction of a millisecond per million sequences), so that the buffers exist before the first chunk leaves
 	uint64_t off = 0, words = 0;
-	double acc = 0, lastLog = 0;
-	int lastNotX = 0;
 	int mx = 0, mn = 2147483647;
-	int64_t tot = 0;
-	// the raw codes go to the device first; the per-sequence count of non-N residues and the range check of the codes
-	// are done there (one coalesced pass) instead of a serial host loop over every base
-	std::vector<int32_t> notXv;
-	uint8_t* d_raw = nullptr;
-	uint64_t* d_rawOff = nullptr;
 	{
-		uint64_t o = 0;
-		for (int i = 0; i < nent; ++i) {
-			if (n[i] < 1) return ctx->fail("sequence %d is empty", i + 1);
-			rawOff[i] = o;
-			o += static_cast<uint64_t>(n[i]);
+		int mxRaw = 0;
+		uint64_t w0 = 0;
+		for (int i = 0; i < nent; ++i) {  // branch free: vectorises
+			const int n0 = n[i];
+			mxRaw = std::max(mxRaw, n0);
+			mn = std::min(mn, n0);
+			off += static_cast<uint32_t>(n0);
+			w0 += (static_cast<uint32_t>(n0) + static_cast<uint32_t>(kPadBases + 31)) >> 5;
 		}
-		rawOff[nent] = o;
-		TRY(upload_raw_and_count(ctx, nent, codes, rawOff, &d_raw, &d_rawOff, notXv));
-	}
-	for (int i = 0; i < nent; ++i) {
-		rawOff[i] = off;
-		const int n0 = n[i];
-		int notX = notXv[i];
-		const int nstore = revcomp ? 2 * n0 + 1 : n0;
-		if (revcomp) notX = nstore;
-		if (notX != 0) {
-			if (notX != lastNotX) { lastNotX = notX; lastLog = std::log(notX); }  // same argument, same glibc result
-			acc += lastLog;
+		if (mn < 1) {
+			for (int i = 0; i < nent; ++i) if (n[i] < 1) return ctx->fail("sequence %d is empty", i + 1);
 		}
-		tot += notX;
-		if (tot > 2147483647LL) return ctx->fail("more than 2^31-1 residues: the reference's int totals overflow (Alignment.h:40-41)");
-		ctx->total[i + 1] = static_cast<int32_t>(tot);
-		ctx->logAcc[i + 1] = acc;
-		ctx->len[i] = nstore;
-		mx = std::max(mx, nstore);
-		mn = std::min(mn, nstore);
-		ctx->wordOff[i] = static_cast<uint32_t>(words);
-		words += (static_cast<uint64_t>(nstore) + kPadBases + 31) / 32;
-		if (words > 0xFFFFFF00ull) return ctx->fail("sequence stream exceeds 2^32 words");
-		off += n0;
+		if (mxRaw > 1000000000) return ctx->fail("sequence longer than 10^9 residues");
+		if (revcomp) {
+			words = 0;
+			for (int i = 0; i < nent; ++i) words += (2ull * static_cast<uint32_t>(n[i]) + 1 + kPadBases + 31) / 32;
+			mx = 2 * mxRaw + 1;
+			mn = 2 * mn + 1;
+		} else {
+			words = w0;
+			mx = mxRaw;
+		}
 	}
-	rawOff[nent] = off;
-	ctx->wordOff[nent] = static_cast<uint32_t>(words);
+	if (words > 0xFFFFFF00ull) return ctx->fail("sequence stream exceeds 2^32 words");
 	ctx->nwords = static_cast<uint32_t>(words);
 	ctx->max_leng = mx;
 	ctx->min_leng = mn;
-	// coarse word -> sequence index
 	const uint32_t nblk = ctx->nwords / kBlkWords + 1;
-	std::vector<uint32_t> blk(nblk);
-	{
-		uint32_t s = 0;
-		for (uint32_t b = 0; b < nblk; ++b) {
-			const uint32_t w = b * kBlkWords;
-			while (s + 1 < static_cast<uint32_t>(nent) && ctx->wordOff[s + 1] <= w) ++s;
-			blk[b] = s;
-		}
-	}
+	CK(ctx->d_raw.ensure(std::max<uint64_t>(1, off)));
 	CK(ctx->d_codes.ensure(static_cast<size_t>(ctx->nwords) + 2));
 	CK(ctx->d_nmask.ensure(static_cast<size_t>(ctx->nwords) + 2));
-	CK(ctx->d_wordOff.ensure(static_cast<size_t>(nent) + 1));
-	CK(ctx->d_len.ensure(nent));
 	CK(ctx->d_blk2seq.ensure(nblk));
-	CK(cudaMemcpyAsync(ctx->d_wordOff.p, ctx->wordOff.data(), ctx->wordOff.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-	CK(cudaMemcpyAsync(ctx->d_len.p, ctx->len.data(), ctx->len.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-	CK(cudaMemcpyAsync(ctx->d_blk2seq.p, blk.data(), blk.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 	ctx->S.codes = ctx->d_codes.p;
 	ctx->S.nmask = ctx->d_nmask.p;
 	ctx->S.wordOff = ctx->d_wordOff.p;
@@ -398,17 +450,102 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	ctx->S.nwords = ctx->nwords;
 	ctx->S.nent = nent;
 	ctx->S.uniformWps = (mx == mn) ? static_cast<uint32_t>((static_cast<uint64_t>(mx) + kPadBases + 31) / 32) : 0u;
-	k_encode<<<cdiv(static_cast<uint64_t>(ctx->nwords) + 2, 256), 256, 0, ctx->stream>>>(d_raw, d_rawOff, ctx->S, ctx->d_codes.p, ctx->d_nmask.p,
-	                                                                                   revcomp ? 1 : 0);
+	k_blk2seq<<<cdiv(static_cast<uint32_t>(nent), 256), 256, 0, ctx->stream>>>(ctx->d_wordOff.p, static_cast<uint32_t>(nent), nblk, ctx->d_blk2seq.p);
 	CKK();
+	// pinned landing buffer of the per-sequence counts
+	if (ctx->h_notXCap < static_cast<size_t>(nent)) {
+		if (ctx->h_notX) cudaFreeHost(ctx->h_notX);
+		ctx->h_notX = nullptr;
+		ctx->h_notXCap = 0;
+		CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_notX), static_cast<size_t>(nent) * 4, cudaHostAllocDefault));
+		ctx->h_notXCap = static_cast<size_t>(nent);
+	}
+	// ---- the same layout on the host (it owns wordOff / len / total), cutting chunks of whole sequences as it goes; every
+	// chunk is queued as soon as it is cut: copy(k) on the copy stream, stats(k) + counts-to-host(k) + encode(k) on the compute stream
+	constexpr uint64_t kChunkBytes = 48ull << 20;
+	struct Chunk { int s0, s1; uint64_t b0, b1; uint32_t w0, w1; };
+	std::vector<Chunk> chunks;
+	auto tFirst = tStart;
+	{
+		Chunk c{0, 0, 0, 0, 0, 0};
+		off = 0;
+		words = 0;
+		for (int i = 0; i < nent; ++i) {
+			const int n0 = n[i];
+			const int nstore = revcomp ? 2 * n0 + 1 : n0;
+			ctx->len[i] = nstore;
+			ctx->wordOff[i] = static_cast<uint32_t>(words);
+			words += (static_cast<uint64_t>(nstore) + kPadBases + 31) / 32;
+			off += static_cast<uint64_t>(n0);
+			if (off - c.b0 < kChunkBytes && i + 1 != nent) continue;
+			c.s1 = i + 1; c.b1 = off; c.w1 = static_cast<uint32_t>(words);
+			const size_t k = chunks.size();
+			chunks.push_back(c);
+			while (ctx->evPool.size() < 2 * (k + 1)) {
+				cudaEvent_t e;
+				CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+				ctx->evPool.push_back(e);
+			}
+			if (trace && k == 0) { CK(cudaEventRecord(ctx->ev0, ctx->copyStream)); tFirst = std::chrono::steady_clock::now(); }
+			CK(cudaMemcpyAsync(ctx->d_raw.p + c.b0, codes + c.b0, c.b1 - c.b0, cudaMemcpyHostToDevice, ctx->copyStream));
+			CK(cudaEventRecord(ctx->evPool[2 * k], ctx->copyStream));
+			if (trace && i + 1 == nent) CK(cudaEventRecord(ctx->ev1, ctx->copyStream));
+			CK(cudaStreamWaitEvent(ctx->stream, ctx->evPool[2 * k], 0));
+			const uint32_t ns = static_cast<uint32_t>(c.s1 - c.s0);
+			k_seq_stats<<<std::min<uint32_t>(cdiv(ns, 8), static_cast<uint32_t>(ctx->numSMs) * 8), 256, 0, ctx->stream>>>(
+				ctx->d_raw.p, ctx->d_rawOff.p, static_cast<uint32_t>(c.s0), static_cast<uint32_t>(c.s1), ctx->d_notX.p, ctx->counters.p);
+			CKK();
+			CK(cudaMemcpyAsync(ctx->h_notX + c.s0, ctx->d_notX.p + c.s0, static_cast<size_t>(ns) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaEventRecord(ctx->evPool[2 * k + 1], ctx->stream));
+			const uint32_t w1 = (i + 1 == nent) ? ctx->nwords + 2 : c.w1;
+			if (w1 > c.w0) {
+				k_encode<<<cdiv(w1 - c.w0, 256), 256, 0, ctx->stream>>>(ctx->d_raw.p, ctx->d_rawOff.p, ctx->S, c.w0, w1, ctx->d_codes.p, ctx->d_nmask.p, revcomp ? 1 : 0);
+				CKK();
+			}
+			c = Chunk{i + 1, i + 1, off, off, static_cast<uint32_t>(words), static_cast<uint32_t>(words)};
+		}
+	}
+	ctx->wordOff[nent] = static_cast<uint32_t>(words);
+	const auto tQueued = std::chrono::steady_clock::now();
+	// ---- calculateSequenceFeatures (seqset.cpp:21-36) on the raw set, then -- with revcomp -- the recount at the end of
+	// createRevcomp (seqset.cpp:165-177) which compares codes with the CHARACTER '0' and therefore counts every
+	// position of the doubled sequence (SURVEY.md A.4).
+	double acc = 0, lastLog = 0;
+	int lastNotX = 0;
+	int64_t tot = 0;
+	for (size_t k = 0; k < chunks.size(); ++k) {
+		CK(cudaEventSynchronize(ctx->evPool[2 * k + 1]));
+		for (int i = chunks[k].s0; i < chunks[k].s1; ++i) {
+			int notX = ctx->h_notX[i];
+			if (revcomp) notX = ctx->len[i];
+			if (notX != 0) {
+				if (notX != lastNotX) { lastNotX = notX; lastLog = std::log(notX); }  // same argument, same glibc result
+				acc += lastLog;
+			}
+			tot += notX;
+			if (tot > 2147483647LL) { cudaStreamSynchronize(ctx->stream); return ctx->fail("more than 2^31-1 residues: the reference's int totals overflow (Alignment.h:40-41)"); }
+			ctx->total[i + 1] = static_cast<int32_t>(tot);
+			ctx->logAcc[i + 1] = acc;
+		}
+	}
+	uint32_t bad = 0;
+	CK(cudaMemcpyAsync(ctx->h_pin + 4, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
+	std::memcpy(&bad, ctx->h_pin + 4, 4);
+	if (bad) return ctx->fail("sequence %u holds a code outside 0..4", bad);
 	if (ctx->d_raw.cap > (8ull << 30)) ctx->d_raw.release();  // the raw codes are only needed for packing
-	(void) d_raw;
-	(void) d_rawOff;
-	init_sum_i(ctx->sum_i, ctx->max_leng);
+	if (ctx->sum_i.size() != static_cast<size_t>(ctx->max_leng) + 1) init_sum_i(ctx->sum_i, ctx->max_leng);
 	ctx->haveModel = false;
 	for (auto& l : ctx->L) l = SiteList();
 	ctx->nBest = 0;
+	if (trace) {
+		const auto tEnd = std::chrono::steady_clock::now();
+		float copyMs = 0;
+		cudaEventElapsedTime(&copyMs, ctx->ev0, ctx->ev1);
+		std::fprintf(stderr, "xxm load_seqset: %zu chunks, first copy issued after %.2f ms, all queued after %.2f ms, copies took %.2f ms, done after %.2f ms\n",
+		             chunks.size(), std::chrono::duration<double, std::milli>(tFirst - tStart).count(),
+		             std::chrono::duration<double, std::milli>(tQueued - tStart).count(), copyMs, std::chrono::duration<double, std::milli>(tEnd - tStart).count());
+	}
 	return 0;
 }
 
@@ -436,14 +573,101 @@ extern "C" int xxm_set_background(xxm_ctx* ctx, int32_t order, const float* rpro
 	return 0;
 }
 
-template <typename T>
-static int upload(xxm_ctx* ctx, DevBuf<T>& d, const std::vector<T>& h) {
-	CK(d.ensure(std::max<size_t>(1, h.size())));
-	if (!h.empty()) CK(cudaMemcpyAsync(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+namespace xxm {
+constexpr int kMaxUpSegs = 16;
+struct UpSegs { void* dst[kMaxUpSegs]; uint32_t off[kMaxUpSegs], bytes[kMaxUpSegs]; };
+// blockIdx.y = segment; bytes are copied one by one (the segments are a few KB)
+__global__ void k_scatter_stage(const uint8_t* __restrict__ stage, UpSegs segs) {
+	const int sgm = blockIdx.y;
+	uint8_t* dst = static_cast<uint8_t*>(segs.dst[sgm]);
+	const uint8_t* src = stage + segs.off[sgm];
+	const uint32_t n = segs.bytes[sgm];
+	if (((reinterpret_cast<uintptr_t>(dst) | segs.off[sgm]) & 3u) == 0) {
+		const uint32_t n4 = n >> 2;
+		for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x)
+			reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(src)[i];
+		for (uint32_t i = (n4 << 2) + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+	} else {
+		for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+	}
+}
+}  // namespace xxm
+
+static int begin_uploads(xxm_ctx* ctx) {
+	if (ctx->stageInFlight) { CK(cudaEventSynchronize(ctx->evStage)); ctx->stageInFlight = false; }
+	ctx->batching = true;
+	ctx->upSegs.clear();
+	ctx->fillJobs.clear();
+	ctx->stageUsed = 0;
 	return 0;
 }
 
-static int stage_part(xxm_ctx* ctx, const TablePart& P, bool single, DevBuf<uint32_t>& rank, DevBuf<uint32_t>* bitmap) {
+// copy what has been staged so far and run the kernels that were waiting for it
+static int flush_uploads(xxm_ctx* ctx) {
+	if (!ctx->upSegs.empty()) {
+		CK(ctx->d_stage.ensure(ctx->stageUsed));
+		CK(cudaMemcpyAsync(ctx->d_stage.p, ctx->h_stage, ctx->stageUsed, cudaMemcpyHostToDevice, ctx->stream));
+		CK(cudaEventRecord(ctx->evStage, ctx->stream));
+		ctx->stageInFlight = true;
+		for (size_t b = 0; b < ctx->upSegs.size(); b += kMaxUpSegs) {
+			UpSegs U{};
+			const int ns = static_cast<int>(std::min<size_t>(kMaxUpSegs, ctx->upSegs.size() - b));
+			uint32_t mx = 4;
+			for (int i = 0; i < ns; ++i) {
+				U.dst[i] = ctx->upSegs[b + i].dst; U.off[i] = ctx->upSegs[b + i].off; U.bytes[i] = ctx->upSegs[b + i].bytes;
+				mx = std::max(mx, U.bytes[i]);
+			}
+			k_scatter_stage<<<dim3(std::min<uint32_t>(64, cdiv(mx / 4, 256)), ns), 256, 0, ctx->stream>>>(ctx->d_stage.p, U);
+			CKK();
+		}
+		ctx->upSegs.clear();
+	}
+	for (const xxm_ctx::FillJob& j : ctx->fillJobs) {
+		k_fill_rank<<<cdiv(j.n, 256), 256, 0, ctx->stream>>>(ctx->d_ids[j.k].p, ctx->d_cls[j.k].p, ctx->d_clsOk[j.k].p, j.n, j.rank, j.bitmap);
+		CKK();
+	}
+	ctx->fillJobs.clear();
+	return 0;
+}
+
+static int end_uploads(xxm_ctx* ctx) {
+	const int r = flush_uploads(ctx);
+	ctx->batching = false;
+	// the pinned buffer is reused by the next batch: begin_uploads waits for this copy first
+	ctx->stageUsed = 0;
+	return r;
+}
+
+template <typename T>
+static int upload(xxm_ctx* ctx, DevBuf<T>& d, const std::vector<T>& h) {
+	CK(d.ensure(std::max<size_t>(1, h.size())));
+	if (h.empty()) return 0;
+	const size_t bytes = h.size() * sizeof(T);
+	if (!ctx->batching || bytes > (1u << 20)) {
+		CK(cudaMemcpyAsync(d.p, h.data(), bytes, cudaMemcpyHostToDevice, ctx->stream));
+		return 0;
+	}
+	const size_t off = (ctx->stageUsed + 15) & ~static_cast<size_t>(15);
+	if (off + bytes > ctx->h_stageCap) {
+		// grow the pinned buffer; segments already staged in this batch are copied first
+		TRY(flush_uploads(ctx));
+		CK(cudaEventSynchronize(ctx->evStage));
+		ctx->stageInFlight = false;
+		if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+		ctx->h_stage = nullptr;
+		ctx->h_stageCap = std::max<size_t>(4u << 20, 2 * (off + bytes));
+		CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_stage), ctx->h_stageCap, cudaHostAllocDefault));
+		ctx->stageUsed = 0;
+		return upload(ctx, d, h);
+	}
+	std::memcpy(ctx->h_stage + off, h.data(), bytes);
+	ctx->stageUsed = off + bytes;
+	ctx->upSegs.push_back(xxm_ctx::UpSeg{d.p, static_cast<uint32_t>(off), static_cast<uint32_t>(bytes)});
+	return 0;
+}
+
+// k = 0 / 1: scratch buffers of the left / right table part
+static int stage_part(xxm_ctx* ctx, const TablePart& P, bool single, DevBuf<uint32_t>& rank, DevBuf<uint32_t>* bitmap, int k) {
 	const size_t size = static_cast<size_t>(1) << (2 * P.len);
 	CK(rank.ensure(size));
 	CK(cudaMemsetAsync(rank.p, 0, size * 4, ctx->stream));
@@ -453,20 +677,24 @@ static int stage_part(xxm_ctx* ctx, const TablePart& P, bool single, DevBuf<uint
 	}
 	std::vector<uint8_t> ok(P.classPval.size());
 	for (size_t c = 0; c < ok.size(); ++c) ok[c] = (P.classPval[c] != 0.0) && !(single && P.classPval[c] == 1.0);
-	TRY(upload(ctx, ctx->d_ids, P.ids));
-	TRY(upload(ctx, ctx->d_cls, P.cls));
-	TRY(upload(ctx, ctx->d_clsOk, ok));
+	TRY(upload(ctx, ctx->d_ids[k], P.ids));
+	TRY(upload(ctx, ctx->d_cls[k], P.cls));
+	TRY(upload(ctx, ctx->d_clsOk[k], ok));
 	const int n = static_cast<int>(P.ids.size());
-	if (n) {
-		k_fill_rank<<<cdiv(n, 256), 256, 0, ctx->stream>>>(ctx->d_ids.p, ctx->d_cls.p, ctx->d_clsOk.p, n, rank.p, bitmap ? bitmap->p : nullptr);
-		CKK();
-	}
+	if (n) ctx->fillJobs.push_back(xxm_ctx::FillJob{k, n, rank.p, bitmap ? bitmap->p : nullptr});
+	if (!ctx->batching) TRY(flush_uploads(ctx));
 	return 0;
 }
 
 static double zoops_final(double pS, double exponent) { return 1 - std::pow(1 - pS, exponent); }  // pValCalculation.h:96
 
+static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions);
 extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions) {
+	const int r = reinitialize_impl(ctx, pwm, cols, ncols, posSetSize, totalPositions);
+	if (r) { ctx->batching = false; ctx->upSegs.clear(); ctx->fillJobs.clear(); ctx->haveModel = false; }
+	return r;
+}
+static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions) {
 	CK(cudaSetDevice(ctx->device));
 	if (!ctx->nent) return ctx->fail("no sequence set loaded");
 	if (!ctx->nm.rprobs) return ctx->fail("no background model set");
@@ -493,7 +721,8 @@ extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* 
 	}
 	M.pruneThr = T.pruneThr;
 	M.corr = std::pow(ctx->opt.overrepCorrection, T.L);  // pOverrepCorrection[i] = pow(overrepCorrection, i), pValCalculation.cpp:23-24
-	TRY(stage_part(ctx, T.part[0], T.nparts == 1, ctx->d_rank0, &ctx->d_hit0));
+	TRY(begin_uploads(ctx));
+	TRY(stage_part(ctx, T.part[0], T.nparts == 1, ctx->d_rank0, &ctx->d_hit0, 0));
 	M.rank0 = ctx->d_rank0.p;
 	M.hit0 = ctx->d_hit0.p;
 	TRY(upload(ctx, ctx->d_cpval0, T.part[0].classPval));
@@ -518,7 +747,7 @@ extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* 
 		TRY(upload(ctx, ctx->d_finalMops, ctx->h_finalMops));
 		TRY(upload(ctx, ctx->d_finalMode, ctx->h_finalMode));
 	} else {
-		TRY(stage_part(ctx, T.part[1], false, ctx->d_rank1, nullptr));
+		TRY(stage_part(ctx, T.part[1], false, ctx->d_rank1, nullptr, 1));
 		M.rank1 = ctx->d_rank1.p;
 		TRY(upload(ctx, ctx->d_cpval1, T.part[1].classPval));
 		TRY(upload(ctx, ctx->d_cscore1, T.part[1].classScore));
@@ -546,6 +775,7 @@ extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* 
 		CK(ctx->d_finalMode.ensure(cap));
 	}
 	TRY(stage_scan(ctx));
+	TRY(end_uploads(ctx));
 	ctx->haveModel = true;
 	return 0;
 }
@@ -686,9 +916,9 @@ static void set_max_sites_mops(xxm_ctx* ctx, int posSetSize) {
 // the scan finds the windows whose left k-mer is in the table; unless ctx->scanFindsOnlySites the caller still has to
 // drop the entries whose finalPval turns out to be >= 1 (or whose right part / product test fails)
 static int run_scan(xxm_ctx* ctx, int nseq, const Values& V, int checkFinal, DevBuf<uint32_t>& oseq, DevBuf<uint32_t>& opos, DevBuf<uint32_t>& ovidx,
-                    DevBuf<float>* oscore, uint32_t* nOut, bool timeIt) {
+                    DevBuf<float>* oscore, uint32_t* nOut, bool timeIt, size_t* deferCap = nullptr) {
 	(void) checkFinal;
-	return run_scan5(ctx, nseq, V, oseq, opos, ovidx, oscore, nOut, timeIt);
+	return run_scan5(ctx, nseq, V, oseq, opos, ovidx, oscore, nOut, timeIt, deferCap);
 }
 
 static int compact_list(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, const uint8_t* flag, uint32_t n, uint32_t* oseq,
@@ -716,6 +946,31 @@ static int compact_list(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, 
 }
 
 // updateMultOcc over an entry list -> keep flags + float scores
+// forward-only overlap removal (k_select_mops_fwd) with the class histogram fused in; nDev != nullptr: n is the capacity
+// and the entry count is read on the device
+static int launch_select_fwd(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, uint32_t n,
+                             const unsigned long long* nDev, int shift, DevBuf<uint8_t>& keep, DevBuf<float>& kscore) {
+	SelectFwdIO f{};
+	f.seq = seq; f.pos = pos; f.vidx = vidx; f.n = n; f.nDev = nDev; f.length = ctx->tab.span; f.shift = shift; f.kscore = kscore.p; f.keep = keep.p;
+	f.counters = ctx->counters.p;
+	const bool wantHist = (V.kind == kFinalTable);
+	if (wantHist) {
+		CK(ctx->hist.ensure(std::max<uint32_t>(1, ctx->nval)));
+		CK(cudaMemsetAsync(ctx->hist.p, 0, ctx->nval * 4ull, ctx->stream));
+		f.hist = ctx->hist.p; f.nval = ctx->nval; f.smemHist = ctx->nval <= 8192;
+	}
+	const size_t sm = (wantHist && f.smemHist) ? ctx->nval * 4ull : 0;
+	uint32_t grid = static_cast<uint32_t>(ctx->numSMs) * 16;
+	if (!nDev) grid = std::min<uint32_t>(cdiv(n, 256 * kSelChunk), grid);  // a thread owns kSelChunk entries per pass
+	k_select_mops_fwd<<<grid, 256, sm, ctx->stream>>>(V, f);
+	CKK();
+	ctx->histValid = wantHist;
+	ctx->histSerial = ++ctx->histCounter;
+	return 0;
+}
+
+static bool select_cap_safe(const xxm_ctx* ctx) { return ctx->max_leng / (ctx->tab.span + 1) + 1 <= ctx->opt.maxMotifsPerSequence; }
+
 static int select_mops(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, uint32_t n, int shift, bool ordered,
                        DevBuf<uint8_t>& keep, DevBuf<float>& kscore, uint32_t* nKept, uint32_t* maxPerSeq) {
 	CK(keep.ensure(std::max<uint32_t>(1, n)));
@@ -730,22 +985,9 @@ static int select_mops(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const
 	io.stk = ctx->stk.p; io.kscore = kscore.p; io.keep = keep.p; io.counters = ctx->counters.p;
 	ctx->histValid = false;
 	// forward-only sets whose per-sequence site count cannot reach the cap: cluster walk with the class histogram fused in
-	const bool capSafe = ctx->max_leng / (ctx->tab.span + 1) + 1 <= ctx->opt.maxMotifsPerSequence;
+	const bool capSafe = select_cap_safe(ctx);
 	if (ordered && !ctx->revcomp && capSafe) {
-		SelectFwdIO f{};
-		f.seq = seq; f.pos = pos; f.vidx = vidx; f.n = n; f.length = ctx->tab.span; f.shift = shift; f.kscore = kscore.p; f.keep = keep.p; f.counters = ctx->counters.p;
-		const bool wantHist = (V.kind == kFinalTable);
-		if (wantHist) {
-			CK(ctx->hist.ensure(std::max<uint32_t>(1, ctx->nval)));
-			CK(cudaMemsetAsync(ctx->hist.p, 0, ctx->nval * 4ull, ctx->stream));
-			f.hist = ctx->hist.p; f.nval = ctx->nval; f.smemHist = ctx->nval <= 8192;
-		}
-		const size_t sm = (wantHist && f.smemHist) ? ctx->nval * 4ull : 0;
-		const uint32_t grid = std::min<uint32_t>(cdiv(n, 256 * kSelChunk), static_cast<uint32_t>(ctx->numSMs) * 16);  // a thread owns kSelChunk entries per pass
-		k_select_mops_fwd<<<grid, 256, sm, ctx->stream>>>(V, f);
-		CKK();
-		ctx->histValid = wantHist;
-		ctx->histSerial = ++ctx->histCounter;
+		TRY(launch_select_fwd(ctx, V, seq, pos, vidx, n, nullptr, shift, keep, kscore));
 	} else {
 		CK(cudaMemsetAsync(keep.p, 0, n, ctx->stream));
 		if (ordered) k_select_mops<<<cdiv(n, 128), 128, 0, ctx->stream>>>(ctx->S, V, io);
@@ -787,6 +1029,24 @@ static int select_slots(xxm_ctx* ctx, const Values& V, const uint32_t* seq, cons
 // =====================================================================================================================
 // a2: full scan
 // =====================================================================================================================
+static void scan_full_set_best(xxm_ctx* ctx, uint32_t n, bool lazyScores) {
+	SiteList& B = ctx->L[XXM_LIST_BEST_STARTPOS];
+	B = SiteList();
+	B.kind = kListCompact; B.seq = ctx->b_seq.p; B.pos = ctx->b_pos.p; B.vidx = ctx->b_vidx.p; B.n = n; B.score = lazyScores ? nullptr : ctx->b_score.p;
+	B.lazyPS = lazyScores ? ctx->b_pSsnap.p : nullptr; B.members = n;
+	B.modelSerial = ctx->modelSerial;
+}
+
+static void scan_full_set_sorted(xxm_ctx* ctx, const Values& V, uint32_t n, uint32_t kept, uint32_t mps, int posSetSize) {
+	SiteList& Sd = ctx->L[XXM_LIST_SORTED_SITES];
+	Sd = SiteList();
+	Sd.kind = kListFlagged; Sd.seq = ctx->b_seq.p; Sd.pos = ctx->b_pos.p; Sd.vidx = ctx->b_vidx.p; Sd.n = n; Sd.score = ctx->s_kscore.p;
+	Sd.keep = ctx->s_keep.p; Sd.members = kept; Sd.maxPerSeq = mps; Sd.tableValued = (V.kind == kFinalTable); Sd.modelSerial = ctx->modelSerial;
+	Sd.histSerial = ctx->histValid ? ctx->histSerial : 0;
+	ctx->nbSites = static_cast<int>(kept);
+	set_max_sites_mops(ctx, posSetSize);
+}
+
 extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t* nbSites, int32_t* nbBestSites, int32_t* maxSites) {
 	CK(cudaSetDevice(ctx->device));
 	if (!ctx->haveModel) return ctx->fail("xxm_scan_full: no model (call xxm_reinitialize)");
@@ -824,20 +1084,58 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 		k_entry_scores<<<cdiv(n, 256), 256, 0, ctx->stream>>>(V, ctx->b_vidx.p, ctx->b_pos.p, n, 0, 0, ctx->b_score.p);
 		CKK();
 	}
-	SiteList& B = ctx->L[XXM_LIST_BEST_STARTPOS];
-	B = SiteList();
-	B.kind = kListCompact; B.seq = ctx->b_seq.p; B.pos = ctx->b_pos.p; B.vidx = ctx->b_vidx.p; B.n = n; B.score = lazyScores ? nullptr : ctx->b_score.p; B.lazyPS = lazyScores ? ctx->b_pSsnap.p : nullptr; B.members = n;
-	B.modelSerial = ctx->modelSerial;
+	scan_full_set_best(ctx, n, lazyScores);
 	// updateMultOcc -> sortedSites
 	uint32_t kept = 0, mps = 0;
 	TRY(select_mops(ctx, V, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, n, 0, true, ctx->s_keep, ctx->s_kscore, &kept, &mps));
-	SiteList& Sd = ctx->L[XXM_LIST_SORTED_SITES];
-	Sd = SiteList();
-	Sd.kind = kListFlagged; Sd.seq = ctx->b_seq.p; Sd.pos = ctx->b_pos.p; Sd.vidx = ctx->b_vidx.p; Sd.n = n; Sd.score = ctx->s_kscore.p;
-	Sd.keep = ctx->s_keep.p; Sd.members = kept; Sd.maxPerSeq = mps; Sd.tableValued = (V.kind == kFinalTable); Sd.modelSerial = ctx->modelSerial;
-	Sd.histSerial = ctx->histValid ? ctx->histSerial : 0;
-	ctx->nbSites = static_cast<int>(kept);
-	set_max_sites_mops(ctx, posSetSize);
+	scan_full_set_sorted(ctx, V, n, kept, mps, posSetSize);
+	*nbSites = ctx->nbSites;
+	*nbBestSites = static_cast<int32_t>(n);
+	*maxSites = ctx->maxSites;
+	return 0;
+}
+
+// The same scan with nothing read back: find, expand, overlap removal (+ histogram) are queued, the hit count and the
+// select counters travel to ctx->h_pin with the caller's next synchronisation, and scan_full_finish does the bookkeeping.
+// Only for the case xxm_optimize_step's fast path handles (one table, no localization, forward strand only).
+static bool scan_full_can_defer(const xxm_ctx* ctx) {
+	return ctx->scanFindsOnlySites && !ctx->revcomp && !ctx->opt.localization && select_cap_safe(ctx) && ctx->M.nparts == 1;
+}
+
+static int scan_full_launch(xxm_ctx* ctx, int32_t posSetSize) {
+	const Values V = make_values(ctx, true);
+	if (V.kind != kFinalTable) return ctx->fail("internal: deferred scan needs table values");
+	uint32_t n = 0;
+	size_t cap = 0;
+	TRY(run_scan(ctx, posSetSize, V, 1, ctx->b_seq, ctx->b_pos, ctx->b_vidx, nullptr, &n, true, &cap));
+	CK(ctx->b_pSsnap.ensure(std::max<uint32_t>(1, ctx->nval)));
+	CK(cudaMemcpyAsync(ctx->b_pSsnap.p, ctx->d_pS.p, ctx->nval * 8ull, cudaMemcpyDeviceToDevice, ctx->stream));
+	const uint32_t capN = static_cast<uint32_t>(std::min<size_t>(cap, 0xFFFFFFF0u));
+	CK(ctx->s_keep.ensure(capN));
+	CK(ctx->s_kscore.ensure(capN));
+	CK(ctx->counters.ensure(8));
+	CK(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
+	TRY(launch_select_fwd(ctx, V, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, capN, reinterpret_cast<const unsigned long long*>(ctx->total64.p), 0, ctx->s_keep, ctx->s_kscore));
+	CK(cudaMemcpyAsync(ctx->h_pin + 1, ctx->counters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	ctx->pend.active = true; ctx->pend.cap = capN; ctx->pend.posSetSize = posSetSize; ctx->pend.scanWords = ctx->wordOff[posSetSize];
+	return 0;
+}
+
+// after the stream has been synchronised; *overflow: the site list did not fit its arrays, the scan has to be redone
+static int scan_full_finish(xxm_ctx* ctx, int32_t* nbSites, int32_t* nbBestSites, int32_t* maxSites, bool* overflow) {
+	ctx->pend.active = false;
+	const unsigned long long tot = ctx->h_pin[0];
+	*overflow = tot > ctx->pend.cap;
+	if (*overflow) { ctx->histValid = false; return 0; }
+	const uint32_t n = static_cast<uint32_t>(tot);
+	uint32_t c[2];
+	std::memcpy(c, ctx->h_pin + 1, 8);
+	scan5_stats(ctx, ctx->pend.scanWords, tot);
+	ctx->nBest = n;
+	scan_full_set_best(ctx, n, true);
+	const Values V = make_values(ctx, true);
+	const uint32_t mps = std::min<uint32_t>(c[0], static_cast<uint32_t>(ctx->max_leng / (ctx->tab.span + 1) + 1));
+	scan_full_set_sorted(ctx, V, n, c[0], mps, ctx->pend.posSetSize);
 	*nbSites = ctx->nbSites;
 	*nbBestSites = static_cast<int32_t>(n);
 	*maxSites = ctx->maxSites;

@@ -14,10 +14,10 @@ constexpr uint64_t kValMask = (1ull << 62) - 1;
 // K1  encode: raw codes (0=N,1..4) -> packed stream, generating the reverse strand on the fly
 //     (createRevcomp, seqset.cpp:128-178: S[n+1] = N, S[n+1+k] = complement(S[n+1-k])).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void k_encode(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rawOff, SeqStream S, uint64_t* __restrict__ codes,
-                         uint32_t* __restrict__ nmask, int revcomp) {
-	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-	if (w >= S.nwords + 2) return;
+__global__ void k_encode(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rawOff, SeqStream S, uint32_t w0, uint32_t w1,
+                         uint64_t* __restrict__ codes, uint32_t* __restrict__ nmask, int revcomp) {
+	const uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x;  // words [w0, w1) of the stream
+	if (w >= w1 || w >= S.nwords + 2) return;
 	if (w >= S.nwords) { codes[w] = 0; nmask[w] = 0xFFFFFFFFu; return; }
 	const uint32_t s = find_seq(S, w);
 	const int n = S.len[s];

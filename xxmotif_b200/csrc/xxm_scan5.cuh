@@ -96,15 +96,38 @@ __global__ void __launch_bounds__(kScan5Threads, 1) k_scan5(const uint64_t* __re
 	}
 }
 
-// even/odd mask (bit 16 + t = window 2t, bit t = window 2t + 1) -> window order
-__device__ __forceinline__ uint32_t spread16(uint32_t x) {
-	x = (x | (x << 8)) & 0x00FF00FFu;
-	x = (x | (x << 4)) & 0x0F0F0F0Fu;
-	x = (x | (x << 2)) & 0x33333333u;
-	x = (x | (x << 1)) & 0x55555555u;
+// even/odd mask (bit 16 + t = window 2t, bit t = window 2t + 1) -> window order: a perfect shuffle of the two halves.  One
+// PRMT swaps the halves and the two middle bytes (the first butterfly stage), three xor-swap stages finish it.
+__device__ __forceinline__ uint32_t eo_to_natural(uint32_t m) {
+	uint32_t x = __byte_perm(m, 0u, 0x1302), t;
+	t = (x ^ (x >> 4)) & 0x00F000F0u; x = x ^ t ^ (t << 4);
+	t = (x ^ (x >> 2)) & 0x0C0C0C0Cu; x = x ^ t ^ (t << 2);
+	t = (x ^ (x >> 1)) & 0x22222222u; x = x ^ t ^ (t << 1);
 	return x;
 }
-__device__ __forceinline__ uint32_t eo_to_natural(uint32_t m) { return spread16(m >> 16) | (spread16(m & 0xFFFFu) << 1); }
+
+// One step of the hit extraction for one word, branch free: if r != 0, clear its highest set bit j, move the shared-memory
+// cursor back by one 16-bit slot and store tagk + j there; if r == 0 nothing happens (bfind gives 0xFFFFFFFF, the shift
+// clamps to 0, the store and the cursor update are predicated off).
+__device__ __forceinline__ void pop_msb(uint32_t& r, uint32_t& cursor, uint32_t tagk) {
+	asm volatile(
+		"{\n"
+		".reg .pred p;\n"
+		".reg .u32 j, b, v;\n"
+		".reg .u16 h;\n"
+		"setp.ne.u32 p, %0, 0;\n"
+		"bfind.u32 j, %0;\n"
+		"shl.b32 b, 1, j;\n"
+		"xor.b32 %0, %0, b;\n"
+		"add.u32 v, %2, j;\n"
+		"cvt.u16.u32 h, v;\n"
+		"@p sub.u32 %1, %1, 2;\n"
+		"@p st.shared.u16 [%1], h;\n"
+		"}"
+		: "+r"(r), "+r"(cursor)
+		: "r"(tagk)
+		: "memory");
+}
 
 constexpr int kExpand5Threads = 256;
 constexpr int kExpand5Queue = 4096;
@@ -236,19 +259,19 @@ __global__ void __launch_bounds__(kExpand5Threads) k_expand5(SeqStream S, Model 
 	const uint32_t myOff = woff + incl - cnt;
 	const bool fits = total <= static_cast<uint32_t>(kExpand5Queue);
 	if (fits) {  // the common case: the whole tile fits the queue
-		// one loop over the 128 windows of the thread (two 64-bit halves): the trip count of a warp is the largest hit
-		// count of a lane, not the sum over the four words of the largest per-word counts
-		uint16_t* q = s_q + myOff;
+		// the four words of the thread in lock step, highest window first, every word filling its queue range backwards: the
+		// trip count of a warp is the largest hit count of any of its 128 words
+		uint32_t r0 = h[0], r1 = h[1], r2 = h[2], r3 = h[3];
+		uint32_t q0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_q + myOff)) + 2u * __popc(r0);  // one past the last slot of word 0
+		uint32_t q1 = q0 + 2u * __popc(r1);
+		uint32_t q2 = q1 + 2u * __popc(r2);
+		uint32_t q3 = q2 + 2u * __popc(r3);
 		const uint32_t tag = static_cast<uint32_t>(4 * tid) << 5;
-		uint64_t rem = (static_cast<uint64_t>(h[1]) << 32) | h[0];
-		while (rem) {
-			*q++ = static_cast<uint16_t>(tag + (__ffsll(static_cast<long long>(rem)) - 1));
-			rem &= rem - 1;
-		}
-		rem = (static_cast<uint64_t>(h[3]) << 32) | h[2];
-		while (rem) {
-			*q++ = static_cast<uint16_t>(tag + 64 + (__ffsll(static_cast<long long>(rem)) - 1));
-			rem &= rem - 1;
+		while (r0 | r1 | r2 | r3) {
+			pop_msb(r0, q0, tag);
+			pop_msb(r1, q1, tag + 32);
+			pop_msb(r2, q2, tag + 64);
+			pop_msb(r3, q3, tag + 96);
 		}
 	}
 	__syncthreads();

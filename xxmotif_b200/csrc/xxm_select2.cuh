@@ -17,7 +17,8 @@ struct SelectFwdIO {
 	const uint32_t* seq;
 	const uint32_t* pos;
 	const uint32_t* vidx;
-	uint32_t n;
+	uint32_t n;          // entries, or -- with nDev -- the capacity of the arrays
+	const unsigned long long* nDev;  // non-null: the number of entries is read from the device (written by the expand kernel before this launch)
 	int length;
 	int shift;           // startPos = pos + shift (only matters for the positional prior)
 	float* kscore;       // [n]
@@ -61,7 +62,8 @@ __global__ void __launch_bounds__(256, 4) k_select_mops_fwd(Values V, SelectFwdI
 	const int lane = threadIdx.x & 31;
 	const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
 	const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
-	const uint64_t nchunks = (static_cast<uint64_t>(io.n) + kSelChunk - 1) / kSelChunk;
+	const uint32_t n = io.nDev ? static_cast<uint32_t>(min(*io.nDev, static_cast<unsigned long long>(io.n))) : io.n;
+	const uint64_t nchunks = (static_cast<uint64_t>(n) + kSelChunk - 1) / kSelChunk;
 	uint32_t kept = 0;
 	auto fin_at = [&](int64_t j, uint32_t pj) -> double {
 		const uint32_t v = io.vidx[j];
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(256, 4) k_select_mops_fwd(Values V, SelectFwdI
 	for (uint64_t c0 = warp * 32; c0 < nchunks; c0 += nwarps * 32) {
 		const uint64_t c = c0 + lane;
 		const int64_t j0 = static_cast<int64_t>(c) * kSelChunk;
-		const int m = (c < nchunks) ? static_cast<int>(min(static_cast<uint64_t>(kSelChunk), static_cast<uint64_t>(io.n) - j0)) : 0;
+		const int m = (c < nchunks) ? static_cast<int>(min(static_cast<uint64_t>(kSelChunk), static_cast<uint64_t>(n) - j0)) : 0;
 		uint32_t sq[kSelChunk], ps[kSelChunk], vi[kSelChunk];
 		if (m == kSelChunk) {
 			const uint4 a0 = *reinterpret_cast<const uint4*>(io.seq + j0), a1 = *reinterpret_cast<const uint4*>(io.seq + j0 + 4);
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(256, 4) k_select_mops_fwd(Values V, SelectFwdI
 			// ---- can a later entry still replace my last kept site?
 			if (st.last >= j0) {
 				const uint32_t mySeq = lastSeq;
-				for (int64_t j = j0 + m; j < static_cast<int64_t>(io.n); ++j) {
+				for (int64_t j = j0 + m; j < static_cast<int64_t>(n); ++j) {
 					const uint32_t pj = io.pos[j];
 					if (io.seq[j] != mySeq || pj > st.lastPos + L) break;
 					const double fj = fin_at(j, pj);
