@@ -22,6 +22,7 @@
 #include "xxm_select2.cuh"
 #include "xxm_scan4.cuh"
 #include "xxm_scan5.cuh"
+#include "xxm_scan6.cuh"
 #include "pair_table.h"
 #include "nccl_dyn.h"
 
@@ -145,7 +146,9 @@ struct xxm_ctx {
 	DevBuf<uint64_t> status, total64;
 	DevBuf<uint32_t> r_seq, d_pbits;
 	DevBuf<uint8_t> d_t8, d_raw;
-	DevBuf<uint32_t> d_pairTab;
+	DevBuf<uint32_t> d_pairTab, d_dead, d_scanCounts;
+	std::vector<int> deadKey;   // (load serial, L, column offsets) d_dead was built for
+	uint64_t loadSerial = 0;
 	DevBuf<unsigned long long> d_xchg;  // value-index histogram + scalars on their way through NCCL
 	std::vector<unsigned long long> h_xchg;
 	unsigned long long* h_pinXchg = nullptr;  // pinned landing buffer of the exchange vector / the count matrix
@@ -263,7 +266,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	// DevBuf members are released explicitly (no destructor: the struct is copied nowhere, but keep it trivial)
 	ctx->d_codes.release(); ctx->d_nmask.release(); ctx->d_wordOff.release(); ctx->d_blk2seq.release(); ctx->d_len.release();
 	ctx->d_rank0.release(); ctx->d_rank1.release(); ctx->d_hit0.release(); for (int k = 0; k < 2; ++k) { ctx->d_ids[k].release(); ctx->d_cls[k].release(); ctx->d_clsOk[k].release(); }
-	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_n.release();
+	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_n.release(); ctx->d_dead.release(); ctx->d_scanCounts.release();
 	for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
 	if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream); if (ctx->h_pinXchg) cudaFreeHost(ctx->h_pinXchg); if (ctx->evStage) cudaEventDestroy(ctx->evStage);
 	ctx->d_cpval0.release(); ctx->d_cpval1.release(); ctx->d_leftProb.release(); ctx->d_cscore0.release(); ctx->d_cscore1.release();
@@ -536,6 +539,8 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	if (ctx->d_raw.cap > (8ull << 30)) ctx->d_raw.release();  // the raw codes are only needed for packing
 	if (ctx->sum_i.size() != static_cast<size_t>(ctx->max_leng) + 1) init_sum_i(ctx->sum_i, ctx->max_leng);
 	ctx->haveModel = false;
+	ctx->loadSerial++;
+	ctx->deadKey.clear();
 	for (auto& l : ctx->L) l = SiteList();
 	ctx->nBest = 0;
 	if (trace) {

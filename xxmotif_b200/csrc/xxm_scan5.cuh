@@ -59,8 +59,11 @@ __device__ __forceinline__ uint32_t scan5_word(const uint32_t (&e)[34]) {
 	return acc;
 }
 
+// dead: windows that cannot be a site whatever the PWM (k_dead_mask, xxm_scan6.cuh), cleared here so that the masks are
+// final; chunkCount[c] = hits of the warp's 64 words, tileCount[c / 16] += the same (one atomic per chunk).
 __global__ void __launch_bounds__(kScan5Threads, 1) k_scan5(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ pairTab,
-                                                           uint32_t* __restrict__ hitmask, uint32_t scanWords) {
+                                                           const uint32_t* __restrict__ dead, uint32_t* __restrict__ hitmask,
+                                                           uint32_t* __restrict__ chunkCount, uint32_t* __restrict__ tileCount, uint32_t scanWords) {
 	extern __shared__ __align__(16) uint8_t smem5[];
 	{
 		uint32_t* s = reinterpret_cast<uint32_t*>(smem5);
@@ -91,8 +94,20 @@ __global__ void __launch_bounds__(kScan5Threads, 1) k_scan5(const uint64_t* __re
 		e[24] = pair_lookup<24>(r, tab); e[25] = pair_lookup<25>(r, tab); e[26] = pair_lookup<26>(r, tab); e[27] = pair_lookup<27>(r, tab);
 		e[28] = pair_lookup<28>(r, tab); e[29] = pair_lookup<29>(r, tab); e[30] = pair_lookup<30>(r, tab); e[31] = pair_lookup<31>(r, tab);
 		e[32] = pair_lookup<32>(r, tab); e[33] = pair_lookup<33>(r, tab);
-		const uint32_t h0 = scan5_word<0>(e), h1 = scan5_word<16>(e);
-		if (w < scanWords) *reinterpret_cast<uint2*>(hitmask + w) = make_uint2(h0, h1);
+		uint32_t h0 = scan5_word<0>(e), h1 = scan5_word<16>(e);
+		uint32_t cnt = 0;
+		if (w < scanWords) {
+			const uint2 d = *reinterpret_cast<const uint2*>(dead + w);
+			h0 &= ~d.x;
+			h1 = (w + 1 < scanWords) ? (h1 & ~d.y) : 0u;
+			*reinterpret_cast<uint2*>(hitmask + w) = make_uint2(h0, h1);
+			cnt = __popc(h0) + __popc(h1);
+		}
+		cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+		if (lane == 0) {
+			chunkCount[c] = cnt;
+			if (cnt) atomicAdd(tileCount + (c >> 4), cnt);
+		}
 	}
 }
 
