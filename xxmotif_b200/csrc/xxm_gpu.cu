@@ -142,6 +142,8 @@ struct xxm_ctx {
 	DevBuf<double> b_pSsnap;
 	DevBuf<float> b_score, s_kscore, e_kscore, slotScore, e_slotScore, tmpScore, u_score;
 	DevBuf<uint8_t> s_keep, e_keep, flag8;
+	DevBuf<uint16_t> s_kcls;      // value index per kept entry of sortedSites (0xFFFF: dropped), valid while kclsSerial == the list's histSerial
+	uint64_t kclsSerial = 0;
 	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
 	DevBuf<uint64_t> status, total64;
 	DevBuf<uint32_t> r_seq, d_pbits;
@@ -159,7 +161,7 @@ struct xxm_ctx {
 	std::vector<uint32_t> h_pairIds, h_pairTab;
 	bool pairOK = false;           // the pair table represents the left table exactly: k_scan5, else k_scan4
 	bool forceGenericScan = false; // tests: always take the generic find kernel
-	DevBuf<uint64_t> d_rawOff;
+	DevBuf<uint64_t> d_rawOff, d_layoutSums;
 	DevBuf<int32_t> d_notX, d_n;
 	int32_t* h_notX = nullptr;  // pinned
 	size_t h_notXCap = 0;
@@ -266,7 +268,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	// DevBuf members are released explicitly (no destructor: the struct is copied nowhere, but keep it trivial)
 	ctx->d_codes.release(); ctx->d_nmask.release(); ctx->d_wordOff.release(); ctx->d_blk2seq.release(); ctx->d_len.release();
 	ctx->d_rank0.release(); ctx->d_rank1.release(); ctx->d_hit0.release(); for (int k = 0; k < 2; ++k) { ctx->d_ids[k].release(); ctx->d_cls[k].release(); ctx->d_clsOk[k].release(); }
-	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_n.release(); ctx->d_dead.release(); ctx->d_scanCounts.release();
+	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_n.release(); ctx->d_dead.release(); ctx->d_scanCounts.release(); ctx->s_kcls.release(); ctx->d_layoutSums.release();
 	for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
 	if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream); if (ctx->h_pinXchg) cudaFreeHost(ctx->h_pinXchg); if (ctx->evStage) cudaEventDestroy(ctx->evStage);
 	ctx->d_cpval0.release(); ctx->d_cpval1.release(); ctx->d_leftProb.release(); ctx->d_cscore0.release(); ctx->d_cscore1.release();
@@ -335,41 +337,63 @@ __global__ void k_seq_stats(const uint8_t* __restrict__ raw, const uint64_t* __r
 	}
 }
 
-// layout of the stream from the raw lengths alone (one block): rawOff (bytes), wordOff (words), len (stored length)
-__global__ void __launch_bounds__(1024) k_seq_layout(const int32_t* __restrict__ n, uint32_t nent, int revcomp, uint64_t* __restrict__ rawOff,
-                                                     uint32_t* __restrict__ wordOff, int32_t* __restrict__ len) {
-	__shared__ uint64_t s_raw[1024];
-	__shared__ uint64_t s_wrd[1024];
-	const uint32_t per = (nent + 1023) / 1024;
-	const uint32_t a = min(nent, threadIdx.x * per), b = min(nent, a + per);
-	uint64_t r = 0, w = 0;
-	for (uint32_t i = a; i < b; ++i) {
-		const uint64_t n0 = static_cast<uint64_t>(n[i]);
-		const uint64_t ns = revcomp ? 2 * n0 + 1 : n0;
-		r += n0;
-		w += (ns + kPadBases + 31) / 32;
-	}
-	s_raw[threadIdx.x] = r;
-	s_wrd[threadIdx.x] = w;
+// layout of the stream from the raw lengths alone: rawOff (bytes), wordOff (words), len (stored length).  Two launches over
+// blocks of 1024 sequences: per-block sums, then every block adds up the sums of the blocks before it and scans its own.
+__device__ __forceinline__ void seq_extent(const int32_t* __restrict__ n, uint32_t i, uint32_t nent, int revcomp, uint64_t* raw, uint64_t* words, uint64_t* stored) {
+	const uint64_t n0 = (i < nent) ? static_cast<uint64_t>(n[i]) : 0ull;
+	const uint64_t ns = revcomp ? 2 * n0 + 1 : n0;
+	*raw = n0;
+	*stored = ns;
+	*words = (i < nent) ? (ns + kPadBases + 31) / 32 : 0ull;
+}
+__global__ void __launch_bounds__(1024) k_seq_layout_sums(const int32_t* __restrict__ n, uint32_t nent, int revcomp, uint64_t* __restrict__ sums) {
+	__shared__ uint64_t s_r[32], s_w[32];
+	const uint32_t i = blockIdx.x * 1024u + threadIdx.x, lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	uint64_t r, w, st;
+	seq_extent(n, i, nent, revcomp, &r, &w, &st);
+#pragma unroll
+	for (int d = 16; d; d >>= 1) { r += __shfl_xor_sync(0xFFFFFFFFu, r, d); w += __shfl_xor_sync(0xFFFFFFFFu, w, d); }
+	if (lane == 0) { s_r[wid] = r; s_w[wid] = w; }
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		uint64_t ar = 0, aw = 0;
-		for (int t = 0; t < 1024; ++t) { const uint64_t x = s_raw[t], y = s_wrd[t]; s_raw[t] = ar; s_wrd[t] = aw; ar += x; aw += y; }
-		rawOff[nent] = ar;
-		wordOff[nent] = static_cast<uint32_t>(aw);
+		for (int k = 0; k < 32; ++k) { ar += s_r[k]; aw += s_w[k]; }
+		sums[2 * blockIdx.x] = ar;
+		sums[2 * blockIdx.x + 1] = aw;
 	}
+}
+__global__ void __launch_bounds__(1024) k_seq_layout(const int32_t* __restrict__ n, uint32_t nent, int revcomp, const uint64_t* __restrict__ sums,
+                                                     uint64_t* __restrict__ rawOff, uint32_t* __restrict__ wordOff, int32_t* __restrict__ len) {
+	__shared__ uint64_t s_r[32], s_w[32], s_pr[32], s_pw[32];
+	const uint32_t i = blockIdx.x * 1024u + threadIdx.x, lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+	uint64_t pr = 0, pw = 0;  // everything before this block
+	for (uint32_t b = threadIdx.x; b < blockIdx.x; b += 1024u) { pr += sums[2 * b]; pw += sums[2 * b + 1]; }
+#pragma unroll
+	for (int d = 16; d; d >>= 1) { pr += __shfl_xor_sync(0xFFFFFFFFu, pr, d); pw += __shfl_xor_sync(0xFFFFFFFFu, pw, d); }
+	uint64_t r, w, st;
+	seq_extent(n, i, nent, revcomp, &r, &w, &st);
+	uint64_t ir = r, iw = w;  // inclusive scans inside the warp
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint64_t a = __shfl_up_sync(0xFFFFFFFFu, ir, d), b2 = __shfl_up_sync(0xFFFFFFFFu, iw, d);
+		if (lane >= static_cast<uint32_t>(d)) { ir += a; iw += b2; }
+	}
+	if (lane == 0) { s_pr[wid] = pr; s_pw[wid] = pw; }
+	if (lane == 31) { s_r[wid] = ir; s_w[wid] = iw; }
 	__syncthreads();
-	r = s_raw[threadIdx.x];
-	w = s_wrd[threadIdx.x];
-	for (uint32_t i = a; i < b; ++i) {
-		const uint64_t n0 = static_cast<uint64_t>(n[i]);
-		const uint64_t ns = revcomp ? 2 * n0 + 1 : n0;
-		rawOff[i] = r;
-		wordOff[i] = static_cast<uint32_t>(w);
-		len[i] = static_cast<int32_t>(ns);
-		r += n0;
-		w += (ns + kPadBases + 31) / 32;
+	uint64_t br = 0, bw = 0;
+#pragma unroll
+	for (int k = 0; k < 32; ++k) {
+		br += s_pr[k]; bw += s_pw[k];
+		if (static_cast<uint32_t>(k) < wid) { br += s_r[k]; bw += s_w[k]; }
 	}
+	const uint64_t er = br + ir - r, ew = bw + iw - w;  // exclusive
+	if (i < nent) {
+		rawOff[i] = er;
+		wordOff[i] = static_cast<uint32_t>(ew);
+		len[i] = static_cast<int32_t>(st);
+	}
+	if (i + 1 == nent) { rawOff[nent] = er + r; wordOff[nent] = static_cast<uint32_t>(ew + w); }
 }
 
 // coarse word -> sequence index: blk2seq[b] = the sequence that owns word b * kBlkWords
@@ -407,8 +431,15 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	CK(ctx->counters.ensure(8));
 	CK(cudaMemsetAsync(ctx->counters.p, 0, 32, ctx->stream));
 	CK(cudaMemcpyAsync(ctx->d_n.p, n, static_cast<size_t>(nent) * 4, cudaMemcpyHostToDevice, ctx->stream));
-	k_seq_layout<<<1, 1024, 0, ctx->stream>>>(ctx->d_n.p, static_cast<uint32_t>(nent), revcomp ? 1 : 0, ctx->d_rawOff.p, ctx->d_wordOff.p, ctx->d_len.p);
-	CKK();
+	{
+		const uint32_t nb = cdiv(static_cast<uint32_t>(nent), 1024);
+		CK(ctx->d_layoutSums.ensure(2ull * nb));
+		k_seq_layout_sums<<<nb, 1024, 0, ctx->stream>>>(ctx->d_n.p, static_cast<uint32_t>(nent), revcomp ? 1 : 0, ctx->d_layoutSums.p);
+		CKK();
+		k_seq_layout<<<nb, 1024, 0, ctx->stream>>>(ctx->d_n.p, static_cast<uint32_t>(nent), revcomp ? 1 : 0, ctx->d_layoutSums.p, ctx->d_rawOff.p,
+		                                            ctx->d_wordOff.p, ctx->d_len.p);
+		CKK();
+	}
 	// ---- sizes first (no stores: a fraction of a millisecond per million sequences), so that the buffers exist before the first chunk leaves
 	uint64_t off = 0, words = 0;
 	int mx = 0, mn = 2147483647;
@@ -954,8 +985,13 @@ static int compact_list(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, 
 // forward-only overlap removal (k_select_mops_fwd) with the class histogram fused in; nDev != nullptr: n is the capacity
 // and the entry count is read on the device
 static int launch_select_fwd(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, uint32_t n,
-                             const unsigned long long* nDev, int shift, DevBuf<uint8_t>& keep, DevBuf<float>& kscore) {
+                             const unsigned long long* nDev, int shift, DevBuf<uint8_t>& keep, DevBuf<float>& kscore, DevBuf<uint16_t>* kcls = nullptr) {
 	SelectFwdIO f{};
+	ctx->kclsSerial = 0;
+	if (kcls && V.kind == kFinalTable && ctx->nval < 0xFFFFu) {
+		CK(kcls->ensure(std::max<uint32_t>(8, n) + 8));
+		f.kcls = kcls->p;
+	}
 	f.seq = seq; f.pos = pos; f.vidx = vidx; f.n = n; f.nDev = nDev; f.length = ctx->tab.span; f.shift = shift; f.kscore = kscore.p; f.keep = keep.p;
 	f.counters = ctx->counters.p;
 	const bool wantHist = (V.kind == kFinalTable);
@@ -971,6 +1007,7 @@ static int launch_select_fwd(xxm_ctx* ctx, const Values& V, const uint32_t* seq,
 	CKK();
 	ctx->histValid = wantHist;
 	ctx->histSerial = ++ctx->histCounter;
+	if (f.kcls) ctx->kclsSerial = ctx->histSerial;
 	return 0;
 }
 
@@ -1120,7 +1157,8 @@ static int scan_full_launch(xxm_ctx* ctx, int32_t posSetSize) {
 	CK(ctx->s_kscore.ensure(capN));
 	CK(ctx->counters.ensure(8));
 	CK(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
-	TRY(launch_select_fwd(ctx, V, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, capN, reinterpret_cast<const unsigned long long*>(ctx->total64.p), 0, ctx->s_keep, ctx->s_kscore));
+	TRY(launch_select_fwd(ctx, V, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, capN, reinterpret_cast<const unsigned long long*>(ctx->total64.p), 0, ctx->s_keep, ctx->s_kscore,
+	                      &ctx->s_kcls));
 	CK(cudaMemcpyAsync(ctx->h_pin + 1, ctx->counters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	ctx->pend.active = true; ctx->pend.cap = capN; ctx->pend.posSetSize = posSetSize; ctx->pend.scanWords = ctx->wordOff[posSetSize];
 	return 0;

@@ -385,6 +385,8 @@ struct CountIO {
 	const float* slotScore;
 	uint32_t n;
 	float thr;
+	const uint16_t* kcls;       // k_count_pwm3: value index of every kept entry, 0xFFFF for dropped ones; chosen if <= maxClass
+	uint32_t maxClass;
 	int firstColumn;            // motifColumns.front(): pos - firstColumn + 1 is the position of PWM column 1
 	unsigned long long* counts; // [31*5] zeroed
 };

@@ -23,6 +23,7 @@ struct SelectFwdIO {
 	int shift;           // startPos = pos + shift (only matters for the positional prior)
 	float* kscore;       // [n]
 	uint8_t* keep;       // [n] (every entry is written)
+	uint16_t* kcls;      // [n] or null: value index of a kept entry, 0xFFFF for a dropped one (what k_count_pwm3 scans)
 	uint32_t* counters;  // [0] += kept sites
 	uint32_t* hist;      // [nval] zeroed, or null
 	uint32_t nval;
@@ -151,10 +152,24 @@ __global__ void __launch_bounds__(256, 4) k_select_mops_fwd(Values V, SelectFwdI
 				*reinterpret_cast<uint2*>(io.keep + j0) = kb;
 				*reinterpret_cast<float4*>(io.kscore + j0) = make_float4(static_cast<float>(fin[0]), static_cast<float>(fin[1]), static_cast<float>(fin[2]), static_cast<float>(fin[3]));
 				*reinterpret_cast<float4*>(io.kscore + j0 + 4) = make_float4(static_cast<float>(fin[4]), static_cast<float>(fin[5]), static_cast<float>(fin[6]), static_cast<float>(fin[7]));
+				if (io.kcls) {
+					uint32_t cw[4];
+#pragma unroll
+					for (int k = 0; k < 4; ++k) {
+						const uint32_t lo = ((keepBits >> (2 * k)) & 1u) ? (vi[2 * k] & 0xFFFFu) : 0xFFFFu;
+						const uint32_t hi = ((keepBits >> (2 * k + 1)) & 1u) ? (vi[2 * k + 1] & 0xFFFFu) : 0xFFFFu;
+						cw[k] = lo | (hi << 16);
+					}
+					*reinterpret_cast<uint4*>(io.kcls + j0) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+				}
 			} else {
 #pragma unroll
 				for (int k = 0; k < kSelChunk; ++k)
-					if (k < m) { io.keep[j0 + k] = (keepBits >> k) & 1u; io.kscore[j0 + k] = static_cast<float>(fin[k]); }
+					if (k < m) {
+						io.keep[j0 + k] = (keepBits >> k) & 1u;
+						io.kscore[j0 + k] = static_cast<float>(fin[k]);
+						if (io.kcls) io.kcls[j0 + k] = ((keepBits >> k) & 1u) ? static_cast<uint16_t>(vi[k]) : static_cast<uint16_t>(0xFFFFu);
+					}
 			}
 			kept += __popc(keepBits);
 		}
@@ -178,9 +193,11 @@ __global__ void __launch_bounds__(256, 4) k_select_mops_fwd(Values V, SelectFwdI
 // that cover the 30-column context (all 32 sites' loads in flight together), aligns them to PWM column 1, and the warp
 // then counts column by column with three ballots (valid, base bit 0, base bit 1).  Lane j keeps the five counters of
 // PWM column j in registers, so there are no atomics until the warp is done.
-__device__ __forceinline__ void count_batch(const SeqStream& S, const CountIO& io, const uint32_t* buf, int m, int lane, uint32_t (&c)[5]) {
-	uint64_t bases = 0;          // 2 bits per PWM column, column 1 in bits [1:0]
-	uint32_t bad = 0xFFFFFFFFu;  // bit j: PWM column j + 1 is outside the sequence or holds an N
+// the 30-column context of the site in buf[lane]: bases = 2 bits per PWM column (column 1 in bits [1:0]); bit j of bad: PWM
+// column j + 1 is outside the sequence or holds an N
+__device__ __forceinline__ void site_context(const SeqStream& S, const CountIO& io, const uint32_t* buf, int m, int lane, uint64_t* basesOut, uint32_t* badOut) {
+	uint64_t bases = 0;
+	uint32_t bad = 0xFFFFFFFFu;
 	if (lane < m) {
 		const uint32_t i = buf[lane];
 		const uint32_t s = io.seq[i] - 1;
@@ -205,6 +222,14 @@ __device__ __forceinline__ void count_batch(const SeqStream& S, const CountIO& i
 			bad = static_cast<uint32_t>(nmv);
 		}
 	}
+	*basesOut = bases;
+	*badOut = bad;
+}
+
+__device__ __forceinline__ void count_batch(const SeqStream& S, const CountIO& io, const uint32_t* buf, int m, int lane, uint32_t (&c)[5]) {
+	uint64_t bases;
+	uint32_t bad;
+	site_context(S, io, buf, m, lane, &bases, &bad);
 #pragma unroll
 	for (int j = 0; j < 30; ++j) {
 		const uint32_t mv = __ballot_sync(0xFFFFFFFFu, !((bad >> j) & 1u));
@@ -263,6 +288,94 @@ __global__ void __launch_bounds__(256) k_count_pwm2(SeqStream S, CountIO io) {
 	__syncthreads();
 	for (int k = threadIdx.x; k < 31 * 5; k += blockDim.x)
 		if (s_cnt[k]) atomicAdd(&io.counts[k], static_cast<unsigned long long>(s_cnt[k]));
+}
+
+// One site per lane, counted with shared-memory atomics: at step t lane l handles PWM column (t + l) mod 30, so the 32 lanes
+// of a step hit different columns.  Only the four base counters are kept; the column total ([.][0]) is their sum.
+__device__ __forceinline__ void count_batch3(const SeqStream& S, const CountIO& io, const uint32_t* buf, int m, int lane, unsigned int* s_cnt) {
+	uint64_t bases;
+	uint32_t bad;
+	site_context(S, io, buf, m, lane, &bases, &bad);
+	if (bad == 0xFFFFFFFFu) return;
+	const uint32_t lo = static_cast<uint32_t>(bases), hi = static_cast<uint32_t>(bases >> 32);
+	int j = lane % 30;
+#pragma unroll 6
+	for (int t = 0; t < 30; ++t) {
+		const uint32_t b = (j < 16 ? lo >> (2 * j) : hi >> (2 * j - 32)) & 3u;
+		if (!((bad >> j) & 1u)) atomicAdd(&s_cnt[(j + 1) * 5 + 1 + b], 1u);
+		j = (j == 29) ? 0 : j + 1;
+	}
+}
+
+// The same counts from the compact class array the select kernel leaves behind: a lane reads eight entries at a time
+// (16 bytes), the few chosen ones (value index <= maxClass; dropped entries carry 0xFFFF) are parked per warp, and
+// count_batch takes them 32 at a time.
+__global__ void __launch_bounds__(256) k_count_pwm3(SeqStream S, CountIO io) {
+	__shared__ unsigned int s_cnt[31 * 5];
+	__shared__ uint32_t s_buf[8][32 + 256];
+	for (int k = threadIdx.x; k < 31 * 5; k += blockDim.x) s_cnt[k] = 0;
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+	uint32_t* buf = s_buf[wid];
+	uint32_t npend = 0;
+	// two 16-bit entries per compare: with maxClass < 0x8000, (maxClass + 0x8000) - (entry & 0x7FFF) keeps bit 15 set iff
+	// (entry & 0x7FFF) <= maxClass, and no borrow crosses into the upper half; entries >= 0x8000 (0xFFFF = dropped) are masked out
+	const uint32_t thr2 = (io.maxClass | (io.maxClass << 16)) | 0x80008000u;
+	for (uint64_t t0 = static_cast<uint64_t>(warp) * 256; t0 < io.n; t0 += static_cast<uint64_t>(nwarps) * 256) {
+		const uint64_t i0 = t0 + 8ull * lane;
+		uint32_t m = 0;  // bit k: entry i0 + k is chosen
+		if (i0 + 8 <= io.n) {
+			const uint4 q = *reinterpret_cast<const uint4*>(io.kcls + i0);
+			const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const uint32_t le = (thr2 - (w4[k] & 0x7FFF7FFFu)) & ~w4[k] & 0x80008000u;
+				m |= ((le >> 15) & 1u) << (2 * k);
+				m |= (le >> 31) << (2 * k + 1);
+			}
+		} else {
+			for (int k = 0; k < 8; ++k)
+				if (i0 + k < io.n && io.kcls[i0 + k] <= io.maxClass) m |= 1u << k;
+		}
+		const uint32_t cnt = __popc(m);
+		uint32_t incl = cnt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+			if (lane >= d) incl += v;
+		}
+		const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+		if (total == 0) continue;
+		uint32_t o = npend + incl - cnt;
+		while (m) {
+			const int k = __ffs(m) - 1;
+			m &= m - 1;
+			buf[o++] = static_cast<uint32_t>(i0) + k;
+		}
+		npend += total;
+		__syncwarp();
+		uint32_t head = 0;
+		while (npend >= 32) {
+			count_batch3(S, io, buf + head, 32, lane, s_cnt);
+			head += 32;
+			npend -= 32;
+		}
+		if (head) {
+			__syncwarp();
+			const uint32_t rest = (static_cast<uint32_t>(lane) < npend) ? buf[head + lane] : 0u;
+			__syncwarp();
+			buf[lane] = rest;
+			__syncwarp();
+		}
+	}
+	if (npend) count_batch3(S, io, buf, static_cast<int>(npend), lane, s_cnt);
+	__syncthreads();
+	for (int k = threadIdx.x; k < 31 * 5; k += blockDim.x) {
+		const unsigned int v = (k % 5 == 0) ? (s_cnt[k + 1] + s_cnt[k + 2] + s_cnt[k + 3] + s_cnt[k + 4]) : s_cnt[k];
+		if (v) atomicAdd(&io.counts[k], static_cast<unsigned long long>(v));
+	}
 }
 
 }  // namespace xxm
