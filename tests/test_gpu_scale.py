@@ -188,13 +188,7 @@ def test_shard_invariance():
         whole.close(); a.close(); b.close()
 
 
-@pytest.mark.parametrize("revcomp,mops", [(False, False), (False, True), (True, True)])
-def test_low_complexity_ragged_vs_oracle(revcomp, mops):
-    """Stress case for the scan machinery: ragged lengths, long TA repeats and poly-A runs (hit clusters hundreds of entries
-    long, tiles with more hits than the expand queue holds), N runs at sequence ends -- bit-exact against the oracle."""
-    import oracle_lib as ol
-    import xxmotif_b200 as xb
-    from xxmotif_b200 import hostprep
+def _low_complexity_set():
     rng = np.random.default_rng(5)
     nseq = 1500
     lens = rng.integers(40, 900, size=nseq).astype(np.int32)
@@ -220,6 +214,17 @@ def test_low_complexity_ragged_vs_oracle(revcomp, mops):
         parts.append(s)
     codes = np.concatenate(parts)
     n = lens
+    return n, codes
+
+
+@pytest.mark.parametrize("revcomp,mops", [(False, False), (False, True), (True, True)])
+def test_low_complexity_ragged_vs_oracle(revcomp, mops):
+    """Stress case for the scan machinery: ragged lengths, long TA repeats and poly-A runs (hit clusters hundreds of entries
+    long, tiles with more hits than the expand queue holds), N runs at sequence ends -- bit-exact against the oracle."""
+    import oracle_lib as ol
+    import xxmotif_b200 as xb
+    from xxmotif_b200 import hostprep
+    n, codes = _low_complexity_set()
     if revcomp:
         n2, c2 = hostprep.revcomp_double(n, codes)
     else:
@@ -251,6 +256,44 @@ def test_low_complexity_ragged_vs_oracle(revcomp, mops):
             ok, nbm, bp, new = ctx.update_pwm_with_best_subset(xb.LIST_SORTED_SITES, pwm, int(cols[0]), nent, False, 0.1)
             ook, onbm, obp, onew = octx.update_pwm_with_best_subset(0, pwm, cols, nent, 0, False, 0.1)
             assert (ok, nbm, bp) == (ook, onbm, obp)
+            assert (new[5:] == onew[5:]).all()
+            pwm = new
+    finally:
+        ctx.close()
+
+
+@pytest.mark.parametrize("mops", [False, True])
+def test_native_step_low_complexity_vs_oracle(mops):
+    """The one-call native step (deferred scan, class-index overlap removal k_select_cls_fwd, lazy float scores) on the
+    stress set: kept sites, their scores, subset choice and the new PWM bit-exact against the oracle, twice in a row."""
+    import oracle_lib as ol
+    import xxmotif_b200 as xb
+    from xxmotif_b200 import hostprep, sharded
+    n, codes = _low_complexity_set()
+    bg, bgl = hostprep.background(n, codes)
+    rp, rc = hostprep.null_model(n, codes, order=2)
+    ctx = xb.Context(0)
+    try:
+        ctx.set_options(mops=mops, bg=bg, bgLog=bgl)
+        ctx.set_background(2, rp, rc)
+        ctx.load_seqset(n, codes, revcomp=False)
+        oset = ol.SeqSet(n, codes, revcomp=False)
+        onm = ol.NullModel(order=2, rprobs=rp, rconds=rc)
+        octx = ol.Ctx(oset, False, mops, False, False, bg, bgl)
+        total, avg, mxl, mnl = ctx.seqset_info()
+        pwm, cols = hostprep.profile_pwm()
+        nent = len(n)
+        enr = (1 - int(cols[0]) + 1, mxl - int(cols[0]) + 1)
+        job = sharded.ShardedRefinement(ctx, None, nent_local=nent, total_local=int(total[nent]), pseudo=0.1, bg=bg, native=True)
+        for it in range(3):
+            new, info = job.optimize_step(pwm, cols, enr)
+            tab = ol.Tables(pwm, cols, nent, int(total[nent]), bgl, onm)
+            octx.scan_full(tab, cols, nent, enr, True)
+            assert (info["nbSites"], info["nbBestSites"], info["maxSites"]) == (octx.nbSites, octx.nbBestSites, octx.maxSites)
+            _site_eq("sites", ctx.get_sites(xb.LIST_SORTED_SITES, xb.ORDER_AS_IS, cap=info["nbSites"] + 8), octx.sites())
+            _site_eq("best", ctx.get_sites(xb.LIST_BEST_STARTPOS, xb.ORDER_BY_SCORE, cap=info["nbBestSites"] + 8), octx.best())
+            ook, onbm, obp, onew = octx.update_pwm_with_best_subset(0, pwm, cols, nent, 0, False, 0.1)
+            assert (info["bestMotifNb"], info["bestPval"]) == (onbm, obp)
             assert (new[5:] == onew[5:]).all()
             pwm = new
     finally:

@@ -20,6 +20,7 @@
 #include "pvalue_tables.h"
 #include "xxm_kernels.cuh"
 #include "xxm_select2.cuh"
+#include "xxm_select3.cuh"
 #include "xxm_scan4.cuh"
 #include "xxm_scan5.cuh"
 #include "xxm_scan6.cuh"
@@ -70,6 +71,7 @@ struct SiteList {
 	uint64_t modelSerial = 0;
 	uint64_t histSerial = 0;        // != 0: ctx->hist already holds this list's value-index histogram (fused into the select kernel)
 	const double* lazyPS = nullptr; // score == nullptr: float(lazyPS[vidx]) on demand (snapshot of the pS table of the scan's model)
+	int lazyDst = 0;                // where ensure_scores writes them: 0 = b_score (bestStartPos), 1 = s_kscore (sortedSites)
 };
 
 }  // namespace
@@ -144,6 +146,12 @@ struct xxm_ctx {
 	DevBuf<uint8_t> s_keep, e_keep, flag8;
 	DevBuf<uint16_t> s_kcls;      // value index per kept entry of sortedSites (0xFFFF: dropped), valid while kclsSerial == the list's histSerial
 	uint64_t kclsSerial = 0;
+	// class order of the current one-table model (stage_class_order): fin[] non-decreasing, T[k] and the number of site classes
+	std::vector<uint16_t> h_clsThr;
+	DevBuf<uint16_t> d_clsThr;
+	bool clsOrderOK = false;
+	uint32_t clsNSite = 0;
+	bool sortedLazy = false;      // the last deferred scan left sortedSites' float scores implicit (k_select_cls_fwd)
 	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
 	DevBuf<uint64_t> status, total64;
 	DevBuf<uint32_t> r_seq, d_pbits;
@@ -268,7 +276,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	// DevBuf members are released explicitly (no destructor: the struct is copied nowhere, but keep it trivial)
 	ctx->d_codes.release(); ctx->d_nmask.release(); ctx->d_wordOff.release(); ctx->d_blk2seq.release(); ctx->d_len.release();
 	ctx->d_rank0.release(); ctx->d_rank1.release(); ctx->d_hit0.release(); for (int k = 0; k < 2; ++k) { ctx->d_ids[k].release(); ctx->d_cls[k].release(); ctx->d_clsOk[k].release(); }
-	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_n.release(); ctx->d_dead.release(); ctx->d_scanCounts.release(); ctx->s_kcls.release(); ctx->d_layoutSums.release();
+	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_n.release(); ctx->d_dead.release(); ctx->d_scanCounts.release(); ctx->s_kcls.release(); ctx->d_clsThr.release(); ctx->d_layoutSums.release();
 	for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
 	if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream); if (ctx->h_pinXchg) cudaFreeHost(ctx->h_pinXchg); if (ctx->evStage) cudaEventDestroy(ctx->evStage);
 	ctx->d_cpval0.release(); ctx->d_cpval1.release(); ctx->d_leftProb.release(); ctx->d_cscore0.release(); ctx->d_cscore1.release();
@@ -730,6 +738,26 @@ extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* 
 	if (r) { ctx->batching = false; ctx->upSegs.clear(); ctx->fillJobs.clear(); ctx->haveModel = false; }
 	return r;
 }
+// Order of the score classes under the mops finalPval table (what a full scan compares, StartPosUpdater-inl.h:99):
+// updateMultOcc's test "(double)float(fin[kept]) <= fin[incoming]" (StartPosUtils.h:18) becomes "incoming >= T[kept]" on class
+// indices when fin[] is non-decreasing in the class index -- checked here, k_select_cls_fwd is used only if it holds.
+static int stage_class_order(xxm_ctx* ctx) {
+	const std::vector<double>& fin = ctx->h_finalMops;
+	const size_t nc = fin.size();
+	ctx->clsOrderOK = nc > 0 && nc <= 4096;
+	for (size_t c = 1; c < nc && ctx->clsOrderOK; ++c)
+		if (!(fin[c - 1] <= fin[c])) ctx->clsOrderOK = false;
+	if (!ctx->clsOrderOK) return 0;
+	ctx->h_clsThr.resize(nc);
+	for (size_t k = 0; k < nc; ++k) {
+		const double f = static_cast<double>(static_cast<float>(fin[k]));
+		ctx->h_clsThr[k] = static_cast<uint16_t>(std::lower_bound(fin.begin(), fin.end(), f) - fin.begin());
+	}
+	ctx->clsNSite = static_cast<uint32_t>(std::lower_bound(fin.begin(), fin.end(), 1.0) - fin.begin());
+	TRY(upload(ctx, ctx->d_clsThr, ctx->h_clsThr));
+	return 0;
+}
+
 static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions) {
 	CK(cudaSetDevice(ctx->device));
 	if (!ctx->nent) return ctx->fail("no sequence set loaded");
@@ -782,7 +810,9 @@ static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* col
 		TRY(upload(ctx, ctx->d_pS, ctx->h_pS));
 		TRY(upload(ctx, ctx->d_finalMops, ctx->h_finalMops));
 		TRY(upload(ctx, ctx->d_finalMode, ctx->h_finalMode));
+		TRY(stage_class_order(ctx));
 	} else {
+		ctx->clsOrderOK = false;
 		TRY(stage_part(ctx, T.part[1], false, ctx->d_rank1, nullptr, 1));
 		M.rank1 = ctx->d_rank1.p;
 		TRY(upload(ctx, ctx->d_cpval1, T.part[1].classPval));
@@ -1011,6 +1041,27 @@ static int launch_select_fwd(xxm_ctx* ctx, const Values& V, const uint32_t* seq,
 	return 0;
 }
 
+// the same on class indices (k_select_cls_fwd, xxm_select3.cuh): mops table values of a one-table model with a verified
+// class order; no float scores are written
+static int launch_select_cls(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, uint32_t n, const unsigned long long* nDev,
+                             DevBuf<uint8_t>& keep, DevBuf<uint16_t>& kcls) {
+	SelectClsIO f{};
+	CK(kcls.ensure(std::max<uint32_t>(8, n) + 8));
+	CK(ctx->hist.ensure(std::max<uint32_t>(1, ctx->nval)));
+	CK(cudaMemsetAsync(ctx->hist.p, 0, ctx->nval * 4ull, ctx->stream));
+	f.seq = seq; f.pos = pos; f.vidx = vidx; f.n = n; f.nDev = nDev; f.length = ctx->tab.span;
+	f.clsThr = ctx->d_clsThr.p; f.nSite = ctx->clsNSite; f.nval = ctx->nval;
+	f.keep = keep.p; f.kcls = kcls.p; f.counters = ctx->counters.p; f.hist = ctx->hist.p;
+	uint32_t grid = static_cast<uint32_t>(ctx->numSMs) * 16;
+	if (!nDev) grid = std::min<uint32_t>(cdiv(n, 256 * kSelChunk), grid);
+	k_select_cls_fwd<<<grid, 32 * kSel3Warps, ctx->nval * 6ull, ctx->stream>>>(f);
+	CKK();
+	ctx->histValid = true;
+	ctx->histSerial = ++ctx->histCounter;
+	ctx->kclsSerial = ctx->histSerial;
+	return 0;
+}
+
 static bool select_cap_safe(const xxm_ctx* ctx) { return ctx->max_leng / (ctx->tab.span + 1) + 1 <= ctx->opt.maxMotifsPerSequence; }
 
 static int select_mops(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, uint32_t n, int shift, bool ordered,
@@ -1079,10 +1130,12 @@ static void scan_full_set_best(xxm_ctx* ctx, uint32_t n, bool lazyScores) {
 	B.modelSerial = ctx->modelSerial;
 }
 
-static void scan_full_set_sorted(xxm_ctx* ctx, const Values& V, uint32_t n, uint32_t kept, uint32_t mps, int posSetSize) {
+static void scan_full_set_sorted(xxm_ctx* ctx, const Values& V, uint32_t n, uint32_t kept, uint32_t mps, int posSetSize, bool lazyScores = false) {
 	SiteList& Sd = ctx->L[XXM_LIST_SORTED_SITES];
 	Sd = SiteList();
-	Sd.kind = kListFlagged; Sd.seq = ctx->b_seq.p; Sd.pos = ctx->b_pos.p; Sd.vidx = ctx->b_vidx.p; Sd.n = n; Sd.score = ctx->s_kscore.p;
+	Sd.kind = kListFlagged; Sd.seq = ctx->b_seq.p; Sd.pos = ctx->b_pos.p; Sd.vidx = ctx->b_vidx.p; Sd.n = n; Sd.score = lazyScores ? nullptr : ctx->s_kscore.p;
+	// (one table, no localization: the mops finalPval of a class is its pS, so the snapshot of the pS table serves both lists)
+	Sd.lazyPS = lazyScores ? ctx->b_pSsnap.p : nullptr; Sd.lazyDst = 1;
 	Sd.keep = ctx->s_keep.p; Sd.members = kept; Sd.maxPerSeq = mps; Sd.tableValued = (V.kind == kFinalTable); Sd.modelSerial = ctx->modelSerial;
 	Sd.histSerial = ctx->histValid ? ctx->histSerial : 0;
 	ctx->nbSites = static_cast<int>(kept);
@@ -1157,8 +1210,12 @@ static int scan_full_launch(xxm_ctx* ctx, int32_t posSetSize) {
 	CK(ctx->s_kscore.ensure(capN));
 	CK(ctx->counters.ensure(8));
 	CK(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
-	TRY(launch_select_fwd(ctx, V, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, capN, reinterpret_cast<const unsigned long long*>(ctx->total64.p), 0, ctx->s_keep, ctx->s_kscore,
-	                      &ctx->s_kcls));
+	ctx->sortedLazy = ctx->clsOrderOK && ctx->M.nparts == 1 && V.finalTab == ctx->d_finalMops.p && !std::getenv("XXM_NO_CLS_SELECT");
+	if (ctx->sortedLazy)
+		TRY(launch_select_cls(ctx, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, capN, reinterpret_cast<const unsigned long long*>(ctx->total64.p), ctx->s_keep, ctx->s_kcls));
+	else
+		TRY(launch_select_fwd(ctx, V, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, capN, reinterpret_cast<const unsigned long long*>(ctx->total64.p), 0, ctx->s_keep,
+		                      ctx->s_kscore, &ctx->s_kcls));
 	CK(cudaMemcpyAsync(ctx->h_pin + 1, ctx->counters.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	ctx->pend.active = true; ctx->pend.cap = capN; ctx->pend.posSetSize = posSetSize; ctx->pend.scanWords = ctx->wordOff[posSetSize];
 	return 0;
@@ -1178,7 +1235,7 @@ static int scan_full_finish(xxm_ctx* ctx, int32_t* nbSites, int32_t* nbBestSites
 	scan_full_set_best(ctx, n, true);
 	const Values V = make_values(ctx, true);
 	const uint32_t mps = std::min<uint32_t>(c[0], static_cast<uint32_t>(ctx->max_leng / (ctx->tab.span + 1) + 1));
-	scan_full_set_sorted(ctx, V, n, c[0], mps, ctx->pend.posSetSize);
+	scan_full_set_sorted(ctx, V, n, c[0], mps, ctx->pend.posSetSize, ctx->sortedLazy);
 	*nbSites = ctx->nbSites;
 	*nbBestSites = static_cast<int32_t>(n);
 	*maxSites = ctx->maxSites;
