@@ -260,6 +260,22 @@ int xxm_get_stats(const xxm_ctx* ctx, xxm_stats* out);
 /* the CUDA stream the context launches on, as a cudaStream_t cast to void* (for external event timing) */
 void* xxm_stream(const xxm_ctx* ctx);
 
+/* ---- 8(f) row 3: k-mer counting for the background models, on the device -------------------------------------------------
+ * xxm_kmer_counts replaces the counting loop of NullModel::init (NullModel.cpp:122-132) over the sequence set loaded by
+ * xxm_load_seqset (as stored: with revcomp the doubled sequences, like the reference after createRevcomp): counts[] is
+ * indexed like NullModel::_counts (sub2ind, base 5, digits 1..4 = ACGT, first character most significant) and needs
+ * nfields >= 1 + 5 + ... + 5^(order+1) entries; exact 64-bit counts (the reference's float counters saturate at 2^24, which
+ * xxm_null_model_from_counts reproduces).  last_ms (may be NULL): device time of the histogram passes.
+ * xxm_null_model_from_counts: the rest of NullModel::init (NullModel.cpp:134-201) on the host, float arithmetic in the
+ *   reference's order -> the two 2^(3(order+1)) float tables xxm_set_background takes.
+ * xxm_null_model_from_seqset = the two together; xxm_background_from_seqset: posBg/negBg and their logs (checkSequenceSet,
+ *   backgroundDistribution.cpp:50-95) from the same device counts. */
+int xxm_kmer_counts(xxm_ctx* ctx, int32_t order, uint64_t* counts, int64_t nfields);
+int xxm_kmer_counts_ms(const xxm_ctx* ctx, float* last_ms);
+int xxm_null_model_from_counts(const uint64_t* counts, int32_t order, float alpha, float beta, float* rprobs, float* rconds);
+int xxm_null_model_from_seqset(xxm_ctx* ctx, int32_t order, float alpha, float beta, float* rprobs, float* rconds);
+int xxm_background_from_seqset(xxm_ctx* ctx, double* bg5, double* bgLog5);
+
 #ifdef __cplusplus
 }
 #endif

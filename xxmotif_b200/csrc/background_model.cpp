@@ -37,9 +37,11 @@ bool next_digits(uint8_t* d, int len, uint8_t lo, uint8_t hi) {
 
 }  // namespace
 
-extern "C" int xxm_host_null_model(int32_t nent, const int32_t* n, const uint8_t* codes, int32_t order, float alpha, float beta, float* rprobs,
-                                   float* rconds) {
-	if (order < 0 || order > 9 || nent < 1) return 1;
+// the model from the k-mer counts (indexed like NullModel::_counts); shared by the host counting loop below and the device
+// histogram (xxm_kmer_counts, xxm_gpu_part6.inc).  The reference increments FLOAT counters, which stop growing at 2^24;
+// integer counting + the same saturation is bit-identical.
+extern "C" int xxm_null_model_from_counts(const uint64_t* counts64, int32_t order, float alpha, float beta, float* rprobs, float* rconds) {
+	if (order < 0 || order > 9) return 1;
 	Tables T;
 	T.order = order;
 	T.pow5.resize(order + 2);
@@ -50,26 +52,7 @@ extern "C" int xxm_host_null_model(int32_t nent, const int32_t* n, const uint8_t
 	T.conds.assign(fields, 0.0f);
 	T.probs.assign(fields, 0.0f);
 	const float factor = 4.0f * alpha;
-
-	// counts of all (k+1)-mers, k = 0..order, that contain no N (NullModel.cpp:122-132).  The reference increments
-	// FLOAT counters, which stop growing at 2^24; integer counting + the same saturation is bit-identical.
-	{
-		std::vector<uint64_t> c(fields, 0);
-		size_t off = 0;
-		for (int s = 0; s < nent; ++s) {
-			const uint8_t* q = codes + off;
-			const int L = n[s];
-			for (int l = 0; l < L; ++l) {
-				int idx = 0;
-				for (int k = 0; k <= order && l + k < L && q[l + k]; ++k) {
-					idx = idx * 5 + q[l + k];  // sub2ind of the (k+1)-mer: appending a digit multiplies by 5
-					c[idx]++;
-				}
-			}
-			off += static_cast<size_t>(L);
-		}
-		for (int i = 0; i < fields; ++i) T.counts[i] = static_cast<float>(std::min<uint64_t>(c[i], 16777216ull));
-	}
+	for (int i = 0; i < fields; ++i) T.counts[i] = static_cast<float>(std::min<uint64_t>(counts64[i], 16777216ull));
 	if (beta > 0)
 		for (int i = 1; i < fields; ++i) T.counts[i] = std::max(0.0f, static_cast<float>(T.counts[i] - beta));
 	float ncounts = 0;
@@ -130,6 +113,29 @@ extern "C" int xxm_host_null_model(int32_t nent, const int32_t* n, const uint8_t
 		} while (next_digits(d.data(), o + 1, 1, 5));
 	}
 	return 0;
+}
+
+// counts of all (k+1)-mers, k = 0..order, that contain no N (NullModel.cpp:122-132), on the host
+extern "C" int xxm_host_null_model(int32_t nent, const int32_t* n, const uint8_t* codes, int32_t order, float alpha, float beta, float* rprobs,
+                                   float* rconds) {
+	if (order < 0 || order > 9 || nent < 1) return 1;
+	int fields = 1 + 5;
+	for (int i = 2, p = 5; i < order + 2; ++i) { p *= 5; fields += p; }
+	std::vector<uint64_t> c(fields, 0);
+	size_t off = 0;
+	for (int s = 0; s < nent; ++s) {
+		const uint8_t* q = codes + off;
+		const int L = n[s];
+		for (int l = 0; l < L; ++l) {
+			int idx = 0;
+			for (int k = 0; k <= order && l + k < L && q[l + k]; ++k) {
+				idx = idx * 5 + q[l + k];  // sub2ind of the (k+1)-mer: appending a digit multiplies by 5
+				c[idx]++;
+			}
+		}
+		off += static_cast<size_t>(L);
+	}
+	return xxm_null_model_from_counts(c.data(), order, alpha, beta, rprobs, rconds);
 }
 
 // mono-nucleotide background of checkSequenceSet (backgroundDistribution.cpp:50-95): counts include code 0, the

@@ -21,6 +21,7 @@
 #include "xxm_kernels.cuh"
 #include "xxm_select2.cuh"
 #include "xxm_select3.cuh"
+#include "xxm_kmerhist.cuh"
 #include "xxm_scan4.cuh"
 #include "xxm_scan5.cuh"
 #include "xxm_scan6.cuh"
@@ -151,6 +152,7 @@ struct xxm_ctx {
 	DevBuf<uint16_t> d_clsThr;
 	bool clsOrderOK = false;
 	uint32_t clsNSite = 0;
+	float lastKmerHistMs = 0;     // device time of the last xxm_kmer_counts (all passes)
 	bool sortedLazy = false;      // the last deferred scan left sortedSites' float scores implicit (k_select_cls_fwd)
 	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
 	DevBuf<uint64_t> status, total64;
@@ -1246,3 +1248,4 @@ static int scan_full_finish(xxm_ctx* ctx, int32_t* nbSites, int32_t* nbBestSites
 #include "xxm_gpu_part3.inc"
 #include "xxm_gpu_part4.inc"
 #include "xxm_gpu_part5.inc"
+#include "xxm_gpu_part6.inc"

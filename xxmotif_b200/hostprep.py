@@ -9,7 +9,8 @@ import numpy as np
 
 from . import capi
 
-EXTRA_EXPORTS = ["xxm_host_null_model", "xxm_host_background"]
+EXTRA_EXPORTS = ["xxm_host_null_model", "xxm_host_background", "xxm_kmer_counts", "xxm_kmer_counts_ms", "xxm_null_model_from_counts",
+                 "xxm_null_model_from_seqset", "xxm_background_from_seqset"]
 
 
 def _lib():
@@ -20,6 +21,11 @@ def _lib():
         L.xxm_host_null_model.argtypes = [i32, vp, vp, i32, flt, flt, vp, vp]
         L.xxm_host_background.restype = i32
         L.xxm_host_background.argtypes = [i32, vp, vp, vp, vp]
+        for name, args in {"xxm_kmer_counts": [vp, i32, vp, C.c_int64], "xxm_kmer_counts_ms": [vp, vp],
+                           "xxm_null_model_from_counts": [vp, i32, flt, flt, vp, vp], "xxm_null_model_from_seqset": [vp, i32, flt, flt, vp, vp],
+                           "xxm_background_from_seqset": [vp, vp, vp]}.items():
+            getattr(L, name).restype = i32
+            getattr(L, name).argtypes = args
         L._hostprep_ready = True
     return L
 
@@ -72,6 +78,65 @@ def null_model(n, codes, order=2, alpha=10.0, beta=0.0):
     if _lib().xxm_host_null_model(len(n), _p(n), _p(codes), order, alpha, beta, _p(rp), _p(rc)):
         raise capi.XxmError("xxm_host_null_model failed")
     return rp, rc
+
+
+def _fields(order):
+    return sum(5 ** k for k in range(order + 2))
+
+
+def kmer_counts_device(ctx, order):
+    """NullModel::init's counting loop over the set loaded in ctx, on the GPU (xxm_kmer_counts): uint64[fields] indexed like
+    NullModel::_counts.  Returns (counts, device milliseconds)."""
+    c = np.zeros(_fields(order), dtype=np.uint64)
+    ctx._ck(_lib().xxm_kmer_counts(ctx.h, order, _p(c), c.size))
+    ms = C.c_float(0)
+    _lib().xxm_kmer_counts_ms(ctx.h, C.byref(ms))
+    return c, ms.value
+
+
+def kmer_counts_host(n, codes, order):
+    """the same counts with numpy (test oracle of the device histogram): all (k+1)-mers, k = 0..order, without N, inside a sequence"""
+    n = np.asarray(n, dtype=np.int64)
+    codes = np.asarray(codes, dtype=np.uint8)
+    c = np.zeros(_fields(order), dtype=np.uint64)
+    seqid = np.repeat(np.arange(len(n)), n)
+    idx = np.zeros(codes.size, dtype=np.int64)
+    ok = np.ones(codes.size, dtype=bool)
+    for k in range(order + 1):
+        m = codes.size - k
+        if m <= 0:
+            break
+        nxt = codes[k:].astype(np.int64)
+        ok = ok[:m] & (nxt != 0) & (seqid[:m] == seqid[k:])
+        idx = idx[:m] * 5 + nxt
+        np.add.at(c, idx[ok], 1) if ok.sum() < 1 << 16 else c.__iadd__(np.bincount(idx[ok], minlength=c.size).astype(np.uint64))
+    return c
+
+
+def null_model_from_counts(counts, order, alpha=10.0, beta=0.0):
+    size = 1 << (3 * (order + 1))
+    rp = np.zeros(size, dtype=np.float32)
+    rc = np.zeros(size, dtype=np.float32)
+    counts = np.ascontiguousarray(counts, dtype=np.uint64)
+    if _lib().xxm_null_model_from_counts(_p(counts), order, alpha, beta, _p(rp), _p(rc)):
+        raise capi.XxmError("xxm_null_model_from_counts failed")
+    return rp, rc
+
+
+def null_model_device(ctx, order=2, alpha=10.0, beta=0.0):
+    """NullModel::init over the set loaded in ctx, k-mer counting on the GPU -> (rprobs, rconds)"""
+    size = 1 << (3 * (order + 1))
+    rp = np.zeros(size, dtype=np.float32)
+    rc = np.zeros(size, dtype=np.float32)
+    ctx._ck(_lib().xxm_null_model_from_seqset(ctx.h, order, alpha, beta, _p(rp), _p(rc)))
+    return rp, rc
+
+
+def background_device(ctx):
+    bg = np.zeros(5)
+    bgl = np.zeros(5)
+    ctx._ck(_lib().xxm_background_from_seqset(ctx.h, _p(bg), _p(bgl)))
+    return bg, bgl
 
 
 IUPAC = {"A": [1], "C": [2], "G": [3], "T": [4], "W": [1, 4], "R": [1, 3], "Y": [2, 4], "S": [2, 3], "K": [3, 4], "M": [1, 2], "N": [1, 2, 3, 4]}
