@@ -24,6 +24,7 @@ struct SeqStream {
 	uint32_t nwords;
 	int32_t nent;
 	uint32_t uniformWps;       // words per sequence when all sequences have the same stored length, else 0
+	int32_t uniformLen;        // that stored length (0 for ragged sets)
 };
 
 // ---------------------------------------------------------------------------------------------------------------

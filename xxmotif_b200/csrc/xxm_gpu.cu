@@ -494,6 +494,7 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	ctx->S.nwords = ctx->nwords;
 	ctx->S.nent = nent;
 	ctx->S.uniformWps = (mx == mn) ? static_cast<uint32_t>((static_cast<uint64_t>(mx) + kPadBases + 31) / 32) : 0u;
+	ctx->S.uniformLen = (mx == mn) ? mx : 0;
 	k_blk2seq<<<cdiv(static_cast<uint32_t>(nent), 256), 256, 0, ctx->stream>>>(ctx->d_wordOff.p, static_cast<uint32_t>(nent), nblk, ctx->d_blk2seq.p);
 	CKK();
 	// pinned landing buffer of the per-sequence counts

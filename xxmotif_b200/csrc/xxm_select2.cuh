@@ -203,7 +203,7 @@ __device__ __forceinline__ void site_context(const SeqStream& S, const CountIO& 
 		const uint32_t s = io.seq[i] - 1;
 		const int g0 = static_cast<int>(io.pos[i]) + io.shift - io.firstColumn;  // 0-based stream offset of PWM column 1 inside the sequence
 		const uint32_t wo = S.uniformWps ? s * S.uniformWps : S.wordOff[s];
-		const int len = S.len[s];
+		const int len = S.uniformWps ? S.uniformLen : S.len[s];
 		const int skip = g0 < 0 ? -g0 : 0;  // columns before the start of the sequence
 		if (skip < 30 && g0 + skip < len) {
 			const int gs = g0 + skip;
