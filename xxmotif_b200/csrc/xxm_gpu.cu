@@ -1213,7 +1213,7 @@ static int scan_full_launch(xxm_ctx* ctx, int32_t posSetSize) {
 	CK(ctx->s_kscore.ensure(capN));
 	CK(ctx->counters.ensure(8));
 	CK(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
-	ctx->sortedLazy = ctx->clsOrderOK && ctx->M.nparts == 1 && V.finalTab == ctx->d_finalMops.p && !std::getenv("XXM_NO_CLS_SELECT");
+	ctx->sortedLazy = ctx->clsOrderOK && ctx->M.nparts == 1 && V.finalTab == ctx->d_finalMops.p && capN <= 0x7FFFFF00u && !std::getenv("XXM_NO_CLS_SELECT");
 	if (ctx->sortedLazy)
 		TRY(launch_select_cls(ctx, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, capN, reinterpret_cast<const unsigned long long*>(ctx->total64.p), ctx->s_keep, ctx->s_kcls));
 	else

@@ -56,21 +56,25 @@ __global__ void __launch_bounds__(32 * kSel3Warps, 4) k_select_cls_fwd(SelectCls
 	uint32_t* const s_pos = s_posAll[wid];
 	uint32_t* const s_seq = s_seqAll[wid];
 	uint16_t* const s_cls = s_clsAll[wid];
-	const uint64_t warp = (static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-	const uint64_t nwarps = (static_cast<uint64_t>(gridDim.x) * blockDim.x) >> 5;
-	const uint32_t n = io.nDev ? static_cast<uint32_t>(min(*io.nDev, static_cast<unsigned long long>(io.n))) : io.n;
-	const uint64_t nchunks = (static_cast<uint64_t>(n) + kSelChunk - 1) / kSelChunk;
+	// all entry indices fit 31 bits (the launcher falls back to k_select_mops_fwd for longer lists): 32-bit index arithmetic
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+	const int n = static_cast<int>(io.nDev ? min(*io.nDev, static_cast<unsigned long long>(io.n)) : io.n);
 	uint32_t kept = 0;
-	for (uint64_t c0 = warp * 32; c0 < nchunks; c0 += nwarps * 32) {
-		const int64_t wj0 = static_cast<int64_t>(c0) * kSelChunk;  // first entry of the warp's window
-		const int64_t wj1 = min(wj0 + kSel3Window, static_cast<int64_t>(n));
-		const int64_t j0 = wj0 + kSelChunk * lane;
-		const int m = (j0 < static_cast<int64_t>(n)) ? static_cast<int>(min(static_cast<int64_t>(kSelChunk), static_cast<int64_t>(n) - j0)) : 0;
+	for (uint32_t uw = warp * kSel3Window; uw < static_cast<uint32_t>(n); uw += nwarps * kSel3Window) {
+		const int wj0 = static_cast<int>(uw);                                    // first entry of the warp's window
+		const uint32_t wlen = static_cast<uint32_t>(min(kSel3Window, n - wj0));  // entries of the warp's window
+		const int r0 = kSelChunk * lane;                                         // first entry of the chunk, relative to the window
+		const int j0 = wj0 + r0;
+		const int m = max(0, min(kSelChunk, n - j0));
+		const uint32_t* const gseq = io.seq + wj0;
+		const uint32_t* const gpos = io.pos + wj0;
+		const uint32_t* const gvid = io.vidx + wj0;
 		uint32_t sq[kSelChunk], ps[kSelChunk], vi[kSelChunk];
 		if (m == kSelChunk) {
-			const uint4 a0 = *reinterpret_cast<const uint4*>(io.seq + j0), a1 = *reinterpret_cast<const uint4*>(io.seq + j0 + 4);
-			const uint4 b0 = *reinterpret_cast<const uint4*>(io.pos + j0), b1 = *reinterpret_cast<const uint4*>(io.pos + j0 + 4);
-			const uint4 v0 = *reinterpret_cast<const uint4*>(io.vidx + j0), v1 = *reinterpret_cast<const uint4*>(io.vidx + j0 + 4);
+			const uint4 a0 = *reinterpret_cast<const uint4*>(gseq + r0), a1 = *reinterpret_cast<const uint4*>(gseq + r0 + 4);
+			const uint4 b0 = *reinterpret_cast<const uint4*>(gpos + r0), b1 = *reinterpret_cast<const uint4*>(gpos + r0 + 4);
+			const uint4 v0 = *reinterpret_cast<const uint4*>(gvid + r0), v1 = *reinterpret_cast<const uint4*>(gvid + r0 + 4);
 			sq[0] = a0.x; sq[1] = a0.y; sq[2] = a0.z; sq[3] = a0.w; sq[4] = a1.x; sq[5] = a1.y; sq[6] = a1.z; sq[7] = a1.w;
 			ps[0] = b0.x; ps[1] = b0.y; ps[2] = b0.z; ps[3] = b0.w; ps[4] = b1.x; ps[5] = b1.y; ps[6] = b1.z; ps[7] = b1.w;
 			vi[0] = v0.x; vi[1] = v0.y; vi[2] = v0.z; vi[3] = v0.w; vi[4] = v1.x; vi[5] = v1.y; vi[6] = v1.z; vi[7] = v1.w;
@@ -78,24 +82,25 @@ __global__ void __launch_bounds__(32 * kSel3Warps, 4) k_select_cls_fwd(SelectCls
 #pragma unroll
 			for (int k = 0; k < kSelChunk; ++k) {
 				const bool in = k < m;
-				sq[k] = in ? io.seq[j0 + k] : 0u;
-				ps[k] = in ? io.pos[j0 + k] : 0u;
-				vi[k] = in ? io.vidx[j0 + k] : kNone;
+				sq[k] = in ? gseq[r0 + k] : 0u;
+				ps[k] = in ? gpos[r0 + k] : 0u;
+				vi[k] = in ? gvid[r0 + k] : kNone;
 			}
 		}
 #pragma unroll
 		for (int k = 0; k < kSelChunk; ++k) vi[k] = min(vi[k], 0xFFFFu);  // (kNone and anything >= nSite: not a site)
 		__syncwarp();  // the previous pass has finished reading the window
-		*reinterpret_cast<uint4*>(s_seq + kSelChunk * lane) = make_uint4(sq[0], sq[1], sq[2], sq[3]);
-		*reinterpret_cast<uint4*>(s_seq + kSelChunk * lane + 4) = make_uint4(sq[4], sq[5], sq[6], sq[7]);
-		*reinterpret_cast<uint4*>(s_pos + kSelChunk * lane) = make_uint4(ps[0], ps[1], ps[2], ps[3]);
-		*reinterpret_cast<uint4*>(s_pos + kSelChunk * lane + 4) = make_uint4(ps[4], ps[5], ps[6], ps[7]);
-		*reinterpret_cast<uint4*>(s_cls + kSelChunk * lane) =
+		*reinterpret_cast<uint4*>(s_seq + r0) = make_uint4(sq[0], sq[1], sq[2], sq[3]);
+		*reinterpret_cast<uint4*>(s_seq + r0 + 4) = make_uint4(sq[4], sq[5], sq[6], sq[7]);
+		*reinterpret_cast<uint4*>(s_pos + r0) = make_uint4(ps[0], ps[1], ps[2], ps[3]);
+		*reinterpret_cast<uint4*>(s_pos + r0 + 4) = make_uint4(ps[4], ps[5], ps[6], ps[7]);
+		*reinterpret_cast<uint4*>(s_cls + r0) =
 			make_uint4(vi[0] | (vi[1] << 16), vi[2] | (vi[3] << 16), vi[4] | (vi[5] << 16), vi[6] | (vi[7] << 16));
 		__syncwarp();
-		auto pos_at = [&](int64_t j) -> uint32_t { return (j >= wj0 && j < wj1) ? s_pos[j - wj0] : io.pos[j]; };
-		auto seq_at = [&](int64_t j) -> uint32_t { return (j >= wj0 && j < wj1) ? s_seq[j - wj0] : io.seq[j]; };
-		auto cls_at = [&](int64_t j) -> uint32_t { return (j >= wj0 && j < wj1) ? static_cast<uint32_t>(s_cls[j - wj0]) : min(io.vidx[j], 0xFFFFu); };
+		// entry r of the window (r < 0 or r >= wlen: outside of it, from global memory)
+		auto pos_at = [&](int r) -> uint32_t { return (static_cast<uint32_t>(r) < wlen) ? s_pos[r] : gpos[r]; };
+		auto seq_at = [&](int r) -> uint32_t { return (static_cast<uint32_t>(r) < wlen) ? s_seq[r] : gseq[r]; };
+		auto cls_at = [&](int r) -> uint32_t { return (static_cast<uint32_t>(r) < wlen) ? static_cast<uint32_t>(s_cls[r]) : min(gvid[r], 0xFFFFu); };
 		// state of the greedy: the kept site a later entry can still replace.  lastEnd = its startPos + length (0: none)
 		uint32_t lastEnd = 0, lastT = 0;
 		int lastK = -1;  // its index inside the chunk, -1: it lies before the chunk
@@ -103,17 +108,17 @@ __global__ void __launch_bounds__(32 * kSel3Warps, 4) k_select_cls_fwd(SelectCls
 		if (m > 0) {
 			// ---- the part of the cluster before the chunk: back to its head, then forward again
 			if (j0 > 0) {
-				uint32_t pp = pos_at(j0 - 1);
-				if (seq_at(j0 - 1) == sq[0] && pp + L >= ps[0]) {
-					int64_t h = j0 - 1;
-					while (h > 0) {
+				uint32_t pp = pos_at(r0 - 1);
+				if (seq_at(r0 - 1) == sq[0] && pp + L >= ps[0]) {
+					int h = r0 - 1;
+					while (h > -wj0) {
 						const uint32_t p2 = pos_at(h - 1);
 						if (seq_at(h - 1) != sq[0] || p2 + L < pp) break;
 						pp = p2;
 						--h;
 					}
-					for (int64_t j = h; j < j0; ++j) {
-						const uint32_t pj = pos_at(j), cj = cls_at(j);
+					for (int r = h; r < r0; ++r) {
+						const uint32_t pj = pos_at(r), cj = cls_at(r);
 						if (cj < nSite && !(lastEnd >= pj && cj >= lastT)) { lastEnd = pj + L; lastT = s_thr[cj]; }
 					}
 				}
@@ -136,11 +141,11 @@ __global__ void __launch_bounds__(32 * kSel3Warps, 4) k_select_cls_fwd(SelectCls
 			}
 			// ---- can a later entry still replace my last kept site?
 			if (lastK >= 0) {
-				const uint32_t mySeq = lastSeq;
-				for (int64_t j = j0 + m; j < static_cast<int64_t>(n); ++j) {
-					const uint32_t pj = pos_at(j);
-					if (seq_at(j) != mySeq || pj > lastEnd) break;
-					if (cls_at(j) >= min(lastT, nSite)) continue;  // not a site, or not better than mine
+				const uint32_t mySeq = lastSeq, better = min(lastT, nSite);
+				for (int r = r0 + m; r < n - wj0; ++r) {
+					const uint32_t pj = pos_at(r);
+					if (seq_at(r) != mySeq || pj > lastEnd) break;
+					if (cls_at(r) >= better) continue;  // not a site, or not better than mine
 					keepBits &= ~(1u << lastK);
 					break;
 				}
