@@ -63,8 +63,10 @@ int xxm_set_options(xxm_ctx* ctx, const xxm_options* opt);
  * replaces: Global::posSet as filled by Alignment::getEntity (seqFormat/Alignment.cpp:149-195) + createRevcomp
  * (seqset.cpp:128-178) + calculateSequenceFeatures (seqset.cpp:21-36).
  * n[i], codes: the sequences BEFORE createRevcomp, codes 0=N,1=A,2=C,3=G,4=T concatenated without separators.
- * The set is packed once (2-bit codes + 1-bit N mask) and stays resident in HBM; with revcomp != 0 the reverse
- * strand is generated on the device.  total[]/avgLength[] follow the reference's arithmetic, quirks included. */
+ * The set is packed once (2-bit codes + 1-bit N mask, reverse strand included when revcomp != 0) by the host cores, chunk
+ * by chunk while earlier chunks are on the bus, so 0.375 bytes per stored base cross PCIe; it then stays resident in HBM.
+ * XXM_PACK_THREADS sets the number of packing threads (default: min(16, host cores)).  total[]/avgLength[] follow the
+ * reference's arithmetic, quirks included. */
 int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp);
 int xxm_seqset_info(const xxm_ctx* ctx, int32_t* total /*[nent+1] or NULL*/, double* avgLength /*[nent+1] or NULL*/,
                     int32_t* max_leng, int32_t* min_leng);
@@ -239,6 +241,11 @@ int xxm_host_background(int32_t nent, const int32_t* n, const uint8_t* codes, do
 int xxm_host_best_subset(const float* score, const int32_t* seq, int32_t nbSites, int32_t posSetSize, int32_t maxSeqCount, int32_t maxSites,
                          int32_t nent, int32_t maxMotifsPerSequence, int32_t oneOccurrence, double plusFrac, int32_t* bestMotifNb,
                          double* bestPval);
+
+/* xxm_host_pack_seqset: the packing step of xxm_load_seqset alone (csrc/host_pack.h), for tests: words = sum over the
+ *   sequences of ceil((stored length + 32) / 32) + 2 entries of codes64 / nmask32 (the last two are the end-of-stream
+ *   guard), notX[nent] = residues that are not N.  Returns the 1-based index of a sequence with a code outside 0..4, or 0. */
+int xxm_host_pack_seqset(int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp, uint64_t* codes64, uint32_t* nmask32, int32_t* notX);
 
 /* xxm_host_pair_table: the table of the full-scan find kernel (csrc/pair_table.h).  ids = the enumerated left k-mers that
  *   count as scan hits (column c in bits [2c+1:2c]), coloff = base offset of each of the len0 left match columns.

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "host_pack.h"
 #include "host_stats.h"
 #include "pair_table.h"
 #include "pvalue_tables.h"
@@ -99,4 +100,12 @@ extern "C" int xxm_host_pair_table(const uint32_t* ids, int64_t nids, const int3
 	const bool ok = build_pair_table(ids, static_cast<size_t>(nids), off, len0, table1024, &lv);
 	*levels = lv;
 	return ok ? 0 : 1;
+}
+
+extern "C" int xxm_host_pack_seqset(int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp, uint64_t* codes64, uint32_t* nmask32, int32_t* notX) {
+	uint64_t words = 0;
+	for (int32_t i = 0; i < nent; ++i) words += stored_words(static_cast<uint32_t>(n[i]), revcomp != 0);
+	const uint32_t bad = pack_range(n, 0, static_cast<uint32_t>(nent), codes, revcomp != 0, codes64, nmask32, notX);
+	for (int k = 0; k < 2; ++k) { codes64[words + k] = 0; nmask32[words + k] = 0xFFFFFFFFu; }
+	return static_cast<int>(bad);
 }

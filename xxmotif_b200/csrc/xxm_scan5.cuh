@@ -37,10 +37,12 @@ __device__ __forceinline__ uint32_t pair_lookup(const uint32_t (&r)[5], const ui
 
 template <int S>
 __device__ __forceinline__ uint32_t gather_flags(uint32_t acc, uint32_t tLo, uint32_t tHi) {
-	// bytes 3 / 1 of a T word hold the sums of its even / odd window; U = [odd(lo), odd(hi), even(lo), even(hi)]
-	const uint32_t u = __byte_perm(tLo, tHi, 0x7351);
-	const uint32_t x = (S == 7) ? u : (u >> (7 - S));
-	return acc | (x & (0x01010101u << S));
+	// bytes 3 / 1 of a T word hold the sums of its even / odd window; bit 7 of a sum is the hit flag.  PRMT with bit 3 of a
+	// selector nibble set replicates the sign of the selected byte: U = [odd(lo), odd(hi), even(lo), even(hi)], every byte
+	// 0x00 or 0xFF, and one and-or picks bit S of every byte
+	uint32_t u;
+	asm("prmt.b32 %0, %1, %2, 0xFBD9;" : "=r"(u) : "r"(tLo), "r"(tHi));
+	return acc | (u & (0x01010101u << S));
 }
 
 template <int G>
@@ -75,15 +77,31 @@ __global__ void __launch_bounds__(kScan5Threads, 1) k_scan5(const uint64_t* __re
 	const uint32_t warp = (blockIdx.x * kScan5Threads + threadIdx.x) >> 5;
 	const uint32_t nwarps = (gridDim.x * kScan5Threads) >> 5;
 	const uint32_t nchunks = (scanWords + 63) / 64;
+	// the loads of a chunk are issued one iteration ahead (8 warps per scheduler do not hide a DRAM round trip otherwise)
+	uint4 nv = make_uint4(0u, 0u, 0u, 0u);
+	uint2 nd = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+	uint32_t ntail = 0;
+	auto fetch = [&](uint32_t c) {
+		const uint32_t w = c * 64 + 2 * lane;
+		nv = make_uint4(0u, 0u, 0u, 0u);
+		nd = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+		ntail = 0;
+		if (c < nchunks && w < scanWords) {
+			nv = __ldg(reinterpret_cast<const uint4*>(codes + w));
+			nd = __ldg(reinterpret_cast<const uint2*>(dead + w));
+			if (lane == 31 && w + 2 <= scanWords) ntail = static_cast<uint32_t>(__ldg(codes + w + 2));
+		}
+	};
+	fetch(warp);
 	for (uint32_t c = warp; c < nchunks; c += nwarps) {
 		const uint32_t w = c * 64 + 2 * lane;
-		uint32_t r[5] = {0, 0, 0, 0, 0};
-		if (w < scanWords) {
-			const uint4 v = *reinterpret_cast<const uint4*>(codes + w);
-			r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w;
-		}
+		const uint4 v = nv;
+		const uint2 d = nd;
+		const uint32_t tail = ntail;
+		fetch(c + nwarps);
+		uint32_t r[5] = {v.x, v.y, v.z, v.w, 0};
 		r[4] = __shfl_down_sync(0xFFFFFFFFu, r[0], 1);
-		if (lane == 31) r[4] = (w + 2 <= scanWords) ? static_cast<uint32_t>(codes[w + 2]) : 0u;
+		if (lane == 31) r[4] = tail;
 		uint32_t e[34];
 		e[0] = pair_lookup<0>(r, tab);   e[1] = pair_lookup<1>(r, tab);   e[2] = pair_lookup<2>(r, tab);   e[3] = pair_lookup<3>(r, tab);
 		e[4] = pair_lookup<4>(r, tab);   e[5] = pair_lookup<5>(r, tab);   e[6] = pair_lookup<6>(r, tab);   e[7] = pair_lookup<7>(r, tab);
@@ -97,7 +115,6 @@ __global__ void __launch_bounds__(kScan5Threads, 1) k_scan5(const uint64_t* __re
 		uint32_t h0 = scan5_word<0>(e), h1 = scan5_word<16>(e);
 		uint32_t cnt = 0;
 		if (w < scanWords) {
-			const uint2 d = *reinterpret_cast<const uint2*>(dead + w);
 			h0 &= ~d.x;
 			h1 = (w + 1 < scanWords) ? (h1 & ~d.y) : 0u;
 			*reinterpret_cast<uint2*>(hitmask + w) = make_uint2(h0, h1);

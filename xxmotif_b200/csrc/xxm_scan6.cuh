@@ -137,42 +137,53 @@ __device__ __forceinline__ HitRec expand6_hit(const SeqStream& S, const Model& M
 }
 
 template <bool kFast>
-__global__ void __launch_bounds__(kExpand6Threads, 5) k_expand6(SeqStream S, Model M, Expand6IO io) {
+__global__ void __launch_bounds__(kExpand6Threads, 6) k_expand6(SeqStream S, Model M, Expand6IO io) {
 	__shared__ __align__(16) uint64_t s_codesAll[kExpand6Warps][kWarpWords + 2];
 	__shared__ uint16_t s_qAll[kExpand6Warps][kWarpQueue];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const uint32_t tile = blockIdx.x;
-	// ---- where this warp's records go: tile offset + the counts of the chunks before it inside the tile
-	uint32_t cc = 0;
-	if (lane < kChunksPerTile) cc = io.chunkCount[tile * kChunksPerTile + lane];
-	const uint32_t mine = __shfl_sync(0xFFFFFFFFu, cc, 2 * wid) + __shfl_sync(0xFFFFFFFFu, cc, 2 * wid + 1);
-	if (mine == 0) return;
-	uint32_t before = (lane < 2 * wid) ? cc : 0u;
-#pragma unroll
-	for (int d = 16; d; d >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, d);
-	const uint64_t base = io.tileOff[tile] + before;
 	uint64_t* s_codes = s_codesAll[wid];
 	uint16_t* s_q = s_qAll[wid];
 	const uint32_t wbase = tile * kTileWords + wid * kWarpWords;
 	const uint32_t w0 = wbase + 4 * lane;
-	// ---- the lane's four masks and four code words (staged for the expansion)
+	// ---- every load of the warp is issued before anything waits: the chunk counts and the tile offset (where the records
+	// go), the lane's four masks and four code words (staged for the expansion).  A warp without a hit -- rare -- has
+	// then read its words for nothing, but nobody pays a second DRAM round trip.
+	uint32_t cc = 0;
+	if (lane < kChunksPerTile) cc = __ldg(io.chunkCount + tile * kChunksPerTile + lane);
+	const uint64_t tileBase = __ldg(io.tileOff + tile);
 	uint32_t h[4];
-	if (w0 + 4 <= io.scanWords && w0 + 4 <= S.nwords + 2) {
-		const uint4 hv = *reinterpret_cast<const uint4*>(io.hitmask + w0);
-		const uint4 ca = *reinterpret_cast<const uint4*>(S.codes + w0);
-		const uint4 cb = *reinterpret_cast<const uint4*>(S.codes + w0 + 2);
+	const bool full = w0 + 4 <= io.scanWords && w0 + 4 <= S.nwords + 2;
+	uint4 ca = make_uint4(0u, 0u, 0u, 0u), cb = ca;
+	if (full) {
+		const uint4 hv = __ldg(reinterpret_cast<const uint4*>(io.hitmask + w0));
+		ca = __ldg(reinterpret_cast<const uint4*>(S.codes + w0));
+		cb = __ldg(reinterpret_cast<const uint4*>(S.codes + w0 + 2));
 		h[0] = hv.x; h[1] = hv.y; h[2] = hv.z; h[3] = hv.w;
-		*reinterpret_cast<uint4*>(s_codes + 4 * lane) = ca;
-		*reinterpret_cast<uint4*>(s_codes + 4 * lane + 2) = cb;
 	} else {
 #pragma unroll
 		for (int k = 0; k < 4; ++k) {
 			const uint32_t w = w0 + k;
 			h[k] = (w < io.scanWords) ? io.hitmask[w] : 0u;
-			s_codes[4 * lane + k] = (w < S.nwords + 2) ? S.codes[w] : 0ull;
+			const uint64_t c = (w < S.nwords + 2) ? S.codes[w] : 0ull;
+			if (k == 0) { ca.x = static_cast<uint32_t>(c); ca.y = static_cast<uint32_t>(c >> 32); }
+			if (k == 1) { ca.z = static_cast<uint32_t>(c); ca.w = static_cast<uint32_t>(c >> 32); }
+			if (k == 2) { cb.x = static_cast<uint32_t>(c); cb.y = static_cast<uint32_t>(c >> 32); }
+			if (k == 3) { cb.z = static_cast<uint32_t>(c); cb.w = static_cast<uint32_t>(c >> 32); }
 		}
 	}
-	if (lane == 0) s_codes[kWarpWords] = (wbase + kWarpWords < S.nwords + 2) ? S.codes[wbase + kWarpWords] : 0ull;
+	uint64_t ctail = 0;
+	if (lane == 0 && wbase + kWarpWords < S.nwords + 2) ctail = __ldg(S.codes + wbase + kWarpWords);
+	// ---- where this warp's records go: tile offset + the counts of the chunks before it inside the tile
+	const uint32_t mine = __shfl_sync(0xFFFFFFFFu, cc, 2 * wid) + __shfl_sync(0xFFFFFFFFu, cc, 2 * wid + 1);
+	if (mine == 0) return;
+	uint32_t before = (lane < 2 * wid) ? cc : 0u;
+#pragma unroll
+	for (int d = 16; d; d >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, d);
+	const uint64_t base = tileBase + before;
+	*reinterpret_cast<uint4*>(s_codes + 4 * lane) = ca;
+	*reinterpret_cast<uint4*>(s_codes + 4 * lane + 2) = cb;
+	if (lane == 0) s_codes[kWarpWords] = ctail;
 #pragma unroll
 	for (int k = 0; k < 4; ++k) h[k] = eo_to_natural(h[k]);
 	const uint32_t cnt = __popc(h[0]) + __popc(h[1]) + __popc(h[2]) + __popc(h[3]);
@@ -185,14 +196,15 @@ __global__ void __launch_bounds__(kExpand6Threads, 5) k_expand6(SeqStream S, Mod
 	const uint32_t myOff = incl - cnt;
 	// records [base, base + mine) of the three output arrays; room = how many of them fit the arrays
 	const uint32_t room = (base < io.cap) ? static_cast<uint32_t>(min(static_cast<uint64_t>(io.cap) - base, static_cast<uint64_t>(mine))) : 0u;
-	uint32_t* const pseq = io.oseq + base;
-	uint32_t* const ppos = io.opos + base;
-	uint32_t* const pvid = io.ovidx + base;
+	uint32_t* pseq = io.oseq + base;
+	uint32_t* ppos = io.opos + base;
+	uint32_t* pvid = io.ovidx + base;
+	asm volatile("" : "+l"(pseq), "+l"(ppos), "+l"(pvid));  // keep the three bases in registers: one IMAD.WIDE per store instead of 64-bit adds per record
 	auto emit = [&](const HitRec& rec, uint32_t q) {
 		if (q < room) {
-			pseq[q] = rec.seq;
-			ppos[q] = rec.pos;
-			pvid[q] = rec.v;
+			asm volatile("st.global.u32 [%0], %1;" ::"l"(pseq + q), "r"(rec.seq) : "memory");
+			asm volatile("st.global.u32 [%0], %1;" ::"l"(ppos + q), "r"(rec.pos) : "memory");
+			asm volatile("st.global.u32 [%0], %1;" ::"l"(pvid + q), "r"(rec.v) : "memory");
 		}
 	};
 	if (mine <= static_cast<uint32_t>(kWarpQueue)) {

@@ -10,7 +10,7 @@ import numpy as np
 from . import capi
 
 EXTRA_EXPORTS = ["xxm_host_null_model", "xxm_host_background", "xxm_kmer_counts", "xxm_kmer_counts_ms", "xxm_null_model_from_counts",
-                 "xxm_null_model_from_seqset", "xxm_background_from_seqset"]
+                 "xxm_null_model_from_seqset", "xxm_background_from_seqset", "xxm_host_pack_seqset"]
 
 
 def _lib():
@@ -21,6 +21,8 @@ def _lib():
         L.xxm_host_null_model.argtypes = [i32, vp, vp, i32, flt, flt, vp, vp]
         L.xxm_host_background.restype = i32
         L.xxm_host_background.argtypes = [i32, vp, vp, vp, vp]
+        L.xxm_host_pack_seqset.restype = i32
+        L.xxm_host_pack_seqset.argtypes = [i32, vp, vp, i32, vp, vp, vp]
         for name, args in {"xxm_kmer_counts": [vp, i32, vp, C.c_int64], "xxm_kmer_counts_ms": [vp, vp],
                            "xxm_null_model_from_counts": [vp, i32, flt, flt, vp, vp], "xxm_null_model_from_seqset": [vp, i32, flt, flt, vp, vp],
                            "xxm_background_from_seqset": [vp, vp, vp]}.items():
@@ -55,6 +57,23 @@ def revcomp_double(n, codes):
         out[d:d + L] = codes[s:s + L]
         out[d + L + 1:d + 2 * L + 1] = comp[codes[s:s + L][::-1]]
     return n2.astype(np.int32), out
+
+
+def pack_seqset(n, codes, revcomp=False):
+    """The packing step of xxm_load_seqset alone (xxm_host_pack_seqset): (code words, N masks, residues per sequence).
+    Raises on a code outside 0..4."""
+    L = _lib()
+    n = np.ascontiguousarray(n, dtype=np.int32)
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    stored = 2 * n.astype(np.int64) + 1 if revcomp else n.astype(np.int64)
+    words = int(((stored + 32 + 31) // 32).sum()) + 2
+    c64 = np.zeros(words, dtype=np.uint64)
+    m32 = np.zeros(words, dtype=np.uint32)
+    notx = np.zeros(len(n), dtype=np.int32)
+    bad = L.xxm_host_pack_seqset(len(n), _p(n), _p(codes), int(revcomp), _p(c64), _p(m32), _p(notx))
+    if bad:
+        raise capi.XxmError("sequence %d holds a code outside 0..4" % bad)
+    return c64, m32, notx
 
 
 def background(n, codes):
