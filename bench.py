@@ -190,7 +190,7 @@ def ours(a):
         os.environ.pop("NCCL_DEBUG", None)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     # packing threads of xxm_load_seqset (the e2e leg): the ranks of one box share its cores
-    pack_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
+    pack_threads = max(1, min(12, (3 * (os.cpu_count() or 1)) // (4 * max(1, world))))
     os.environ.setdefault("XXM_PACK_THREADS", str(pack_threads))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

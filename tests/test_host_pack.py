@@ -63,3 +63,17 @@ def test_pack_rejects_bad_code():
     codes[50 + 37] = 200
     with pytest.raises(capi.XxmError):
         hostprep.pack_seqset(n, codes, True)
+
+
+def test_pack_sse2_path_in_subprocess():
+    """The AVX2 variant is chosen at load time; XXM_PACK_NO_AVX2 forces the SSE2 one, checked in a fresh process."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("XXM_PACK_NO_AVX2"):
+        pytest.skip("already the SSE2 run")
+    env = dict(os.environ, XXM_PACK_NO_AVX2="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_host_pack.py"), "-q", "-x", "-k", "layout or runs or bad"],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr

@@ -8,6 +8,10 @@
 #if defined(__SSE2__)
 #include <emmintrin.h>
 #endif
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define XXM_HAVE_AVX2_DISPATCH 1
+#endif
 
 namespace xxm {
 namespace {
@@ -82,6 +86,51 @@ inline void pack32(const uint8_t* r, uint64_t* c, uint32_t* m, PackAcc& A) {
 #endif
 }
 
+#if defined(XXM_HAVE_AVX2_DISPATCH)
+// The same packing with 256-bit registers (one register per 32 bases), chosen at run time when the CPU has AVX2.
+alignas(32) const uint8_t kTailMask[64] = {255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 255,
+                                          255, 255, 255, 255, 255, 255, 255, 255, 255, 255, 0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0,
+                                          0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0,   0};
+// nblocks full blocks, then -- if tail != 0 -- one block of which only the first `tail` bytes belong to the sequence (the
+// caller guarantees that 32 bytes can be read there); the bytes beyond them read as N
+// kStream: the words are written past the caches (nobody reads them before the DMA engine does; the staging buffer is
+// larger than the last-level cache, and a normal store would first read every line it is about to overwrite)
+template <bool kStream>
+__attribute__((target("avx2"))) void pack_blocks_avx2(const uint8_t* r, uint32_t nblocks, uint32_t tail, uint64_t* c, uint32_t* m, uint64_t* nN, uint32_t* bad) {
+	const __m256i zero = _mm256_setzero_si256(), one = _mm256_set1_epi8(1), three = _mm256_set1_epi8(3), four = _mm256_set1_epi8(4);
+	const __m256i lowNib = _mm256_set1_epi32(0x000F000F), lowByte = _mm256_set1_epi32(0x000000FF);
+	// bytes 0, 4, 8, 12 of each 128-bit lane -> its low dword
+	const __m256i gather = _mm256_setr_epi8(0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, 4, 8, 12, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1);
+	__m256i nacc = zero, badv = zero, total = zero;
+	uint32_t pending = 0;
+	const uint32_t nall = nblocks + (tail ? 1u : 0u);
+	for (uint32_t k = 0; k < nall; ++k) {
+		if ((k & 1u) == 0) _mm_prefetch(reinterpret_cast<const char*>(r + 32ull * k + 1024), _MM_HINT_T0);
+		__m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(r + 32ull * k));
+		if (k == nblocks) v = _mm256_and_si256(v, _mm256_loadu_si256(reinterpret_cast<const __m256i*>(kTailMask + 32 - tail)));
+		const __m256i z = _mm256_cmpeq_epi8(v, zero);
+		const uint32_t mk = static_cast<uint32_t>(_mm256_movemask_epi8(z));
+		if (kStream) _mm_stream_si32(reinterpret_cast<int*>(m + k), static_cast<int>(mk));
+		else m[k] = mk;
+		nacc = _mm256_sub_epi8(nacc, z);  // + 1 per N
+		badv = _mm256_or_si256(badv, _mm256_or_si256(_mm256_cmpgt_epi8(v, four), v));
+		if (++pending == 255) { total = _mm256_add_epi64(total, _mm256_sad_epu8(nacc, zero)); nacc = zero; pending = 0; }
+		__m256i x = _mm256_and_si256(_mm256_subs_epu8(v, one), three);
+		x = _mm256_and_si256(_mm256_or_si256(x, _mm256_srli_epi16(x, 6)), lowNib);
+		x = _mm256_and_si256(_mm256_or_si256(x, _mm256_srli_epi32(x, 12)), lowByte);
+		x = _mm256_shuffle_epi8(x, gather);
+		const uint64_t ck = static_cast<uint32_t>(_mm256_extract_epi32(x, 0)) | (static_cast<uint64_t>(static_cast<uint32_t>(_mm256_extract_epi32(x, 4))) << 32);
+		if (kStream) _mm_stream_si64(reinterpret_cast<long long*>(c + k), static_cast<long long>(ck));
+		else c[k] = ck;
+	}
+	total = _mm256_add_epi64(total, _mm256_sad_epu8(nacc, zero));
+	*nN += static_cast<uint64_t>(_mm256_extract_epi64(total, 0)) + static_cast<uint64_t>(_mm256_extract_epi64(total, 1)) +
+	       static_cast<uint64_t>(_mm256_extract_epi64(total, 2)) + static_cast<uint64_t>(_mm256_extract_epi64(total, 3));
+	*bad |= static_cast<uint32_t>(_mm256_movemask_epi8(badv));
+}
+const bool g_haveAvx2 = __builtin_cpu_supports("avx2") && std::getenv("XXM_PACK_NO_AVX2") == nullptr;
+#endif
+
 // order of the 32 two-bit groups of x reversed
 inline uint64_t reverse_groups(uint64_t x) {
 	x = __builtin_bswap64(x);
@@ -99,17 +148,35 @@ inline uint32_t reverse_bits(uint32_t x) {
 
 }  // namespace
 
-uint32_t pack_sequence(const uint8_t* raw, uint32_t n0, bool revcomp, uint64_t* codes, uint32_t* nmask, bool* bad) {
+uint32_t pack_sequence(const uint8_t* raw, uint32_t n0, bool revcomp, uint64_t* codes, uint32_t* nmask, bool* bad, bool canOverread) {
 	const uint64_t words = stored_words(n0, revcomp);
 	const uint32_t fullBlocks = n0 / 32, tail = n0 % 32;
 	const uint32_t fwdWords = fullBlocks + (tail ? 1u : 0u);
 	PackAcc A;
-	for (uint32_t k = 0; k < fullBlocks; ++k) pack32(raw + 32ull * k, codes + k, nmask + k, A);
-	if (tail) {
-		uint8_t buf[32];
-		std::memset(buf, 0, sizeof buf);
-		std::memcpy(buf, raw + 32ull * fullBlocks, tail);
-		pack32(buf, codes + fullBlocks, nmask + fullBlocks, A);
+#if defined(XXM_HAVE_AVX2_DISPATCH)
+	if (g_haveAvx2 && (tail == 0 || canOverread)) {
+		if (revcomp) {
+			pack_blocks_avx2<false>(raw, fullBlocks, tail, codes, nmask, &A.nN, &A.bad);  // the reverse strand reads these words back
+		} else {
+			pack_blocks_avx2<true>(raw, fullBlocks, tail, codes, nmask, &A.nN, &A.bad);
+			for (uint64_t k = fwdWords; k < words; ++k) {
+				_mm_stream_si64(reinterpret_cast<long long*>(codes + k), 0);
+				_mm_stream_si32(reinterpret_cast<int*>(nmask + k), -1);
+			}
+			A.flush();
+			if (A.bad) *bad = true;
+			return n0 - (static_cast<uint32_t>(A.nN) - (tail ? 32u - tail : 0u));
+		}
+	} else
+#endif
+	{
+		for (uint32_t k = 0; k < fullBlocks; ++k) pack32(raw + 32ull * k, codes + k, nmask + k, A);
+		if (tail) {
+			uint8_t buf[32];
+			std::memset(buf, 0, sizeof buf);
+			std::memcpy(buf, raw + 32ull * fullBlocks, tail);
+			pack32(buf, codes + fullBlocks, nmask + fullBlocks, A);
+		}
 	}
 	A.flush();
 	const uint32_t nN = static_cast<uint32_t>(A.nN) - (tail ? 32u - tail : 0u);  // the zero padding of the tail block counted as N
@@ -152,18 +219,24 @@ uint32_t pack_sequence(const uint8_t* raw, uint32_t n0, bool revcomp, uint64_t* 
 	return n0 - nN;
 }
 
-uint32_t pack_range(const int32_t* n, uint32_t s0, uint32_t s1, const uint8_t* raw, bool revcomp, uint64_t* codes, uint32_t* nmask, int32_t* notX) {
+uint32_t pack_range(const int32_t* n, uint32_t s0, uint32_t s1, const uint8_t* raw, uint64_t rawAvail, bool revcomp, uint64_t* codes, uint32_t* nmask, int32_t* notX) {
 	uint32_t badSeq = 0;
 	for (uint32_t s = s0; s < s1; ++s) {
 		const uint32_t n0 = static_cast<uint32_t>(n[s]);
 		bool bad = false;
-		notX[s - s0] = static_cast<int32_t>(pack_sequence(raw, n0, revcomp, codes, nmask, &bad));
+		// the tail block of a sequence may be read as a full 32 bytes when the array still holds that many
+		const bool canOverread = (n0 / 32) * 32ull + 32 <= rawAvail;
+		notX[s - s0] = static_cast<int32_t>(pack_sequence(raw, n0, revcomp, codes, nmask, &bad, canOverread));
 		if (bad && !badSeq) badSeq = s + 1;
 		const uint64_t w = stored_words(n0, revcomp);
 		raw += n0;
+		rawAvail -= n0;
 		codes += w;
 		nmask += w;
 	}
+#if defined(__SSE2__)
+	_mm_sfence();  // streaming stores visible before the chunk is reported as packed
+#endif
 	return badSeq;
 }
 
@@ -173,7 +246,7 @@ int pack_threads_default() {
 		if (t >= 1) return std::min(t, 256);
 	}
 	const unsigned hc = std::thread::hardware_concurrency();
-	return static_cast<int>(std::max(1u, std::min(16u, hc ? hc : 1u)));
+	return static_cast<int>(std::max(1u, std::min(12u, hc ? (3 * hc + 3) / 4 : 1u)));  // the calling thread and the driver's threads need cores too
 }
 
 }  // namespace xxm

@@ -17,12 +17,13 @@ inline uint64_t stored_words(uint32_t n0, bool revcomp) {
 }
 
 // Packs one sequence of n0 raw codes into `words` = stored_words(n0, revcomp) words at codes[] / nmask[].
-// Returns the number of residues that are not N; *bad is set if a code lies outside 0..4.
-uint32_t pack_sequence(const uint8_t* raw, uint32_t n0, bool revcomp, uint64_t* codes, uint32_t* nmask, bool* bad);
+// Returns the number of residues that are not N; *bad is set if a code lies outside 0..4.  canOverread: the 32 bytes of
+// the last, partial block of the sequence may be read (they belong to the following sequences of the same array).
+uint32_t pack_sequence(const uint8_t* raw, uint32_t n0, bool revcomp, uint64_t* codes, uint32_t* nmask, bool* bad, bool canOverread = false);
 
-// Packs sequences [s0, s1): raw codes of sequence s0 start at raw, its words at codes / nmask; notX[s - s0] receives the
-// residue counts.  Returns the 1-based index of a sequence with a code outside 0..4, or 0.
-uint32_t pack_range(const int32_t* n, uint32_t s0, uint32_t s1, const uint8_t* raw, bool revcomp, uint64_t* codes, uint32_t* nmask, int32_t* notX);
+// Packs sequences [s0, s1): raw codes of sequence s0 start at raw (rawAvail bytes remain in the array from there), its
+// words at codes / nmask; notX[s - s0] receives the residue counts.  Returns the 1-based index of a sequence with a code outside 0..4, or 0.
+uint32_t pack_range(const int32_t* n, uint32_t s0, uint32_t s1, const uint8_t* raw, uint64_t rawAvail, bool revcomp, uint64_t* codes, uint32_t* nmask, int32_t* notX);
 
 int pack_threads_default();
 

@@ -486,7 +486,7 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	const bool rc = revcomp != 0;
 	auto packChunk = [&](uint32_t k) {
 		Chunk& c = chunks[k];
-		c.bad = pack_range(n, static_cast<uint32_t>(c.s0), static_cast<uint32_t>(c.s1), codes + c.b0, rc, hCodes + c.w0, hMask + c.w0, ctx->notX.data() + c.s0);
+		c.bad = pack_range(n, static_cast<uint32_t>(c.s0), static_cast<uint32_t>(c.s1), codes + c.b0, rawTotal - c.b0, rc, hCodes + c.w0, hMask + c.w0, ctx->notX.data() + c.s0);
 		done[k].store(1, std::memory_order_release);
 	};
 	auto worker = [&]() {

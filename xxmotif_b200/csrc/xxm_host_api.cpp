@@ -103,9 +103,9 @@ extern "C" int xxm_host_pair_table(const uint32_t* ids, int64_t nids, const int3
 }
 
 extern "C" int xxm_host_pack_seqset(int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp, uint64_t* codes64, uint32_t* nmask32, int32_t* notX) {
-	uint64_t words = 0;
-	for (int32_t i = 0; i < nent; ++i) words += stored_words(static_cast<uint32_t>(n[i]), revcomp != 0);
-	const uint32_t bad = pack_range(n, 0, static_cast<uint32_t>(nent), codes, revcomp != 0, codes64, nmask32, notX);
+	uint64_t words = 0, rawTotal = 0;
+	for (int32_t i = 0; i < nent; ++i) { words += stored_words(static_cast<uint32_t>(n[i]), revcomp != 0); rawTotal += static_cast<uint32_t>(n[i]); }
+	const uint32_t bad = pack_range(n, 0, static_cast<uint32_t>(nent), codes, rawTotal, revcomp != 0, codes64, nmask32, notX);
 	for (int k = 0; k < 2; ++k) { codes64[words + k] = 0; nmask32[words + k] = 0xFFFFFFFFu; }
 	return static_cast<int>(bad);
 }
