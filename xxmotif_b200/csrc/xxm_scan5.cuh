@@ -77,31 +77,25 @@ __global__ void __launch_bounds__(kScan5Threads, 1) k_scan5(const uint64_t* __re
 	const uint32_t warp = (blockIdx.x * kScan5Threads + threadIdx.x) >> 5;
 	const uint32_t nwarps = (gridDim.x * kScan5Threads) >> 5;
 	const uint32_t nchunks = (scanWords + 63) / 64;
-	// the loads of a chunk are issued one iteration ahead (8 warps per scheduler do not hide a DRAM round trip otherwise)
-	uint4 nv = make_uint4(0u, 0u, 0u, 0u);
-	uint2 nd = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-	uint32_t ntail = 0;
-	auto fetch = [&](uint32_t c) {
+	// the loads of a chunk are issued one chunk ahead (8 warps per scheduler do not hide a DRAM round trip otherwise); two
+	// register sets alternate, so nothing is moved between them
+	struct Chunk { uint4 v; uint2 d; uint32_t tail; };
+	auto fetch = [&](Chunk& k, uint32_t c) {
 		const uint32_t w = c * 64 + 2 * lane;
-		nv = make_uint4(0u, 0u, 0u, 0u);
-		nd = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-		ntail = 0;
+		k.v = make_uint4(0u, 0u, 0u, 0u);
+		k.d = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+		k.tail = 0;
 		if (c < nchunks && w < scanWords) {
-			nv = __ldg(reinterpret_cast<const uint4*>(codes + w));
-			nd = __ldg(reinterpret_cast<const uint2*>(dead + w));
-			if (lane == 31 && w + 2 <= scanWords) ntail = static_cast<uint32_t>(__ldg(codes + w + 2));
+			k.v = __ldg(reinterpret_cast<const uint4*>(codes + w));
+			k.d = __ldg(reinterpret_cast<const uint2*>(dead + w));
+			if (lane == 31 && w + 2 <= scanWords) k.tail = static_cast<uint32_t>(__ldg(codes + w + 2));
 		}
 	};
-	fetch(warp);
-	for (uint32_t c = warp; c < nchunks; c += nwarps) {
+	auto process = [&](const Chunk& k, uint32_t c) {
 		const uint32_t w = c * 64 + 2 * lane;
-		const uint4 v = nv;
-		const uint2 d = nd;
-		const uint32_t tail = ntail;
-		fetch(c + nwarps);
-		uint32_t r[5] = {v.x, v.y, v.z, v.w, 0};
+		uint32_t r[5] = {k.v.x, k.v.y, k.v.z, k.v.w, 0};
 		r[4] = __shfl_down_sync(0xFFFFFFFFu, r[0], 1);
-		if (lane == 31) r[4] = tail;
+		if (lane == 31) r[4] = k.tail;
 		uint32_t e[34];
 		e[0] = pair_lookup<0>(r, tab);   e[1] = pair_lookup<1>(r, tab);   e[2] = pair_lookup<2>(r, tab);   e[3] = pair_lookup<3>(r, tab);
 		e[4] = pair_lookup<4>(r, tab);   e[5] = pair_lookup<5>(r, tab);   e[6] = pair_lookup<6>(r, tab);   e[7] = pair_lookup<7>(r, tab);
@@ -115,8 +109,8 @@ __global__ void __launch_bounds__(kScan5Threads, 1) k_scan5(const uint64_t* __re
 		uint32_t h0 = scan5_word<0>(e), h1 = scan5_word<16>(e);
 		uint32_t cnt = 0;
 		if (w < scanWords) {
-			h0 &= ~d.x;
-			h1 = (w + 1 < scanWords) ? (h1 & ~d.y) : 0u;
+			h0 &= ~k.d.x;
+			h1 = (w + 1 < scanWords) ? (h1 & ~k.d.y) : 0u;
 			*reinterpret_cast<uint2*>(hitmask + w) = make_uint2(h0, h1);
 			cnt = __popc(h0) + __popc(h1);
 		}
@@ -125,6 +119,15 @@ __global__ void __launch_bounds__(kScan5Threads, 1) k_scan5(const uint64_t* __re
 			chunkCount[c] = cnt;
 			if (cnt) atomicAdd(tileCount + (c >> 4), cnt);
 		}
+	};
+	Chunk A, B;
+	fetch(A, warp);
+	for (uint32_t c = warp; c < nchunks; c += 2 * nwarps) {
+		fetch(B, c + nwarps);
+		process(A, c);
+		if (c + nwarps >= nchunks) break;
+		fetch(A, c + 2 * nwarps);
+		process(B, c + nwarps);
 	}
 }
 
