@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample-seqs", type=int, default=60000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-refine-run", action="store_true")
+    ap.add_argument("--refine-sample-seqs", type=int, default=30000)
     return ap.parse_args()
 
 
@@ -94,6 +96,26 @@ def run_reference_sample(nseq, seqlen, steps, warmup, nproc):
         ms.append(1000.0 * j["seconds"] / max(1, j["steps"]))
     subprocess.call(["rm", "-rf", tmp])
     return tot, sum(ms) / len(ms), wall
+
+
+def run_reference_refine(nseq, seqlen):
+    """The unmodified reference's MotifContainer::iterate of the jump-start motif (ref_harness refine) on an nseq sample."""
+    from xxmotif_b200 import hostprep
+    tmp = tempfile.mkdtemp(prefix="xxm_bench_refine_")
+    try:
+        prof = os.path.join(tmp, "tata.prof")
+        with open(prof, "w") as fh:
+            fh.write(PROFILE_TXT)
+        n, codes = hostprep.synthetic_set(nseq, seqlen, seed=4)
+        fa = os.path.join(tmp, "in.fa")
+        write_fasta(fa, n, codes)
+        o = subprocess.run([HARNESS, "refine", os.path.join(tmp, "out"), fa, "--batch", "-p", prof], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL).stdout.decode()
+        line = [x for x in o.splitlines() if x.startswith("{")]
+        if not line:
+            raise RuntimeError("reference harness produced no result")
+        return json.loads(line[-1])
+    finally:
+        subprocess.call(["rm", "-rf", tmp])
 
 
 def reference_arm(a):
@@ -325,6 +347,33 @@ def ours(a):
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
+    # ---- "end-to-end s" of the metric: the whole refinement of the jump-start motif (MotifContainer::iterate's per-motif loop:
+    # optimizeMotif + maximizeMotifLength until the p-value stops improving) on the resident set, one xxm_iterate_motif call
+    if world == 1 and not a.no_refine_run:
+        try:
+            from xxmotif_b200 import refine
+            _, _, mxl, _ = ctx.seqset_info()
+            c0 = int(cols[0])
+            mot = refine.Motif(pwm0, cols, nent, enr=(1 - c0, 1 - c0, int(mxl) - c0 + 1), siteCap=max(1 << 20, 2 * nent))
+            R = refine.Refiner(ctx, totalPositions=int(total[nent]), revcomp=False, localization=False, maximizeMotifLength=True, minMatchPositions=5,
+                               maxMatchPositions=17, pseudo=0.1, neff_pwm=10.0)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rounds = R.iterate_motif(mot)
+            torch.cuda.synchronize()
+            gpu_s = time.perf_counter() - t0
+            rr = {"gpu_seconds": gpu_s, "sequences": nent, "rounds": int(rounds), "match_columns": [int(mot.cols[0]), int(mot.cols[-1])],
+                  "sites": int(mot.m.nsites), "log_pval": float(mot.pval),
+                  "what": "xxm_iterate_motif of the TATA profile on the resident set (set load not included)"}
+            if not a.no_cpu_baseline and os.path.exists(HARNESS):
+                ns = min(a.refine_sample_seqs, a.nseq)
+                rj = run_reference_refine(ns, a.seqlen)
+                rr.update({"reference_seconds_sample": rj["seconds"], "reference_sample_sequences": ns,
+                           "reference_seconds_scaled": rj["seconds"] * nent / ns, "reference_cores": 1,
+                           "reference_sample_result": {"match_columns": [rj["firstCol"], rj["lastCol"]], "sites": rj["nsites"], "log_pval": rj["pval"]}})
+            out["refine_run"] = rr
+        except Exception as ex:
+            out["refine_run"] = {"failed": str(ex)}
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             if os.path.exists(HARNESS):

@@ -199,12 +199,13 @@ static int run_bench(int steps, int warmup, Motif* m) {
 }
 
 int main(int argc, char** argv) {
-	if (argc < 5) { fprintf(stderr, "usage: ref_harness trace TRACE OUTDIR SEQ [flags] | bench STEPS WARMUP OUTDIR SEQ [flags]\n"); return 2; }
+	if (argc < 5) { fprintf(stderr, "usage: ref_harness trace TRACE OUTDIR SEQ [flags] | bench STEPS WARMUP OUTDIR SEQ [flags] | refine OUTDIR SEQ [flags]\n"); return 2; }
 	const bool bench = strcmp(argv[1], "bench") == 0;
-	int shift = bench ? 3 : 2;
+	const bool refine = strcmp(argv[1], "refine") == 0;  /* refine OUTDIR SEQ [flags]: MotifContainer::iterate of the start motif, timed */
+	int shift = bench ? 3 : (refine ? 1 : 2);
 	int steps = 0, warmup = 0;
 	std::string trace_path;
-	if (bench) { steps = atoi(argv[2]); warmup = atoi(argv[3]); } else trace_path = argv[2];
+	if (bench) { steps = atoi(argv[2]); warmup = atoi(argv[3]); } else if (!refine) trace_path = argv[2];
 
 	/* the reference prints its banner/progress on stdout: keep stdout clean for the JSON line */
 	int saved_stdout = dup(1);
@@ -224,6 +225,18 @@ int main(int argc, char** argv) {
 	if (bench) {
 		fflush(stdout); dup2(saved_stdout, 1);
 		return run_bench(steps, warmup, m);
+	}
+	if (refine) {
+		const double t0 = now_s();
+		startModels.iterate(Global::maximizeMotifLength, false);
+		const double dt = now_s() - t0;
+		fflush(stdout); dup2(saved_stdout, 1);
+		const motif_columns_type& c = m->getMotifColumns();
+		printf("{\"impl\": \"reference\", \"mode\": \"refine\", \"seconds\": %.6f, \"nent\": %d, \"firstCol\": %d, \"lastCol\": %d, \"ncols\": %d, "
+		       "\"nsites\": %d, \"pval\": %.17g}\n",
+		       dt, Global::posSet->nent, c.front(), c.back(), (int) c.size(), (int) m->getStartPosList().size(), m->getPval());
+		fflush(stdout);
+		return 0;
 	}
 
 	g_tr = fopen(trace_path.c_str(), "wb");

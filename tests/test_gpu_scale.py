@@ -298,3 +298,40 @@ def test_native_step_low_complexity_vs_oracle(mops):
             pwm = new
     finally:
         ctx.close()
+
+
+def test_bench_workload_refinement_matches_reference():
+    """The whole per-motif loop (xxm_iterate_motif) on a 10k-sequence sample of the bench workload against the unmodified
+    reference's MotifContainer::iterate run on the same sequences here (oracle/_ref/ref_harness refine): bit-identical
+    match columns, site count and log p-value."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    if not os.path.exists(bench.HARNESS):
+        pytest.skip("oracle/_ref/ref_harness not built")
+    import xxmotif_b200 as xb
+    from xxmotif_b200 import hostprep, refine
+    nseq, seqlen = 10000, 1000
+    ref = bench.run_reference_refine(nseq, seqlen)
+    n, codes = hostprep.synthetic_set(nseq, seqlen, seed=4)
+    bg, bgl = hostprep.background(n, codes)
+    rp, rc = hostprep.null_model(n, codes, order=2)
+    ctx = xb.Context(0)
+    try:
+        ctx.set_options(mops=False, oops=False, localization=False, bg=bg, bgLog=bgl)
+        ctx.set_background(2, rp, rc)
+        ctx.load_seqset(n, codes, revcomp=False)
+        total, _, mxl, _ = ctx.seqset_info()
+        pwm0, cols = hostprep.profile_pwm()
+        c0 = int(cols[0])
+        mot = refine.Motif(pwm0, cols, nseq, enr=(1 - c0, 1 - c0, int(mxl) - c0 + 1), siteCap=1 << 20)
+        R = refine.Refiner(ctx, totalPositions=int(total[nseq]), revcomp=False, localization=False, maximizeMotifLength=True, minMatchPositions=5,
+                           maxMatchPositions=17, pseudo=0.1, neff_pwm=10.0)
+        R.iterate_motif(mot)
+        assert [int(mot.cols[0]), int(mot.cols[-1]), len(mot.cols)] == [ref["firstCol"], ref["lastCol"], ref["ncols"]]
+        assert int(mot.m.nsites) == ref["nsites"]
+        assert float(mot.pval) == ref["pval"]
+    finally:
+        ctx.close()
