@@ -63,9 +63,10 @@ int xxm_set_options(xxm_ctx* ctx, const xxm_options* opt);
  * replaces: Global::posSet as filled by Alignment::getEntity (seqFormat/Alignment.cpp:149-195) + createRevcomp
  * (seqset.cpp:128-178) + calculateSequenceFeatures (seqset.cpp:21-36).
  * n[i], codes: the sequences BEFORE createRevcomp, codes 0=N,1=A,2=C,3=G,4=T concatenated without separators.
- * The set is packed once (2-bit codes + 1-bit N mask, reverse strand included when revcomp != 0) by the host cores, chunk
- * by chunk while earlier chunks are on the bus, so 0.375 bytes per stored base cross PCIe; it then stays resident in HBM.
- * XXM_PACK_THREADS sets the number of packing threads (default: min(12, 3/4 of the host cores)).  total[]/avgLength[] follow the
+ * The set is packed once (2-bit codes + 1-bit N mask, reverse strand included when revcomp != 0) and then stays resident in
+ * HBM.  With at least 6 packing threads (XXM_PACK_THREADS, default min(12, 3/4 of the host cores)) the host cores pack it
+ * chunk by chunk while earlier chunks are on the bus, so 0.375 bytes per stored base cross PCIe; with fewer, the raw bytes
+ * are copied and packed on the device.  total[]/avgLength[] follow the
  * reference's arithmetic, quirks included. */
 int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp);
 int xxm_seqset_info(const xxm_ctx* ctx, int32_t* total /*[nent+1] or NULL*/, double* avgLength /*[nent+1] or NULL*/,

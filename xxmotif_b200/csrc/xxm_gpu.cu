@@ -161,7 +161,7 @@ struct xxm_ctx {
 	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
 	DevBuf<uint64_t> status, total64;
 	DevBuf<uint32_t> r_seq, d_pbits;
-	DevBuf<uint8_t> d_t8;
+	DevBuf<uint8_t> d_t8, d_raw;
 	DevBuf<uint32_t> d_pairTab, d_dead, d_scanCounts;
 	std::vector<int> deadKey;   // (load serial, L, column offsets) d_dead was built for
 	uint64_t loadSerial = 0;
@@ -176,8 +176,12 @@ struct xxm_ctx {
 	bool pairOK = false;           // the pair table represents the left table exactly: k_scan5, else k_scan4
 	bool forceGenericScan = false; // tests: always take the generic find kernel
 	DevBuf<uint64_t> d_rawOff, d_layoutSums;
-	DevBuf<int32_t> d_n;
+	DevBuf<int32_t> d_notX, d_n;
 	std::vector<int32_t> notX;  // residues that are not N, per sequence (host_pack.h)
+	int32_t* h_notX = nullptr;  // pinned landing buffer of the same counts when the device packs
+	size_t h_notXCap = 0;
+	cudaStream_t copyStream = nullptr;
+	std::vector<cudaEvent_t> evPool;
 	uint8_t* h_pack = nullptr;  // pinned staging of the packed stream: h_packCap code words, then as many N masks
 	size_t h_packCap = 0;
 	DevBuf<unsigned long long> d_counts;
@@ -281,7 +285,9 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	// DevBuf members are released explicitly (no destructor: the struct is copied nowhere, but keep it trivial)
 	ctx->d_codes.release(); ctx->d_nmask.release(); ctx->d_wordOff.release(); ctx->d_blk2seq.release(); ctx->d_len.release();
 	ctx->d_rank0.release(); ctx->d_rank1.release(); ctx->d_hit0.release(); for (int k = 0; k < 2; ++k) { ctx->d_ids[k].release(); ctx->d_cls[k].release(); ctx->d_clsOk[k].release(); }
-	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_pack) cudaFreeHost(ctx->h_pack); ctx->d_n.release(); ctx->d_dead.release(); ctx->d_scanCounts.release(); ctx->s_kcls.release(); ctx->d_clsThr.release(); ctx->d_layoutSums.release();
+	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_pack) cudaFreeHost(ctx->h_pack); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_raw.release(); ctx->d_notX.release(); ctx->d_n.release(); ctx->d_dead.release(); ctx->d_scanCounts.release(); ctx->s_kcls.release(); ctx->d_clsThr.release(); ctx->d_layoutSums.release();
+	for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
+	if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 	if (ctx->h_pinXchg) cudaFreeHost(ctx->h_pinXchg); if (ctx->evStage) cudaEventDestroy(ctx->evStage);
 	ctx->d_cpval0.release(); ctx->d_cpval1.release(); ctx->d_leftProb.release(); ctx->d_cscore0.release(); ctx->d_cscore1.release();
 	ctx->d_memoKey.release(); ctx->d_memoVal.release(); ctx->d_memoState.release(); ctx->d_flags32.release();
@@ -316,6 +322,39 @@ extern "C" int xxm_get_stats(const xxm_ctx* ctx, xxm_stats* out) { *out = ctx->s
 // a1: sequence set
 // =====================================================================================================================
 namespace xxm {
+// per sequence: number of residues that are not N (code 0); any code > 4 raises the flag.  One warp per sequence of [s0, s1).
+__global__ void k_seq_stats(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rawOff, uint32_t s0, uint32_t s1, int32_t* __restrict__ notX,
+                            uint32_t* __restrict__ bad) {
+	const int lane = threadIdx.x & 31;
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+	for (uint32_t s = s0 + warp; s < s1; s += nwarps) {
+		const uint64_t a = rawOff[s], b = rawOff[s + 1];
+		uint32_t cnt = 0, err = 0;
+		// 16 bytes per lane once the pointer is aligned
+		uint64_t i = a;
+		const uint64_t aUp = min(b, (a + 15) & ~static_cast<uint64_t>(15));
+		for (uint64_t k = i + lane; k < aUp; k += 32) { const uint8_t c = raw[k]; cnt += (c != 0); err |= (c > 4); }
+		i = aUp;
+		const uint64_t nv = (b - i) / 16;
+		for (uint64_t v = lane; v < nv; v += 32) {
+			const uint4 q = *reinterpret_cast<const uint4*>(raw + i + 16 * v);
+			const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+			for (int t = 0; t < 4; ++t) {
+				const uint32_t x = w4[t];
+				// bytes != 0 (for codes 0..7): bit 0 | bit 1 | bit 2; codes > 4: bit 2 and (bit 0 or bit 1), or any higher bit (then the count is moot)
+				const uint32_t nz = (x | (x >> 1) | (x >> 2)) & 0x01010101u;
+				cnt += __popc(nz);
+				err |= (x & 0xF8F8F8F8u) | ((x >> 2) & (x | (x >> 1)) & 0x01010101u);
+			}
+		}
+		for (uint64_t k = i + 16 * nv + lane; k < b; k += 32) { const uint8_t c = raw[k]; cnt += (c != 0); err |= (c > 4); }
+		for (int d = 16; d; d >>= 1) { cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d); err |= __shfl_xor_sync(0xFFFFFFFFu, err, d); }
+		if (lane == 0) { notX[s] = static_cast<int32_t>(cnt); if (err) atomicExch(bad, s + 1); }
+	}
+}
+
 // layout of the stream from the raw lengths alone: rawOff (bytes), wordOff (words), len (stored length).  Two launches over
 // blocks of 1024 sequences: per-block sums, then every block adds up the sums of the blocks before it and scans its own.
 __device__ __forceinline__ void seq_extent(const int32_t* __restrict__ n, uint32_t i, uint32_t nent, int revcomp, uint64_t* raw, uint64_t* words, uint64_t* stored) {
@@ -384,84 +423,12 @@ __global__ void k_blk2seq(const uint32_t* __restrict__ wordOff, uint32_t nent, u
 }
 }  // namespace xxm
 
-// a1.  The host cores pack the set into the device layout (host_pack.h) in chunks of whole sequences; every finished chunk
-// goes on the bus at once (0.375 bytes per stored base), and the host folds the residue counts of a chunk into total[] /
-// avgLength[] while the next chunks are being packed and copied.
-extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp) {
-	CK(cudaSetDevice(ctx->device));
-	if (nent <= 0) return ctx->fail("empty sequence set");
-	static const bool trace = std::getenv("XXM_TRACE") != nullptr;
-	const auto tStart = std::chrono::steady_clock::now();
-	ctx->nent = nent;
-	ctx->revcomp = revcomp != 0;
-	ctx->len.resize(nent);
-	ctx->total.resize(static_cast<size_t>(nent) + 1);
-	ctx->logAcc.resize(static_cast<size_t>(nent) + 1);
-	ctx->total[0] = 0;
-	ctx->logAcc[0] = 0.0;
-	ctx->wordOff.resize(static_cast<size_t>(nent) + 1);
-	// ---- layout on the device from the lengths alone
-	CK(ctx->d_n.ensure(nent));
-	CK(ctx->d_rawOff.ensure(static_cast<size_t>(nent) + 1));
-	CK(ctx->d_wordOff.ensure(static_cast<size_t>(nent) + 1));
-	CK(ctx->d_len.ensure(nent));
-	CK(cudaMemcpyAsync(ctx->d_n.p, n, static_cast<size_t>(nent) * 4, cudaMemcpyHostToDevice, ctx->stream));
-	{
-		const uint32_t nb = cdiv(static_cast<uint32_t>(nent), 1024);
-		CK(ctx->d_layoutSums.ensure(2ull * nb));
-		k_seq_layout_sums<<<nb, 1024, 0, ctx->stream>>>(ctx->d_n.p, static_cast<uint32_t>(nent), revcomp ? 1 : 0, ctx->d_layoutSums.p);
-		CKK();
-		k_seq_layout<<<nb, 1024, 0, ctx->stream>>>(ctx->d_n.p, static_cast<uint32_t>(nent), revcomp ? 1 : 0, ctx->d_layoutSums.p, ctx->d_rawOff.p,
-		                                            ctx->d_wordOff.p, ctx->d_len.p);
-		CKK();
-	}
-	// ---- sizes first (no stores: a fraction of a millisecond per million sequences), so that the buffers exist before the first chunk leaves
+// The packing step on the host cores (host_pack.h): worker threads pack chunks of whole sequences into a pinned staging
+// buffer, every finished chunk goes on the bus at once (0.375 bytes per stored base), and this thread folds the residue
+// counts of a chunk into total[] / avgLength[] while the next chunks are being packed and copied.
+static int load_pack_on_host(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp, uint64_t rawTotal, int nthreads, bool trace,
+                             std::chrono::steady_clock::time_point tStart) {
 	uint64_t off = 0, words = 0;
-	int mx = 0, mn = 2147483647;
-	{
-		int mxRaw = 0;
-		uint64_t w0 = 0;
-		for (int i = 0; i < nent; ++i) {  // branch free: vectorises
-			const int n0 = n[i];
-			mxRaw = std::max(mxRaw, n0);
-			mn = std::min(mn, n0);
-			off += static_cast<uint32_t>(n0);
-			w0 += (static_cast<uint32_t>(n0) + static_cast<uint32_t>(kPadBases + 31)) >> 5;
-		}
-		if (mn < 1) {
-			for (int i = 0; i < nent; ++i) if (n[i] < 1) return ctx->fail("sequence %d is empty", i + 1);
-		}
-		if (mxRaw > 1000000000) return ctx->fail("sequence longer than 10^9 residues");
-		if (revcomp) {
-			words = 0;
-			for (int i = 0; i < nent; ++i) words += (2ull * static_cast<uint32_t>(n[i]) + 1 + kPadBases + 31) / 32;
-			mx = 2 * mxRaw + 1;
-			mn = 2 * mn + 1;
-		} else {
-			words = w0;
-			mx = mxRaw;
-		}
-	}
-	if (words > 0xFFFFFF00ull) return ctx->fail("sequence stream exceeds 2^32 words");
-	const uint64_t rawTotal = off;
-	ctx->nwords = static_cast<uint32_t>(words);
-	ctx->max_leng = mx;
-	ctx->min_leng = mn;
-	const uint32_t nblk = ctx->nwords / kBlkWords + 1;
-	CK(ctx->d_codes.ensure(static_cast<size_t>(ctx->nwords) + 2));
-	CK(ctx->d_nmask.ensure(static_cast<size_t>(ctx->nwords) + 2));
-	CK(ctx->d_blk2seq.ensure(nblk));
-	ctx->S.codes = ctx->d_codes.p;
-	ctx->S.nmask = ctx->d_nmask.p;
-	ctx->S.wordOff = ctx->d_wordOff.p;
-	ctx->S.len = ctx->d_len.p;
-	ctx->S.blk2seq = ctx->d_blk2seq.p;
-	ctx->S.nwords = ctx->nwords;
-	ctx->S.nent = nent;
-	ctx->S.uniformWps = (mx == mn) ? static_cast<uint32_t>((static_cast<uint64_t>(mx) + kPadBases + 31) / 32) : 0u;
-	ctx->S.uniformLen = (mx == mn) ? mx : 0;
-	k_blk2seq<<<cdiv(static_cast<uint32_t>(nent), 256), 256, 0, ctx->stream>>>(ctx->d_wordOff.p, static_cast<uint32_t>(nent), nblk, ctx->d_blk2seq.p);
-	CKK();
 	// pinned staging of the packed words (kept across loads): code words, then N masks
 	const size_t wordsAll = static_cast<size_t>(ctx->nwords) + 2;
 	if (ctx->h_packCap < wordsAll) {
@@ -499,7 +466,6 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 			packChunk(k);
 		}
 	};
-	int nthreads = (rawTotal < (4ull << 20)) ? 0 : pack_threads_default();
 	if (nthreads == 1) nthreads = 0;  // one packer: this thread
 	struct Joiner {
 		std::vector<std::thread> t;
@@ -576,18 +542,210 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	CK(cudaStreamSynchronize(ctx->stream));  // the staging buffer is reused by the next load
 	if (badSeq) return ctx->fail("sequence %u holds a code outside 0..4", badSeq);
 	if (overflow) return ctx->fail("more than 2^31-1 residues: the reference's int totals overflow (Alignment.h:40-41)");
+	if (trace) {
+		const auto tEnd = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "xxm load_seqset (host pack): %u chunks, %d packing threads, first copy issued after %.2f ms, all cut after %.2f ms, done after %.2f ms\n", ncut,
+		             nthreads ? nthreads : 1, std::chrono::duration<double, std::milli>(tFirst - tStart).count(),
+		             std::chrono::duration<double, std::milli>(tQueued - tStart).count(), std::chrono::duration<double, std::milli>(tEnd - tStart).count());
+	}
+	return 0;
+}
+
+// The packing step on the device, for hosts with few cores per GPU: the raw codes travel in chunks of whole sequences on a
+// copy stream (1 byte per base over PCIe); behind every chunk the per-sequence statistics (non-N residues, range check) and
+// the packing kernel run on the compute stream, and the host folds the statistics of a chunk into total[] / avgLength[]
+// while the next chunks are still on the bus.
+static int load_pack_on_device(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp, uint64_t rawTotal, bool trace,
+                               std::chrono::steady_clock::time_point tStart) {
+	uint64_t off = 0, words = 0;
+	if (!ctx->copyStream) CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+	CK(ctx->d_raw.ensure(std::max<uint64_t>(1, rawTotal)));
+	CK(ctx->d_notX.ensure(nent));
+	CK(ctx->counters.ensure(8));
+	CK(cudaMemsetAsync(ctx->counters.p, 0, 32, ctx->stream));
+	// pinned landing buffer of the per-sequence counts
+	if (ctx->h_notXCap < static_cast<size_t>(nent)) {
+		if (ctx->h_notX) cudaFreeHost(ctx->h_notX);
+		ctx->h_notX = nullptr;
+		ctx->h_notXCap = 0;
+		CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_notX), static_cast<size_t>(nent) * 4, cudaHostAllocDefault));
+		ctx->h_notXCap = static_cast<size_t>(nent);
+	}
+	// ---- the same layout on the host (it owns wordOff / len / total), cutting chunks of whole sequences as it goes; every
+	// chunk is queued as soon as it is cut: copy(k) on the copy stream, stats(k) + counts-to-host(k) + encode(k) on the compute stream
+	constexpr uint64_t kChunkBytes = 48ull << 20;
+	struct Chunk { int s0, s1; uint64_t b0, b1; uint32_t w0, w1; };
+	std::vector<Chunk> chunks;
+	auto tFirst = tStart;
+	{
+		Chunk c{0, 0, 0, 0, 0, 0};
+		off = 0;
+		words = 0;
+		for (int i = 0; i < nent; ++i) {
+			const int n0 = n[i];
+			const int nstore = revcomp ? 2 * n0 + 1 : n0;
+			ctx->len[i] = nstore;
+			ctx->wordOff[i] = static_cast<uint32_t>(words);
+			words += (static_cast<uint64_t>(nstore) + kPadBases + 31) / 32;
+			off += static_cast<uint64_t>(n0);
+			if (off - c.b0 < kChunkBytes && i + 1 != nent) continue;
+			c.s1 = i + 1; c.b1 = off; c.w1 = static_cast<uint32_t>(words);
+			const size_t k = chunks.size();
+			chunks.push_back(c);
+			while (ctx->evPool.size() < 2 * (k + 1)) {
+				cudaEvent_t e;
+				CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+				ctx->evPool.push_back(e);
+			}
+			if (trace && k == 0) { CK(cudaEventRecord(ctx->ev0, ctx->copyStream)); tFirst = std::chrono::steady_clock::now(); }
+			CK(cudaMemcpyAsync(ctx->d_raw.p + c.b0, codes + c.b0, c.b1 - c.b0, cudaMemcpyHostToDevice, ctx->copyStream));
+			CK(cudaEventRecord(ctx->evPool[2 * k], ctx->copyStream));
+			if (trace && i + 1 == nent) CK(cudaEventRecord(ctx->ev1, ctx->copyStream));
+			CK(cudaStreamWaitEvent(ctx->stream, ctx->evPool[2 * k], 0));
+			const uint32_t ns = static_cast<uint32_t>(c.s1 - c.s0);
+			k_seq_stats<<<std::min<uint32_t>(cdiv(ns, 8), static_cast<uint32_t>(ctx->numSMs) * 8), 256, 0, ctx->stream>>>(
+				ctx->d_raw.p, ctx->d_rawOff.p, static_cast<uint32_t>(c.s0), static_cast<uint32_t>(c.s1), ctx->d_notX.p, ctx->counters.p);
+			CKK();
+			CK(cudaMemcpyAsync(ctx->h_notX + c.s0, ctx->d_notX.p + c.s0, static_cast<size_t>(ns) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+			CK(cudaEventRecord(ctx->evPool[2 * k + 1], ctx->stream));
+			const uint32_t w1 = (i + 1 == nent) ? ctx->nwords + 2 : c.w1;
+			if (w1 > c.w0) {
+				k_encode<<<cdiv(w1 - c.w0, 256), 256, 0, ctx->stream>>>(ctx->d_raw.p, ctx->d_rawOff.p, ctx->S, c.w0, w1, ctx->d_codes.p, ctx->d_nmask.p, revcomp ? 1 : 0);
+				CKK();
+			}
+			c = Chunk{i + 1, i + 1, off, off, static_cast<uint32_t>(words), static_cast<uint32_t>(words)};
+		}
+	}
+	ctx->wordOff[nent] = static_cast<uint32_t>(words);
+	const auto tQueued = std::chrono::steady_clock::now();
+	// ---- calculateSequenceFeatures (seqset.cpp:21-36) on the raw set, then -- with revcomp -- the recount at the end of
+	// createRevcomp (seqset.cpp:165-177) which compares codes with the CHARACTER '0' and therefore counts every
+	// position of the doubled sequence.
+	double acc = 0, lastLog = 0;
+	int lastNotX = 0;
+	int64_t tot = 0;
+	for (size_t k = 0; k < chunks.size(); ++k) {
+		CK(cudaEventSynchronize(ctx->evPool[2 * k + 1]));
+		for (int i = chunks[k].s0; i < chunks[k].s1; ++i) {
+			int notX = ctx->h_notX[i];
+			if (revcomp) notX = ctx->len[i];
+			if (notX != 0) {
+				if (notX != lastNotX) { lastNotX = notX; lastLog = std::log(notX); }  // same argument, same glibc result
+				acc += lastLog;
+			}
+			tot += notX;
+			if (tot > 2147483647LL) { cudaStreamSynchronize(ctx->stream); return ctx->fail("more than 2^31-1 residues: the reference's int totals overflow (Alignment.h:40-41)"); }
+			ctx->total[i + 1] = static_cast<int32_t>(tot);
+			ctx->logAcc[i + 1] = acc;
+		}
+	}
+	uint32_t bad = 0;
+	CK(cudaMemcpyAsync(ctx->h_pin + 4, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	std::memcpy(&bad, ctx->h_pin + 4, 4);
+	if (bad) return ctx->fail("sequence %u holds a code outside 0..4", bad);
+	if (ctx->d_raw.cap > (8ull << 30)) ctx->d_raw.release();  // the raw codes are only needed for packing
+	if (trace) {
+		const auto tEnd = std::chrono::steady_clock::now();
+		float copyMs = 0;
+		cudaEventElapsedTime(&copyMs, ctx->ev0, ctx->ev1);
+		std::fprintf(stderr, "xxm load_seqset (device pack): %zu chunks, first copy issued after %.2f ms, all queued after %.2f ms, copies took %.2f ms, done after %.2f ms\n",
+		             chunks.size(), std::chrono::duration<double, std::milli>(tFirst - tStart).count(),
+		             std::chrono::duration<double, std::milli>(tQueued - tStart).count(), copyMs, std::chrono::duration<double, std::milli>(tEnd - tStart).count());
+	}
+	return 0;
+}
+
+// a1.  Layout from the lengths, then the packing step where it is cheaper: on the host cores when there are at least
+// kMinPackThreads of them for this GPU (XXM_PACK_THREADS, default min(12, 3/4 of the cores)), else on the device.
+extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp) {
+	CK(cudaSetDevice(ctx->device));
+	if (nent <= 0) return ctx->fail("empty sequence set");
+	static const bool trace = std::getenv("XXM_TRACE") != nullptr;
+	const auto tStart = std::chrono::steady_clock::now();
+	ctx->nent = nent;
+	ctx->revcomp = revcomp != 0;
+	ctx->len.resize(nent);
+	ctx->total.resize(static_cast<size_t>(nent) + 1);
+	ctx->logAcc.resize(static_cast<size_t>(nent) + 1);
+	ctx->total[0] = 0;
+	ctx->logAcc[0] = 0.0;
+	ctx->wordOff.resize(static_cast<size_t>(nent) + 1);
+	// ---- layout on the device from the lengths alone
+	CK(ctx->d_n.ensure(nent));
+	CK(ctx->d_rawOff.ensure(static_cast<size_t>(nent) + 1));
+	CK(ctx->d_wordOff.ensure(static_cast<size_t>(nent) + 1));
+	CK(ctx->d_len.ensure(nent));
+	CK(cudaMemcpyAsync(ctx->d_n.p, n, static_cast<size_t>(nent) * 4, cudaMemcpyHostToDevice, ctx->stream));
+	{
+		const uint32_t nb = cdiv(static_cast<uint32_t>(nent), 1024);
+		CK(ctx->d_layoutSums.ensure(2ull * nb));
+		k_seq_layout_sums<<<nb, 1024, 0, ctx->stream>>>(ctx->d_n.p, static_cast<uint32_t>(nent), revcomp ? 1 : 0, ctx->d_layoutSums.p);
+		CKK();
+		k_seq_layout<<<nb, 1024, 0, ctx->stream>>>(ctx->d_n.p, static_cast<uint32_t>(nent), revcomp ? 1 : 0, ctx->d_layoutSums.p, ctx->d_rawOff.p,
+		                                            ctx->d_wordOff.p, ctx->d_len.p);
+		CKK();
+	}
+	// ---- sizes first (no stores: a fraction of a millisecond per million sequences), so that the buffers exist before the first chunk leaves
+	uint64_t off = 0, words = 0;
+	int mx = 0, mn = 2147483647;
+	{
+		int mxRaw = 0;
+		uint64_t w0 = 0;
+		for (int i = 0; i < nent; ++i) {  // branch free: vectorises
+			const int n0 = n[i];
+			mxRaw = std::max(mxRaw, n0);
+			mn = std::min(mn, n0);
+			off += static_cast<uint32_t>(n0);
+			w0 += (static_cast<uint32_t>(n0) + static_cast<uint32_t>(kPadBases + 31)) >> 5;
+		}
+		if (mn < 1) {
+			for (int i = 0; i < nent; ++i) if (n[i] < 1) return ctx->fail("sequence %d is empty", i + 1);
+		}
+		if (mxRaw > 1000000000) return ctx->fail("sequence longer than 10^9 residues");
+		if (revcomp) {
+			words = 0;
+			for (int i = 0; i < nent; ++i) words += (2ull * static_cast<uint32_t>(n[i]) + 1 + kPadBases + 31) / 32;
+			mx = 2 * mxRaw + 1;
+			mn = 2 * mn + 1;
+		} else {
+			words = w0;
+			mx = mxRaw;
+		}
+	}
+	if (words > 0xFFFFFF00ull) return ctx->fail("sequence stream exceeds 2^32 words");
+	const uint64_t rawTotal = off;
+	ctx->nwords = static_cast<uint32_t>(words);
+	ctx->max_leng = mx;
+	ctx->min_leng = mn;
+	const uint32_t nblk = ctx->nwords / kBlkWords + 1;
+	CK(ctx->d_codes.ensure(static_cast<size_t>(ctx->nwords) + 2));
+	CK(ctx->d_nmask.ensure(static_cast<size_t>(ctx->nwords) + 2));
+	CK(ctx->d_blk2seq.ensure(nblk));
+	ctx->S.codes = ctx->d_codes.p;
+	ctx->S.nmask = ctx->d_nmask.p;
+	ctx->S.wordOff = ctx->d_wordOff.p;
+	ctx->S.len = ctx->d_len.p;
+	ctx->S.blk2seq = ctx->d_blk2seq.p;
+	ctx->S.nwords = ctx->nwords;
+	ctx->S.nent = nent;
+	ctx->S.uniformWps = (mx == mn) ? static_cast<uint32_t>((static_cast<uint64_t>(mx) + kPadBases + 31) / 32) : 0u;
+	ctx->S.uniformLen = (mx == mn) ? mx : 0;
+	k_blk2seq<<<cdiv(static_cast<uint32_t>(nent), 256), 256, 0, ctx->stream>>>(ctx->d_wordOff.p, static_cast<uint32_t>(nent), nblk, ctx->d_blk2seq.p);
+	CKK();
+	const int nthreads = pack_threads_default();
+	constexpr int kMinPackThreads = 6;  // 3 threads pack ~17 GB/s of bases, the bus takes raw bytes at 20-48 GB/s (profiles/README.md)
+	if (nthreads >= kMinPackThreads || rawTotal < (4ull << 20)) {
+		TRY(load_pack_on_host(ctx, nent, n, codes, revcomp, rawTotal, rawTotal < (4ull << 20) ? 0 : nthreads, trace, tStart));
+	} else {
+		TRY(load_pack_on_device(ctx, nent, n, codes, revcomp, rawTotal, trace, tStart));
+	}
 	if (ctx->sum_i.size() != static_cast<size_t>(ctx->max_leng) + 1) init_sum_i(ctx->sum_i, ctx->max_leng);
 	ctx->haveModel = false;
 	ctx->loadSerial++;
 	ctx->deadKey.clear();
 	for (auto& l : ctx->L) l = SiteList();
 	ctx->nBest = 0;
-	if (trace) {
-		const auto tEnd = std::chrono::steady_clock::now();
-		std::fprintf(stderr, "xxm load_seqset: %u chunks, %d packing threads, first copy issued after %.2f ms, all cut after %.2f ms, done after %.2f ms\n", ncut,
-		             nthreads ? nthreads : 1, std::chrono::duration<double, std::milli>(tFirst - tStart).count(),
-		             std::chrono::duration<double, std::milli>(tQueued - tStart).count(), std::chrono::duration<double, std::milli>(tEnd - tStart).count());
-	}
 	return 0;
 }
 

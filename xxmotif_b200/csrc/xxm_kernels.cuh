@@ -10,6 +10,34 @@ constexpr uint64_t kFlagAgg = 1ull << 62;   // decoupled look-back: tile aggrega
 constexpr uint64_t kFlagIncl = 2ull << 62;  // inclusive prefix available
 constexpr uint64_t kValMask = (1ull << 62) - 1;
 
+// ---------------------------------------------------------------------------------------------------------------
+// K1  encode: raw codes (0=N,1..4) -> packed stream, generating the reverse strand on the fly
+//     (createRevcomp, seqset.cpp:128-178: S[n+1] = N, S[n+1+k] = complement(S[n+1-k])).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_encode(const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rawOff, SeqStream S, uint32_t w0, uint32_t w1,
+                         uint64_t* __restrict__ codes, uint32_t* __restrict__ nmask, int revcomp) {
+	const uint32_t w = w0 + blockIdx.x * blockDim.x + threadIdx.x;  // words [w0, w1) of the stream
+	if (w >= w1 || w >= S.nwords + 2) return;
+	if (w >= S.nwords) { codes[w] = 0; nmask[w] = 0xFFFFFFFFu; return; }
+	const uint32_t s = find_seq(S, w);
+	const int n = S.len[s];
+	const int n0 = revcomp ? (n - 1) / 2 : n;
+	const uint8_t* r = raw + rawOff[s];
+	uint64_t c = 0;
+	uint32_t m = 0;
+	const int q0 = static_cast<int>(w - S.wordOff[s]) * 32 + 1;
+	for (int j = 0; j < 32; ++j) {
+		const int q = q0 + j;
+		int code = 0;
+		if (q <= n0) code = r[q - 1];
+		else if (revcomp && q > n0 + 1 && q <= n) { const int f = r[2 * n0 + 2 - q - 1]; code = f ? 5 - f : 0; }
+		if (code == 0) m |= 1u << j;
+		else c |= static_cast<uint64_t>(code - 1) << (2 * j);
+	}
+	codes[w] = c;
+	nmask[w] = m;
+}
+
 // scatter compact (id, class) lists into the dense rank table and the "can be a site" bitmap
 __global__ void k_fill_rank(const uint32_t* __restrict__ ids, const uint32_t* __restrict__ cls, const uint8_t* __restrict__ clsOk, int n,
                             uint32_t* __restrict__ rank, uint32_t* __restrict__ bitmap) {
