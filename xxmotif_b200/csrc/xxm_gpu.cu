@@ -1266,7 +1266,7 @@ static int select_slots(xxm_ctx* ctx, const Values& V, const uint32_t* seq, cons
 		SlotIO io{};
 		io.seq = seq; io.pos = pos; io.vidx = vidx; io.n = n; io.shift = shift;
 		io.slotIdx = sIdx.p; io.slotScore = sScore.p; io.counters = ctx->counters.p;
-		if (ordered) k_select_zoops<<<cdiv(n, 128), 128, 0, ctx->stream>>>(V, io);
+		if (ordered) k_select_zoops<<<cdiv(n, static_cast<uint32_t>(kZoopsTile)), 256, 0, ctx->stream>>>(V, io);
 		else k_select_zoops_serial<<<1, 32, 0, ctx->stream>>>(V, io);
 		CKK();
 		CK(cudaMemcpyAsync(nFilled, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));

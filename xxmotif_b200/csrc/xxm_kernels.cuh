@@ -264,13 +264,62 @@ __device__ __forceinline__ void zoops_walk(const Values& V, const SlotIO& io, ui
 		}
 	}
 }
-__global__ void k_select_zoops(Values V, SlotIO io) {
-	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= io.n) return;
-	if (i > 0 && io.seq[i - 1] == io.seq[i]) return;
-	uint32_t b = i + 1;
-	while (b < io.n && io.seq[b] == io.seq[i]) ++b;
-	zoops_walk(V, io, i, b);
+// Ordered lists (one contiguous run per sequence).  A block stages the finalPval and the sequence of 1024 entries in shared
+// memory (coalesced loads, all table gathers in flight together); the thread that owns the first entry of a run then folds
+// the run in list order out of shared memory -- past the end of the tile out of global memory, which happens once per tile --
+// with the slot in registers, and writes the slot once.  (The first version walked every run out of global memory with the
+// slot in global memory: a chain of ~20 dependent round trips per sequence, 847 us for 2.05e7 candidates.)
+constexpr int kZoopsTile = 1024;
+__global__ void __launch_bounds__(256) k_select_zoops(Values V, SlotIO io) {
+	__shared__ double s_f[kZoopsTile];
+	__shared__ uint32_t s_seq[kZoopsTile];
+	const uint32_t base = blockIdx.x * kZoopsTile;
+	const bool needPos = V.kind != kFinalTable && V.kind != kFinalPerCand;
+#pragma unroll
+	for (int k = 0; k < kZoopsTile / 256; ++k) {
+		const uint32_t r = k * 256 + threadIdx.x, i = base + r;
+		uint32_t sq = 0;      // (sequence numbers start at 1)
+		double f = 2.0;       // never below a slot score
+		if (i < io.n) {
+			sq = io.seq[i];
+			const uint32_t v = io.vidx[i];
+			if (v != kNone) f = final_of(V, v, i, needPos ? static_cast<int>(io.pos[i]) + io.shift : 0);
+		}
+		s_seq[r] = sq;
+		s_f[r] = f;
+	}
+	__syncthreads();
+	uint32_t filled = 0;
+#pragma unroll
+	for (int k = 0; k < kZoopsTile / 256; ++k) {
+		const uint32_t r = 4 * threadIdx.x + k, i = base + r;
+		if (i >= io.n) break;
+		const uint32_t sq = s_seq[r];
+		const uint32_t prev = r ? s_seq[r - 1] : (i ? io.seq[i - 1] : 0u);
+		if (sq == prev) continue;  // not the head of a run
+		float slot = 1.0f;
+		uint32_t idx = kNone;
+		uint32_t j = r;
+		for (; j < static_cast<uint32_t>(kZoopsTile) && s_seq[j] == sq; ++j) {
+			const double f = s_f[j];
+			if (f < static_cast<double>(slot)) { slot = static_cast<float>(f); idx = base + j; }
+		}
+		if (j == static_cast<uint32_t>(kZoopsTile)) {
+			for (uint32_t g = base + kZoopsTile; g < io.n && io.seq[g] == sq; ++g) {
+				const uint32_t v = io.vidx[g];
+				if (v == kNone) continue;
+				const double f = final_of(V, v, g, needPos ? static_cast<int>(io.pos[g]) + io.shift : 0);
+				if (f < static_cast<double>(slot)) { slot = static_cast<float>(f); idx = g; }
+			}
+		}
+		if (idx != kNone) {
+			io.slotIdx[sq - 1] = idx;
+			io.slotScore[sq - 1] = slot;
+			++filled;
+		}
+	}
+	filled = __reduce_add_sync(0xFFFFFFFFu, filled);
+	if ((threadIdx.x & 31) == 0 && filled) atomicAdd(&io.counters[0], filled);
 }
 __global__ void k_select_zoops_serial(Values V, SlotIO io) {
 	if (blockIdx.x == 0 && threadIdx.x == 0) zoops_walk(V, io, 0, io.n);
