@@ -265,10 +265,11 @@ __device__ __forceinline__ void zoops_walk(const Values& V, const SlotIO& io, ui
 	}
 }
 // Ordered lists (one contiguous run per sequence).  A block stages the finalPval and the sequence of 1024 entries in shared
-// memory (coalesced loads, all table gathers in flight together); the thread that owns the first entry of a run then folds
-// the run in list order out of shared memory -- past the end of the tile out of global memory, which happens once per tile --
-// with the slot in registers, and writes the slot once.  (The first version walked every run out of global memory with the
-// slot in global memory: a chain of ~20 dependent round trips per sequence, 847 us for 2.05e7 candidates.)
+// memory (coalesced loads, all table gathers in flight together); the heads of the runs that start in the tile are
+// compacted, and one thread per head folds its run in list order out of shared memory -- past the end of the tile out of
+// global memory, which happens once per tile -- with the slot in registers, and writes the slot once.  (The first version
+// walked every run out of global memory with the slot in global memory: a chain of ~20 dependent round trips per sequence,
+// 847 us for 2.05e7 candidates.)
 constexpr int kZoopsTile = 1024;
 __global__ void __launch_bounds__(256) k_select_zoops(Values V, SlotIO io) {
 	__shared__ double s_f[kZoopsTile];
@@ -289,14 +290,38 @@ __global__ void __launch_bounds__(256) k_select_zoops(Values V, SlotIO io) {
 		s_f[r] = f;
 	}
 	__syncthreads();
-	uint32_t filled = 0;
+	// the heads of the runs that start in this tile, compacted: every walking warp has all its lanes busy
+	__shared__ uint16_t s_head[kZoopsTile];
+	__shared__ uint32_t s_wsum[8];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t hm = 0;  // bit k: entry 4 * tid + k is the head of a run
 #pragma unroll
-	for (int k = 0; k < kZoopsTile / 256; ++k) {
+	for (int k = 0; k < 4; ++k) {
 		const uint32_t r = 4 * threadIdx.x + k, i = base + r;
 		if (i >= io.n) break;
-		const uint32_t sq = s_seq[r];
 		const uint32_t prev = r ? s_seq[r - 1] : (i ? io.seq[i - 1] : 0u);
-		if (sq == prev) continue;  // not the head of a run
+		if (s_seq[r] != prev) hm |= 1u << k;
+	}
+	const uint32_t cnt = __popc(hm);
+	uint32_t incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+		if (lane >= d) incl += t;
+	}
+	if (lane == 31) s_wsum[wid] = incl;
+	__syncthreads();
+	uint32_t off = incl - cnt, nheads = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) { if (k < wid) off += s_wsum[k]; nheads += s_wsum[k]; }
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+		if ((hm >> k) & 1u) s_head[off++] = static_cast<uint16_t>(4 * threadIdx.x + k);
+	__syncthreads();
+	uint32_t filled = 0;
+	for (uint32_t h = threadIdx.x; h < nheads; h += 256) {
+		const uint32_t r = s_head[h];
+		const uint32_t sq = s_seq[r];
 		float slot = 1.0f;
 		uint32_t idx = kNone;
 		uint32_t j = r;
@@ -319,7 +344,7 @@ __global__ void __launch_bounds__(256) k_select_zoops(Values V, SlotIO io) {
 		}
 	}
 	filled = __reduce_add_sync(0xFFFFFFFFu, filled);
-	if ((threadIdx.x & 31) == 0 && filled) atomicAdd(&io.counters[0], filled);
+	if (lane == 0 && filled) atomicAdd(&io.counters[0], filled);
 }
 __global__ void k_select_zoops_serial(Values V, SlotIO io) {
 	if (blockIdx.x == 0 && threadIdx.x == 0) zoops_walk(V, io, 0, io.n);
@@ -412,11 +437,24 @@ __global__ void k_hist_vidx(const uint32_t* __restrict__ vidx, const uint8_t* __
 	if (i >= n || !keep[i]) return;
 	atomicAdd(&hist[vidx[i]], 1u);
 }
-__global__ void k_hist_slots(const uint32_t* __restrict__ slotIdx, const uint32_t* __restrict__ vidx, uint32_t nslots, uint32_t* __restrict__ hist) {
-	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= nslots) return;
-	const uint32_t i = slotIdx[s];
-	if (i != kNone) atomicAdd(&hist[vidx[i]], 1u);
+// nvalShared != 0: the bins fit shared memory (dynamic, nvalShared * 4 bytes) -- per-block histogram, flushed once; the
+// slots of ~10^6 sequences fall into a few hundred value indices, which serialises plain global atomics (168 us per call)
+__global__ void __launch_bounds__(256) k_hist_slots(const uint32_t* __restrict__ slotIdx, const uint32_t* __restrict__ vidx, uint32_t nslots,
+                                                    uint32_t* __restrict__ hist, uint32_t nvalShared) {
+	extern __shared__ uint32_t s_hs[];
+	for (uint32_t k = threadIdx.x; k < nvalShared; k += blockDim.x) s_hs[k] = 0;
+	if (nvalShared) __syncthreads();
+	for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < nslots; s += gridDim.x * blockDim.x) {
+		const uint32_t i = slotIdx[s];
+		if (i == kNone) continue;
+		const uint32_t v = vidx[i];
+		if (v < nvalShared) atomicAdd(&s_hs[v], 1u);
+		else atomicAdd(&hist[v], 1u);
+	}
+	if (!nvalShared) return;
+	__syncthreads();
+	for (uint32_t k = threadIdx.x; k < nvalShared; k += blockDim.x)
+		if (s_hs[k]) atomicAdd(&hist[k], s_hs[k]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
