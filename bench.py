@@ -260,7 +260,7 @@ def ours(a):
     for _ in range(3):  # keep the GPU busy while nvidia-smi starts sampling
         pwm, info = step(pwm)
     # ---- timed region: K steps, barrier + synchronize on both sides, CUDA events on the library's stream
-    scan_ms, find_ms, scan_bytes = [], [], []
+    scan_ms, find_ms, scan_bytes, scan_bytes_ref = [], [], [], []
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
@@ -275,6 +275,7 @@ def ours(a):
         scan_ms.append(st["last_scan_ms"])
         find_ms.append(st["last_find_ms"])
         scan_bytes.append(0.375 * st["last_scan_bases"] + 12.0 * st["last_scan_hits"])
+        scan_bytes_ref.append(1.0 * st["last_scan_bases"] + 12.0 * st["last_scan_hits"])
     e1.record(stream)
     torch.cuda.synchronize()
     if dist:
@@ -331,7 +332,7 @@ def ours(a):
     achieved = (sum(scan_bytes) / len(scan_bytes)) / (avg_ms / 1000.0) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "scan_traffic_bytes.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and a.nseq == 1000000 and a.seqlen == 1000:  # the capture belongs to the default workload
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
@@ -339,7 +340,10 @@ def ours(a):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": "full scan = k_scan5 (find, dead windows cleared, per-chunk counts) + k_tile_scan + k_expand6 (ordered site records)", "kernel_ms": avg_ms,
                 "find_ms": sum(find_ms) / len(find_ms), "expand_ms": avg_ms - sum(find_ms) / len(find_ms), "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s",
-                "algorithmic_bytes": "0.375 B per stored base + 12 B per hit", "step_share": avg_ms / ms_per_step}
+                "algorithmic_bytes": "0.375 B per stored base + 12 B per hit", "step_share": avg_ms / ms_per_step,
+                # the same figure against the nominal 8 TB/s, and in the reference's own representation (1 B per base)
+                "frac_of_nominal_8TBs": achieved / 8000.0,
+                "achieved_at_1B_per_base": (sum(scan_bytes_ref) / len(scan_bytes_ref)) / (avg_ms / 1000.0) / 1e9}
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_per_step,
