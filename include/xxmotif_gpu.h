@@ -245,8 +245,10 @@ int xxm_host_best_subset(const float* score, const int32_t* seq, int32_t nbSites
 
 /* xxm_host_pack_seqset: the packing step of xxm_load_seqset alone (csrc/host_pack.h), for tests: words = sum over the
  *   sequences of ceil((stored length + 32) / 32) + 2 entries of codes64 / nmask32 (the last two are the end-of-stream
- *   guard), notX[nent] = residues that are not N.  Returns the 1-based index of a sequence with a code outside 0..4, or 0. */
-int xxm_host_pack_seqset(int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp, uint64_t* codes64, uint32_t* nmask32, int32_t* notX);
+ *   guard), notX[nent] = residues that are not N; threads > 1 packs contiguous blocks of sequences concurrently, as the load
+ *   does.  Returns the 1-based index of a sequence with a code outside 0..4, or 0. */
+int xxm_host_pack_seqset(int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp, int32_t threads, uint64_t* codes64, uint32_t* nmask32,
+                         int32_t* notX);
 
 /* xxm_host_pair_table: the table of the full-scan find kernel (csrc/pair_table.h).  ids = the enumerated left k-mers that
  *   count as scan hits (column c in bits [2c+1:2c]), coloff = base offset of each of the len0 left match columns.

@@ -77,3 +77,21 @@ def test_pack_sse2_path_in_subprocess():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_host_pack.py"), "-q", "-x", "-k", "layout or runs or bad"],
                        env=env, cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("revcomp", [False, True])
+def test_pack_threads_agree(revcomp):
+    """Blocks of sequences packed concurrently (streaming stores into disjoint word ranges, as xxm_load_seqset does chunk by
+    chunk) give the words of the single-threaded pass."""
+    rng = np.random.default_rng(3)
+    n = rng.integers(1, 700, size=5000).astype(np.int32)
+    codes = rng.integers(0, 5, size=int(n.sum()), dtype=np.uint8)
+    a = hostprep.pack_seqset(n, codes, revcomp, threads=1)
+    for t in (2, 5, 8):
+        b = hostprep.pack_seqset(n, codes, revcomp, threads=t)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    codes[int(n[:4000].sum()) + 3] = 9
+    with pytest.raises(capi.XxmError) as e:
+        hostprep.pack_seqset(n, codes, revcomp, threads=4)
+    assert "sequence 4001" in str(e.value)

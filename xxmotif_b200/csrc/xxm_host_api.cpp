@@ -3,6 +3,7 @@
 #include "../../include/xxmotif_gpu.h"
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "host_pack.h"
@@ -102,10 +103,34 @@ extern "C" int xxm_host_pair_table(const uint32_t* ids, int64_t nids, const int3
 	return ok ? 0 : 1;
 }
 
-extern "C" int xxm_host_pack_seqset(int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp, uint64_t* codes64, uint32_t* nmask32, int32_t* notX) {
+extern "C" int xxm_host_pack_seqset(int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp, int32_t threads, uint64_t* codes64,
+                                    uint32_t* nmask32, int32_t* notX) {
 	uint64_t words = 0, rawTotal = 0;
 	for (int32_t i = 0; i < nent; ++i) { words += stored_words(static_cast<uint32_t>(n[i]), revcomp != 0); rawTotal += static_cast<uint32_t>(n[i]); }
-	const uint32_t bad = pack_range(n, 0, static_cast<uint32_t>(nent), codes, rawTotal, revcomp != 0, codes64, nmask32, notX);
+	uint32_t bad = 0;
+	if (threads <= 1 || nent < 2 * threads) {
+		bad = pack_range(n, 0, static_cast<uint32_t>(nent), codes, rawTotal, revcomp != 0, codes64, nmask32, notX);
+	} else {
+		// contiguous blocks of sequences, one per thread, packed concurrently into disjoint word ranges (what xxm_load_seqset
+		// does chunk by chunk)
+		std::vector<uint32_t> s0(static_cast<size_t>(threads) + 1), badOf(threads, 0);
+		std::vector<uint64_t> b0(static_cast<size_t>(threads) + 1), w0(static_cast<size_t>(threads) + 1);
+		uint64_t b = 0, w = 0;
+		int t = 0;
+		for (int32_t i = 0; i < nent; ++i) {
+			while (t <= threads - 1 && static_cast<int64_t>(i) == static_cast<int64_t>(nent) * t / threads) { s0[t] = static_cast<uint32_t>(i); b0[t] = b; w0[t] = w; ++t; }
+			b += static_cast<uint32_t>(n[i]);
+			w += stored_words(static_cast<uint32_t>(n[i]), revcomp != 0);
+		}
+		s0[threads] = static_cast<uint32_t>(nent); b0[threads] = b; w0[threads] = w;
+		std::vector<std::thread> pool;
+		for (int k = 0; k < threads; ++k)
+			pool.emplace_back([&, k] {
+				badOf[k] = pack_range(n, s0[k], s0[k + 1], codes + b0[k], rawTotal - b0[k], revcomp != 0, codes64 + w0[k], nmask32 + w0[k], notX + s0[k]);
+			});
+		for (auto& th : pool) th.join();
+		for (int k = 0; k < threads && !bad; ++k) bad = badOf[k];
+	}
 	for (int k = 0; k < 2; ++k) { codes64[words + k] = 0; nmask32[words + k] = 0xFFFFFFFFu; }
 	return static_cast<int>(bad);
 }

@@ -22,7 +22,7 @@ def _lib():
         L.xxm_host_background.restype = i32
         L.xxm_host_background.argtypes = [i32, vp, vp, vp, vp]
         L.xxm_host_pack_seqset.restype = i32
-        L.xxm_host_pack_seqset.argtypes = [i32, vp, vp, i32, vp, vp, vp]
+        L.xxm_host_pack_seqset.argtypes = [i32, vp, vp, i32, i32, vp, vp, vp]
         for name, args in {"xxm_kmer_counts": [vp, i32, vp, C.c_int64], "xxm_kmer_counts_ms": [vp, vp],
                            "xxm_null_model_from_counts": [vp, i32, flt, flt, vp, vp], "xxm_null_model_from_seqset": [vp, i32, flt, flt, vp, vp],
                            "xxm_background_from_seqset": [vp, vp, vp]}.items():
@@ -59,7 +59,7 @@ def revcomp_double(n, codes):
     return n2.astype(np.int32), out
 
 
-def pack_seqset(n, codes, revcomp=False):
+def pack_seqset(n, codes, revcomp=False, threads=1):
     """The packing step of xxm_load_seqset alone (xxm_host_pack_seqset): (code words, N masks, residues per sequence).
     Raises on a code outside 0..4."""
     L = _lib()
@@ -70,7 +70,7 @@ def pack_seqset(n, codes, revcomp=False):
     c64 = np.zeros(words, dtype=np.uint64)
     m32 = np.zeros(words, dtype=np.uint32)
     notx = np.zeros(len(n), dtype=np.int32)
-    bad = L.xxm_host_pack_seqset(len(n), _p(n), _p(codes), int(revcomp), _p(c64), _p(m32), _p(notx))
+    bad = L.xxm_host_pack_seqset(len(n), _p(n), _p(codes), int(revcomp), int(threads), _p(c64), _p(m32), _p(notx))
     if bad:
         raise capi.XxmError("sequence %d holds a code outside 0..4" % bad)
     return c64, m32, notx
