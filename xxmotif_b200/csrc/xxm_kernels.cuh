@@ -477,39 +477,6 @@ struct CountIO {
 	int firstColumn;            // motifColumns.front(): pos - firstColumn + 1 is the position of PWM column 1
 	unsigned long long* counts; // [31*5] zeroed
 };
-__global__ void __launch_bounds__(256) k_count_pwm(SeqStream S, CountIO io) {
-	__shared__ unsigned int s_cnt[31 * 5];
-	for (int k = threadIdx.x; k < 31 * 5; k += blockDim.x) s_cnt[k] = 0;
-	__syncthreads();
-	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t < io.n) {
-		uint32_t i = t;
-		bool use = true;
-		if (io.idx) i = io.idx[t];
-		else if (io.slotIdx) { i = io.slotIdx[t]; use = (i != kNone) && io.slotScore[t] <= io.thr; }
-		else use = io.keep[i] && io.kscore[i] <= io.thr;
-		if (use) {
-			const uint32_t s = io.seq[i] - 1;
-			const int n = S.len[s];
-			const int p0 = static_cast<int>(io.pos[i]) + io.shift - io.firstColumn + 1;
-			const uint32_t wo = S.wordOff[s];
-			for (int j = 1; j <= 30; ++j) {
-				const int p = p0 + j - 1;
-				if (p < 1 || p > n) continue;
-				const uint32_t g = static_cast<uint32_t>(p - 1);
-				const uint32_t w = wo + (g >> 5);
-				if ((S.nmask[w] >> (g & 31)) & 1u) continue;
-				const uint32_t b = static_cast<uint32_t>(S.codes[w] >> (2 * (g & 31))) & 3u;
-				atomicAdd(&s_cnt[j * 5 + b + 1], 1u);
-				atomicAdd(&s_cnt[j * 5], 1u);
-			}
-		}
-	}
-	__syncthreads();
-	for (int k = threadIdx.x; k < 31 * 5; k += blockDim.x)
-		if (s_cnt[k]) atomicAdd(&io.counts[k], static_cast<unsigned long long>(s_cnt[k]));
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // stable LSD radix sort on 32-bit keys with an index payload (sortSitesByScore, StartPosUtils.h:68-70: positive
 // float scores order like their bit patterns; stability == glibc's merge-sort qsort).
