@@ -267,6 +267,10 @@ typedef struct {
 	float last_find_ms;      /* device time of the find kernel alone (the rest of last_scan_ms is the expand kernel) */
 } xxm_stats;
 int xxm_get_stats(const xxm_ctx* ctx, xxm_stats* out);
+/* host-side phase times of xxm_optimize_step summed over the steps since the last reset, in microseconds: table build and
+ * staging | launching scan + overlap removal + exchange | waiting for them | subset choice | launching the recount | waiting
+ * for it | PWM from the counts.  (Where does a step spend the time the kernels do not account for?) */
+int xxm_step_phases(xxm_ctx* ctx, double* us7, int64_t* nsteps, int32_t reset);
 /* the CUDA stream the context launches on, as a cudaStream_t cast to void* (for external event timing) */
 void* xxm_stream(const xxm_ctx* ctx);
 

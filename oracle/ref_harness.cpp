@@ -184,16 +184,38 @@ static int run_bench(int steps, int warmup, Motif* m) {
 	for (int i = 1; i <= m->getPosSetSize(); i++) windows += std::max(0, Global::posSet->entity[i]->n - length0 + 1);
 	int bestMotifNb = 0; double bestPval = 0;
 	double t0 = 0;
+	std::vector<double> pwm0;  /* the start motif as initStartMotif left it: what a parity test feeds the other implementation */
+	for (int i = 0; i <= PWM_LENGTH; i++)
+		for (int a = 0; a <= 4; a++) pwm0.push_back(i == 0 ? 0.0 : m->getPWM()[i][a]);
+	const region enr0 = m->getEnrichment();
 	for (int it = 0; it < warmup + steps; it++) {
 		if (it == warmup) t0 = now_s();
 		kg.reinitialize(m->getPWM(), m->getMotifColumns(), m->getPosSetSize(), Global::posSet->total[m->getPosSetSize()]);
 		sp.fill_sites_with_possible_startPositions(kg, true, m);
 		sp.update_PWM_with_bestSubset(m, bestMotifNb, bestPval, false, Global::pseudo);
+		/* with --localization the per-motif loop re-estimates the enriched region from the candidate list after every
+		   optimizeMotif (MotifContainer.cpp:241); doing it after every step gives the next step a real positional prior */
+		if (Global::usePositionalProbs) m->updateEnrichedRegion(sp.getBestStartPos());
 	}
 	double dt = now_s() - t0;
 	printf("{\"impl\": \"reference\", \"steps\": %d, \"warmup\": %d, \"windows_per_step\": %lld, \"seconds\": %.6f, "
-	       "\"windows_per_s\": %.6e, \"nbSites\": %d, \"nbBestSites\": %d, \"bestMotifNb\": %d, \"bestPval\": %.17g}\n",
-	       steps, warmup, windows, dt, (double) windows * steps / dt, sp.nbSites, sp.nbBestSites, bestMotifNb, bestPval);
+	       "\"windows_per_s\": %.6e, \"nbSites\": %d, \"nbBestSites\": %d, \"maxSites\": %d, \"bestMotifNb\": %d, \"bestPval\": %.17g",
+	       steps, warmup, windows, dt, (double) windows * steps / dt, sp.nbSites, sp.nbBestSites, sp.maxSites, bestMotifNb, bestPval);
+	/* the state after the last step, so that a parity test can compare more than scalars: the PWM the steps ended on */
+	printf(", \"nent\": %d, \"posSetSize\": %d, \"total\": %d, \"revcomp\": %d, \"mops\": %d, \"localization\": %d, \"order\": %d, \"enr\": [%d, %d, %d], \"cols\": [",
+	       Global::posSet->nent, m->getPosSetSize(), Global::posSet->total[m->getPosSetSize()], (int) Global::revcomp, (int) Global::multipleOccurrence,
+	       (int) Global::usePositionalProbs, Global::order, m->getEnrichment().max, m->getEnrichment().startRegion, m->getEnrichment().endRegion);
+	{
+		const motif_columns_type& c = m->getMotifColumns();
+		bool first = true;
+		for (motif_columns_type::const_iterator it = c.begin(); it != c.end(); ++it) { printf("%s%d", first ? "" : ", ", *it); first = false; }
+	}
+	printf("], \"pwm\": [");
+	for (int i = 0; i <= PWM_LENGTH; i++)
+		for (int a = 0; a <= 4; a++) printf("%s%.17g", (i || a) ? ", " : "", i == 0 ? 0.0 : m->getPWM()[i][a]);
+	printf("], \"enr0\": [%d, %d, %d], \"pwm0\": [", enr0.max, enr0.startRegion, enr0.endRegion);
+	for (size_t i = 0; i < pwm0.size(); i++) printf("%s%.17g", i ? ", " : "", pwm0[i]);
+	printf("]}\n");
 	fflush(stdout);
 	return 0;
 }

@@ -21,7 +21,7 @@ EXPORTS = [
     "xxm_reinitialize", "xxm_tables_info", "xxm_tables_get", "xxm_window_pvals", "xxm_scan_full", "xxm_rescore", "xxm_scan_oops",
     "xxm_rescore_startposlist", "xxm_update_pwm_with_best_subset", "xxm_startposlist_best_subset", "xxm_startposlist_from_elong",
     "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset", "xxm_host_pair_table",
-    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step",
+    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases",
 ]
 
 
@@ -93,6 +93,7 @@ def load_library():
         "xxm_comm_init": [vp, i32, i32, vp],
         "xxm_comm_destroy": [vp],
         "xxm_optimize_step": [vp, vp, vp, i32, i32, i32, i32, i32, dbl, P(XxmStepInfo)],
+        "xxm_step_phases": [vp, vp, P(C.c_int64), i32],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -303,6 +304,14 @@ class Context:
         self._ck(self.L.xxm_get_stats(self.h, C.byref(s)))
         return {"launches": s.launches, "last_scan_ms": s.last_scan_ms, "last_scan_bases": s.last_scan_bases, "last_scan_hits": s.last_scan_hits,
                 "last_find_ms": s.last_find_ms}
+
+    def step_phases(self, reset=True):
+        """average host-side phase times of xxm_optimize_step since the last reset, microseconds per step"""
+        us = np.zeros(7, dtype=np.float64)
+        k = C.c_int64(0)
+        self._ck(self.L.xxm_step_phases(self.h, _p(us), C.byref(k), int(reset)))
+        names = ["tables", "launch_scan", "wait_scan", "choose", "launch_count", "wait_count", "pwm"]
+        return {nm: (float(v) / k.value if k.value else 0.0) for nm, v in zip(names, us)}, int(k.value)
 
     def stream(self):
         return self.L.xxm_stream(self.h)

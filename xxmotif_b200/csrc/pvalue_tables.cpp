@@ -277,7 +277,7 @@ private:
 
 }  // namespace
 
-void build_pvalue_tables(const double* pwm, const int32_t* cols, int ncols, int posSetSize, int totalPositions, const double* bgLog,
+void build_pvalue_tables(const double* pwm, const int32_t* cols, int ncols, int64_t posSetSize, int64_t totalPositions, const double* bgLog,
                          const NullModelView& nm, PvalueTables& t) {
 	t.error = 0;
 	t.L = ncols;

@@ -42,7 +42,7 @@ struct PvalueTables {
 	std::vector<double> leftClassProb;  // per left class: sum of prob over its ids (list order)
 };
 
-void build_pvalue_tables(const double* pwm31x5, const int32_t* cols, int ncols, int posSetSize, int totalPositions,
+void build_pvalue_tables(const double* pwm31x5, const int32_t* cols, int ncols, int64_t posSetSize, int64_t totalPositions,
                          const double* bgLog5, const NullModelView& nm, PvalueTables& out);
 
 }  // namespace xxm

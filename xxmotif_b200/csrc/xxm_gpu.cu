@@ -195,6 +195,8 @@ struct xxm_ctx {
 	int nbSites = 0, maxSites = 0;
 
 	LogSum logsum;
+	double phaseUs[7] = {0, 0, 0, 0, 0, 0, 0};  // xxm_step_phases
+	int64_t phaseSteps = 0;
 
 	int fail(const char* fmt, ...) {
 		char buf[512];
@@ -240,6 +242,7 @@ static void xxm_segv_handler(int sig) {
 	raise(sig);
 }
 
+extern "C" void xxm_destroy(xxm_ctx* ctx);
 extern "C" int xxm_create(int device, xxm_ctx** out) {
 	*out = nullptr;
 	if (std::getenv("XXM_DEBUG_SEGV")) { signal(SIGSEGV, xxm_segv_handler); signal(SIGABRT, xxm_segv_handler); }  // debugging aid: native backtrace on a crash
@@ -266,6 +269,16 @@ extern "C" int xxm_create(int device, xxm_ctx** out) {
 	if (cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_pin), 64, cudaHostAllocDefault) != cudaSuccess) {
 		g_create_error = "cannot allocate pinned memory";
 		delete ctx;
+		return 1;
+	}
+	// opt-in shared-memory sizes are per DEVICE, not per process: set them for the device of every new context
+	if (cudaFuncSetAttribute(k_scan5, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairTabWords * 4) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_scan4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 32 * 1024) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_scan4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 16) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_scan4<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_scan4<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) {
+		g_create_error = std::string("cannot opt in to large shared memory: ") + cudaGetErrorString(cudaGetLastError());
+		xxm_destroy(ctx);
 		return 1;
 	}
 	ctx->opt.maxMotifsPerSequence = 1000;
@@ -663,7 +676,15 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	if (nent <= 0) return ctx->fail("empty sequence set");
 	static const bool trace = std::getenv("XXM_TRACE") != nullptr;
 	const auto tStart = std::chrono::steady_clock::now();
-	ctx->nent = nent;
+	// whatever happens below, the previous set is gone: a failed load must not leave a valid-looking model over a partly
+	// overwritten stream (nent is restored only on success)
+	ctx->haveModel = false;
+	ctx->loadSerial++;
+	ctx->deadKey.clear();
+	for (auto& l : ctx->L) l = SiteList();
+	ctx->nBest = 0;
+	ctx->nent = 0;
+	ctx->pend.active = false;
 	ctx->revcomp = revcomp != 0;
 	ctx->len.resize(nent);
 	ctx->total.resize(static_cast<size_t>(nent) + 1);
@@ -741,11 +762,7 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 		TRY(load_pack_on_device(ctx, nent, n, codes, revcomp, rawTotal, trace, tStart));
 	}
 	if (ctx->sum_i.size() != static_cast<size_t>(ctx->max_leng) + 1) init_sum_i(ctx->sum_i, ctx->max_leng);
-	ctx->haveModel = false;
-	ctx->loadSerial++;
-	ctx->deadKey.clear();
-	for (auto& l : ctx->L) l = SiteList();
-	ctx->nBest = 0;
+	ctx->nent = nent;
 	return 0;
 }
 

@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(256) k_count_pwm2(SeqStream S, CountIO io) {
 	uint32_t* buf = s_buf[wid];
 	uint32_t c[5] = {0, 0, 0, 0, 0};
 	int npend = 0;
+	uint32_t nsel = 0;  // chosen sites of this warp: row 0 of the count matrix is unused by the PWM and carries their number
 	for (uint32_t t0 = warp * 32; t0 < io.n; t0 += nwarps * 32) {
 		const uint32_t t = t0 + lane;
 		uint32_t i = t;
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(256) k_count_pwm2(SeqStream S, CountIO io) {
 		const uint32_t chosen = __ballot_sync(0xFFFFFFFFu, use);
 		if (use) buf[npend + __popc(chosen & ((1u << lane) - 1u))] = i;
 		npend += __popc(chosen);
+		nsel += __popc(chosen);
 		__syncwarp();
 		if (npend >= 32) {
 			count_batch(S, io, buf, 32, lane, c);
@@ -280,6 +282,7 @@ __global__ void __launch_bounds__(256) k_count_pwm2(SeqStream S, CountIO io) {
 		}
 	}
 	if (npend) count_batch(S, io, buf, npend, lane, c);
+	if (lane == 0 && nsel) atomicAdd(&s_cnt[0], nsel);
 	if (lane >= 1 && lane <= 30) {
 #pragma unroll
 		for (int k = 0; k < 5; ++k)

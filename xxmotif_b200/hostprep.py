@@ -158,7 +158,7 @@ def background_device(ctx):
     return bg, bgl
 
 
-IUPAC = {"A": [1], "C": [2], "G": [3], "T": [4], "W": [1, 4], "R": [1, 3], "Y": [2, 4], "S": [2, 3], "K": [3, 4], "M": [1, 2], "N": [1, 2, 3, 4]}
+IUPAC = {"A": [1], "C": [2], "G": [3], "T": [4], "W": [1, 4], "R": [1, 3], "Y": [2, 4], "S": [2, 3], "K": [3, 4], "M": [1, 2], "N": [1, 2, 3, 4], ".": [1, 2, 3, 4]}
 
 
 def synthetic_set(nseq, length, motif="TATAWAWR", frac=0.5, seed=4, chunk=1 << 16):

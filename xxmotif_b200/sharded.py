@@ -197,7 +197,7 @@ class ShardedRefinement:
     """optimizeMotif iterations (Iterate_Motif.cpp:26-32) over a sharded set; `ctx` is the rank's xxmotif_b200.Context."""
 
     def __init__(self, ctx, dist, nent_local, total_local, pseudo=0.1, revcomp=False, oneOccurrence=False, maxSeqCount=1000, plusFrac=0.0,
-                 bg=None, native=True):
+                 bg=None, native=True, comm_ready=False):
         """native=True: the whole step is one C-ABI call (xxm_optimize_step) and the two small reductions run over NCCL on
         the library's stream, device to device.  native=False: the split-phase entry points with the exchange in Python
         (any torch.distributed backend; this is also what the CPU/gloo test drives)."""
@@ -215,7 +215,7 @@ class ShardedRefinement:
         self.oneOccurrence, self.maxSeqCount, self.plusFrac = oneOccurrence, maxSeqCount, plusFrac
         self.bg = bg
         self.last_d2h_bytes = 0
-        if self.native and dist is not None and dist.get_world_size() > 1:
+        if self.native and dist is not None and dist.get_world_size() > 1 and not comm_ready:  # comm_ready: the context already has its communicator
             import torch
             idt = torch.zeros(128, dtype=torch.uint8, device=device)
             if dist.get_rank() == 0:
