@@ -127,3 +127,25 @@ def test_pair_table_declines_non_threshold_sets():
     assert not ok
     ok, tab, lv = capi.host_pair_table(np.zeros(0, dtype=np.uint32), np.arange(8, dtype=np.int32))
     assert ok and lv == 0 and not tab.any()
+
+
+def test_many_runs_sweep_matches_literal_sweep():
+    """Lists whose scores are not table valued reach getBestSubset as tens of thousands of runs: the threaded evaluation over
+    dense LOG_sum_i windows (host_stats.cpp: best_subset_from_runs) must pick what the literal site-by-site sweep picks."""
+    from xxmotif_b200 import capi, sharded
+    rng = np.random.default_rng(3)
+    nruns = 30000
+    scores = np.sort(np.unique((10.0 ** rng.uniform(-9, -0.5, size=nruns)).astype(np.float32)))
+    counts = rng.integers(1, 4, size=len(scores)).astype(np.int64)
+    nb = int(counts.sum())
+    maxSites = 50 * nb
+    K, bp, last = sharded.choose_subset(scores, counts, nb, nb * 10, maxSites)
+    site_scores = np.repeat(scores, counts)
+    seq = np.arange(1, nb + 1, dtype=np.int32)
+    K2, bp2 = capi.host_best_subset(site_scores, seq, nb, maxSites, nb)
+    assert (K, bp) == (K2, bp2) and K > 1
+    assert last == site_scores[K - 1]
+    # the same runs below the threading threshold (sequential path) agree with themselves on a prefix
+    K3, bp3, _ = sharded.choose_subset(scores[:1500], counts[:1500], int(counts[:1500].sum()), nb * 10, maxSites)
+    K4, bp4 = capi.host_best_subset(np.repeat(scores[:1500], counts[:1500]), seq[:int(counts[:1500].sum())], nb, maxSites, nb)
+    assert (K3, bp3) == (K4, bp4)

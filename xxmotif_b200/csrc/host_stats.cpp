@@ -60,12 +60,63 @@ double LogSum::at(int64_t i) {
 	return acc;
 }
 
-double order_statistics_pvalue(LogSum& ls, int64_t motifNb, int64_t N, double p) {
+static void parallel_logs(std::vector<double>& logs, int64_t first, int64_t cnt) {
+	logs.resize(static_cast<size_t>(cnt));
+	const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+	if (cnt < (1 << 16) || nt == 1) {
+		for (int64_t k = 0; k < cnt; ++k) logs[k] = std::log(static_cast<double>(first + k));
+		return;
+	}
+	std::vector<std::thread> th;
+	const int64_t per = (cnt + nt - 1) / nt;
+	for (unsigned t = 0; t < nt; ++t) {
+		const int64_t a = t * per, b = std::min<int64_t>(cnt, a + per);
+		if (a >= b) break;
+		th.emplace_back([&logs, a, b, first]() {
+			for (int64_t k = a; k < b; ++k) logs[k] = std::log(static_cast<double>(first + k));
+		});
+	}
+	for (auto& x : th) x.join();
+}
+
+void LogSum::dense(int which, int64_t lo, int64_t hi) {
+	lo = std::max<int64_t>(0, lo);
+	if (hi < lo) return;
+	Window& w = win_[which & 1];
+	if (!w.v.empty() && w.lo <= lo && hi < w.lo + static_cast<int64_t>(w.v.size())) return;  // already covered
+	extend(hi);
+	const int64_t c = lo / kStride;           // accumulate from the checkpoint at or below lo
+	const int64_t first = c * kStride;        // value known: ckpt_[c]
+	std::vector<double> logs;
+	parallel_logs(logs, first + 1, hi - first);
+	w.lo = lo;
+	w.v.assign(static_cast<size_t>(hi - lo + 1), 0.0);
+	double acc = ckpt_[static_cast<size_t>(c)];
+	if (first >= lo) w.v[static_cast<size_t>(first - lo)] = acc;
+	for (int64_t k = first + 1; k <= hi; ++k) {
+		acc = logs[static_cast<size_t>(k - first - 1)] + acc;
+		if (k >= lo) w.v[static_cast<size_t>(k - lo)] = acc;
+	}
+}
+
+double LogSum::at_dense(int64_t i) const {
+	if (i <= 0) return 0.0;
+	for (const Window& w : win_)
+		if (!w.v.empty() && i >= w.lo && i < w.lo + static_cast<int64_t>(w.v.size())) return w.v[static_cast<size_t>(i - w.lo)];
+	const int64_t c = i / kStride;  // (the caller has reserved the checkpoints)
+	double acc = ckpt_[static_cast<size_t>(c)];
+	for (int64_t k = c * kStride + 1; k <= i; ++k) acc = std::log(static_cast<double>(k)) + acc;
+	return acc;
+}
+
+// calculateOrderStatisticsPvalue (utils.h:80-102); AT(i) = LogTable::LOG_sum_i[i]
+template <class AT>
+static inline double order_statistics_pvalue_impl(AT&& at, int64_t motifNb, int64_t N, double p) {
 	if (N * p > motifNb || p == 1) return 0;
 	double sum_K_1, delta_K_1;
 	int64_t K = 0;
 	// log_binomial(N, motifNb, p): LOG_sum_i[N] - LOG_sum_i[k] - LOG_sum_i[N-k] + k*log(prob) + (N-k)*log(1-prob)
-	double logN = (ls.at(N) - ls.at(motifNb) - ls.at(N - motifNb) + motifNb * std::log(p) + (N - motifNb) * std::log(1 - p));
+	double logN = (at(N) - at(motifNb) - at(N - motifNb) + motifNb * std::log(p) + (N - motifNb) * std::log(1 - p));
 	double alpha_K_1, sum_K = 0;
 	while (K < N - motifNb) {
 		alpha_K_1 = (p * (N - (K + motifNb))) / ((1 - p) * ((K + motifNb) + 1));
@@ -77,6 +128,10 @@ double order_statistics_pvalue(LogSum& ls, int64_t motifNb, int64_t N, double p)
 		K++;
 	}
 	return logN;
+}
+
+double order_statistics_pvalue(LogSum& ls, int64_t motifNb, int64_t N, double p) {
+	return order_statistics_pvalue_impl([&ls](int64_t i) { return ls.at(i); }, motifNb, N, p);
 }
 
 float fast_log(float x) {
@@ -173,7 +228,9 @@ struct Sweep {
 	bool any = false;
 	// one evaluation point at the end of a run of equal scores (StartPosUpdater.h:186-225)
 	void evaluate(int motifCounter, int64_t iPlus1, float score) {
-		const double pValue = order_statistics_pvalue(ls, motifCounter, maxSites, static_cast<double>(score));
+		evaluate_with(motifCounter, iPlus1, score, order_statistics_pvalue(ls, motifCounter, maxSites, static_cast<double>(score)));
+	}
+	void evaluate_with(int motifCounter, int64_t iPlus1, float score, double pValue) {
 		if (pValue < c.bestPval || oneOccurrence) {
 			c.bestPval = pValue;
 			c.bestMotifNbPlus = c.bestMotifNb = motifCounter;
@@ -204,12 +261,50 @@ SubsetChoice best_subset_from_runs(LogSum& ls, const std::vector<ScoreRun>& runs
 	if (!runs.empty()) sw.c.lastScore = runs[0].score;
 	const int64_t lim = std::min(nbSites, limit);
 	int64_t cum = 0;
-	for (const ScoreRun& r : runs) {
-		if (r.score == 1.0f) break;  // :163
-		cum += r.count;
-		if (cum > lim) break;        // the loop ends inside this run: its end is never evaluated (:162, :184)
-		sw.evaluate(static_cast<int>(cum), cum, r.score);
+	if (runs.size() < 2048) {
+		for (const ScoreRun& r : runs) {
+			if (r.score == 1.0f) break;  // :163
+			cum += r.count;
+			if (cum > lim) break;        // the loop ends inside this run: its end is never evaluated (:162, :184)
+			sw.evaluate(static_cast<int>(cum), cum, r.score);
+		}
+		return sw.c;
 	}
+	// Very many runs (scores that are not table valued): the evaluation points are independent of each other, only the
+	// comparison against the running best is sequential.  All p-values are computed first -- the two LOG_sum_i ranges the
+	// points read materialised once (LogSum::dense), the points spread over the host threads -- and the reference's sweep
+	// then runs over the stored values.
+	std::vector<int64_t> cums;
+	cums.reserve(runs.size());
+	for (const ScoreRun& r : runs) {
+		if (r.score == 1.0f) break;
+		cum += r.count;
+		if (cum > lim) break;
+		cums.push_back(cum);
+	}
+	const size_t m = cums.size();
+	if (!m) return sw.c;
+	ls.reserve(maxSites);
+	ls.dense(0, cums.front(), cums.back());
+	ls.dense(1, maxSites - cums.back(), maxSites - cums.front());
+	std::vector<double> pv(m);
+	{
+		const LogSum& cls = ls;
+		const double lsN = ls.at(maxSites);
+		auto at = [&cls, lsN, maxSites](int64_t i) { return i == maxSites ? lsN : cls.at_dense(i); };
+		const unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+		std::vector<std::thread> th;
+		const size_t per = (m + nt - 1) / nt;
+		for (unsigned t = 0; t < nt; ++t) {
+			const size_t a = t * per, b = std::min(m, a + per);
+			if (a >= b) break;
+			th.emplace_back([&, a, b]() {
+				for (size_t k = a; k < b; ++k) pv[k] = order_statistics_pvalue_impl(at, cums[k], maxSites, static_cast<double>(runs[k].score));
+			});
+		}
+		for (auto& x : th) x.join();
+	}
+	for (size_t k = 0; k < m; ++k) sw.evaluate_with(static_cast<int>(cums[k]), cums[k], runs[k].score, pv[k]);
 	return sw.c;
 }
 

@@ -14,8 +14,16 @@ class LogSum {
 public:
 	double at(int64_t i);
 	void reserve(int64_t upTo);  // extend the checkpoints (multi-threaded log(), sequential accumulation)
+	// Dense windows for sweeps over very many score runs (site scores that are not table valued: localization, more than 8
+	// match columns): every entry of [lo, hi] materialised -- log() in parallel, accumulation sequential from the checkpoint
+	// below lo, so every value is the reference's -- after which at_dense() is a thread-safe O(1) read.  Two windows are
+	// kept (the sweep reads LOG_sum_i[K] and LOG_sum_i[N - K]); a window that already covers [lo, hi] is reused.
+	void dense(int which, int64_t lo, int64_t hi);
+	double at_dense(int64_t i) const;  // window hit, else the checkpoint walk without the cache (thread safe)
 
 private:
+	struct Window { int64_t lo = 0; std::vector<double> v; };
+	Window win_[2];
 	static constexpr int64_t kStride = 128;
 	std::vector<double> ckpt_{0.0};  // ckpt_[c] = LOG_sum_i[c * kStride]
 	int64_t lastIdx_[4] = {-1, -1, -1, -1};

@@ -25,6 +25,7 @@
 #include "xxm_kernels.cuh"
 #include "xxm_select2.cuh"
 #include "xxm_select3.cuh"
+#include "xxm_select4.cuh"
 #include "xxm_kmerhist.cuh"
 #include "xxm_scan4.cuh"
 #include "xxm_scan5.cuh"
@@ -160,6 +161,11 @@ struct xxm_ctx {
 	bool sortedLazy = false;      // the last deferred scan left sortedSites' float scores implicit (k_select_cls_fwd)
 	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
 	DevBuf<uint64_t> status, total64;
+	DevBuf<uint32_t> cmpCounts, runStart, memoIdx;
+	DevBuf<uint8_t> memoFlag;
+	DevBuf<double> memoTmp;
+	std::vector<double> h_memoVals;
+	DevBuf<unsigned long long> runPack;
 	DevBuf<uint32_t> r_seq, d_pbits;
 	DevBuf<uint8_t> d_t8, d_raw;
 	DevBuf<uint32_t> d_pairTab, d_dead, d_scanCounts;
@@ -192,9 +198,14 @@ struct xxm_ctx {
 	bool histValid = false;      // ctx->hist holds the value-index histogram of the list made by the last select_mops
 	uint64_t histSerial = 0, histCounter = 0;
 	SiteList L[3];
-	int nbSites = 0, maxSites = 0;
+	int nbSites = 0;
+	int64_t nbSitesGlobal = 0;  // sites of all ranks seen by the last subset choice on a sharded set
+	int64_t maxSites = 0;  // (8 x 10^9 windows of a sharded set exceed the reference's int)
 
 	LogSum logsum;
+	// the sharded set (xxm_gpu_part7.inc): global counts, valid while synced for the current load
+	struct ShardInfo { bool synced = false; uint64_t loadSerial = 0; int64_t nent = 0, total = 0, seqOffset = 0; double logAcc = 0; int maxLeng = 0; } G;
+	const int32_t* notXPtr = nullptr;  // residues that are not N per sequence of the current load (host or device packing path)
 	double phaseUs[7] = {0, 0, 0, 0, 0, 0, 0};  // xxm_step_phases
 	int64_t phaseSteps = 0;
 
@@ -228,6 +239,25 @@ struct xxm_ctx {
 
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
 static int stage_scan(xxm_ctx* ctx);  // xxm_gpu_scan5.inc
+
+#define NCK(call)                                                                                              \
+	do {                                                                                                       \
+		ncclResult_t r__ = (call);                                                                             \
+		if (r__ != ncclSuccess) return ctx->fail("%s failed: %s", #call, nccl_api().GetErrorString(r__));      \
+	} while (0)
+
+static int ensure_pinned_xchg(xxm_ctx* ctx, size_t bytes) {
+	if (ctx->h_pinXchgCap >= bytes) return 0;
+	if (ctx->h_pinXchg) cudaFreeHost(ctx->h_pinXchg);
+	ctx->h_pinXchg = nullptr;
+	ctx->h_pinXchgCap = 0;
+	const size_t want = std::max<size_t>(bytes + bytes / 4, 1u << 16);
+	CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_pinXchg), want, cudaHostAllocDefault));
+	ctx->h_pinXchgCap = want;
+	return 0;
+}
+
+#include "xxm_gpu_part7.inc"
 
 // =====================================================================================================================
 // life cycle
@@ -276,7 +306,9 @@ extern "C" int xxm_create(int device, xxm_ctx** out) {
 	    cudaFuncSetAttribute(k_scan4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 32 * 1024) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_scan4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 16) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_scan4<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
-	    cudaFuncSetAttribute(k_scan4<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess) {
+	    cudaFuncSetAttribute(k_scan4<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_select_cls_rc, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 6) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_memo_eval_list, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
 		g_create_error = std::string("cannot opt in to large shared memory: ") + cudaGetErrorString(cudaGetLastError());
 		xxm_destroy(ctx);
 		return 1;
@@ -309,7 +341,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	ctx->u_seq.release(); ctx->u_pos.release(); ctx->u_vidx.release(); ctx->b_score.release(); ctx->b_pSsnap.release(); ctx->s_kscore.release(); ctx->e_kscore.release();
 	ctx->slotScore.release(); ctx->tmpScore.release(); ctx->s_keep.release(); ctx->e_keep.release(); ctx->flag8.release(); ctx->stk.release();
 	ctx->slotIdx.release(); ctx->e_slotIdx.release(); ctx->e_slotScore.release(); ctx->u_score.release(); ctx->counters.release(); ctx->hist.release(); ctx->idxA.release(); ctx->idxB.release(); ctx->keysA.release();
-	ctx->keysB.release(); ctx->rsHist.release(); ctx->status.release(); ctx->total64.release(); ctx->d_counts.release(); ctx->d_sites.release();
+	ctx->keysB.release(); ctx->rsHist.release(); ctx->cmpCounts.release(); ctx->memoIdx.release(); ctx->memoFlag.release(); ctx->memoTmp.release(); ctx->runStart.release(); ctx->runPack.release(); ctx->status.release(); ctx->total64.release(); ctx->d_counts.release(); ctx->d_sites.release();
 	ctx->d_hf.release(); ctx->d_hb.release();
 	ctx->r_seq.release(); ctx->d_pbits.release(); ctx->d_t8.release(); ctx->d_pairTab.release();
 	cudaEventDestroy(ctx->ev0);
@@ -553,6 +585,7 @@ static int load_pack_on_host(xxm_ctx* ctx, int32_t nent, const int32_t* n, const
 	CK(cudaMemcpyAsync(ctx->d_codes.p + ctx->nwords, hCodes + ctx->nwords, 16, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaMemcpyAsync(ctx->d_nmask.p + ctx->nwords, hMask + ctx->nwords, 8, cudaMemcpyHostToDevice, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));  // the staging buffer is reused by the next load
+	ctx->notXPtr = ctx->notX.data();
 	if (badSeq) return ctx->fail("sequence %u holds a code outside 0..4", badSeq);
 	if (overflow) return ctx->fail("more than 2^31-1 residues: the reference's int totals overflow (Alignment.h:40-41)");
 	if (trace) {
@@ -656,6 +689,7 @@ static int load_pack_on_device(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	CK(cudaMemcpyAsync(ctx->h_pin + 4, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
 	std::memcpy(&bad, ctx->h_pin + 4, 4);
+	ctx->notXPtr = ctx->h_notX;
 	if (bad) return ctx->fail("sequence %u holds a code outside 0..4", bad);
 	if (ctx->d_raw.cap > (8ull << 30)) ctx->d_raw.release();  // the raw codes are only needed for packing
 	if (trace) {
@@ -939,6 +973,12 @@ static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* col
 	for (int i = 0; i < ncols; ++i)
 		if (cols[i] < 1 || cols[i] > XXM_PWM_LENGTH || (i && cols[i] <= cols[i - 1])) return ctx->fail("invalid match columns");
 	if (posSetSize < 1 || posSetSize > ctx->nent) return ctx->fail("posSetSize out of range");
+	if (ctx->comm) {
+		// a sharded set: the thresholds of the tables follow the WHOLE set (branch_and_bound-inl.h:186-187, :417)
+		TRY(shard_sync(ctx));
+		if (posSetSize != ctx->nent) return ctx->fail("with a communicator attached every call refers to the whole sharded set: posSetSize must be the rank's sequence count");
+		build_pvalue_tables(pwm, cols, ncols, ctx->G.nent, ctx->G.total, ctx->opt.bgLog, ctx->nm, ctx->tab);
+	} else
 	build_pvalue_tables(pwm, cols, ncols, posSetSize, totalPositions, ctx->opt.bgLog, ctx->nm, ctx->tab);
 	const PvalueTables& T = ctx->tab;
 	if (T.error == 1) return ctx->fail("gapped motif with >8 match columns and a left part spanning >10 positions: reference behaviour undefined");
@@ -965,7 +1005,7 @@ static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* col
 	TRY(upload(ctx, ctx->d_cpval0, T.part[0].classPval));
 	TRY(upload(ctx, ctx->d_cscore0, T.part[0].classScore));
 	M.cpval0 = ctx->d_cpval0.p; M.cscore0 = ctx->d_cscore0.p; M.nclass0 = static_cast<int>(T.part[0].classPval.size());
-	const double exponent = ctx->avg_length(posSetSize) - T.span + 1;
+	const double exponent = set_avg_length(ctx, posSetSize) - T.span + 1;
 	ctx->memoModeValid = false;
 	ctx->posProbValid = false;
 	if (T.nparts == 1) {
@@ -994,7 +1034,9 @@ static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* col
 		M.cpval1 = ctx->d_cpval1.p; M.cscore1 = ctx->d_cscore1.p; M.leftProb = ctx->d_leftProb.p;
 		M.nclass1 = static_cast<int>(T.part[1].classPval.size());
 		// memo capacity: distinct scores <= enumerated left ids x enumerated right ids
-		uint64_t want = 4ull * std::max<uint64_t>(1, T.part[0].ids.size()) * std::max<uint64_t>(1, T.part[1].ids.size());
+		// (... and <= the windows that can survive the product test: a generous 1/32 of the stored bases)
+		uint64_t want = 4ull * std::min<uint64_t>(std::max<uint64_t>(1, T.part[0].ids.size()) * std::max<uint64_t>(1, T.part[1].ids.size()),
+		                                          std::max<uint64_t>(1u << 16, static_cast<uint64_t>(ctx->nwords)));
 		uint32_t cap = 1u << 12;
 		while (cap < want && cap < (1u << 24)) cap <<= 1;
 		CK(ctx->d_memoKey.ensure(cap));
@@ -1060,39 +1102,50 @@ static int stage_pos_prob(xxm_ctx* ctx, int motifLength, int firstMotifColumn, i
 	return 0;
 }
 
-// evaluate fresh memo slots; with needMode also fill the ZOOPS/OOPS finalPval of every occupied slot on the host
-// (1 - pow(1 - pS, avgLength - length + 1) needs the C library's pow to be bit-identical)
+// evaluate fresh memo slots; with needMode also fill the ZOOPS/OOPS finalPval of the occupied slots that lack it, on the host
+// (1 - pow(1 - pS, avgLength - length + 1) needs the C library's pow to be bit-identical).  The table is
+// sparse (a few 10^4 .. 10^6 distinct scores in up to 2^24 slots), so both steps run over compacted slot lists.
+static int compact_list(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, const uint8_t* flag, uint32_t n, uint32_t* oseq,
+                        uint32_t* opos, uint32_t* ovidx, uint32_t* oidx, uint32_t* nOut, const uint32_t* keys = nullptr);
 static int finalize_memo(xxm_ctx* ctx, bool needMode) {
 	if (ctx->M.nparts != 2) return 0;
 	const uint32_t cap = ctx->M.memoCap;
-	k_memo_eval<<<cdiv(cap, 128), 128, 0, ctx->stream>>>(ctx->M);
+	CK(ctx->memoFlag.ensure(cap));
+	CK(ctx->memoIdx.ensure(cap));
+	uint32_t* h_ovf = reinterpret_cast<uint32_t*>(ctx->h_pin + 5);
+	CK(cudaMemcpyAsync(h_ovf, ctx->M.memoOverflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	k_memo_flag<<<cdiv(cap, 256), 256, 0, ctx->stream>>>(ctx->M.memoKey, ctx->M.memoState, cap, 0u, ctx->memoFlag.p);
 	CKK();
-	k_memo_values<<<cdiv(cap, 256), 256, 0, ctx->stream>>>(ctx->M, ctx->d_pS.p, ctx->d_finalMops.p);
-	CKK();
-	uint32_t ovf = 0;
-	CK(cudaMemcpyAsync(&ovf, ctx->M.memoOverflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
-	const bool roundTrip = needMode;
-	std::vector<int32_t> keys;
-	if (roundTrip) {
-		keys.resize(cap);
-		ctx->h_pS.resize(cap);
-		CK(cudaMemcpyAsync(keys.data(), ctx->M.memoKey, static_cast<size_t>(cap) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		CK(cudaMemcpyAsync(ctx->h_pS.data(), ctx->d_pS.p, static_cast<size_t>(cap) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	uint32_t nf = 0;
+	TRY(compact_list(ctx, nullptr, nullptr, nullptr, ctx->memoFlag.p, cap, nullptr, nullptr, nullptr, ctx->memoIdx.p, &nf, nullptr));  // synchronises
+	if (*h_ovf) return ctx->fail("memo table of the >8-column path overflowed (capacity %u)", cap);
+	if (nf) {
+		const size_t tabBytes = static_cast<size_t>(ctx->M.nclass0 + ctx->M.nclass1) * 12;
+		const int smemTables = tabBytes <= 200 * 1024;
+		k_memo_eval_list<<<cdiv(nf, 128), 128, smemTables ? tabBytes : 0, ctx->stream>>>(ctx->M, ctx->memoIdx.p, nf, smemTables, ctx->d_pS.p, ctx->d_finalMops.p);
+		CKK();
 	}
+	if (!needMode) return 0;
+	k_memo_flag<<<cdiv(cap, 256), 256, 0, ctx->stream>>>(ctx->M.memoKey, ctx->M.memoState, cap, 1u, ctx->memoFlag.p);
+	CKK();
+	uint32_t nm = 0;
+	TRY(compact_list(ctx, nullptr, nullptr, nullptr, ctx->memoFlag.p, cap, nullptr, nullptr, nullptr, ctx->memoIdx.p, &nm, nullptr));
+	if (!nm) return 0;
+	CK(ctx->memoTmp.ensure(nm));
+	k_gather_f64<<<cdiv(nm, 256), 256, 0, ctx->stream>>>(ctx->d_pS.p, ctx->memoIdx.p, nm, ctx->memoTmp.p);
+	CKK();
+	ctx->h_memoVals.resize(nm);
+	CK(cudaMemcpyAsync(ctx->h_memoVals.data(), ctx->memoTmp.p, static_cast<size_t>(nm) * 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
-	if (ovf) return ctx->fail("memo table of the >8-column path overflowed (capacity %u)", cap);
-	if (roundTrip) {
-		const double exponent = ctx->avg_length(ctx->modelPosSetSize) - ctx->tab.span + 1;
-		ctx->h_finalMode.assign(cap, 1.0);
-		for (uint32_t h = 0; h < cap; ++h) {
-			if (keys[h] == kMemoEmpty) continue;
-			const double pS = ctx->h_pS[h];
-			ctx->h_finalMode[h] = (pS == 1.0) ? 1.0 : zoops_final(pS, exponent);
-		}
-		CK(cudaMemcpyAsync(ctx->d_finalMode.p, ctx->h_finalMode.data(), static_cast<size_t>(cap) * 8, cudaMemcpyHostToDevice, ctx->stream));
-	} else if (needMode) {
-		CK(cudaMemcpyAsync(ctx->d_finalMode.p, ctx->d_finalMops.p, static_cast<size_t>(cap) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+	const double exponent = set_avg_length(ctx, ctx->modelPosSetSize) - ctx->tab.span + 1;
+	for (uint32_t k = 0; k < nm; ++k) {
+		const double pS = ctx->h_memoVals[k];
+		ctx->h_memoVals[k] = (pS == 1.0) ? 1.0 : zoops_final(pS, exponent);
 	}
+	CK(cudaMemcpyAsync(ctx->memoTmp.p, ctx->h_memoVals.data(), static_cast<size_t>(nm) * 8, cudaMemcpyHostToDevice, ctx->stream));
+	k_scatter_mode<<<cdiv(nm, 256), 256, 0, ctx->stream>>>(ctx->memoTmp.p, ctx->memoIdx.p, nm, ctx->d_finalMode.p, ctx->M.memoState);
+	CKK();
+	CK(cudaStreamSynchronize(ctx->stream));  // h_memoVals is reused by the next call
 	return 0;
 }
 
@@ -1142,9 +1195,9 @@ static int compute_per_candidate(xxm_ctx* ctx, const uint32_t* d_seq, const uint
 
 static void set_max_sites_mops(xxm_ctx* ctx, int posSetSize) {
 	const int length = ctx->tab.span;
-	ctx->maxSites = ctx->total[posSetSize] - posSetSize * (length - 1);
-	if (ctx->revcomp) ctx->maxSites = ctx->total[posSetSize] - 2 * posSetSize * (length - 1);
+	ctx->maxSites = set_total(ctx, posSetSize) - (ctx->revcomp ? 2 : 1) * set_nent(ctx, posSetSize) * (length - 1);  // StartPosUpdater-inl.h:135-138
 }
+static int32_t clamp_i32(int64_t v) { return static_cast<int32_t>(std::min<int64_t>(v, 2147483647LL)); }
 
 // =====================================================================================================================
 // scan machinery
@@ -1160,27 +1213,28 @@ static int run_scan(xxm_ctx* ctx, int nseq, const Values& V, int checkFinal, Dev
 	return run_scan5(ctx, nseq, V, oseq, opos, ovidx, oscore, nOut, timeIt, deferCap);
 }
 
+// selected = flag byte set, or (keys != nullptr) head of a run of equal keys
 static int compact_list(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, const uint8_t* flag, uint32_t n, uint32_t* oseq,
-                        uint32_t* opos, uint32_t* ovidx, uint32_t* oidx, uint32_t* nOut) {
+                        uint32_t* opos, uint32_t* ovidx, uint32_t* oidx, uint32_t* nOut, const uint32_t* keys) {
 	*nOut = 0;
 	if (!n) return 0;
-	const uint32_t ntiles = cdiv(n, 256);
-	CK(ctx->status.ensure(ntiles + 1));
+	const uint32_t ntiles = cdiv(n, kCmpTile);
+	CK(ctx->status.ensure(static_cast<size_t>(ntiles) + 2));
+	CK(ctx->cmpCounts.ensure(ntiles));
 	CK(ctx->total64.ensure(2));
-	CK(ctx->counters.ensure(8));
-	CK(cudaMemsetAsync(ctx->status.p, 0, (static_cast<size_t>(ntiles) + 1) * 8, ctx->stream));
-	CK(cudaMemsetAsync(ctx->total64.p, 0, 16, ctx->stream));
-	CK(cudaMemsetAsync(ctx->counters.p + 4, 0, 4, ctx->stream));
 	CompactIO io{};
-	io.seq = seq; io.pos = pos; io.vidx = vidx; io.flag = flag; io.n = n;
+	io.seq = seq; io.pos = pos; io.vidx = vidx; io.flag = flag; io.keys = keys; io.n = n;
 	io.oseq = oseq; io.opos = opos; io.ovidx = ovidx; io.oidx = oidx;
-	io.status = ctx->status.p; io.ticket = ctx->counters.p + 4; io.total = ctx->total64.p;
-	k_compact<<<std::min<uint32_t>(ntiles, ctx->numSMs * 8), 256, 0, ctx->stream>>>(io, ntiles);
+	io.tileCount = ctx->cmpCounts.p; io.tileOff = ctx->status.p;
+	k_cmp_count<<<ntiles, 256, 0, ctx->stream>>>(io);
 	CKK();
-	uint64_t tot = 0;
-	CK(cudaMemcpyAsync(&tot, ctx->total64.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+	k_tile_scan<<<cdiv(ntiles, 1024), 1024, 0, ctx->stream>>>(ctx->cmpCounts.p, ntiles, ctx->status.p, ctx->total64.p);
+	CKK();
+	k_cmp_scatter<<<ntiles, 256, 0, ctx->stream>>>(io);
+	CKK();
+	CK(cudaMemcpyAsync(ctx->h_pin + 3, ctx->total64.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
 	CK(cudaStreamSynchronize(ctx->stream));
-	*nOut = static_cast<uint32_t>(tot);
+	*nOut = static_cast<uint32_t>(ctx->h_pin[3]);
 	return 0;
 }
 
@@ -1235,7 +1289,29 @@ static int launch_select_cls(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* 
 	return 0;
 }
 
-static bool select_cap_safe(const xxm_ctx* ctx) { return ctx->max_leng / (ctx->tab.span + 1) + 1 <= ctx->opt.maxMotifsPerSequence; }
+// --revcomp: forward rule + reverse-strand look-back on class indices (k_select_cls_rc, xxm_select4.cuh); also reports the
+// largest number of kept sites of one sequence in counters[1]
+static int launch_select_cls_rc(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, uint32_t n, const unsigned long long* nDev,
+                                DevBuf<uint8_t>& keep, DevBuf<uint16_t>& kcls) {
+	SelectRcIO f{};
+	CK(kcls.ensure(std::max<uint32_t>(8, n) + 8));
+	CK(ctx->stk.ensure(std::max<uint32_t>(8, n) + 8));
+	CK(ctx->hist.ensure(std::max<uint32_t>(1, ctx->nval)));
+	CK(cudaMemsetAsync(ctx->hist.p, 0, ctx->nval * 4ull, ctx->stream));
+	f.seq = seq; f.pos = pos; f.vidx = vidx; f.n = n; f.nDev = nDev; f.length = ctx->tab.span;
+	f.clsThr = ctx->d_clsThr.p; f.nSite = ctx->clsNSite; f.nval = ctx->nval;
+	f.stk = ctx->stk.p; f.keep = keep.p; f.kcls = kcls.p; f.counters = ctx->counters.p; f.hist = ctx->hist.p;
+	uint32_t grid = static_cast<uint32_t>(ctx->numSMs) * 6;
+	if (!nDev) grid = std::max<uint32_t>(1, std::min<uint32_t>(cdiv(n, kSel4Tile), grid));
+	k_select_cls_rc<<<grid, kSel4Threads, ctx->nval * 6ull, ctx->stream>>>(ctx->S, f);
+	CKK();
+	ctx->histValid = true;
+	ctx->histSerial = ++ctx->histCounter;
+	ctx->kclsSerial = ctx->histSerial;
+	return 0;
+}
+
+static bool select_cap_safe(const xxm_ctx* ctx) { return set_max_leng(ctx) / (ctx->tab.span + 1) + 1 <= ctx->opt.maxMotifsPerSequence; }
 
 static int select_mops(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, uint32_t n, int shift, bool ordered,
                        DevBuf<uint8_t>& keep, DevBuf<float>& kscore, uint32_t* nKept, uint32_t* maxPerSeq) {
@@ -1315,11 +1391,23 @@ static void scan_full_set_sorted(xxm_ctx* ctx, const Values& V, uint32_t n, uint
 	set_max_sites_mops(ctx, posSetSize);
 }
 
+static bool scan_full_can_defer(const xxm_ctx* ctx);
+static int scan_full_launch(xxm_ctx* ctx, int32_t posSetSize);
+static int scan_full_finish(xxm_ctx* ctx, int32_t* nbSites, int32_t* nbBestSites, int32_t* maxSites, bool* overflow);
 extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t* nbSites, int32_t* nbBestSites, int32_t* maxSites) {
 	CK(cudaSetDevice(ctx->device));
 	if (!ctx->haveModel) return ctx->fail("xxm_scan_full: no model (call xxm_reinitialize)");
 	if (posSetSize < 1 || posSetSize > ctx->nent) return ctx->fail("posSetSize out of range");
 	const PvalueTables& T = ctx->tab;
+	if (scan_full_can_defer(ctx) && !std::getenv("XXM_NO_DEFER")) {
+		// the same launches xxm_optimize_step queues (find, expand, class-index overlap removal + histogram), read back at once
+		TRY(scan_full_launch(ctx, posSetSize));
+		CK(cudaStreamSynchronize(ctx->stream));
+		bool overflow = false;
+		TRY(scan_full_finish(ctx, nbSites, nbBestSites, maxSites, &overflow));
+		if (!overflow) return 0;
+		// the site arrays were too small: the ordinary path below grows them
+	}
 	if (ctx->opt.localization) TRY(stage_pos_prob(ctx, T.span, ctx->modelFirstCol, enrStart, enrEnd, 0));
 	const Values V = make_values(ctx, true);  // the full scan always uses mops = true (StartPosUpdater-inl.h:99)
 	uint32_t n = 0;
@@ -1359,7 +1447,7 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 	scan_full_set_sorted(ctx, V, n, kept, mps, posSetSize);
 	*nbSites = ctx->nbSites;
 	*nbBestSites = static_cast<int32_t>(n);
-	*maxSites = ctx->maxSites;
+	*maxSites = clamp_i32(ctx->maxSites);
 	return 0;
 }
 
@@ -1367,7 +1455,9 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 // select counters travel to ctx->h_pin with the caller's next synchronisation, and scan_full_finish does the bookkeeping.
 // Only for the case xxm_optimize_step's fast path handles (one table, no localization, forward strand only).
 static bool scan_full_can_defer(const xxm_ctx* ctx) {
-	return ctx->scanFindsOnlySites && !ctx->revcomp && !ctx->opt.localization && select_cap_safe(ctx) && ctx->M.nparts == 1;
+	// (--revcomp sets need the class-index kernel: there is no float-score variant of the reverse-strand look-back that runs
+	// off a device-side entry count)
+	return ctx->scanFindsOnlySites && !ctx->opt.localization && select_cap_safe(ctx) && ctx->M.nparts == 1 && (!ctx->revcomp || ctx->clsOrderOK);
 }
 
 static int scan_full_launch(xxm_ctx* ctx, int32_t posSetSize) {
@@ -1383,8 +1473,11 @@ static int scan_full_launch(xxm_ctx* ctx, int32_t posSetSize) {
 	CK(ctx->s_kscore.ensure(capN));
 	CK(ctx->counters.ensure(8));
 	CK(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
-	ctx->sortedLazy = ctx->clsOrderOK && ctx->M.nparts == 1 && V.finalTab == ctx->d_finalMops.p && capN <= 0x7FFFFF00u && !std::getenv("XXM_NO_CLS_SELECT");
-	if (ctx->sortedLazy)
+	ctx->sortedLazy = ctx->clsOrderOK && ctx->M.nparts == 1 && V.finalTab == ctx->d_finalMops.p && capN <= 0x7FFFFF00u && (ctx->revcomp || !std::getenv("XXM_NO_CLS_SELECT"));
+	if (ctx->revcomp && !ctx->sortedLazy) return ctx->fail("internal: deferred --revcomp scan without a class order");
+	if (ctx->sortedLazy && ctx->revcomp)
+		TRY(launch_select_cls_rc(ctx, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, capN, reinterpret_cast<const unsigned long long*>(ctx->total64.p), ctx->s_keep, ctx->s_kcls));
+	else if (ctx->sortedLazy)
 		TRY(launch_select_cls(ctx, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, capN, reinterpret_cast<const unsigned long long*>(ctx->total64.p), ctx->s_keep, ctx->s_kcls));
 	else
 		TRY(launch_select_fwd(ctx, V, ctx->b_seq.p, ctx->b_pos.p, ctx->b_vidx.p, capN, reinterpret_cast<const unsigned long long*>(ctx->total64.p), 0, ctx->s_keep,
@@ -1407,11 +1500,12 @@ static int scan_full_finish(xxm_ctx* ctx, int32_t* nbSites, int32_t* nbBestSites
 	ctx->nBest = n;
 	scan_full_set_best(ctx, n, true);
 	const Values V = make_values(ctx, true);
-	const uint32_t mps = std::min<uint32_t>(c[0], static_cast<uint32_t>(ctx->max_leng / (ctx->tab.span + 1) + 1));
+	uint32_t mps = std::min<uint32_t>(c[0], static_cast<uint32_t>(ctx->max_leng / (ctx->tab.span + 1) + 1));
+	if (ctx->revcomp) mps = c[1];  // k_select_cls_rc reports it
 	scan_full_set_sorted(ctx, V, n, c[0], mps, ctx->pend.posSetSize, ctx->sortedLazy);
 	*nbSites = ctx->nbSites;
 	*nbBestSites = static_cast<int32_t>(n);
-	*maxSites = ctx->maxSites;
+	*maxSites = clamp_i32(ctx->maxSites);
 	return 0;
 }
 
