@@ -56,3 +56,28 @@ def test_gpu_steps_match_reference(name):
     ref, n, codes, neg = mc.run_reference(w, STEPS)
     got = gpu_steps(w, ref, n, codes, neg, STEPS)
     mc.compare_with_reference(ref, got)
+
+
+@pytest.mark.parametrize("name,nseq", [("cfg5", 120000), ("cols12", 80000), ("cols17", 30000)])
+def test_sweep_prefilter_equals_full_sweep(name, nseq):
+    """Lists whose scores are not table valued (localization; two p-value tables) choose their subset from 10^4..10^6 runs of
+    equal scores.  The device prefilter (k_sweep_eval: approximate evaluation of every run, exact evaluation of the ones within
+    3e-4 of the minimum) must pick exactly what the exact sweep over all runs picks: same subset size, log p-value and PWM."""
+    import os
+    if not mc.have_reference():
+        pytest.skip("oracle/_ref/ref_harness not built")
+    w = W.by_name(name).scaled(nseq)
+    ref, _, _, _ = mc.run_reference(W.by_name(name).scaled(1500), 1)  # only for the start motif
+    n, codes = w.positive_set()
+    ref = dict(ref, posSetSize=len(n), total=int(n.astype(np.int64).sum()))
+    os.environ.pop("XXM_NO_SWEEP_PREFILTER", None)
+    a = gpu_steps(w, ref, n, codes, None, 3)
+    os.environ["XXM_NO_SWEEP_PREFILTER"] = "1"
+    try:
+        b = gpu_steps(w, ref, n, codes, None, 3)
+    finally:
+        os.environ.pop("XXM_NO_SWEEP_PREFILTER", None)
+    for k in ("nbSites", "nbBestSites", "maxSites", "bestMotifNb", "bestPval", "enr"):
+        assert a[k] == b[k], "%s: %r (prefilter) != %r (full sweep)" % (k, a[k], b[k])
+    assert (np.asarray(a["pwm"]) == np.asarray(b["pwm"])).all()
+    assert a["bestMotifNb"] > 100

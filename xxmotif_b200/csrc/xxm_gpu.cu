@@ -165,7 +165,8 @@ struct xxm_ctx {
 	DevBuf<uint8_t> memoFlag;
 	DevBuf<double> memoTmp;
 	std::vector<double> h_memoVals;
-	DevBuf<unsigned long long> runPack;
+	DevBuf<unsigned long long> runPack, sweepCand;
+	DevBuf<double> sweepApprox;
 	DevBuf<uint32_t> r_seq, d_pbits;
 	DevBuf<uint8_t> d_t8, d_raw;
 	DevBuf<uint32_t> d_pairTab, d_dead, d_scanCounts;
@@ -341,7 +342,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	ctx->u_seq.release(); ctx->u_pos.release(); ctx->u_vidx.release(); ctx->b_score.release(); ctx->b_pSsnap.release(); ctx->s_kscore.release(); ctx->e_kscore.release();
 	ctx->slotScore.release(); ctx->tmpScore.release(); ctx->s_keep.release(); ctx->e_keep.release(); ctx->flag8.release(); ctx->stk.release();
 	ctx->slotIdx.release(); ctx->e_slotIdx.release(); ctx->e_slotScore.release(); ctx->u_score.release(); ctx->counters.release(); ctx->hist.release(); ctx->idxA.release(); ctx->idxB.release(); ctx->keysA.release();
-	ctx->keysB.release(); ctx->rsHist.release(); ctx->cmpCounts.release(); ctx->memoIdx.release(); ctx->memoFlag.release(); ctx->memoTmp.release(); ctx->runStart.release(); ctx->runPack.release(); ctx->status.release(); ctx->total64.release(); ctx->d_counts.release(); ctx->d_sites.release();
+	ctx->keysB.release(); ctx->rsHist.release(); ctx->cmpCounts.release(); ctx->memoIdx.release(); ctx->memoFlag.release(); ctx->memoTmp.release(); ctx->runStart.release(); ctx->runPack.release(); ctx->sweepCand.release(); ctx->sweepApprox.release(); ctx->status.release(); ctx->total64.release(); ctx->d_counts.release(); ctx->d_sites.release();
 	ctx->d_hf.release(); ctx->d_hb.release();
 	ctx->r_seq.release(); ctx->d_pbits.release(); ctx->d_t8.release(); ctx->d_pairTab.release();
 	cudaEventDestroy(ctx->ev0);
@@ -1096,7 +1097,7 @@ extern "C" int xxm_tables_get(const xxm_ctx* ctx, int32_t part, double* pvalues,
 // value tables
 // =====================================================================================================================
 static int stage_pos_prob(xxm_ctx* ctx, int motifLength, int firstMotifColumn, int enrStart, int enrEnd, int offset) {
-	init_positional_probs(ctx->posProb, ctx->max_leng, ctx->revcomp, motifLength, firstMotifColumn, enrStart, enrEnd, offset);
+	init_positional_probs(ctx->posProb, set_max_leng(ctx), ctx->revcomp, motifLength, firstMotifColumn, enrStart, enrEnd, offset);  // Global::posSet->max_leng: of the whole (sharded) set
 	TRY(upload(ctx, ctx->d_posProb, ctx->posProb));
 	ctx->posProbValid = true;
 	return 0;
