@@ -232,6 +232,14 @@ int xxm_optimize_step(xxm_ctx* ctx, double* pwm31x5, const int32_t* cols, int32_
 int xxm_host_tables(const double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions, const double* bgLog5,
                     int32_t order, const float* rprobs, const float* rconds, int32_t part, int64_t* info, double* pvalues, double* probs,
                     int32_t* classScore, int32_t* classCount, int64_t* classIds);
+/* xxm_device_tables: SURVEY 8(f) row 1 -- the same construction ON THE DEVICE for one-part models (at most 8 match columns):
+ *   all 4^len branch-and-bound paths tested in parallel (the recursion's visiting order is the numeric order of the path
+ *   index), stable sort by integer score through rank by counting, class p-values accumulated leaf by leaf by one lane --
+ *   bit-identical to xxm_host_tables.  Needs xxm_set_options (bgLog) and xxm_set_background; outputs as xxm_host_tables
+ *   (part 0); last_ms (may be NULL): device time of the build kernels.  xxm_reinitialize takes this path when the environment
+ *   variable XXM_DEVICE_TABLES is set. */
+int xxm_device_tables(xxm_ctx* ctx, const double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions, int64_t* info,
+                      double* pvalues, int32_t* classScore, int32_t* classCount, int64_t* classIds, float* last_ms);
 /* xxm_host_null_model: NullModel::init(sequences, alpha = pseudocountsFactor, beta = countsOffset, order, gaps = true,
  *   freqs = NULL) (NullModel.cpp:64-201) -> the two 2^(3(order+1)) float tables xxm_set_background takes.  n/codes are the
  *   sequences as the reference holds them when the model is trained (AFTER createRevcomp if --revcomp).

@@ -21,7 +21,7 @@ EXPORTS = [
     "xxm_reinitialize", "xxm_tables_info", "xxm_tables_get", "xxm_window_pvals", "xxm_scan_full", "xxm_rescore", "xxm_scan_oops",
     "xxm_rescore_startposlist", "xxm_update_pwm_with_best_subset", "xxm_startposlist_best_subset", "xxm_startposlist_from_elong",
     "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset", "xxm_host_pair_table",
-    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases",
+    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables",
 ]
 
 
@@ -94,6 +94,7 @@ def load_library():
         "xxm_comm_destroy": [vp],
         "xxm_optimize_step": [vp, vp, vp, i32, i32, i32, i32, i32, dbl, P(XxmStepInfo)],
         "xxm_step_phases": [vp, vp, P(C.c_int64), i32],
+        "xxm_device_tables": [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, P(C.c_float)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -304,6 +305,20 @@ class Context:
         self._ck(self.L.xxm_get_stats(self.h, C.byref(s)))
         return {"launches": s.launches, "last_scan_ms": s.last_scan_ms, "last_scan_bases": s.last_scan_bases, "last_scan_hits": s.last_scan_hits,
                 "last_find_ms": s.last_find_ms}
+
+    def device_tables(self, pwm, cols, posSetSize, totalPositions):
+        """the p-value table of a one-part model built on the device (xxm_device_tables): the dict Context.tables() returns + device ms"""
+        pwm = np.ascontiguousarray(pwm, dtype=np.float64).reshape(155)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        info = np.zeros(9, dtype=np.int64)
+        ms = C.c_float(0)
+        self._ck(self.L.xxm_device_tables(self.h, _p(pwm), _p(cols), len(cols), posSetSize, totalPositions, _p(info), None, None, None, None, C.byref(ms)))
+        pv = np.zeros(info[3], dtype=np.float64)
+        cs = np.zeros(info[5], dtype=np.int32)
+        cc = np.zeros(info[5], dtype=np.int32)
+        ci = np.zeros(info[7], dtype=np.int64)
+        self._ck(self.L.xxm_device_tables(self.h, _p(pwm), _p(cols), len(cols), posSetSize, totalPositions, _p(info), _p(pv), _p(cs), _p(cc), _p(ci), C.byref(ms)))
+        return {"L": int(info[0]), "maxk": int(info[1]), "nparts": int(info[2]), "pvalues": [pv], "classes": [(cs, cc, ci)], "probs": None}, ms.value
 
     def step_phases(self, reset=True):
         """average host-side phase times of xxm_optimize_step since the last reset, microseconds per step"""

@@ -277,8 +277,9 @@ private:
 
 }  // namespace
 
-void build_pvalue_tables(const double* pwm, const int32_t* cols, int ncols, int64_t posSetSize, int64_t totalPositions, const double* bgLog,
-                         const NullModelView& nm, PvalueTables& t) {
+// the part of reinitialize (branch_and_bound-inl.h:183-258) that does not enumerate anything
+static void model_header_impl(const double* pwm, const int32_t* cols, int ncols, int64_t posSetSize, int64_t totalPositions, const double* bgLog,
+                              PvalueTables& t, double (*tlin)[5]) {
 	t.error = 0;
 	t.L = ncols;
 	t.maxk = 8;
@@ -289,19 +290,60 @@ void build_pvalue_tables(const double* pwm, const int32_t* cols, int ncols, int6
 	for (int i = 0; i < ncols; ++i) t.coloff[i] = cols[i] - cols[0];
 	for (int i = 1; i < ncols; ++i) t.gaps[i - 1] = cols[i] - cols[i - 1] - 1;
 	t.gaps[ncols - 1] = 0;
-	Builder b(t, nm);
 	for (int i = 1; i <= ncols; ++i) {
 		double sum = 0;
 		for (int a = 1; a <= 4; ++a) {
 			t.logodds[i][a] = pwm[cols[i - 1] * 5 + a] - bgLog[a];
-			b.t_lin_[i][a] = std::exp(pwm[cols[i - 1] * 5 + a]);
-			sum += b.t_lin_[i][a];
+			const double lin = std::exp(pwm[cols[i - 1] * 5 + a]);
+			if (tlin) tlin[i][a] = lin;
+			sum += lin;
 		}
 		t.logodds[i][0] = 0;
 		if (std::fabs(sum - 1) >= 1e-3) t.error = 2;  // the reference asserts (branch_and_bound-inl.h:223)
 	}
 	t.part[1] = TablePart();
 	t.leftClassProb.clear();
+}
+
+void model_header(const double* pwm, const int32_t* cols, int ncols, int64_t posSetSize, int64_t totalPositions, const double* bgLog, PvalueTables& t) {
+	model_header_impl(pwm, cols, ncols, posSetSize, totalPositions, bgLog, t, nullptr);
+}
+
+// rowSwap / colSwap / swappedPWM / S_max of the left part (the same statements as Builder::order_columns), as data for the
+// device build
+void part_plan(const PvalueTables& t, int len, PartPlan& P) {
+	int row[34][5], col[34];
+	for (int c = 1; c <= len; ++c) {
+		int* r = row[c];
+		r[1] = 1;
+		for (int j = 2; j <= 4; ++j) {
+			int s = j;
+			while (s > 1 && t.logodds[c][r[s - 1]] < t.logodds[c][j]) { r[s] = r[s - 1]; --s; }
+			r[s] = j;
+		}
+	}
+	col[1] = 1;
+	for (int c = 2; c <= len; ++c) {
+		int s = c;
+		while (s > 1 && t.logodds[col[s - 1]][row[col[s - 1]][1]] < t.logodds[c][row[c][1]]) { col[s] = col[s - 1]; --s; }
+		col[s] = c;
+	}
+	P.len = len;
+	for (int c = 1; c <= len; ++c) {
+		for (int j = 1; j <= 4; ++j) {
+			P.sw[c][j] = t.logodds[col[c]][row[col[c]][j]];
+			P.code[c][j] = row[col[c]][j] - 1;
+		}
+		P.shift[c] = 2 * (col[c] - 1);
+	}
+	P.smax[len + 1] = 0;
+	for (int c = len; c > 0; --c) P.smax[c] = (c < len) ? P.smax[c + 1] + P.sw[c][1] : P.sw[c][1];
+}
+
+void build_pvalue_tables(const double* pwm, const int32_t* cols, int ncols, int64_t posSetSize, int64_t totalPositions, const double* bgLog,
+                         const NullModelView& nm, PvalueTables& t) {
+	Builder b(t, nm);
+	model_header_impl(pwm, cols, ncols, posSetSize, totalPositions, bgLog, t, b.t_lin_);
 	if (t.nparts == 1) {
 		b.build_part(0, 1, t.L, 0, false, 0);
 		return;

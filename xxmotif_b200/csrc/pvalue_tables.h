@@ -42,6 +42,18 @@ struct PvalueTables {
 	std::vector<double> leftClassProb;  // per left class: sum of prob over its ids (list order)
 };
 
+// pieces of the construction the device build (xxm_tables_device.cuh) shares with the host build: the model header
+// (log-odds, gaps, thresholds) and the visiting order of create_similar_kmers_rec for the left part of `len` columns
+struct PartPlan {
+	int len;
+	double sw[9][5];   // [level 1..len][rank 1..4] log-odds of the level's column, descending
+	double smax[10];   // [level] best score still reachable from this level on
+	int shift[9];      // [level] bit position of the level's column in the k-mer id
+	int code[9][5];    // [level][rank] base code 0..3
+};
+void model_header(const double* pwm31x5, const int32_t* cols, int ncols, int64_t posSetSize, int64_t totalPositions, const double* bgLog5, PvalueTables& out);
+void part_plan(const PvalueTables& t, int len, PartPlan& out);
+
 void build_pvalue_tables(const double* pwm31x5, const int32_t* cols, int ncols, int64_t posSetSize, int64_t totalPositions,
                          const double* bgLog5, const NullModelView& nm, PvalueTables& out);
 

@@ -30,6 +30,7 @@
 #include "xxm_scan4.cuh"
 #include "xxm_scan5.cuh"
 #include "xxm_scan6.cuh"
+#include "xxm_tables_device.cuh"
 #include "pair_table.h"
 #include "nccl_dyn.h"
 
@@ -162,6 +163,12 @@ struct xxm_ctx {
 	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
 	DevBuf<uint64_t> status, total64;
 	DevBuf<uint32_t> cmpCounts, runStart, memoIdx;
+	// device table build (xxm_gpu_part8.inc)
+	DevBuf<float> d_nmProbs, d_nmConds;
+	bool nmOnDevice = false;
+	DevBuf<int32_t> tbScore[2], tbClassScore, tbClassCount;
+	DevBuf<uint32_t> tbId[2], tbCls;
+	DevBuf<double> tbProb[2], tbClassPval;
 	DevBuf<uint8_t> memoFlag;
 	DevBuf<double> memoTmp;
 	std::vector<double> h_memoVals;
@@ -342,7 +349,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	ctx->u_seq.release(); ctx->u_pos.release(); ctx->u_vidx.release(); ctx->b_score.release(); ctx->b_pSsnap.release(); ctx->s_kscore.release(); ctx->e_kscore.release();
 	ctx->slotScore.release(); ctx->tmpScore.release(); ctx->s_keep.release(); ctx->e_keep.release(); ctx->flag8.release(); ctx->stk.release();
 	ctx->slotIdx.release(); ctx->e_slotIdx.release(); ctx->e_slotScore.release(); ctx->u_score.release(); ctx->counters.release(); ctx->hist.release(); ctx->idxA.release(); ctx->idxB.release(); ctx->keysA.release();
-	ctx->keysB.release(); ctx->rsHist.release(); ctx->cmpCounts.release(); ctx->memoIdx.release(); ctx->memoFlag.release(); ctx->memoTmp.release(); ctx->runStart.release(); ctx->runPack.release(); ctx->sweepCand.release(); ctx->sweepApprox.release(); ctx->status.release(); ctx->total64.release(); ctx->d_counts.release(); ctx->d_sites.release();
+	ctx->keysB.release(); ctx->rsHist.release(); ctx->d_nmProbs.release(); ctx->d_nmConds.release(); for (int k = 0; k < 2; ++k) { ctx->tbScore[k].release(); ctx->tbId[k].release(); ctx->tbProb[k].release(); } ctx->tbCls.release(); ctx->tbClassScore.release(); ctx->tbClassCount.release(); ctx->tbClassPval.release(); ctx->cmpCounts.release(); ctx->memoIdx.release(); ctx->memoFlag.release(); ctx->memoTmp.release(); ctx->runStart.release(); ctx->runPack.release(); ctx->sweepCand.release(); ctx->sweepApprox.release(); ctx->status.release(); ctx->total64.release(); ctx->d_counts.release(); ctx->d_sites.release();
 	ctx->d_hf.release(); ctx->d_hb.release();
 	ctx->r_seq.release(); ctx->d_pbits.release(); ctx->d_t8.release(); ctx->d_pairTab.release();
 	cudaEventDestroy(ctx->ev0);
@@ -821,6 +828,7 @@ extern "C" int xxm_set_background(xxm_ctx* ctx, int32_t order, const float* rpro
 	ctx->nm.order = order;
 	ctx->nm.rprobs = ctx->rprobs.data();
 	ctx->nm.rconds = ctx->rconds.data();
+	ctx->nmOnDevice = false;
 	ctx->haveModel = false;
 	return 0;
 }
@@ -940,6 +948,7 @@ static int stage_part(xxm_ctx* ctx, const TablePart& P, bool single, DevBuf<uint
 
 static double zoops_final(double pS, double exponent) { return 1 - std::pow(1 - pS, exponent); }  // pValCalculation.h:96
 
+static int device_build_part0(xxm_ctx* ctx, PvalueTables& T, float* ms);  // xxm_gpu_part8.inc
 static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions);
 extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions) {
 	const int r = reinitialize_impl(ctx, pwm, cols, ncols, posSetSize, totalPositions);
@@ -979,6 +988,10 @@ static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* col
 		TRY(shard_sync(ctx));
 		if (posSetSize != ctx->nent) return ctx->fail("with a communicator attached every call refers to the whole sharded set: posSetSize must be the rank's sequence count");
 		build_pvalue_tables(pwm, cols, ncols, ctx->G.nent, ctx->G.total, ctx->opt.bgLog, ctx->nm, ctx->tab);
+	} else if (ncols <= 8 && std::getenv("XXM_DEVICE_TABLES")) {
+		// the enumeration, the stable sort and the cumulative class p-values on the device
+		model_header(pwm, cols, ncols, posSetSize, totalPositions, ctx->opt.bgLog, ctx->tab);
+		if (ctx->tab.error == 0) TRY(device_build_part0(ctx, ctx->tab, nullptr));
 	} else
 	build_pvalue_tables(pwm, cols, ncols, posSetSize, totalPositions, ctx->opt.bgLog, ctx->nm, ctx->tab);
 	const PvalueTables& T = ctx->tab;
@@ -1515,3 +1528,4 @@ static int scan_full_finish(xxm_ctx* ctx, int32_t* nbSites, int32_t* nbBestSites
 #include "xxm_gpu_part4.inc"
 #include "xxm_gpu_part5.inc"
 #include "xxm_gpu_part6.inc"
+#include "xxm_gpu_part8.inc"
