@@ -155,6 +155,8 @@ int xxm_logodds_hist(xxm_ctx* ctx, const double* pwm31x5, const int32_t* cols, i
 int xxm_update_enriched_region(xxm_ctx* ctx, int32_t firstMotifColumn, int32_t motifLength, int32_t* enr);
 int xxm_host_positional_pval(int32_t max_leng, int32_t revcomp, int32_t enrMax, int32_t firstMotifColumn, int32_t motifLength, const int32_t* sitePos,
                              int32_t nSites, double* out);
+/* the same for the set loaded in ctx; on a sharded set every rank passes its own sites and the sum runs over all ranks */
+int xxm_positional_pval(xxm_ctx* ctx, int32_t enrMax, int32_t firstMotifColumn, int32_t motifLength, const int32_t* sitePos, int32_t nSites, double* out);
 
 /* ---- the callers of the path, re-stated above this ABI -----------------------------------
  * xxm_motif mirrors the part of class Motif (refinementPhase/Motif.h) that the refinement loop reads and writes.

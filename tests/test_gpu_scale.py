@@ -335,3 +335,48 @@ def test_bench_workload_refinement_matches_reference():
         assert float(mot.pval) == ref["pval"]
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("revcomp", [False, True])
+def test_per_sequence_cap_vs_oracle(revcomp):
+    """Global::maxMotifsPerSequence (--maxSeqOcc) binding: getBestSubset skips the sites beyond the cap of their sequence and
+    Motif::updatePWM_OOL counts the first K that are not (Motif.cpp:634-646) -- subset size, p-value and PWM against the oracle."""
+    import oracle_lib as ol
+    import xxmotif_b200 as xb
+    from xxmotif_b200 import hostprep
+    n, codes = hostprep.synthetic_set(2500, 600, seed=17, frac=0.8)
+    rng = np.random.default_rng(5)
+    for s in rng.integers(0, 2500, size=400):  # a few extra instances per sequence, so that the cap of 2 binds
+        for _ in range(4):
+            p = int(rng.integers(0, 592))
+            codes[s * 600 + p:s * 600 + p + 8] = [4, 1, 4, 1, 1, 1, 4, 1]
+    n2, c2 = hostprep.revcomp_double(n, codes) if revcomp else (n, codes)
+    bg, bgl = hostprep.background(n2, c2)
+    rp, rc = hostprep.null_model(n2, c2, order=2)
+    ctx = xb.Context(0)
+    try:
+        ctx.set_options(mops=True, bg=bg, bgLog=bgl, maxMotifsPerSequence=2)
+        ctx.set_background(2, rp, rc)
+        ctx.load_seqset(n, codes, revcomp=revcomp)
+        oset = ol.SeqSet(n, codes, revcomp=revcomp)
+        onm = ol.NullModel(order=2, rprobs=rp, rconds=rc)
+        octx = ol.Ctx(oset, revcomp, True, False, False, bg, bgl, maxMotifsPerSequence=2)
+        total, _, mxl, _ = ctx.seqset_info()
+        pwm, cols = hostprep.profile_pwm()
+        nent = len(n)
+        enr = (1 - int(cols[0]) + 1, mxl - int(cols[0]) + 1)
+        for it in range(3):
+            ctx.reinitialize(pwm, cols, nent, int(total[nent]))
+            tab = ol.Tables(pwm, cols, nent, int(total[nent]), bgl, onm)
+            nb, nbest, mx = ctx.scan_full(nent, enr)
+            octx.scan_full(tab, cols, nent, enr, True)
+            assert (nb, nbest, mx) == (octx.nbSites, octx.nbBestSites, octx.maxSites)
+            ok, nbm, bp, new = ctx.update_pwm_with_best_subset(xb.LIST_SORTED_SITES, pwm, int(cols[0]), nent, False, 0.1)
+            ook, onbm, obp, onew = octx.update_pwm_with_best_subset(0, pwm, cols, nent, 0, False, 0.1)
+            assert (ok, nbm, bp) == (ook, onbm, obp)
+            assert (new[5:] == onew[5:]).all()
+            pwm = new
+        kept = ctx.get_sites(xb.LIST_SORTED_SITES, xb.ORDER_AS_IS, cap=nb + 8)
+        assert np.bincount(kept["sequence"]).max() > 2  # the cap did bind
+    finally:
+        ctx.close()

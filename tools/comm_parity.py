@@ -8,6 +8,8 @@ ragged lengths) every rank loads its block of the sequences into a context with 
   * three optimizeMotif steps (xxm_optimize_step: histogram exchange or run exchange, count all-reduce),
   * one candidate re-score under a longer column set + its subset choice and PWM recount (xxm_rescore,
     xxm_update_pwm_with_best_subset on the sharded lists),
+  * the whole per-motif refinement loop (xxm_iterate_motif: optimizeMotif + maximizeMotifLength over all column variants
+    until the p-value stops improving),
 while rank 0 also runs the same calls on ONE context holding the whole set.  Everything the calls return must be identical:
 global site counts, optimal subset size, log p-value and every PWM entry.  Rank 0 writes one JSON object; exit code 1 on a
 mismatch."""
@@ -44,6 +46,24 @@ def run_calls(ctx, w, n, codes, pwm0, cols, enr):
     upd, nb, bp, e1 = ctx.update_pwm_with_best_subset(xb.LIST_SORTED_SITES_ELONG, pwm, int(tmp[0]), nent, True, 0.1)
     out.append(("rescore", int(upd), int(nb), float(bp), e1[5:].tobytes()))
     return out
+
+
+def run_refinement(ctx, w, n, pwm0, cols, sharded):
+    """the whole per-motif loop (xxm_iterate_motif: optimizeMotif + maximizeMotifLength with all column variants until the p-value
+    stops improving) on whatever ctx holds; the site count is summed over the ranks"""
+    from xxmotif_b200 import refine
+    nent = len(n)
+    total, _, mxl, _ = ctx.seqset_info()
+    c0 = int(cols[0])
+    raw_max = int(n.max())
+    mot = refine.Motif(pwm0, cols, nent, enr=(1 - c0, 1 - c0, raw_max - c0 + 1), siteCap=1 << 20)
+    R = refine.Refiner(ctx, totalPositions=int(total[nent]), revcomp=w.revcomp, localization=w.localization, maximizeMotifLength=True, minMatchPositions=5,
+                       maxMatchPositions=17, pseudo=0.1, neff_pwm=10.0)
+    rounds = R.iterate_motif(mot)
+    ns = torch.tensor([int(mot.m.nsites)], device="cuda", dtype=torch.int64)
+    if sharded:
+        dist.all_reduce(ns)
+    return ("refine", int(rounds), [int(c) for c in mot.cols], float(mot.pval), int(ns.item()), float(mot.m.worstScore)), float(mot.m.posPval)
 
 
 def main():
@@ -84,8 +104,11 @@ def main():
         ctx.set_background(w.order, rp, rc)
         ctx.load_seqset(n[lo:hi], codes[off[lo]:off[hi]], revcomp=w.revcomp)
         err = None
+        pp = None
         try:
             got = run_calls(ctx, w, n[lo:hi], codes[off[lo]:off[hi]], pwm0, cols, enr)
+            r, pp = run_refinement(ctx, w, n[lo:hi], pwm0, cols, True)
+            got.append(r)
         except xb.XxmError as ex:
             got, err = None, str(ex)
         entry = {"workload": w.describe(), "sequences": nseq, "match_columns": int(len(cols))}
@@ -97,11 +120,16 @@ def main():
                 solo.set_background(w.order, rp, rc)
                 solo.load_seqset(n, codes, revcomp=w.revcomp)
                 want = run_calls(solo, w, n, codes, pwm0, cols, enr)
+                r1, pp1 = run_refinement(solo, w, n, pwm0, cols, False)
+                want.append(r1)
             finally:
                 solo.close()
             same = got is not None and got == want
-            entry.update({"identical": bool(same), "error": err, "single_gpu": [list(x[1:4]) for x in want],
-                          "sharded": [list(x[1:4]) for x in got] if got else None})
+            if pp is not None and pp1 is not None:  # the positional log sum is added up in a different order: equal to rounding
+                same = same and abs(pp - pp1) <= 1e-9 * max(1.0, abs(pp1))
+                entry["posPval"] = [pp, pp1]
+            entry.update({"identical": bool(same), "error": err, "single_gpu": [list(x[1:5]) if x[0] == "refine" else list(x[1:4]) for x in want],
+                          "sharded": [list(x[1:5]) if x[0] == "refine" else list(x[1:4]) for x in got] if got else None})
             bad[0] = 0 if same else 1
         dist.broadcast(bad, src=0)
         if rank == 0:

@@ -117,9 +117,23 @@ static double combined_pval_log(double logProd, int n) {
 }
 
 bool positional_pval(int max_leng, bool revcomp, int enrMax, int firstMotifColumn, int motifLength, const int32_t* sitePos, int nSites, double* out) {
+	double logProd = 0;
+	int trivial = 0;
 	*out = 0.0;
+	if (!positional_logprod(max_leng, revcomp, enrMax, firstMotifColumn, motifLength, sitePos, nSites, &logProd, &trivial)) return false;
+	if (!trivial) *out = positional_combine(logProd, nSites);
+	return true;
+}
+
+double positional_combine(double logProd, int64_t nSites) { return combined_pval_log(logProd, static_cast<int>(nSites)); }
+
+// the sum over the sites of setPositionalPval (StartPosUpdater.cpp:228-262); *trivial = 1 where the reference returns 0 before it
+bool positional_logprod(int max_leng, bool revcomp, int enrMax, int firstMotifColumn, int motifLength, const int32_t* sitePos, int nSites, double* out,
+                        int* trivial) {
+	*out = 0.0;
+	*trivial = 0;
 	int peak = enrMax + firstMotifColumn - 1;
-	if (peak <= 1) return true;
+	if (peak <= 1) { *trivial = 1; return true; }
 	int L = max_leng;
 	if (revcomp) L = (L - 1) / 2;
 	const int L1 = L - motifLength + 1;
@@ -143,7 +157,7 @@ bool positional_pval(int max_leng, bool revcomp, int enrMax, int firstMotifColum
 		}
 		logProd += std::log(static_cast<double>(d + 1) / static_cast<double>(L1));
 	}
-	*out = combined_pval_log(logProd, nSites);
+	*out = logProd;
 	return true;
 }
 

@@ -58,11 +58,10 @@ void set_cols(xxm_motif* m, const Cols& c) {
 }
 
 int set_positional_pval(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* P) {
-	int32_t mx = 0, mn = 0;
-	if (xxm_seqset_info(ctx, nullptr, nullptr, &mx, &mn)) return 1;
 	const Cols c = cols_of(m);
 	double p = 0;
-	const int rc = xxm_host_positional_pval(mx, P->revcomp, m->enr[0], c.front(), c.span(), m->sitePos, m->nsites, &p);
+	(void) P;
+	const int rc = xxm_positional_pval(ctx, m->enr[0], c.front(), c.span(), m->sitePos, m->nsites, &p);
 	if (rc) return rc;
 	m->posPval = p;
 	return 0;

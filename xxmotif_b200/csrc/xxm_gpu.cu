@@ -142,7 +142,8 @@ struct xxm_ctx {
 	uint32_t nval = 0;
 	DevBuf<double> d_pS, d_finalMops, d_finalMode, d_posProb, d_perCand;
 	std::vector<double> h_pS, h_finalMops, h_finalMode;  // nparts == 1: per class; nparts == 2: per slot after a round trip
-	bool memoModeValid = false;
+	bool memoModeValid = false;  // one-table models: h_finalMode / d_finalMode hold the mode table of the current model
+	double modeExponent = 0;
 	std::vector<double> posProb, sum_i;
 	bool posProbValid = false;
 
@@ -172,6 +173,7 @@ struct xxm_ctx {
 	DevBuf<uint8_t> memoFlag;
 	DevBuf<double> memoTmp;
 	std::vector<double> h_memoVals;
+	std::vector<int32_t> h_sortedSeq;  // sequence of every site in score order, kept when a per-sequence cap binds
 	DevBuf<unsigned long long> runPack, sweepCand;
 	DevBuf<double> sweepApprox;
 	DevBuf<uint32_t> r_seq, d_pbits;
@@ -207,6 +209,8 @@ struct xxm_ctx {
 	uint64_t histSerial = 0, histCounter = 0;
 	SiteList L[3];
 	int nbSites = 0;
+	float lastChoiceScore[3] = {0, 0, 0};  // score of the last site of the optimal subset last chosen on a list
+	bool lastChoiceValid[3] = {false, false, false};
 	int64_t nbSitesGlobal = 0;  // sites of all ranks seen by the last subset choice on a sharded set
 	int64_t maxSites = 0;  // (8 x 10^9 windows of a sharded set exceed the reference's int)
 
@@ -1025,18 +1029,20 @@ static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* col
 	if (T.nparts == 1) {
 		const size_t nc = T.part[0].classPval.size();
 		ctx->nval = static_cast<uint32_t>(nc);
-		ctx->h_pS.resize(nc); ctx->h_finalMops.resize(nc); ctx->h_finalMode.resize(nc);
+		ctx->h_pS.resize(nc); ctx->h_finalMops.resize(nc);
 		for (size_t c = 0; c < nc; ++c) {
 			const double v = T.part[0].classPval[c];
-			if (v == 0.0 || v == 1.0) { ctx->h_pS[c] = 1; ctx->h_finalMops[c] = 1; ctx->h_finalMode[c] = 1; continue; }
+			if (v == 0.0 || v == 1.0) { ctx->h_pS[c] = 1; ctx->h_finalMops[c] = 1; continue; }
 			const double pS = v * M.corr;
 			ctx->h_pS[c] = pS;
 			ctx->h_finalMops[c] = pS;
-			ctx->h_finalMode[c] = zoops_final(pS, exponent);
 		}
+		// the ZOOPS / OOPS table (one glibc pow per class) is only built when a call with mops = false needs it
+		// (ensure_mode_table): a full-scan step never does
+		ctx->modeExponent = exponent;
 		TRY(upload(ctx, ctx->d_pS, ctx->h_pS));
 		TRY(upload(ctx, ctx->d_finalMops, ctx->h_finalMops));
-		TRY(upload(ctx, ctx->d_finalMode, ctx->h_finalMode));
+		CK(ctx->d_finalMode.ensure(std::max<size_t>(1, nc)));
 		TRY(stage_class_order(ctx));
 	} else {
 		ctx->clsOrderOK = false;
@@ -1121,8 +1127,19 @@ static int stage_pos_prob(xxm_ctx* ctx, int motifLength, int firstMotifColumn, i
 // sparse (a few 10^4 .. 10^6 distinct scores in up to 2^24 slots), so both steps run over compacted slot lists.
 static int compact_list(xxm_ctx* ctx, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, const uint8_t* flag, uint32_t n, uint32_t* oseq,
                         uint32_t* opos, uint32_t* ovidx, uint32_t* oidx, uint32_t* nOut, const uint32_t* keys = nullptr);
+// one-table models: finalPval of every class for mops = false, 1 - pow(1 - pS, avgLength - length + 1) (pValCalculation.h:96)
+static int ensure_mode_table(xxm_ctx* ctx) {
+	if (ctx->M.nparts != 1 || ctx->memoModeValid) return 0;
+	const size_t nc = ctx->h_pS.size();
+	ctx->h_finalMode.resize(nc);
+	for (size_t c = 0; c < nc; ++c) ctx->h_finalMode[c] = (ctx->h_pS[c] == 1.0) ? 1.0 : zoops_final(ctx->h_pS[c], ctx->modeExponent);
+	if (nc) CK(cudaMemcpyAsync(ctx->d_finalMode.p, ctx->h_finalMode.data(), nc * 8, cudaMemcpyHostToDevice, ctx->stream));
+	ctx->memoModeValid = true;
+	return 0;
+}
+
 static int finalize_memo(xxm_ctx* ctx, bool needMode) {
-	if (ctx->M.nparts != 2) return 0;
+	if (ctx->M.nparts != 2) return needMode ? ensure_mode_table(ctx) : 0;
 	const uint32_t cap = ctx->M.memoCap;
 	CK(ctx->memoFlag.ensure(cap));
 	CK(ctx->memoIdx.ensure(cap));

@@ -6,7 +6,7 @@ import numpy as np
 
 from . import capi
 
-EXTRA_EXPORTS = ["xxm_update_enriched_region", "xxm_host_positional_pval"]
+EXTRA_EXPORTS = ["xxm_update_enriched_region", "xxm_host_positional_pval", "xxm_positional_pval"]
 
 
 def _lib():
