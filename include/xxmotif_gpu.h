@@ -132,6 +132,12 @@ int xxm_startposlist_best_subset(xxm_ctx* ctx, int32_t firstColumn, int32_t posS
 /* replaces fill_startPosList_with_elongSites (StartPosUpdater.cpp:114-134) */
 int xxm_startposlist_from_elong(xxm_ctx* ctx, int32_t bestMotifNb, int32_t firstTmpColumn, int32_t* outSeq, int32_t* outPos, int32_t cap,
                                 int32_t* nOut, double* worstScore);
+/* maximizeMotifLength only uses the site list of the best column variant (Iterate_Motif.cpp:117-125 overwrites the list at every
+ * improvement).  xxm_elong_keep sets the current sortedSites_elong aside on the device (no copy: the following re-scores write a
+ * second set of buffers); xxm_startposlist_from_kept = xxm_startposlist_from_elong on the list set aside, called once at the end */
+int xxm_elong_keep(xxm_ctx* ctx);
+int xxm_startposlist_from_kept(xxm_ctx* ctx, int32_t bestMotifNb, int32_t firstTmpColumn, int32_t* outSeq, int32_t* outPos, int32_t cap,
+                               int32_t* nOut, double* worstScore);
 /* replaces set_BindingSites (StartPosUpdater.cpp:65-76) with ThresholdChecker "<thr": sites sorted by start position */
 int xxm_set_binding_sites(xxm_ctx* ctx, double thr, xxm_site* out, int32_t cap, int32_t* nOut);
 /* replaces getBestStartPos()/getSortedSites() (StartPosUpdater.h:46-47) + sortSitesByScore/sortSitesByStartPos
@@ -281,6 +287,9 @@ int xxm_get_stats(const xxm_ctx* ctx, xxm_stats* out);
  * staging | launching scan + overlap removal + exchange | waiting for them | subset choice | launching the recount | waiting
  * for it | PWM from the counts.  (Where does a step spend the time the kernels do not account for?) */
 int xxm_step_phases(xxm_ctx* ctx, double* us7, int64_t* nsteps, int32_t reset);
+/* with XXM_TRACE set in the environment the library sums the wall time of every C-ABI call (and of named sections inside
+ * some of them) per name; xxm_trace_dump prints the table to stderr and clears it (xxm_destroy does the same) */
+int xxm_trace_dump(void);
 /* the CUDA stream the context launches on, as a cudaStream_t cast to void* (for external event timing) */
 void* xxm_stream(const xxm_ctx* ctx);
 

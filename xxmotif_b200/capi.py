@@ -21,7 +21,7 @@ EXPORTS = [
     "xxm_reinitialize", "xxm_tables_info", "xxm_tables_get", "xxm_window_pvals", "xxm_scan_full", "xxm_rescore", "xxm_scan_oops",
     "xxm_rescore_startposlist", "xxm_update_pwm_with_best_subset", "xxm_startposlist_best_subset", "xxm_startposlist_from_elong",
     "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset", "xxm_host_pair_table",
-    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables",
+    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables", "xxm_trace_dump", "xxm_elong_keep", "xxm_startposlist_from_kept",
 ]
 
 
@@ -94,6 +94,9 @@ def load_library():
         "xxm_comm_destroy": [vp],
         "xxm_optimize_step": [vp, vp, vp, i32, i32, i32, i32, i32, dbl, P(XxmStepInfo)],
         "xxm_step_phases": [vp, vp, P(C.c_int64), i32],
+        "xxm_trace_dump": [],
+        "xxm_elong_keep": [vp],
+        "xxm_startposlist_from_kept": [vp, i32, i32, vp, vp, i32, P(i32), P(dbl)],
         "xxm_device_tables": [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, P(C.c_float)],
     }
     for name, args in sig.items():

@@ -8,6 +8,8 @@
 
 namespace xxm {
 
+static void parallel_logs(std::vector<double>& logs, int64_t first, int64_t cnt);
+
 void LogSum::extend(int64_t upTo) {
 	// LOG_sum_i[i] = LOG_i[i] + LOG_sum_i[i-1], LOG_i[i] = log(i) (LogTable.cpp:26-31).  log() is evaluated in parallel
 	// blocks, the accumulation stays strictly sequential so that every partial sum rounds like the reference's.
@@ -47,8 +49,28 @@ void LogSum::extend(int64_t upTo) {
 
 void LogSum::reserve(int64_t upTo) { extend(upTo); }
 
+// every entry of [0, upTo] (at most kPrefixMax) materialised once: the site counts a sweep reads (LOG_sum_i[K]) are small
+// next to N, and a sweep over thousands of runs should not pay up to 127 logarithms for each
+void LogSum::dense_prefix(int64_t upTo) {
+	upTo = std::min<int64_t>(upTo, kPrefixMax);
+	const int64_t have = static_cast<int64_t>(prefix_.size()) - 1;
+	if (upTo <= have) return;
+	const int64_t want = std::min<int64_t>(kPrefixMax, std::max<int64_t>(upTo, 2 * std::max<int64_t>(have, 1 << 16)));
+	std::vector<double> logs;
+	const int64_t first = std::max<int64_t>(have, 0);
+	parallel_logs(logs, first + 1, want - first);
+	if (prefix_.empty()) prefix_.push_back(0.0);
+	double acc = prefix_.back();
+	prefix_.reserve(static_cast<size_t>(want) + 1);
+	for (int64_t k = first + 1; k <= want; ++k) {
+		acc = logs[static_cast<size_t>(k - first - 1)] + acc;
+		prefix_.push_back(acc);
+	}
+}
+
 double LogSum::at(int64_t i) {
 	if (i <= 0) return 0.0;  // LOG_sum_i[0] = 0
+	if (i < static_cast<int64_t>(prefix_.size())) return prefix_[static_cast<size_t>(i)];
 	for (int k = 0; k < 4; ++k) if (lastIdx_[k] == i) return lastVal_[k];
 	const int64_t c = i / kStride;
 	if (c >= static_cast<int64_t>(ckpt_.size())) extend(i);
@@ -101,6 +123,7 @@ void LogSum::dense(int which, int64_t lo, int64_t hi) {
 
 double LogSum::at_dense(int64_t i) const {
 	if (i <= 0) return 0.0;
+	if (i < static_cast<int64_t>(prefix_.size())) return prefix_[static_cast<size_t>(i)];
 	for (const Window& w : win_)
 		if (!w.v.empty() && i >= w.lo && i < w.lo + static_cast<int64_t>(w.v.size())) return w.v[static_cast<size_t>(i - w.lo)];
 	const int64_t c = i / kStride;  // (the caller has reserved the checkpoints)
@@ -261,7 +284,12 @@ SubsetChoice best_subset_from_runs(LogSum& ls, const std::vector<ScoreRun>& runs
 	if (!runs.empty()) sw.c.lastScore = runs[0].score;
 	const int64_t lim = std::min(nbSites, limit);
 	int64_t cum = 0;
-	if (runs.size() < 2048) {
+	{
+		int64_t tot = 0;
+		for (const ScoreRun& r : runs) tot += r.count;
+		if (runs.size() > 64) ls.dense_prefix(std::min(tot, lim));
+	}
+	if (runs.size() < 16384) {
 		for (const ScoreRun& r : runs) {
 			if (r.score == 1.0f) break;  // :163
 			cum += r.count;

@@ -19,11 +19,14 @@ public:
 	// below lo, so every value is the reference's -- after which at_dense() is a thread-safe O(1) read.  Two windows are
 	// kept (the sweep reads LOG_sum_i[K] and LOG_sum_i[N - K]); a window that already covers [lo, hi] is reused.
 	void dense(int which, int64_t lo, int64_t hi);
+	void dense_prefix(int64_t upTo);  // [0, min(upTo, kPrefixMax)] materialised for good (grown geometrically); at() reads it first
 	double at_dense(int64_t i) const;  // window hit, else the checkpoint walk without the cache (thread safe)
 
 private:
 	struct Window { int64_t lo = 0; std::vector<double> v; };
 	Window win_[2];
+	static constexpr int64_t kPrefixMax = 1 << 24;  // 128 MB of doubles at most
+	std::vector<double> prefix_;
 	static constexpr int64_t kStride = 128;
 	std::vector<double> ckpt_{0.0};  // ckpt_[c] = LOG_sum_i[c * kStride]
 	int64_t lastIdx_[4] = {-1, -1, -1, -1};

@@ -120,20 +120,26 @@ extern "C" int xxm_maximize_motif_length(xxm_ctx* ctx, xxm_motif* m, const xxm_r
 				noChange = (front == 0 && back == 0);
 				for (int32_t col : tmp.c)
 					for (int a = 1; a <= 4; ++a) bestElong[col * 5 + a] = elong[col * 5 + a];
-				realSeq.assign(static_cast<size_t>(bestMotifNb), 0);
-				realPos.assign(static_cast<size_t>(bestMotifNb), 0);
-				int32_t n = 0;
-				double worst = 1;
-				if (xxm_startposlist_from_elong(ctx, bestMotifNb, tmp.front(), realSeq.data(), realPos.data(), bestMotifNb, &n, &worst)) return 1;
-				realSeq.resize(static_cast<size_t>(n));
-				realPos.resize(static_cast<size_t>(n));
-				m->worstScore = worst;
+				// fill_startPosList_with_elongSites(realStartPosList, bestMotifNb, tmpColumns) (Iterate_Motif.cpp:117-125): the list of
+				// an earlier best variant is overwritten by the next one, so the device list is only set aside here and
+				// materialised once, below, for the variant that won
+				if (xxm_elong_keep(ctx)) return 1;
 			}
 		}
 	}
 	if (P->elongPWM) std::memcpy(P->elongPWM, elong.data(), sizeof(double) * 31 * 5);
 	*noChangeOut = noChange;
 	if (bestMotifNb == 0) return 0;
+	{
+		realSeq.assign(static_cast<size_t>(bestMotifNb), 0);
+		realPos.assign(static_cast<size_t>(bestMotifNb), 0);
+		int32_t n = 0;
+		double worst = 1;
+		if (xxm_startposlist_from_kept(ctx, bestMotifNb, bestElongation.front(), realSeq.data(), realPos.data(), bestMotifNb, &n, &worst)) return 1;
+		realSeq.resize(static_cast<size_t>(n));
+		realPos.resize(static_cast<size_t>(n));
+		m->worstScore = worst;
+	}
 	m->pval = bestPval;
 	set_cols(m, bestElongation);
 	const int newFirst = (XXM_PWM_LENGTH - bestElongation.span()) / 2 + 1;
@@ -179,10 +185,27 @@ extern "C" int xxm_iterate_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_pa
 		++*rounds;
 		if (loop > 0 && bestPval >= oldPval) loop = 0;
 	} while (loop > 0);
-	// m->getStartPosList().sort(StartPos::cmpStartPos), MotifContainer.cpp:262
-	std::vector<std::pair<int32_t, int32_t>> s(static_cast<size_t>(m->nsites));
-	for (int32_t i = 0; i < m->nsites; ++i) s[i] = {m->siteSeq[i], m->sitePos[i]};
-	std::stable_sort(s.begin(), s.end());
-	for (int32_t i = 0; i < m->nsites; ++i) { m->siteSeq[i] = s[i].first; m->sitePos[i] = s[i].second; }
+	// m->getStartPosList().sort(StartPos::cmpStartPos), MotifContainer.cpp:262: by (sequence, position).  A stable LSD radix
+	// sort on the 64-bit key (positions may be negative: biased), 16 bits per pass, only the passes whose digit varies
+	{
+		const size_t n = static_cast<size_t>(m->nsites);
+		std::vector<uint64_t> a(n), b(n);
+		uint64_t orAll = 0, andAll = ~0ull;
+		for (size_t i = 0; i < n; ++i) {
+			a[i] = (static_cast<uint64_t>(static_cast<uint32_t>(m->siteSeq[i])) << 32) | (static_cast<uint32_t>(m->sitePos[i]) ^ 0x80000000u);
+			orAll |= a[i]; andAll &= a[i];
+		}
+		std::vector<uint32_t> cnt(65537);
+		for (int pass = 0; pass < 4; ++pass) {
+			const int sh = 16 * pass;
+			if ((((orAll ^ andAll) >> sh) & 0xFFFFull) == 0) continue;  // the same digit everywhere
+			std::fill(cnt.begin(), cnt.end(), 0u);
+			for (size_t i = 0; i < n; ++i) cnt[((a[i] >> sh) & 0xFFFFull) + 1]++;
+			for (int d = 0; d < 65536; ++d) cnt[d + 1] += cnt[d];
+			for (size_t i = 0; i < n; ++i) b[cnt[(a[i] >> sh) & 0xFFFFull]++] = a[i];
+			a.swap(b);
+		}
+		for (size_t i = 0; i < n; ++i) { m->siteSeq[i] = static_cast<int32_t>(a[i] >> 32); m->sitePos[i] = static_cast<int32_t>(static_cast<uint32_t>(a[i]) ^ 0x80000000u); }
+	}
 	return 0;
 }

@@ -36,6 +36,49 @@
 
 using namespace xxm;
 
+// NVTX ranges: one per C-ABI call (nsys / ncu --nvtx show which call of the reference's loop a kernel belongs to)
+#include <nvtx3/nvToolsExt.h>
+namespace {
+// XXM_TRACE: wall time per C-ABI entry point, summed per name and printed when a context is destroyed
+struct CallTimes {
+	struct E { const char* name; uint64_t n; double us; };
+	std::vector<E> e;
+	bool on = std::getenv("XXM_TRACE") != nullptr;
+	void add(const char* name, double us) {
+		for (E& x : e) if (x.name == name) { x.n++; x.us += us; return; }
+		e.push_back(E{name, 1, us});
+	}
+	void print() {
+		if (!on || e.empty()) return;
+		std::sort(e.begin(), e.end(), [](const E& a, const E& b) { return a.us > b.us; });
+		for (const E& x : e) std::fprintf(stderr, "xxm calls: %-36s n=%6llu total %10.1f us  avg %9.1f us\n", x.name, static_cast<unsigned long long>(x.n), x.us, x.us / x.n);
+		e.clear();
+	}
+};
+CallTimes g_callTimes;
+struct NvtxRange {
+	const char* name;
+	std::chrono::steady_clock::time_point t0;
+	explicit NvtxRange(const char* nm) : name(nm) { nvtxRangePushA(nm); if (g_callTimes.on) t0 = std::chrono::steady_clock::now(); }
+	~NvtxRange() {
+		nvtxRangePop();
+		if (g_callTimes.on) g_callTimes.add(name, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count());
+	}
+};
+}  // namespace
+#define XXM_NVTX(name) NvtxRange nvtx_range__(name)
+// XXM_TRACE: named time marks inside a call (summed like the calls themselves)
+struct TraceMark {
+	std::chrono::steady_clock::time_point t;
+	TraceMark() { if (g_callTimes.on) t = std::chrono::steady_clock::now(); }
+	void mark(const char* name) {
+		if (!g_callTimes.on) return;
+		const auto n = std::chrono::steady_clock::now();
+		g_callTimes.add(name, std::chrono::duration<double, std::micro>(n - t).count());
+		t = n;
+	}
+};
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -150,8 +193,15 @@ struct xxm_ctx {
 	// ---- lists
 	DevBuf<uint32_t> b_seq, b_pos, b_vidx, t_seq, t_pos, t_vidx, u_seq, u_pos, u_vidx;
 	DevBuf<double> b_pSsnap;
-	DevBuf<float> b_score, s_kscore, e_kscore, slotScore, e_slotScore, tmpScore, u_score;
-	DevBuf<uint8_t> s_keep, e_keep, flag8;
+	DevBuf<float> b_score, s_kscore, e_kscoreSet[2], slotScore, e_slotScoreSet[2], tmpScore, u_score;
+	DevBuf<uint8_t> s_keep, e_keepSet[2], flag8;
+	// sortedSites_elong is double buffered: xxm_elong_keep sets the current list aside (the best column variant so far) and the
+	// following re-scores write the other set
+	int eSet = 0;
+	SiteList keptElong;
+	int keptNbSites = 0;
+	float keptLastScore = 0;
+	bool keptLastScoreValid = false;
 	DevBuf<uint16_t> s_kcls;      // value index per kept entry of sortedSites (0xFFFF: dropped), valid while kclsSerial == the list's histSerial
 	uint64_t kclsSerial = 0;
 	// class order of the current one-table model (stage_class_order): fin[] non-decreasing, T[k] and the number of site classes
@@ -161,7 +211,7 @@ struct xxm_ctx {
 	uint32_t clsNSite = 0;
 	float lastKmerHistMs = 0;     // device time of the last xxm_kmer_counts (all passes)
 	bool sortedLazy = false;      // the last deferred scan left sortedSites' float scores implicit (k_select_cls_fwd)
-	DevBuf<uint32_t> stk, slotIdx, e_slotIdx, counters, hist, idxA, idxB, keysA, keysB, rsHist;
+	DevBuf<uint32_t> stk, slotIdx, e_slotIdxSet[2], counters, hist, idxA, idxB, keysA, keysB, rsHist;
 	DevBuf<uint64_t> status, total64;
 	DevBuf<uint32_t> cmpCounts, runStart, memoIdx;
 	// device table build (xxm_gpu_part8.inc)
@@ -173,6 +223,7 @@ struct xxm_ctx {
 	DevBuf<uint8_t> memoFlag;
 	DevBuf<double> memoTmp;
 	std::vector<double> h_memoVals;
+	std::vector<xxm_site> h_sites;     // landing buffer of materialised site lists
 	std::vector<int32_t> h_sortedSeq;  // sequence of every site in score order, kept when a per-sequence cap binds
 	DevBuf<unsigned long long> runPack, sweepCand;
 	DevBuf<double> sweepApprox;
@@ -336,6 +387,7 @@ extern "C" int xxm_create(int device, xxm_ctx** out) {
 extern "C" int xxm_comm_destroy(xxm_ctx* ctx);
 extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	if (!ctx) return;
+	g_callTimes.print();
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	xxm_comm_destroy(ctx);
@@ -350,9 +402,9 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	ctx->d_memoKey.release(); ctx->d_memoVal.release(); ctx->d_memoState.release(); ctx->d_flags32.release();
 	ctx->d_pS.release(); ctx->d_finalMops.release(); ctx->d_finalMode.release(); ctx->d_posProb.release(); ctx->d_perCand.release();
 	ctx->b_seq.release(); ctx->b_pos.release(); ctx->b_vidx.release(); ctx->t_seq.release(); ctx->t_pos.release(); ctx->t_vidx.release();
-	ctx->u_seq.release(); ctx->u_pos.release(); ctx->u_vidx.release(); ctx->b_score.release(); ctx->b_pSsnap.release(); ctx->s_kscore.release(); ctx->e_kscore.release();
-	ctx->slotScore.release(); ctx->tmpScore.release(); ctx->s_keep.release(); ctx->e_keep.release(); ctx->flag8.release(); ctx->stk.release();
-	ctx->slotIdx.release(); ctx->e_slotIdx.release(); ctx->e_slotScore.release(); ctx->u_score.release(); ctx->counters.release(); ctx->hist.release(); ctx->idxA.release(); ctx->idxB.release(); ctx->keysA.release();
+	ctx->u_seq.release(); ctx->u_pos.release(); ctx->u_vidx.release(); ctx->b_score.release(); ctx->b_pSsnap.release(); ctx->s_kscore.release(); for (int k = 0; k < 2; ++k) { ctx->e_kscoreSet[k].release(); ctx->e_slotScoreSet[k].release(); ctx->e_keepSet[k].release(); ctx->e_slotIdxSet[k].release(); }
+	ctx->slotScore.release(); ctx->tmpScore.release(); ctx->s_keep.release(); ctx->flag8.release(); ctx->stk.release();
+	ctx->slotIdx.release(); ctx->u_score.release(); ctx->counters.release(); ctx->hist.release(); ctx->idxA.release(); ctx->idxB.release(); ctx->keysA.release();
 	ctx->keysB.release(); ctx->rsHist.release(); ctx->d_nmProbs.release(); ctx->d_nmConds.release(); for (int k = 0; k < 2; ++k) { ctx->tbScore[k].release(); ctx->tbId[k].release(); ctx->tbProb[k].release(); } ctx->tbCls.release(); ctx->tbClassScore.release(); ctx->tbClassCount.release(); ctx->tbClassPval.release(); ctx->cmpCounts.release(); ctx->memoIdx.release(); ctx->memoFlag.release(); ctx->memoTmp.release(); ctx->runStart.release(); ctx->runPack.release(); ctx->sweepCand.release(); ctx->sweepApprox.release(); ctx->status.release(); ctx->total64.release(); ctx->d_counts.release(); ctx->d_sites.release();
 	ctx->d_hf.release(); ctx->d_hb.release();
 	ctx->r_seq.release(); ctx->d_pbits.release(); ctx->d_t8.release(); ctx->d_pairTab.release();
@@ -372,6 +424,8 @@ extern "C" int xxm_set_options(xxm_ctx* ctx, const xxm_options* opt) {
 	return 0;
 }
 
+// XXM_TRACE: print and clear the per-call wall times collected so far
+extern "C" int xxm_trace_dump(void) { g_callTimes.print(); return 0; }
 extern "C" void* xxm_stream(const xxm_ctx* ctx) { return reinterpret_cast<void*>(ctx->stream); }
 extern "C" int xxm_get_stats(const xxm_ctx* ctx, xxm_stats* out) { *out = ctx->stats; return 0; }
 
@@ -718,6 +772,7 @@ static int load_pack_on_device(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 // a1.  Layout from the lengths, then the packing step where it is cheaper: on the host cores when there are at least
 // kMinPackThreads of them for this GPU (XXM_PACK_THREADS, default min(12, 3/4 of the cores)), else on the device.
 extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp) {
+	XXM_NVTX("xxm_load_seqset");
 	CK(cudaSetDevice(ctx->device));
 	if (nent <= 0) return ctx->fail("empty sequence set");
 	static const bool trace = std::getenv("XXM_TRACE") != nullptr;
@@ -728,6 +783,7 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	ctx->loadSerial++;
 	ctx->deadKey.clear();
 	for (auto& l : ctx->L) l = SiteList();
+	ctx->keptElong = SiteList();
 	ctx->nBest = 0;
 	ctx->nent = 0;
 	ctx->pend.active = false;
@@ -825,6 +881,7 @@ extern "C" int xxm_seqset_info(const xxm_ctx* ctx, int32_t* total, double* avgLe
 // a5: background + model
 // =====================================================================================================================
 extern "C" int xxm_set_background(xxm_ctx* ctx, int32_t order, const float* rprobs, const float* rconds) {
+	XXM_NVTX("xxm_set_background");
 	if (order < 0 || order > 9) return ctx->fail("background order %d not supported", order);
 	const size_t n = static_cast<size_t>(1) << (3 * (order + 1));
 	ctx->rprobs.assign(rprobs, rprobs + n);
@@ -955,6 +1012,7 @@ static double zoops_final(double pS, double exponent) { return 1 - std::pow(1 - 
 static int device_build_part0(xxm_ctx* ctx, PvalueTables& T, float* ms);  // xxm_gpu_part8.inc
 static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions);
 extern "C" int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions) {
+	XXM_NVTX("xxm_reinitialize");
 	const int r = reinitialize_impl(ctx, pwm, cols, ncols, posSetSize, totalPositions);
 	if (r) { ctx->batching = false; ctx->upSegs.clear(); ctx->fillJobs.clear(); ctx->haveModel = false; }
 	return r;
@@ -1426,6 +1484,7 @@ static bool scan_full_can_defer(const xxm_ctx* ctx);
 static int scan_full_launch(xxm_ctx* ctx, int32_t posSetSize);
 static int scan_full_finish(xxm_ctx* ctx, int32_t* nbSites, int32_t* nbBestSites, int32_t* maxSites, bool* overflow);
 extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t* nbSites, int32_t* nbBestSites, int32_t* maxSites) {
+	XXM_NVTX("xxm_scan_full");
 	CK(cudaSetDevice(ctx->device));
 	if (!ctx->haveModel) return ctx->fail("xxm_scan_full: no model (call xxm_reinitialize)");
 	if (posSetSize < 1 || posSetSize > ctx->nent) return ctx->fail("posSetSize out of range");

@@ -182,9 +182,11 @@ __global__ void k_eval_list(SeqStream S, Model M, const uint32_t* __restrict__ s
 	const uint32_t s = seq[i] - 1;
 	const int p = static_cast<int>(pos[i]) + shift;
 	uint32_t v = kNone;
-	if (p >= 1 && p + M.span - 1 <= S.len[s]) {  // :181
+	// (sets of one length: no gathers from the per-sequence arrays)
+	const int len = S.uniformWps ? S.uniformLen : S.len[s];
+	if (p >= 1 && p + M.span - 1 <= len) {  // :181
 		const uint32_t g = static_cast<uint32_t>(p - 1);
-		const uint32_t w = S.wordOff[s] + (g >> 5);
+		const uint32_t w = (S.uniformWps ? s * S.uniformWps : S.wordOff[s]) + (g >> 5);
 		v = eval_window(M, S.codes[w], S.codes[w + 1], S.nmask[w], S.nmask[w + 1], g & 31);
 	}
 	vidx[i] = v;
