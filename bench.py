@@ -631,13 +631,18 @@ def _ours(a):
             mot = refine.Motif(pwm0, cols, nent, enr=(1 - c0, 1 - c0, int(mxl) - c0 + 1), siteCap=max(1 << 20, 2 * nent))
             R = refine.Refiner(ctx, totalPositions=int(total[nent]), revcomp=False, localization=False, maximizeMotifLength=True, minMatchPositions=5,
                                maxMatchPositions=17, pseudo=0.1, neff_pwm=10.0)
-            torch.cuda.synchronize()
-            l0 = ctx.stats()["launches"]
-            t0 = time.perf_counter()
-            rounds = R.iterate_motif(mot)
-            torch.cuda.synchronize()
-            gpu_s = time.perf_counter() - t0
-            rr = {"gpu_seconds": gpu_s, "sequences": nent, "rounds": int(rounds), "match_columns": [int(mot.cols[0]), int(mot.cols[-1])],
+            secs = []
+            for _ in range(2):  # the first run on a context also pays for buffers it allocates (a real run refines hundreds of motifs on one context)
+                mot = refine.Motif(pwm0, cols, nent, enr=(1 - c0, 1 - c0, int(mxl) - c0 + 1), siteCap=max(1 << 20, 2 * nent))
+                torch.cuda.synchronize()
+                l0 = ctx.stats()["launches"]
+                t0 = time.perf_counter()
+                rounds = R.iterate_motif(mot)
+                torch.cuda.synchronize()
+                secs.append(time.perf_counter() - t0)
+            gpu_s = secs[-1]
+            rr = {"gpu_seconds": gpu_s, "gpu_seconds_first_run_on_context": secs[0], "sequences": nent, "rounds": int(rounds),
+                  "match_columns": [int(mot.cols[0]), int(mot.cols[-1])],
                   "sites": int(mot.m.nsites), "log_pval": float(mot.pval), "gpu_launches": int(ctx.stats()["launches"] - l0),
                   "what": "xxm_iterate_motif of the TATA profile on the resident set (set load not included)"}
             if not a.no_cpu_baseline and os.path.exists(HARNESS):

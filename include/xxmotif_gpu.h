@@ -287,6 +287,9 @@ int xxm_get_stats(const xxm_ctx* ctx, xxm_stats* out);
  * staging | launching scan + overlap removal + exchange | waiting for them | subset choice | launching the recount | waiting
  * for it | PWM from the counts.  (Where does a step spend the time the kernels do not account for?) */
 int xxm_step_phases(xxm_ctx* ctx, double* us7, int64_t* nsteps, int32_t reset);
+/* with XXM_DEBUG_GUARDS set in the environment every device buffer carries a 256-byte canary behind its last element;
+ * xxm_check_guards counts the buffers of the process whose canary a kernel overwrote (damaged must be 0) */
+int xxm_check_guards(xxm_ctx* ctx, int32_t* checked, int32_t* damaged);
 /* with XXM_TRACE set in the environment the library sums the wall time of every C-ABI call (and of named sections inside
  * some of them) per name; xxm_trace_dump prints the table to stderr and clears it (xxm_destroy does the same) */
 int xxm_trace_dump(void);

@@ -21,7 +21,7 @@ EXPORTS = [
     "xxm_reinitialize", "xxm_tables_info", "xxm_tables_get", "xxm_window_pvals", "xxm_scan_full", "xxm_rescore", "xxm_scan_oops",
     "xxm_rescore_startposlist", "xxm_update_pwm_with_best_subset", "xxm_startposlist_best_subset", "xxm_startposlist_from_elong",
     "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset", "xxm_host_pair_table",
-    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables", "xxm_trace_dump", "xxm_elong_keep", "xxm_startposlist_from_kept",
+    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables", "xxm_trace_dump", "xxm_elong_keep", "xxm_startposlist_from_kept", "xxm_check_guards",
 ]
 
 
@@ -95,6 +95,7 @@ def load_library():
         "xxm_optimize_step": [vp, vp, vp, i32, i32, i32, i32, i32, dbl, P(XxmStepInfo)],
         "xxm_step_phases": [vp, vp, P(C.c_int64), i32],
         "xxm_trace_dump": [],
+        "xxm_check_guards": [vp, P(i32), P(i32)],
         "xxm_elong_keep": [vp],
         "xxm_startposlist_from_kept": [vp, i32, i32, vp, vp, i32, P(i32), P(dbl)],
         "xxm_device_tables": [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, P(C.c_float)],
@@ -322,6 +323,12 @@ class Context:
         ci = np.zeros(info[7], dtype=np.int64)
         self._ck(self.L.xxm_device_tables(self.h, _p(pwm), _p(cols), len(cols), posSetSize, totalPositions, _p(info), _p(pv), _p(cs), _p(cc), _p(ci), C.byref(ms)))
         return {"L": int(info[0]), "maxk": int(info[1]), "nparts": int(info[2]), "pvalues": [pv], "classes": [(cs, cc, ci)], "probs": None}, ms.value
+
+    def check_guards(self):
+        """(buffers checked, buffers with an overwritten canary) -- needs XXM_DEBUG_GUARDS in the environment at load time"""
+        a, b = C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.xxm_check_guards(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def step_phases(self, reset=True):
         """average host-side phase times of xxm_optimize_step since the last reset, microseconds per step"""

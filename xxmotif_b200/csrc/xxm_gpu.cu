@@ -83,21 +83,44 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// XXM_DEBUG_GUARDS: every device buffer gets a 256-byte canary behind its last element; xxm_check_guards verifies that no
+// kernel wrote past the end of any buffer (compute-sanitizer is not available on every pool; tests/test_gpu_guards.py runs the
+// ragged / low-complexity stress cases and the golden replays under it)
+constexpr size_t kGuardBytes = 256;
+struct GuardRegistry {
+	bool on = std::getenv("XXM_DEBUG_GUARDS") != nullptr;
+	std::vector<std::pair<void*, size_t>> bufs;  // (device pointer, user bytes)
+	void add(void* p, size_t bytes) { bufs.emplace_back(p, bytes); }
+	void remove(void* p) {
+		for (size_t i = 0; i < bufs.size(); ++i)
+			if (bufs[i].first == p) { bufs[i] = bufs.back(); bufs.pop_back(); return; }
+	}
+};
+GuardRegistry g_guards;
+
 template <typename T>
 struct DevBuf {
 	T* p = nullptr;
 	size_t cap = 0;
 	cudaError_t ensure(size_t n) {
 		if (n <= cap) return cudaSuccess;
-		if (p) cudaFree(p);
-		p = nullptr;
-		cap = 0;
+		release();
 		size_t want = n + n / 8 + 64;
-		cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
-		if (e == cudaSuccess) cap = want;
+		cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T) + (g_guards.on ? kGuardBytes : 0));
+		if (e == cudaSuccess) {
+			cap = want;
+			if (g_guards.on) {
+				cudaMemset(reinterpret_cast<uint8_t*>(p) + want * sizeof(T), 0xA5, kGuardBytes);
+				g_guards.add(p, want * sizeof(T));
+			}
+		}
 		return e;
 	}
-	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	void release() {
+		if (p) { if (g_guards.on) g_guards.remove(p); cudaFree(p); }
+		p = nullptr;
+		cap = 0;
+	}
 };
 
 // a device-resident site list (members of StartPosUpdater: bestStartPos / sortedSites / sortedSites_elong)
@@ -424,6 +447,22 @@ extern "C" int xxm_set_options(xxm_ctx* ctx, const xxm_options* opt) {
 	return 0;
 }
 
+// XXM_DEBUG_GUARDS: number of device buffers whose canary was overwritten (0 = clean); *checked = buffers looked at
+extern "C" int xxm_check_guards(xxm_ctx* ctx, int32_t* checked, int32_t* damaged) {
+	CK(cudaSetDevice(ctx->device));
+	CK(cudaDeviceSynchronize());
+	*checked = 0;
+	*damaged = 0;
+	if (!g_guards.on) return ctx->fail("xxm_check_guards: set XXM_DEBUG_GUARDS in the environment before the library is loaded");
+	uint8_t tail[kGuardBytes];
+	for (const auto& b : g_guards.bufs) {
+		CK(cudaMemcpy(tail, static_cast<uint8_t*>(b.first) + b.second, kGuardBytes, cudaMemcpyDeviceToHost));
+		++*checked;
+		for (size_t i = 0; i < kGuardBytes; ++i)
+			if (tail[i] != 0xA5) { ++*damaged; break; }
+	}
+	return 0;
+}
 // XXM_TRACE: print and clear the per-call wall times collected so far
 extern "C" int xxm_trace_dump(void) { g_callTimes.print(); return 0; }
 extern "C" void* xxm_stream(const xxm_ctx* ctx) { return reinterpret_cast<void*>(ctx->stream); }
