@@ -52,7 +52,17 @@ struct SelectRcIO {
 };
 
 // the reference's loop, literally, over entries [a, b) of one sequence in global memory (runs that leave their tile)
-__device__ __noinline__ uint32_t select_rc_walk_global(const SelectRcIO& io, const uint16_t* s_thr, uint32_t* s_hist, uint32_t a, uint32_t b, int seqLen) {
+// (arguments by value: a reference to the kernel's parameter struct would force a copy of it into local memory)
+struct RcGlobalArgs {
+	const uint32_t* pos;
+	const uint32_t* vidx;
+	uint32_t* stk;
+	uint8_t* keep;
+	uint16_t* kcls;
+	uint32_t nSite;
+	int length;
+};
+__device__ __noinline__ uint32_t select_rc_walk_global(RcGlobalArgs io, const uint16_t* s_thr, uint32_t* s_hist, uint32_t a, uint32_t b, int seqLen) {
 	const int L = io.length;
 	uint32_t* stk = io.stk + a;
 	int kc = 0;
@@ -95,7 +105,7 @@ __device__ __noinline__ uint32_t select_rc_walk_global(const SelectRcIO& io, con
 	return static_cast<uint32_t>(kc);
 }
 
-__global__ void __launch_bounds__(kSel4Threads) k_select_cls_rc(SeqStream S, SelectRcIO io) {
+__global__ void __launch_bounds__(kSel4Threads, 6) k_select_cls_rc(SeqStream S, SelectRcIO io) {
 	extern __shared__ __align__(16) uint8_t smem4[];
 	uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem4);
 	uint16_t* s_thr = reinterpret_cast<uint16_t*>(s_hist + io.nval);
@@ -190,7 +200,8 @@ __global__ void __launch_bounds__(kSel4Threads) k_select_cls_rc(SeqStream S, Sel
 				uint32_t e = base + tlen;
 				while (e < n && io.seq[e] == sq) ++e;
 				s_last = r0;
-				const uint32_t kc = select_rc_walk_global(io, s_thr, s_hist, base + r0, e, seqLen);
+				const RcGlobalArgs ga{io.pos, io.vidx, io.stk, io.keep, io.kcls, io.nSite, io.length};
+				const uint32_t kc = select_rc_walk_global(ga, s_thr, s_hist, base + r0, e, seqLen);
 				keptTot += kc;
 				keptMax = max(keptMax, kc);
 				continue;
