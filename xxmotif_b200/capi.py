@@ -21,7 +21,7 @@ EXPORTS = [
     "xxm_reinitialize", "xxm_tables_info", "xxm_tables_get", "xxm_window_pvals", "xxm_scan_full", "xxm_rescore", "xxm_scan_oops",
     "xxm_rescore_startposlist", "xxm_update_pwm_with_best_subset", "xxm_startposlist_best_subset", "xxm_startposlist_from_elong",
     "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset", "xxm_host_pair_table",
-    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables", "xxm_trace_dump", "xxm_elong_keep", "xxm_startposlist_from_kept", "xxm_check_guards",
+    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables", "xxm_trace_dump", "xxm_elong_keep", "xxm_startposlist_from_kept", "xxm_check_guards", "xxm_set_global_counts", "xxm_seqset_logsum",
 ]
 
 
@@ -96,6 +96,8 @@ def load_library():
         "xxm_step_phases": [vp, vp, P(C.c_int64), i32],
         "xxm_trace_dump": [],
         "xxm_check_guards": [vp, P(i32), P(i32)],
+        "xxm_set_global_counts": [vp, C.c_int64, C.c_int64, dbl, i32],
+        "xxm_seqset_logsum": [vp, P(dbl)],
         "xxm_elong_keep": [vp],
         "xxm_startposlist_from_kept": [vp, i32, i32, vp, vp, i32, P(i32), P(dbl)],
         "xxm_device_tables": [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, P(C.c_float)],
@@ -323,6 +325,17 @@ class Context:
         ci = np.zeros(info[7], dtype=np.int64)
         self._ck(self.L.xxm_device_tables(self.h, _p(pwm), _p(cols), len(cols), posSetSize, totalPositions, _p(info), _p(pv), _p(cs), _p(cc), _p(ci), C.byref(ms)))
         return {"L": int(info[0]), "maxk": int(info[1]), "nparts": int(info[2]), "pvalues": [pv], "classes": [(cs, cc, ci)], "probs": None}, ms.value
+
+    def set_global_counts(self, nentGlobal, totalGlobal, sumLogLength=float("nan"), maxLengGlobal=None):
+        """counts of the whole sharded set for the split-phase path (xxm_set_global_counts)"""
+        if maxLengGlobal is None:
+            maxLengGlobal = self.seqset_info()[2]
+        self._ck(self.L.xxm_set_global_counts(self.h, int(nentGlobal), int(totalGlobal), float(sumLogLength), int(maxLengGlobal)))
+
+    def seqset_logsum(self):
+        v = C.c_double(0.0)
+        self._ck(self.L.xxm_seqset_logsum(self.h, C.byref(v)))
+        return v.value
 
     def check_guards(self):
         """(buffers checked, buffers with an overwritten canary) -- needs XXM_DEBUG_GUARDS in the environment at load time"""

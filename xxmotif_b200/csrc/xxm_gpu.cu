@@ -290,7 +290,7 @@ struct xxm_ctx {
 
 	LogSum logsum;
 	// the sharded set (xxm_gpu_part7.inc): global counts, valid while synced for the current load
-	struct ShardInfo { bool synced = false; uint64_t loadSerial = 0; int64_t nent = 0, total = 0, seqOffset = 0; double logAcc = 0; int maxLeng = 0; } G;
+	struct ShardInfo { bool synced = false, external = false, haveLogAcc = false; uint64_t loadSerial = 0; int64_t nent = 0, total = 0, seqOffset = 0; double logAcc = 0; int maxLeng = 0; } G;
 	const int32_t* notXPtr = nullptr;  // residues that are not N per sequence of the current load (host or device packing path)
 	double phaseUs[7] = {0, 0, 0, 0, 0, 0, 0};  // xxm_step_phases
 	int64_t phaseSteps = 0;
@@ -823,6 +823,7 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	ctx->deadKey.clear();
 	for (auto& l : ctx->L) l = SiteList();
 	ctx->keptElong = SiteList();
+	ctx->G.external = false;
 	ctx->nBest = 0;
 	ctx->nent = 0;
 	ctx->pend.active = false;
@@ -1088,6 +1089,11 @@ static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* col
 		// a sharded set: the thresholds of the tables follow the WHOLE set (branch_and_bound-inl.h:186-187, :417)
 		TRY(shard_sync(ctx));
 		if (posSetSize != ctx->nent) return ctx->fail("with a communicator attached every call refers to the whole sharded set: posSetSize must be the rank's sequence count");
+		build_pvalue_tables(pwm, cols, ncols, ctx->G.nent, ctx->G.total, ctx->opt.bgLog, ctx->nm, ctx->tab);
+	} else if (ctx->G.external) {
+		// the caller runs the exchange itself (split-phase entry points) and has told us the counts of the whole set
+		if (ctx->G.loadSerial != ctx->loadSerial) return ctx->fail("xxm_set_global_counts must be repeated after xxm_load_seqset");
+		if (posSetSize != ctx->nent) return ctx->fail("with global counts set every call refers to the whole sharded set: posSetSize must be the rank's sequence count");
 		build_pvalue_tables(pwm, cols, ncols, ctx->G.nent, ctx->G.total, ctx->opt.bgLog, ctx->nm, ctx->tab);
 	} else if (ncols <= 8 && std::getenv("XXM_DEVICE_TABLES")) {
 		// the enumeration, the stable sort and the cumulative class p-values on the device

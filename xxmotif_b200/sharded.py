@@ -178,6 +178,23 @@ class Exchange:
         tot = [sum(int(t[1 + j]) for t in all_lens) for j in range(len(scalars))]
         return scs, cns, tot
 
+    def sum_scalars(self, vals):
+        """sum of a few doubles over the ranks"""
+        if not self.dist:
+            return list(vals)
+        import torch
+        t = torch.tensor(list(vals), dtype=torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.cpu()]
+
+    def max_scalar(self, v):
+        if not self.dist:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
     def sum_counts(self, counts):
         if not self.dist:
             return counts
@@ -215,6 +232,7 @@ class ShardedRefinement:
         self.oneOccurrence, self.maxSeqCount, self.plusFrac = oneOccurrence, maxSeqCount, plusFrac
         self.bg = bg
         self.last_d2h_bytes = 0
+        self._global_set = False
         if self.native and dist is not None and dist.get_world_size() > 1 and not comm_ready:  # comm_ready: the context already has its communicator
             import torch
             idt = torch.zeros(128, dtype=torch.uint8, device=device)
@@ -229,6 +247,14 @@ class ShardedRefinement:
             new, info = ctx.optimize_step(pwm, cols, self.nent_local, self.total_local, enr, self.pseudo)
             self.last_d2h_bytes = 8 * (ctx.nval_hint() + 3) + 155 * 8 + 64
             return new, info
+        if self.ex.world > 1 and not self._global_set:
+            # the tables, maxSites and the ZOOPS exponent follow the WHOLE set (branch_and_bound-inl.h:186-187, :417): sum the
+            # counts over the ranks once and hand them to the context (xxm_set_global_counts)
+            _, _, mxl, _ = ctx.seqset_info()
+            g = self.ex.sum_scalars([float(self.nent_local), float(self.total_local), ctx.seqset_logsum()])
+            gmx = self.ex.max_scalar(float(mxl))
+            ctx.set_global_counts(int(round(g[0])), int(round(g[1])), g[2], int(round(gmx)))
+            self._global_set = True
         ctx.reinitialize(pwm, cols, self.nent_local, self.total_local)
         nbSites, nbBest, _ = ctx.scan_full(self.nent_local, enr)
         sc, cn = score_runs(ctx, capi.LIST_SORTED_SITES)
