@@ -232,11 +232,40 @@ typedef struct {
  * Valid until the next xxm_load_seqset; contexts with a communicator derive all of this themselves. */
 int xxm_set_global_counts(xxm_ctx* ctx, int64_t nentGlobal, int64_t totalGlobal, double sumLogLength, int32_t maxLengGlobal);
 int xxm_seqset_logsum(const xxm_ctx* ctx, double* sumLogLength);
+/* the running log sum continued over this rank's sequences, one addition per sequence: chained through the ranks in order it is
+ * the reference's sequential sum (seqset.cpp:31-34), bit for bit */
+int xxm_seqset_logsum_from(const xxm_ctx* ctx, double start, double* end);
 int xxm_comm_unique_id(uint8_t* id128);
 int xxm_comm_init(xxm_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t* id128);
 int xxm_comm_destroy(xxm_ctx* ctx);
 int xxm_optimize_step(xxm_ctx* ctx, double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions, int32_t enrStart,
                       int32_t enrEnd, double pseudo, xxm_step_info* info);
+
+/* ---- multi-device context: ONE host thread, several GPUs ---------------------------------------------------------------
+ * The reference is single-threaded.  xxm_multi owns one context per device (devices 0..ngpus-1), cuts the set
+ * into contiguous blocks of sequences balanced by residues, runs every call on all devices concurrently (one worker thread per
+ * device inside the library) and presents the union: counts summed, site lists concatenated in sequence order or merged stably by
+ * score.  The shards are given the counts of the whole set, so tables, maxSites and the ZOOPS exponent are the whole set's.
+ * With ngpus = 1 every call is a pass-through.  With more than one device every call refers to the whole set (posSetSize = nent).
+ * This is the surface integration/xxmotif_gpu_binding.cpp uses (XXM_DEVICES=N). */
+typedef struct xxm_multi xxm_multi;
+int xxm_multi_create(int32_t ngpus, xxm_multi** out);
+int xxm_multi_create_on(const int32_t* devices /*[ngpus] or NULL = 0..ngpus-1*/, int32_t ngpus, xxm_multi** out);
+void xxm_multi_destroy(xxm_multi* m);
+const char* xxm_multi_last_error(const xxm_multi* m);
+int32_t xxm_multi_devices(const xxm_multi* m);
+int xxm_multi_set_options(xxm_multi* m, const xxm_options* opt);
+int xxm_multi_set_background(xxm_multi* m, int32_t order, const float* rprobs, const float* rconds);
+int xxm_multi_load_seqset(xxm_multi* m, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp);
+int xxm_multi_seqset_info(const xxm_multi* m, int32_t* total, double* avgLength /*unused, may be NULL*/, int32_t* max_leng, int32_t* min_leng);
+int xxm_multi_reinitialize(xxm_multi* m, const double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions);
+int xxm_multi_scan_full(xxm_multi* m, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t* nbSites, int32_t* nbBestSites, int32_t* maxSites);
+int xxm_multi_rescore(xxm_multi* m, int32_t firstMotifColumn, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t palin, int32_t* nbSites,
+                      int32_t* maxSites);
+int xxm_multi_scan_oops(xxm_multi* m, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t* nbSites, int32_t* maxSites);
+int xxm_multi_rescore_startposlist(xxm_multi* m, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t nSites, const int32_t* siteSeq,
+                                   const int32_t* sitePos, int32_t instanceThreshold, int32_t* nbSites, int32_t* maxSites);
+int xxm_multi_get_sites(xxm_multi* m, int32_t which, int32_t order, int32_t palin, xxm_site* out, int32_t cap, int32_t* nOut);
 
 /* ---- host-side pieces of the path, callable without a device (unit tests of the host logic) -------------------------
  * xxm_host_tables: the table construction xxm_reinitialize performs (branch_and_bound-inl.h:183-603), without staging.

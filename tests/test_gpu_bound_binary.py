@@ -42,8 +42,7 @@ def _files(root):
     return sorted(out)
 
 
-@pytest.mark.parametrize("name,w,extra", CASES, ids=[c[0] for c in CASES])
-def test_bound_binary_writes_the_reference_files(name, w, extra):
+def _compare_with_reference(w, extra, env=None):
     if not (os.path.exists(REF) and os.path.exists(BOUND)):
         pytest.skip("oracle/_ref/XXmotif or XXmotif_bound not built (make -C oracle ref bound)")
     tmp = tempfile.mkdtemp(prefix="xxm_bound_")
@@ -60,7 +59,7 @@ def test_bound_binary_writes_the_reference_files(name, w, extra):
         outs = {}
         for tag, exe in (("ref", REF), ("gpu", BOUND)):
             out = os.path.join(tmp, tag)
-            r = subprocess.run([exe, out, fa] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            r = subprocess.run([exe, out, fa] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=dict(os.environ, **(env or {})))
             assert r.returncode == 0, "%s failed: %s" % (exe, r.stderr.decode()[-1500:])
             outs[tag] = out
         fr, fg = _files(outs["ref"]), _files(outs["gpu"])
@@ -70,6 +69,21 @@ def test_bound_binary_writes_the_reference_files(name, w, extra):
         assert not diff, "files differ from the reference's: %s" % diff
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+@pytest.mark.parametrize("name,w,extra", CASES, ids=[c[0] for c in CASES])
+def test_bound_binary_writes_the_reference_files(name, w, extra):
+    _compare_with_reference(w, extra)
+
+
+@pytest.mark.parametrize("name,w,extra", CASES, ids=[c[0] for c in CASES])
+def test_bound_binary_on_two_devices(name, w, extra):
+    """XXM_DEVICES=2: the reference's single host thread drives two GPUs through xxm_multi (the set cut into two blocks of
+    sequences, the counts of the whole set on both, lists concatenated / merged) -- the files stay the reference's."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    _compare_with_reference(w, extra, {"XXM_DEVICES": "2"})
 
 
 def test_bound_binary_full_discovery():

@@ -21,7 +21,10 @@ EXPORTS = [
     "xxm_reinitialize", "xxm_tables_info", "xxm_tables_get", "xxm_window_pvals", "xxm_scan_full", "xxm_rescore", "xxm_scan_oops",
     "xxm_rescore_startposlist", "xxm_update_pwm_with_best_subset", "xxm_startposlist_best_subset", "xxm_startposlist_from_elong",
     "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset", "xxm_host_pair_table",
-    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables", "xxm_trace_dump", "xxm_elong_keep", "xxm_startposlist_from_kept", "xxm_check_guards", "xxm_set_global_counts", "xxm_seqset_logsum",
+    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables", "xxm_trace_dump", "xxm_elong_keep", "xxm_startposlist_from_kept", "xxm_check_guards", "xxm_set_global_counts", "xxm_seqset_logsum", "xxm_seqset_logsum_from",
+    "xxm_multi_create", "xxm_multi_create_on", "xxm_multi_destroy", "xxm_multi_last_error", "xxm_multi_devices", "xxm_multi_set_options", "xxm_multi_set_background",
+    "xxm_multi_load_seqset", "xxm_multi_seqset_info", "xxm_multi_reinitialize", "xxm_multi_scan_full", "xxm_multi_rescore", "xxm_multi_scan_oops",
+    "xxm_multi_rescore_startposlist", "xxm_multi_get_sites",
 ]
 
 
@@ -98,10 +101,23 @@ def load_library():
         "xxm_check_guards": [vp, P(i32), P(i32)],
         "xxm_set_global_counts": [vp, C.c_int64, C.c_int64, dbl, i32],
         "xxm_seqset_logsum": [vp, P(dbl)],
+        "xxm_seqset_logsum_from": [vp, dbl, P(dbl)],
         "xxm_elong_keep": [vp],
         "xxm_startposlist_from_kept": [vp, i32, i32, vp, vp, i32, P(i32), P(dbl)],
         "xxm_device_tables": [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, P(C.c_float)],
     }
+    # the multi-device layer mirrors the signatures of the calls it wraps
+    for name in ("set_options", "set_background", "load_seqset", "seqset_info", "reinitialize", "scan_full", "rescore", "scan_oops", "rescore_startposlist",
+                 "get_sites"):
+        sig["xxm_multi_" + name] = sig["xxm_" + name]
+    sig["xxm_multi_create"] = [i32, P(vp)]
+    sig["xxm_multi_create_on"] = [vp, i32, P(vp)]
+    L.xxm_multi_destroy.restype = None
+    L.xxm_multi_destroy.argtypes = [vp]
+    L.xxm_multi_last_error.restype = C.c_char_p
+    L.xxm_multi_last_error.argtypes = [vp]
+    L.xxm_multi_devices.restype = i32
+    L.xxm_multi_devices.argtypes = [vp]
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.restype = i32
@@ -353,6 +369,42 @@ class Context:
 
     def stream(self):
         return self.L.xxm_stream(self.h)
+
+
+class _MultiEntryPoints:
+    """xxm_foo -> xxm_multi_foo, so that MultiContext reuses Context's marshalling; calls without a multi-device form raise."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        if not name.startswith("xxm_") or not hasattr(self._lib, "xxm_multi_" + name[4:]):
+            raise XxmError("%s has no multi-device form (include/xxmotif_gpu.h, xxm_multi)" % name)
+        return getattr(self._lib, "xxm_multi_" + name[4:])
+
+
+class MultiContext(Context):
+    """xxm_multi: ONE host thread, several GPUs -- the calls the reference-side binding makes, over shards of the set."""
+
+    def __init__(self, ngpus):
+        lib = load_library()
+        h = C.c_void_p()
+        if lib.xxm_multi_create(ngpus, C.byref(h)):
+            raise XxmError(lib.xxm_multi_last_error(None).decode())
+        self.L = _MultiEntryPoints(lib)
+        self._lib = lib
+        self.h = h
+        self.nent = 0
+        self.ncols = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.xxm_multi_destroy(self.h)
+            self.h = None
+
+    def _ck(self, rc):
+        if rc:
+            raise XxmError(self._lib.xxm_multi_last_error(self.h).decode())
 
 
 def host_tables(pwm, cols, posSetSize, totalPositions, bgLog, order, rprobs, rconds):
