@@ -143,6 +143,8 @@ int xxm_set_binding_sites(xxm_ctx* ctx, double thr, xxm_site* out, int32_t cap, 
 /* replaces getBestStartPos()/getSortedSites() (StartPosUpdater.h:46-47) + sortSitesByScore/sortSitesByStartPos
  * (StartPosUtils.h:68-78): copies a device-resident list to the host in the requested order */
 int xxm_get_sites(xxm_ctx* ctx, int32_t which, int32_t order, int32_t palin, xxm_site* out, int32_t cap, int32_t* nOut);
+/* the number of elements xxm_get_sites would write for this list and order (no device work) */
+int xxm_sites_count(xxm_ctx* ctx, int32_t which, int32_t order, int32_t* n);
 
 /* ---- a14: forward / reverse-complement log-odds histogram ----------------------------------------------------------
  * replaces the counting loops of Output::printScoreDistribution (output.cpp:1033-1078) with

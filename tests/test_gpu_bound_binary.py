@@ -77,13 +77,13 @@ def test_bound_binary_writes_the_reference_files(name, w, extra):
 
 
 @pytest.mark.parametrize("name,w,extra", CASES, ids=[c[0] for c in CASES])
-def test_bound_binary_on_two_devices(name, w, extra):
-    """XXM_DEVICES=2: the reference's single host thread drives two GPUs through xxm_multi (the set cut into two blocks of
-    sequences, the counts of the whole set on both, lists concatenated / merged) -- the files stay the reference's."""
+def test_bound_binary_on_several_devices(name, w, extra):
+    """XXM_DEVICES=N (all GPUs of the box): the reference's single host thread drives them through xxm_multi (the set cut into
+    N blocks of sequences, the counts of the whole set on each, lists concatenated / merged) -- the files stay the reference's."""
     import torch
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs (gpurun --gpus 2)")
-    _compare_with_reference(w, extra, {"XXM_DEVICES": "2"})
+        pytest.skip("needs at least two GPUs (gpurun --gpus 2)")
+    _compare_with_reference(w, extra, {"XXM_DEVICES": str(min(8, torch.cuda.device_count()))})
 
 
 def test_bound_binary_full_discovery():

@@ -1,8 +1,8 @@
 """xxm_multi (include/xxmotif_gpu.h): one host thread driving several GPUs.  Every call the reference-side binding makes
 (reinitialize, full scan, candidate re-score, OOPS scan, start-position-list re-score, the lists) must give, over shards of the set
 on N devices, exactly what one context gives over the whole set: counts, maxSites, and the lists element for element (scores
-bit for bit -- the shards work with the tables of the whole set).  N = 1 (pass-through) runs on any box; N = 2 needs two GPUs
-(gpurun --gpus 2)."""
+bit for bit -- the shards work with the tables of the whole set).  N = 1 (pass-through) runs on any box; N = 2 and N = 8 need as many GPUs
+(gpurun --gpus N)."""
 import numpy as np
 import pytest
 
@@ -69,7 +69,7 @@ def _same(a, b):
             assert a[k] == b[k], k
 
 
-@pytest.mark.parametrize("ngpus", [1, 2])
+@pytest.mark.parametrize("ngpus", [1, 2, 8])
 @pytest.mark.parametrize("oops", [False, True], ids=["zoops_mops", "oops"])
 @pytest.mark.parametrize("name", list(CASES))
 def test_multi_device_context_gives_the_single_context_results(name, oops, ngpus):

@@ -11,14 +11,88 @@
 #include "../../include/xxmotif_gpu.h"
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
+
+namespace {
+// One worker thread per device beyond the first, alive as long as the context: the caller's thread runs shard 0 itself.  A worker
+// spins for a short while after a job (the calls of a refinement step come in bursts) and then sleeps on a condition variable.
+class Workers {
+public:
+	explicit Workers(int n) : rc_(static_cast<size_t>(n), 0) {
+		for (int r = 1; r < n; ++r) th_.emplace_back([this, r]() { loop(r); });
+	}
+	~Workers() {
+		{
+			std::lock_guard<std::mutex> g(mu_);
+			stop_ = true;
+			gen_.fetch_add(1);
+		}
+		start_.notify_all();
+		for (auto& t : th_) t.join();
+	}
+	// f(r) for every r concurrently; returns the index of the first shard that failed, or -1
+	int run(const std::function<int(int)>& f) {
+		const int n = static_cast<int>(rc_.size());
+		job_ = &f;
+		pending_.store(n - 1, std::memory_order_release);
+		if (n > 1) {
+			{
+				std::lock_guard<std::mutex> g(mu_);
+				gen_.fetch_add(1, std::memory_order_release);
+			}
+			start_.notify_all();
+		}
+		rc_[0] = f(0);
+		for (int spin = 0; spin < kSpin && pending_.load(std::memory_order_acquire); ++spin) std::this_thread::yield();
+		if (pending_.load(std::memory_order_acquire)) {
+			std::unique_lock<std::mutex> g(mu_);
+			done_.wait(g, [&]() { return pending_.load(std::memory_order_acquire) == 0; });
+		}
+		for (int r = 0; r < n; ++r)
+			if (rc_[r]) return r;
+		return -1;
+	}
+
+private:
+	static constexpr int kSpin = 2000;
+	void loop(int r) {
+		uint64_t seen = 0;
+		for (;;) {
+			for (int spin = 0; spin < kSpin && gen_.load(std::memory_order_acquire) == seen; ++spin) std::this_thread::yield();
+			if (gen_.load(std::memory_order_acquire) == seen) {
+				std::unique_lock<std::mutex> g(mu_);
+				start_.wait(g, [&]() { return gen_.load(std::memory_order_acquire) != seen; });
+			}
+			seen = gen_.load(std::memory_order_acquire);
+			if (stop_) return;
+			rc_[static_cast<size_t>(r)] = (*job_)(r);
+			if (pending_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
+				std::lock_guard<std::mutex> g(mu_);
+				done_.notify_one();
+			}
+		}
+	}
+	std::vector<std::thread> th_;
+	std::vector<int> rc_;
+	std::mutex mu_;
+	std::condition_variable start_, done_;
+	std::atomic<uint64_t> gen_{0};
+	std::atomic<int> pending_{0};
+	const std::function<int(int)>* job_ = nullptr;
+	bool stop_ = false;
+};
+}  // namespace
 
 struct xxm_multi {
 	std::vector<xxm_ctx*> ctx;
@@ -35,18 +109,13 @@ struct xxm_multi {
 		err = buf;
 		return 1;
 	}
+	std::unique_ptr<Workers> workers;
+	std::vector<std::unique_ptr<xxm_site[]>> tmp;  // per-shard staging for lists merged by score (uninitialised, grown on demand)
+	std::vector<size_t> tmpCap;
 	// run f(r) for every shard concurrently; the first failure is reported
 	int each(const std::function<int(int)>& f) {
-		const int n = static_cast<int>(ctx.size());
-		std::vector<int> rc(n, 0);
-		if (n == 1) rc[0] = f(0);
-		else {
-			std::vector<std::thread> th;
-			for (int r = 0; r < n; ++r) th.emplace_back([&, r]() { rc[r] = f(r); });
-			for (auto& t : th) t.join();
-		}
-		for (int r = 0; r < n; ++r)
-			if (rc[r]) { err = std::string("device ") + std::to_string(r) + ": " + xxm_last_error(ctx[r]); return 1; }
+		const int bad = workers->run(f);
+		if (bad >= 0) { err = std::string("device ") + std::to_string(bad) + ": " + xxm_last_error(ctx[bad]); return 1; }
 		return 0;
 	}
 	int shards() const { return static_cast<int>(ctx.size()); }
@@ -69,6 +138,9 @@ extern "C" int xxm_multi_create_on(const int32_t* devices, int32_t ngpus, xxm_mu
 		}
 		m->ctx.push_back(c);
 	}
+	m->workers.reset(new Workers(ngpus));
+	m->tmp.resize(static_cast<size_t>(ngpus));
+	m->tmpCap.assign(static_cast<size_t>(ngpus), 0);
 	*out = m;
 	return 0;
 }
@@ -76,6 +148,7 @@ extern "C" int xxm_multi_create(int32_t ngpus, xxm_multi** out) { return xxm_mul
 
 extern "C" void xxm_multi_destroy(xxm_multi* m) {
 	if (!m) return;
+	m->workers.reset();
 	for (xxm_ctx* c : m->ctx) xxm_destroy(c);
 	delete m;
 }
@@ -220,39 +293,80 @@ extern "C" int xxm_multi_rescore_startposlist(xxm_multi* m, int32_t posSetSize, 
 }
 
 // the union of a device-resident list: shard lists concatenated in sequence order (as-is / by start position) or merged stably
-// by score (ties keep sequence order, like the reference's stable qsort over its scan-ordered array)
+// by score (ties keep sequence order, like the reference's stable sort over its scan-ordered array)
 extern "C" int xxm_multi_get_sites(xxm_multi* m, int32_t which, int32_t order, int32_t palin, xxm_site* out, int32_t cap, int32_t* nOut) {
 	const int S = m->shards();
 	if (S == 1) {
 		if (xxm_get_sites(m->ctx[0], which, order, palin, out, cap, nOut)) return m->fail("%s", xxm_last_error(m->ctx[0]));
 		return 0;
 	}
-	std::vector<std::vector<xxm_site>> part(S);
-	std::vector<int32_t> cnt(S, 0);
-	if (m->each([&](int r) {
-		    part[r].resize(static_cast<size_t>(std::max(cap, 1)));
-		    const int rc = xxm_get_sites(m->ctx[r], which, order, palin, part[r].data(), cap, &cnt[r]);
-		    return (rc && cnt[r] > cap) ? 0 : rc;  // too small an output is reported below, with the count of the whole list
-	    }))
-		return 1;
-	int64_t tot = 0;
+	std::vector<int32_t> cnt(static_cast<size_t>(S), 0);
+	std::vector<int64_t> off(static_cast<size_t>(S) + 1, 0);
 	for (int r = 0; r < S; ++r) {
-		for (int32_t i = 0; i < cnt[r]; ++i) part[r][i].sequence += m->first[r];
-		tot += cnt[r];
+		if (xxm_sites_count(m->ctx[r], which, order, &cnt[r])) return m->fail("%s", xxm_last_error(m->ctx[r]));
+		off[r + 1] = off[r] + cnt[r];
 	}
+	const int64_t tot = off[S];
 	*nOut = static_cast<int32_t>(tot);
 	if (tot > cap) return m->fail("xxm_multi_get_sites: output capacity %d < %lld sites", cap, static_cast<long long>(tot));
-	if (order != XXM_ORDER_BY_SCORE) {
-		int64_t o = 0;
-		for (int r = 0; r < S; ++r) { std::copy(part[r].begin(), part[r].begin() + cnt[r], out + o); o += cnt[r]; }
-		return 0;
-	}
-	std::vector<int32_t> at(S, 0);
-	for (int64_t o = 0; o < tot; ++o) {
-		int best = -1;
+	const bool merge = (order == XXM_ORDER_BY_SCORE);
+	if (merge)
 		for (int r = 0; r < S; ++r)
-			if (at[r] < cnt[r] && (best < 0 || part[r][at[r]].score < part[best][at[best]].score)) best = r;
-		out[o] = part[best][at[best]++];
+			if (m->tmpCap[r] < static_cast<size_t>(cnt[r])) {
+				m->tmpCap[r] = static_cast<size_t>(cnt[r]) + static_cast<size_t>(cnt[r]) / 4 + 1;
+				m->tmp[r].reset(new xxm_site[m->tmpCap[r]]);
+			}
+	// every shard writes its block (straight into the output unless the blocks have to be merged) and shifts its sequence numbers
+	if (m->each([&](int r) {
+		    xxm_site* dst = merge ? m->tmp[r].get() : out + off[r];
+		    int32_t k = 0;
+		    if (xxm_get_sites(m->ctx[r], which, order, palin, dst, cnt[r], &k)) return 1;
+		    if (k != cnt[r]) return 1;
+		    const int32_t add = m->first[r];
+		    for (int32_t i = 0; i < k; ++i) dst[i].sequence += add;
+		    return 0;
+	    }))
+		return 1;
+	if (!merge) return 0;
+	// P pieces of the score axis merged concurrently: thresholds from a sample, the bounds of a piece by bisection in every block
+	const int P = static_cast<int>(std::min<int64_t>(std::max<int64_t>(1, tot / 65536), std::max(S, std::min(16, static_cast<int>(std::thread::hardware_concurrency()) / 2))));
+	std::vector<float> sample;
+	for (int r = 0; r < S; ++r)
+		for (int k = 0; k < 256 && cnt[r]; ++k) sample.push_back(m->tmp[r][static_cast<size_t>((static_cast<int64_t>(cnt[r]) * k) / 256)].score);
+	std::sort(sample.begin(), sample.end());
+	std::vector<std::vector<int32_t>> lo(static_cast<size_t>(P) + 1, std::vector<int32_t>(static_cast<size_t>(S), 0));
+	for (int p = 1; p < P; ++p) {
+		if (sample.empty()) break;
+		const float t = sample[sample.size() * static_cast<size_t>(p) / static_cast<size_t>(P)];
+		for (int r = 0; r < S; ++r) {
+			const xxm_site* b = m->tmp[r].get();
+			lo[p][r] = static_cast<int32_t>(std::lower_bound(b, b + cnt[r], t, [](const xxm_site& a, float v) { return a.score < v; }) - b);
+		}
+	}
+	for (int r = 0; r < S; ++r) lo[P][r] = cnt[r];
+	auto piece = [&](int p) {
+		int64_t o = 0;
+		for (int r = 0; r < S; ++r) o += lo[p][r];
+		std::vector<int32_t> at(lo[p]);
+		const std::vector<int32_t>& end = lo[p + 1];
+		for (;;) {
+			int best = -1;
+			float bs = 0;
+			for (int r = 0; r < S; ++r)
+				if (at[r] < end[r]) {
+					const float sc = m->tmp[r][at[r]].score;
+					if (best < 0 || sc < bs) { best = r; bs = sc; }
+				}
+			if (best < 0) break;
+			out[o++] = m->tmp[best][at[best]++];
+		}
+	};
+	if (P == 1) piece(0);
+	else {
+		std::vector<std::thread> th;
+		for (int p = 1; p < P; ++p) th.emplace_back(piece, p);
+		piece(0);
+		for (auto& t : th) t.join();
 	}
 	return 0;
 }
