@@ -243,6 +243,15 @@ int xxm_comm_destroy(xxm_ctx* ctx);
 int xxm_optimize_step(xxm_ctx* ctx, double* pwm31x5, const int32_t* cols, int32_t ncols, int32_t posSetSize, int32_t totalPositions, int32_t enrStart,
                       int32_t enrEnd, double pseudo, xxm_step_info* info);
 
+/* ---- the counting loop of the elongation phase's seed search ---------------------------------------
+ * ElongCandidates::countAllOccurrences (src/elongationPhase/elongationCandidates.cpp:234-262): for every start position of
+ * sequences 1..nseq whose `ncoding` coding characters (character l at base offset offset[l] = l + gap[l-1]; gap positions may
+ * hold N) are all non-N, count the gapped k-mer.  counts[id], id = sum_l (code_l - 1) * 4^(ncoding-1-l): the reference's id
+ * with 2 instead of 4 bits per character (its IUPAC merge, :264-273, starts from exactly these 4^ncoding entries).
+ * firstHalfOnly = 1: seed types PALINDROME / TANDEM under --revcomp walk only the first (n - span + 1) / 2 start positions of
+ * the doubled sequence (:245).  With a communicator attached the counts are those of the whole sharded set. */
+int xxm_count_gapped_kmers(xxm_ctx* ctx, int32_t nseq, int32_t ncoding, const int32_t* offset, int32_t firstHalfOnly, uint32_t* counts);
+
 /* ---- multi-device context: ONE host thread, several GPUs ---------------------------------------------------------------
  * The reference is single-threaded.  xxm_multi owns one context per device (devices 0..ngpus-1), cuts the set
  * into contiguous blocks of sequences balanced by residues, runs every call on all devices concurrently (one worker thread per
@@ -268,6 +277,7 @@ int xxm_multi_scan_oops(xxm_multi* m, int32_t posSetSize, int32_t enrStart, int3
 int xxm_multi_rescore_startposlist(xxm_multi* m, int32_t posSetSize, int32_t enrStart, int32_t enrEnd, int32_t nSites, const int32_t* siteSeq,
                                    const int32_t* sitePos, int32_t instanceThreshold, int32_t* nbSites, int32_t* maxSites);
 int xxm_multi_get_sites(xxm_multi* m, int32_t which, int32_t order, int32_t palin, xxm_site* out, int32_t cap, int32_t* nOut);
+int xxm_multi_count_gapped_kmers(xxm_multi* m, int32_t nseq, int32_t ncoding, const int32_t* offset, int32_t firstHalfOnly, uint32_t* counts);
 
 /* ---- host-side pieces of the path, callable without a device (unit tests of the host logic) -------------------------
  * xxm_host_tables: the table construction xxm_reinitialize performs (branch_and_bound-inl.h:183-603), without staging.

@@ -25,7 +25,9 @@
  * and reads their (private) result buffers; it is compiled with
  * -fno-access-control for that purpose.
  *
+ *   ElongCandidates::countAllOccurrences src/elongationPhase/elongationCandidates.cpp:234 (mode "gapped")
  * usage:
+ *   ref_harness gapped five|pal|tandem OUTFILE OUTDIR SEQFILE [reference flags]   -> counts of every gap pattern (binary)
  *   ref_harness trace TRACEFILE OUTDIR SEQFILE [reference flags, must include -m or -p]
  *   ref_harness bench STEPS WARMUP OUTDIR SEQFILE [reference flags]   -> one JSON line on stdout
  */
@@ -46,6 +48,7 @@
 #include "refinementPhase/MotifContainer.h"
 #include "refinementPhase/Refine_Motifs.h"
 #include "refinementPhase/Iterate_Motif.h"
+#include "elongationPhase/elongationCandidates.h"
 
 typedef Kmer_Generator_Reloaded<dna_hash_t> KGen;
 
@@ -220,7 +223,57 @@ static int run_bench(int steps, int warmup, Motif* m) {
 	return 0;
 }
 
+/* ElongCandidates::countAllOccurrences for every gap pattern of one seed type.  File: int32 ncoding,
+ * int32 npatterns, int32 firstHalfOnly, double seconds; per pattern int32 offset[ncoding] (l + gap[l-1]) and uint32 counts[4^ncoding]
+ * (first character most significant), read from countIUPAC at the ids without IUPAC characters. */
+static int run_gapped(const char* typeName, const char* outFile) {
+	motif_type type = strcmp(typeName, "pal") == 0 ? PALINDROME : (strcmp(typeName, "tandem") == 0 ? TANDEM : FIVEMERS);
+	FILE* f = fopen(outFile, "wb");
+	if (!f) { perror("gapped"); return 1; }
+	int npat = 0;
+	double secs = 0;
+	std::vector<int32_t> body;
+	int ncoding = 0;
+	const int have = type == FIVEMERS ? (int) (sizeof(ElongCandidates::gaps) / sizeof(ElongCandidates::gaps[0])) : 16;
+	for (int k = 0; k < have; k++) {
+		{
+			ElongCandidates ec(k, type, 1e-3);
+			ncoding = ElongCandidates::coding_characters;
+			const uint8_t* gap = type == FIVEMERS ? ElongCandidates::gaps[k] : ElongCandidates::gaps_palindrome[k];
+			const double t0 = now_s();
+			ec.countAllOccurrences();
+			secs += now_s() - t0;
+			body.push_back(0);
+			for (int l = 1; l < ncoding; l++) body.push_back(l + gap[l - 1]);
+			for (uint32_t id = 0; id < ElongCandidates::POW_4_coding; id++) {
+				uint32_t id16 = 0;
+				for (int l = 0; l < ncoding; l++) id16 = (id16 << 4) + ((id >> (2 * (ncoding - 1 - l))) & 3u);
+				body.push_back((int32_t) ElongCandidates::countIUPAC[id16]);
+			}
+			npat++;
+		}
+	}
+	int32_t head[3] = {ncoding, npat, (type == PALINDROME && Global::revcomp) ? 1 : 0};
+	fwrite(head, 4, 3, f);
+	fwrite(&secs, 8, 1, f);
+	fwrite(body.data(), 4, body.size(), f);
+	fclose(f);
+	return 0;
+}
+
 int main(int argc, char** argv) {
+	if (argc >= 6 && strcmp(argv[1], "gapped") == 0) {
+		int saved = dup(1);
+		fflush(stdout);
+		dup2(2, 1);
+		std::vector<char*> av; av.push_back(argv[0]);
+		for (int i = 4; i < argc; i++) av.push_back(argv[i]);
+		Global G((int) av.size(), av.data());
+		LogTable L;
+		const int rc = run_gapped(argv[2], argv[3]);
+		fflush(stdout); dup2(saved, 1);
+		return rc;
+	}
 	if (argc < 5) { fprintf(stderr, "usage: ref_harness trace TRACE OUTDIR SEQ [flags] | bench STEPS WARMUP OUTDIR SEQ [flags] | refine OUTDIR SEQ [flags]\n"); return 2; }
 	const bool bench = strcmp(argv[1], "bench") == 0;
 	const bool refine = strcmp(argv[1], "refine") == 0;  /* refine OUTDIR SEQ [flags]: MotifContainer::iterate of the start motif, timed */

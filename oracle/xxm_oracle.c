@@ -120,6 +120,32 @@ int64_t xo_seqset_flat(const xo_seqset* s, uint8_t* out) {
 }
 
 /* ===================================================================== */
+/* elongation phase: gapped k-mer counts          */
+/* ===================================================================== */
+/* the counting loop of ElongCandidates::countAllOccurrences, elongationPhase/elongationCandidates.cpp:234-262: character l of
+ * the k-mer sits at j + offset[l] (offset[l] = l + gap[l-1], :251); a start position counts if none of its coding characters
+ * is an N (:241-258); seqLen = n - coding - gap[coding-2] + 1 (:244), halved for PALINDROME under --revcomp (:245).
+ * counts[id]: first character most significant, 2 bits per character (the reference keeps 4 bits per character). */
+void xo_count_gapped_kmers(const xo_seqset* s, int32_t nseq, int32_t ncoding, const int32_t* offset, int32_t firstHalfOnly, uint32_t* counts) {
+	memset(counts, 0, sizeof(uint32_t) << (2 * ncoding));
+	for (int32_t i = 0; i < nseq; i++) {
+		const uint8_t* seq = s->S[i];
+		int32_t seqLen = s->n[i] - offset[ncoding - 1];
+		if (firstHalfOnly) seqLen /= 2;
+		for (int32_t j = 1; j <= seqLen; j++) {
+			uint32_t id = 0;
+			int ok = 1;
+			for (int32_t l = 0; l < ncoding; l++) {
+				const int base = (int) seq[j + offset[l]] - 1;
+				if (base < 0) { ok = 0; break; }
+				id = (id << 2) + (uint32_t) base;
+			}
+			if (ok) counts[id]++;
+		}
+	}
+}
+
+/* ===================================================================== */
 /* background                                                            */
 /* ===================================================================== */
 /* checkSequenceSet, backgroundDistribution.cpp:30-95 (mono-nucleotide part only) */

@@ -59,6 +59,8 @@ const int32_t* xo_seqset_n(const xo_seqset*);        /* [nent], 0-based array of
 const int32_t* xo_seqset_total(const xo_seqset*);    /* [nent+1] */
 const double* xo_seqset_avgLength(const xo_seqset*); /* [nent+1] */
 int64_t xo_seqset_flat(const xo_seqset*, uint8_t* out); /* concatenated S[0][1..n]; returns byte count (out may be NULL) */
+/* ElongCandidates::countAllOccurrences' counting loop (elongationCandidates.cpp:234-262); counts[4^ncoding] */
+void xo_count_gapped_kmers(const xo_seqset*, int32_t nseq, int32_t ncoding, const int32_t* offset, int32_t firstHalfOnly, uint32_t* counts);
 
 /* ---- background (backgroundDistribution.cpp:30-95, NullModel.cpp:88-326) ---- */
 void xo_background(const xo_seqset*, double* bg5, double* bgLog5);

@@ -69,6 +69,7 @@ def lib():
         "xo_order_statistics_pvalue": (dbl, [vp, i32, i32, dbl]), "xo_fast_log": (flt, [flt]),
         "xo_logodds_hist": (None, [vp, vp, vp, i32, i32, vp, vp, i32, P(dbl), P(dbl)]),
         "xo_positional_pval": (dbl, [vp, i32, i32, i32, vp, i32]),
+        "xo_count_gapped_kmers": (None, [vp, i32, i32, vp, i32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -136,6 +137,13 @@ class SeqSet:
         sz = self.L.xo_seqset_flat(self.h, None)
         out = np.zeros(sz, dtype=np.uint8)
         self.L.xo_seqset_flat(self.h, _ptr(out))
+        return out
+
+    def count_gapped_kmers(self, nseq, offsets, firstHalfOnly=False):
+        """ElongCandidates::countAllOccurrences' counting loop (elongationCandidates.cpp:234-262)"""
+        off = np.ascontiguousarray(offsets, dtype=np.int32)
+        out = np.zeros(4 ** len(off), dtype=np.uint32)
+        self.L.xo_count_gapped_kmers(self.h, nseq, len(off), _ptr(off), int(firstHalfOnly), _ptr(out))
         return out
 
     def background(self):

@@ -21,7 +21,7 @@ EXPORTS = [
     "xxm_reinitialize", "xxm_tables_info", "xxm_tables_get", "xxm_window_pvals", "xxm_scan_full", "xxm_rescore", "xxm_scan_oops",
     "xxm_rescore_startposlist", "xxm_update_pwm_with_best_subset", "xxm_startposlist_best_subset", "xxm_startposlist_from_elong",
     "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset", "xxm_host_pair_table",
-    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables", "xxm_trace_dump", "xxm_elong_keep", "xxm_startposlist_from_kept", "xxm_check_guards", "xxm_set_global_counts", "xxm_seqset_logsum", "xxm_seqset_logsum_from", "xxm_sites_count",
+    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables", "xxm_trace_dump", "xxm_elong_keep", "xxm_startposlist_from_kept", "xxm_check_guards", "xxm_set_global_counts", "xxm_seqset_logsum", "xxm_seqset_logsum_from", "xxm_sites_count", "xxm_count_gapped_kmers", "xxm_multi_count_gapped_kmers",
     "xxm_multi_create", "xxm_multi_create_on", "xxm_multi_destroy", "xxm_multi_last_error", "xxm_multi_devices", "xxm_multi_set_options", "xxm_multi_set_background",
     "xxm_multi_load_seqset", "xxm_multi_seqset_info", "xxm_multi_reinitialize", "xxm_multi_scan_full", "xxm_multi_rescore", "xxm_multi_scan_oops",
     "xxm_multi_rescore_startposlist", "xxm_multi_get_sites",
@@ -103,13 +103,14 @@ def load_library():
         "xxm_seqset_logsum": [vp, P(dbl)],
         "xxm_seqset_logsum_from": [vp, dbl, P(dbl)],
         "xxm_sites_count": [vp, i32, i32, P(i32)],
+        "xxm_count_gapped_kmers": [vp, i32, i32, vp, i32, vp],
         "xxm_elong_keep": [vp],
         "xxm_startposlist_from_kept": [vp, i32, i32, vp, vp, i32, P(i32), P(dbl)],
         "xxm_device_tables": [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, P(C.c_float)],
     }
     # the multi-device layer mirrors the signatures of the calls it wraps
     for name in ("set_options", "set_background", "load_seqset", "seqset_info", "reinitialize", "scan_full", "rescore", "scan_oops", "rescore_startposlist",
-                 "get_sites"):
+                 "get_sites", "count_gapped_kmers"):
         sig["xxm_multi_" + name] = sig["xxm_" + name]
     sig["xxm_multi_create"] = [i32, P(vp)]
     sig["xxm_multi_create_on"] = [vp, i32, P(vp)]
@@ -353,6 +354,13 @@ class Context:
         v = C.c_double(0.0)
         self._ck(self.L.xxm_seqset_logsum(self.h, C.byref(v)))
         return v.value
+
+    def count_gapped_kmers(self, nseq, offsets, firstHalfOnly=False):
+        """ElongCandidates::countAllOccurrences' counting loop: counts[4^k], first character most significant"""
+        off = np.ascontiguousarray(offsets, dtype=np.int32)
+        out = np.zeros(4 ** len(off), dtype=np.uint32)
+        self._ck(self.L.xxm_count_gapped_kmers(self.h, nseq, len(off), _p(off), int(firstHalfOnly), _p(out)))
+        return out
 
     def check_guards(self):
         """(buffers checked, buffers with an overwritten canary) -- needs XXM_DEBUG_GUARDS in the environment at load time"""

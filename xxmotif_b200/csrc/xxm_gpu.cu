@@ -27,6 +27,7 @@
 #include "xxm_select3.cuh"
 #include "xxm_select4.cuh"
 #include "xxm_kmerhist.cuh"
+#include "xxm_gappedhist.cuh"
 #include "xxm_scan4.cuh"
 #include "xxm_scan5.cuh"
 #include "xxm_scan6.cuh"
@@ -253,6 +254,8 @@ struct xxm_ctx {
 	DevBuf<uint32_t> r_seq, d_pbits;
 	DevBuf<uint8_t> d_t8, d_raw;
 	DevBuf<uint32_t> d_pairTab, d_dead, d_scanCounts;
+	DevBuf<uint32_t> d_gapped;      // bins of xxm_count_gapped_kmers
+	std::vector<uint32_t> h_gapped;
 	std::vector<int> deadKey;   // (load serial, L, column offsets) d_dead was built for
 	uint64_t loadSerial = 0;
 	DevBuf<unsigned long long> d_xchg;  // value-index histogram + scalars on their way through NCCL
@@ -417,7 +420,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	// DevBuf members are released explicitly (no destructor: the struct is copied nowhere, but keep it trivial)
 	ctx->d_codes.release(); ctx->d_nmask.release(); ctx->d_wordOff.release(); ctx->d_blk2seq.release(); ctx->d_len.release();
 	ctx->d_rank0.release(); ctx->d_rank1.release(); ctx->d_hit0.release(); for (int k = 0; k < 2; ++k) { ctx->d_ids[k].release(); ctx->d_cls[k].release(); ctx->d_clsOk[k].release(); }
-	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_pack) cudaFreeHost(ctx->h_pack); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_raw.release(); ctx->d_notX.release(); ctx->d_n.release(); ctx->d_dead.release(); ctx->d_scanCounts.release(); ctx->s_kcls.release(); ctx->d_clsThr.release(); ctx->d_layoutSums.release();
+	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_pack) cudaFreeHost(ctx->h_pack); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_raw.release(); ctx->d_notX.release(); ctx->d_n.release(); ctx->d_dead.release(); ctx->d_gapped.release(); ctx->d_scanCounts.release(); ctx->s_kcls.release(); ctx->d_clsThr.release(); ctx->d_layoutSums.release();
 	for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
 	if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 	if (ctx->h_pinXchg) cudaFreeHost(ctx->h_pinXchg); if (ctx->evStage) cudaEventDestroy(ctx->evStage);
@@ -1650,3 +1653,4 @@ static int scan_full_finish(xxm_ctx* ctx, int32_t* nbSites, int32_t* nbBestSites
 #include "xxm_gpu_part5.inc"
 #include "xxm_gpu_part6.inc"
 #include "xxm_gpu_part8.inc"
+#include "xxm_gpu_part9.inc"

@@ -370,3 +370,23 @@ extern "C" int xxm_multi_get_sites(xxm_multi* m, int32_t which, int32_t order, i
 	}
 	return 0;
 }
+
+// every shard counts its sequences, the counts are added up
+extern "C" int xxm_multi_count_gapped_kmers(xxm_multi* m, int32_t nseq, int32_t ncoding, const int32_t* offset, int32_t firstHalfOnly, uint32_t* counts) {
+	const int S = m->shards();
+	if (S == 1) {
+		if (xxm_count_gapped_kmers(m->ctx[0], nseq, ncoding, offset, firstHalfOnly, counts)) return m->fail("%s", xxm_last_error(m->ctx[0]));
+		return 0;
+	}
+	if (whole_set_only(m, nseq)) return 1;
+	if (ncoding < 1 || ncoding > 7) return m->fail("xxm_multi_count_gapped_kmers: 1..7 coding characters");
+	const size_t nb = static_cast<size_t>(1) << (2 * ncoding);
+	std::vector<std::vector<uint32_t>> part(static_cast<size_t>(S), std::vector<uint32_t>(nb));
+	if (m->each([&](int r) { return xxm_count_gapped_kmers(m->ctx[r], m->local_n(r), ncoding, offset, firstHalfOnly, part[r].data()); })) return 1;
+	for (size_t i = 0; i < nb; ++i) {
+		uint32_t s = 0;
+		for (int r = 0; r < S; ++r) s += part[r][i];
+		counts[i] = s;
+	}
+	return 0;
+}
