@@ -22,13 +22,19 @@ namespace {
 
 xxm_multi* g_ctx = NULL;
 
-void die(const char* what) {
+void die(const char* what) { xxm_binding_die(what); }
+#define XXM_OK(call) do { if (call) die(#call); } while (0)
+
+xxm_multi* context() { return xxm_binding_context(); }
+
+}  // namespace
+
+void xxm_binding_die(const char* what) {
 	fprintf(stderr, "libxxmotif_gpu: %s: %s\n", what, xxm_multi_last_error(g_ctx));
 	exit(-1);  /* the reference's own error convention */
 }
-#define XXM_OK(call) do { if (call) die(#call); } while (0)
 
-xxm_multi* context() {
+xxm_multi* xxm_binding_context() {
 	if (g_ctx) return g_ctx;
 	const char* dev = getenv("XXM_DEVICE");
 	const char* ndev = getenv("XXM_DEVICES");
@@ -56,6 +62,8 @@ xxm_multi* context() {
 	XXM_OK(xxm_multi_load_seqset(g_ctx, set->nent, n.data(), codes.data(), Global::revcomp ? 1 : 0));
 	return g_ctx;
 }
+
+namespace {
 
 void reinitialize(xxm_multi* ctx, double** pwm, const motif_columns_type& columns, int posSetSize) {
 	double flat[31 * 5];

@@ -25,5 +25,10 @@ void StartPosUpdater::fill_elongSites_with_possible_startPositions<XxmDnaKmerGen
                                                                                         motif_columns_type& tmpColumns, bool palin);
 template <>
 void StartPosUpdater::fill_sites_with_possible_startPositions_oops<XxmDnaKmerGenerator>(XxmDnaKmerGenerator& kmerHash, Motif* motif);
+
+/* the one context of the process (created, configured and given Global::posSet at the first call), shared by the bindings */
+struct xxm_multi;
+xxm_multi* xxm_binding_context();
+void xxm_binding_die(const char* what);
 #endif
 #endif

@@ -86,10 +86,12 @@ def test_bound_binary_on_several_devices(name, w, extra):
     _compare_with_reference(w, extra, {"XXM_DEVICES": str(min(8, torch.cuda.device_count()))})
 
 
-def test_bound_binary_full_discovery():
+@pytest.mark.parametrize("flags", [[], ["--type", "PALINDROME", "--revcomp"], ["--type", "TANDEM"]], ids=["all_seed_types", "palindrome_revcomp", "tandem"])
+def test_bound_binary_full_discovery(flags):
     """No start motif: the reference's whole pipeline -- seed discovery, elongation, merging, refinement of ~150 motifs,
-    ranking, output -- with every window loop of the refinement path served by the library (tens of thousands of small calls
-    through the binding).  ~2 x 1 minute of host work, so only with XXM_BOUND_FULL=1 (profiles/ holds the record of a run)."""
+    ranking, output -- with the counting loop of the seed search (ElongCandidates::countAllOccurrences, SURVEY 8(f) row 4) and
+    every window loop of the refinement path served by the library (tens of thousands of small calls through the binding).
+    ~2 x 1 minute of host work per case, so only with XXM_BOUND_FULL=1 (profiles/ holds the record of a run)."""
     if not os.environ.get("XXM_BOUND_FULL"):
         pytest.skip("set XXM_BOUND_FULL=1 to run the full-discovery comparison (minutes of CPU seed search)")
     if not (os.path.exists(REF) and os.path.exists(BOUND)):
@@ -103,14 +105,14 @@ def test_bound_binary_full_discovery():
         secs = {}
         for tag, exe in (("ref", REF), ("gpu", BOUND)):
             t0 = time.time()
-            r = subprocess.run([exe, os.path.join(tmp, tag), fa, "--batch"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            r = subprocess.run([exe, os.path.join(tmp, tag), fa, "--batch"] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
             secs[tag] = time.time() - t0
             assert r.returncode == 0, r.stderr.decode()[-1500:]
         fr, fg = _files(os.path.join(tmp, "ref")), _files(os.path.join(tmp, "gpu"))
         assert fr == fg
         diff = [f for f in fr if not filecmp.cmp(os.path.join(tmp, "ref", f), os.path.join(tmp, "gpu", f), shallow=False)]
         motifs = open(os.path.join(tmp, "ref", "s_MotifFile.txt")).read().count("Motif Number")
-        print("full discovery: %d motifs reported, reference %.1f s, bound %.1f s, differing files: %s" % (motifs, secs["ref"], secs["gpu"], diff))
+        print("full discovery %s: %d motifs reported, reference %.1f s, bound %.1f s, differing files: %s" % (" ".join(flags) or "(defaults)", motifs, secs["ref"], secs["gpu"], diff))
         assert not diff and motifs > 10
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

@@ -113,6 +113,13 @@ def kmer_counts_device(ctx, order):
     return c, ms.value
 
 
+def kmer_counts_ms(ctx):
+    """device milliseconds of the last xxm_kmer_counts / xxm_count_gapped_kmers on this context"""
+    ms = C.c_float(0)
+    _lib().xxm_kmer_counts_ms(ctx.h, C.byref(ms))
+    return ms.value
+
+
 def kmer_counts_host(n, codes, order):
     """the same counts with numpy (test oracle of the device histogram): all (k+1)-mers, k = 0..order, without N, inside a sequence"""
     n = np.asarray(n, dtype=np.int64)
