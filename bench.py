@@ -547,14 +547,21 @@ def _ours(a):
     e2e_value = windows_local * world * e2e_steps / (e2e_ms / 1000.0)
     packed_words = int(((n.astype(np.int64) + 32 + 31) // 32).sum()) + 2
     host_pack = int(os.environ["XXM_PACK_THREADS"]) >= 6   # xxm_load_seqset packs on the host cores when it has that many, else on the device
-    if host_pack:
+    raw_chunks, all_chunks = ctx.last_load_info()
+    if all_chunks:  # 2-5 host threads per GPU: both at once
+        fr = raw_chunks / all_chunks
+        h2d = int(fr * codes.size + (1 - fr) * 12 * packed_words + 4 * nent + 64 * 1024)
+        d2h = int(job.last_d2h_bytes + fr * 4 * nent)
+        how = ("%s host threads pack 8 MB chunks from the back of the set while raw chunks from the front cross the bus and are packed on the device: "
+               "%d of %d chunks went raw in the last step" % (os.environ["XXM_PACK_THREADS"], raw_chunks, all_chunks))
+    elif host_pack:
         h2d = int(12 * packed_words + 4 * nent + 64 * 1024)   # packed stream (8 B codes + 4 B N mask per 32 bases) + lengths + the per-model tables of the step
         d2h = int(job.last_d2h_bytes)                          # step results
         how = "%s host threads pack 8 MB chunks into the 2-bit layout, each chunk copied as soon as it is packed" % os.environ["XXM_PACK_THREADS"]
     else:
         h2d = int(codes.size + 4 * nent + 64 * 1024)           # raw codes + lengths + tables
         d2h = int(job.last_d2h_bytes + 4 * nent)               # step results + per-sequence residue counts
-        how = "fewer than 6 host cores per GPU: raw bytes copied in chunks, statistics and packing on the device behind them"
+        how = "one host core per GPU: raw bytes copied in chunks, statistics and packing on the device behind them"
 
     # ---- roofline of the dominant kernel (full scan): algorithmic bytes / measured kernel time.  Bytes per SURVEY 8(d):
     # 0.375 B per base of the sequences (sum of n_i -- the padding between sequences is not counted) + 12 B per hit

@@ -71,6 +71,10 @@ int xxm_set_options(xxm_ctx* ctx, const xxm_options* opt);
 int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp);
 int xxm_seqset_info(const xxm_ctx* ctx, int32_t* total /*[nent+1] or NULL*/, double* avgLength /*[nent+1] or NULL*/,
                     int32_t* max_leng, int32_t* min_leng);
+/* how the last xxm_load_seqset moved the set when it used both packing paths at once (2-5 host threads per GPU: raw chunks from
+ * the front of the set over the bus, packed on the device, while the host threads pack chunks from the back): rawChunks of chunks
+ * went raw; 0 of 0 when one path did everything.  XXM_LOAD_PATH=host|device|hybrid overrides the choice. */
+int xxm_last_load_info(const xxm_ctx* ctx, int32_t* rawChunks, int32_t* chunks);
 
 /* ---- a5: background + p-value tables -------------------------------------------------------------------------------
  * xxm_set_background replaces the NullModel statics read by calculate_kmer_probability (NullModel.cpp:42-54,

@@ -21,7 +21,7 @@ EXPORTS = [
     "xxm_reinitialize", "xxm_tables_info", "xxm_tables_get", "xxm_window_pvals", "xxm_scan_full", "xxm_rescore", "xxm_scan_oops",
     "xxm_rescore_startposlist", "xxm_update_pwm_with_best_subset", "xxm_startposlist_best_subset", "xxm_startposlist_from_elong",
     "xxm_set_binding_sites", "xxm_get_sites", "xxm_logodds_hist", "xxm_get_stats", "xxm_stream", "xxm_host_tables", "xxm_host_best_subset", "xxm_host_pair_table",
-    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables", "xxm_trace_dump", "xxm_elong_keep", "xxm_startposlist_from_kept", "xxm_check_guards", "xxm_set_global_counts", "xxm_seqset_logsum", "xxm_seqset_logsum_from", "xxm_sites_count", "xxm_count_gapped_kmers", "xxm_multi_count_gapped_kmers",
+    "xxm_comm_unique_id", "xxm_comm_init", "xxm_comm_destroy", "xxm_optimize_step", "xxm_step_phases", "xxm_device_tables", "xxm_trace_dump", "xxm_elong_keep", "xxm_startposlist_from_kept", "xxm_check_guards", "xxm_set_global_counts", "xxm_seqset_logsum", "xxm_seqset_logsum_from", "xxm_sites_count", "xxm_last_load_info", "xxm_count_gapped_kmers", "xxm_multi_count_gapped_kmers",
     "xxm_multi_create", "xxm_multi_create_on", "xxm_multi_destroy", "xxm_multi_last_error", "xxm_multi_devices", "xxm_multi_set_options", "xxm_multi_set_background",
     "xxm_multi_load_seqset", "xxm_multi_seqset_info", "xxm_multi_reinitialize", "xxm_multi_scan_full", "xxm_multi_rescore", "xxm_multi_scan_oops",
     "xxm_multi_rescore_startposlist", "xxm_multi_get_sites",
@@ -103,6 +103,7 @@ def load_library():
         "xxm_seqset_logsum": [vp, P(dbl)],
         "xxm_seqset_logsum_from": [vp, dbl, P(dbl)],
         "xxm_sites_count": [vp, i32, i32, P(i32)],
+        "xxm_last_load_info": [vp, P(i32), P(i32)],
         "xxm_count_gapped_kmers": [vp, i32, i32, vp, i32, vp],
         "xxm_elong_keep": [vp],
         "xxm_startposlist_from_kept": [vp, i32, i32, vp, vp, i32, P(i32), P(dbl)],
@@ -177,6 +178,12 @@ class Context:
         assert int(n.sum(dtype=np.int64)) == codes.size
         self._ck(self.L.xxm_load_seqset(self.h, len(n), _p(n), _p(codes), int(revcomp)))
         self.nent = len(n)
+
+    def last_load_info(self):
+        """(chunks that went over the bus raw, all chunks) of the last load when both packing paths worked at once, else (0, 0)"""
+        a, b = C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.xxm_last_load_info(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def seqset_info(self):
         total = np.zeros(self.nent + 1, dtype=np.int32)

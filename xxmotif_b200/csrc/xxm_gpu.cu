@@ -15,6 +15,7 @@
 #include <cstring>
 #include <atomic>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -233,6 +234,7 @@ struct xxm_ctx {
 	DevBuf<uint16_t> d_clsThr;
 	bool clsOrderOK = false;
 	uint32_t clsNSite = 0;
+	int lastLoadRawChunks = 0, lastLoadChunks = 0;  // hybrid load: how many chunks went over the bus raw
 	float lastKmerHistMs = 0;     // device time of the last xxm_kmer_counts (all passes)
 	bool sortedLazy = false;      // the last deferred scan left sortedSites' float scores implicit (k_select_cls_fwd)
 	DevBuf<uint32_t> stk, slotIdx, e_slotIdxSet[2], counters, hist, idxA, idxB, keysA, keysB, rsHist;
@@ -811,6 +813,193 @@ static int load_pack_on_device(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	return 0;
 }
 
+// Both at once, for hosts with a few cores per GPU (8 ranks on a 32-core box): the bus carries raw chunks from the FRONT of the
+// set (packed behind it by k_seq_stats / k_encode, as in load_pack_on_device) while the worker threads pack chunks from the BACK
+// (as in load_pack_on_host) and their packed words follow at 0.375 B per base; the two meet wherever the hardware of the day puts
+// the balance.  At most kRawDepth raw chunks are in flight, so the bus is never committed far ahead of the packers.
+static int load_pack_hybrid(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp, uint64_t rawTotal, int nthreads, bool trace,
+                            std::chrono::steady_clock::time_point tStart) {
+	if (!ctx->copyStream) CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+	CK(ctx->d_raw.ensure(std::max<uint64_t>(1, rawTotal)));
+	CK(ctx->d_notX.ensure(nent));
+	CK(ctx->counters.ensure(8));
+	CK(cudaMemsetAsync(ctx->counters.p, 0, 32, ctx->stream));
+	if (ctx->h_notXCap < static_cast<size_t>(nent)) {
+		if (ctx->h_notX) cudaFreeHost(ctx->h_notX);
+		ctx->h_notX = nullptr;
+		ctx->h_notXCap = 0;
+		CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_notX), static_cast<size_t>(nent) * 4, cudaHostAllocDefault));
+		ctx->h_notXCap = static_cast<size_t>(nent);
+	}
+	const size_t wordsAll = static_cast<size_t>(ctx->nwords) + 2;
+	if (ctx->h_packCap < wordsAll) {
+		if (ctx->h_pack) cudaFreeHost(ctx->h_pack);
+		ctx->h_pack = nullptr;
+		ctx->h_packCap = 0;
+		CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_pack), wordsAll * 12, cudaHostAllocDefault));
+		ctx->h_packCap = wordsAll;
+	}
+	uint64_t* const hCodes = reinterpret_cast<uint64_t*>(ctx->h_pack);
+	uint32_t* const hMask = reinterpret_cast<uint32_t*>(ctx->h_pack + ctx->h_packCap * 8);
+	ctx->notX.resize(nent);
+	// ---- chunks of whole sequences, cut by this thread as it lays the stream out (it owns wordOff / len)
+	constexpr uint64_t kChunkBytes = 8ull << 20;
+	constexpr int kRawDepth = 3;
+	struct Chunk { int s0, s1; uint64_t b0, b1; uint32_t w0, w1; uint32_t bad; };
+	std::vector<Chunk> chunks;
+	chunks.reserve(static_cast<size_t>(rawTotal / kChunkBytes) + 2);  // the workers read it while nothing is appended any more
+	// who takes which chunk: the bus from the front, the packers (started once the cut is complete) from the back
+	std::mutex claimMu;
+	int front = 0, back = 0;  // [front, back) is cut and unclaimed
+	auto claimFront = [&]() { std::lock_guard<std::mutex> g(claimMu); return front < back ? front++ : -1; };
+	auto claimBack = [&]() { std::lock_guard<std::mutex> g(claimMu); return back > front ? --back : -1; };
+	int rawIssued = 0, rawDone = 0;   // raw chunks are 0 .. rawIssued-1
+	auto issueRaw = [&](int k) -> int {
+		while (ctx->evPool.size() < 2 * static_cast<size_t>(k + 1)) {
+			cudaEvent_t e;
+			CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+			ctx->evPool.push_back(e);
+		}
+		const Chunk& c = chunks[k];
+		CK(cudaMemcpyAsync(ctx->d_raw.p + c.b0, codes + c.b0, c.b1 - c.b0, cudaMemcpyHostToDevice, ctx->copyStream));
+		CK(cudaEventRecord(ctx->evPool[2 * k], ctx->copyStream));
+		CK(cudaStreamWaitEvent(ctx->stream, ctx->evPool[2 * k], 0));
+		const uint32_t ns = static_cast<uint32_t>(c.s1 - c.s0);
+		k_seq_stats<<<std::min<uint32_t>(cdiv(ns, 8), static_cast<uint32_t>(ctx->numSMs) * 8), 256, 0, ctx->stream>>>(
+			ctx->d_raw.p, ctx->d_rawOff.p, static_cast<uint32_t>(c.s0), static_cast<uint32_t>(c.s1), ctx->d_notX.p, ctx->counters.p);
+		CKK();
+		CK(cudaMemcpyAsync(ctx->h_notX + c.s0, ctx->d_notX.p + c.s0, static_cast<size_t>(ns) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		if (c.w1 > c.w0) {
+			k_encode<<<cdiv(c.w1 - c.w0, 256), 256, 0, ctx->stream>>>(ctx->d_raw.p, ctx->d_rawOff.p, ctx->S, c.w0, c.w1, ctx->d_codes.p, ctx->d_nmask.p, revcomp ? 1 : 0);
+			CKK();
+		}
+		CK(cudaEventRecord(ctx->evPool[2 * k + 1], ctx->stream));
+		return 0;
+	};
+	// calculateSequenceFeatures / createRevcomp recount, in sequence order (see load_pack_on_host): the raw chunks are folded as
+	// their counts arrive, the packed ones after the loop
+	double acc = 0, lastLog = 0;
+	int lastNotX = 0;
+	int64_t tot = 0;
+	bool overflow = false;
+	auto fold = [&](int k, bool raw) {
+		const Chunk& c = chunks[k];
+		if (raw) std::memcpy(ctx->notX.data() + c.s0, ctx->h_notX + c.s0, static_cast<size_t>(c.s1 - c.s0) * 4);
+		for (int i = c.s0; i < c.s1; ++i) {
+			int notX = ctx->notX[i];
+			if (revcomp) notX = ctx->len[i];
+			if (notX != 0) {
+				if (notX != lastNotX) { lastNotX = notX; lastLog = std::log(notX); }  // same argument, same glibc result
+				acc += lastLog;
+			}
+			tot += notX;
+			if (tot > 2147483647LL) overflow = true;
+			ctx->total[i + 1] = static_cast<int32_t>(tot);
+			ctx->logAcc[i + 1] = acc;
+		}
+	};
+	// one turn of the bus side: fold what has arrived, put the next raw chunk on the bus if fewer than kRawDepth are in flight
+	bool claimsOpen = true, cutComplete = false;
+	auto pumpRaw = [&](bool* progress) -> int {
+		while (rawDone < rawIssued && cudaEventQuery(ctx->evPool[2 * rawDone + 1]) == cudaSuccess) { fold(rawDone++, true); *progress = true; }
+		if (claimsOpen && rawIssued - rawDone < kRawDepth) {
+			const int k = claimFront();
+			if (k >= 0) { TRY(issueRaw(k)); rawIssued = k + 1; *progress = true; }
+			else if (cutComplete) claimsOpen = false;  // front met back
+		}
+		return 0;
+	};
+	{
+		uint64_t off = 0, words = 0;
+		Chunk c{0, 0, 0, 0, 0, 0, 0};
+		for (int i = 0; i < nent; ++i) {
+			const int n0 = n[i];
+			const int nstore = revcomp ? 2 * n0 + 1 : n0;
+			ctx->len[i] = nstore;
+			ctx->wordOff[i] = static_cast<uint32_t>(words);
+			words += (static_cast<uint64_t>(nstore) + kPadBases + 31) / 32;
+			off += static_cast<uint64_t>(n0);
+			if (off - c.b0 < kChunkBytes && i + 1 != nent) continue;
+			c.s1 = i + 1; c.b1 = off; c.w1 = static_cast<uint32_t>(words);
+			chunks.push_back(c);
+			// the bus starts while the rest is still being cut -- but only chunks of the first half, the packers get their share
+			if (chunks.size() * kChunkBytes < rawTotal / 2) {
+				back = static_cast<int>(chunks.size());
+				bool dummy = false;
+				TRY(pumpRaw(&dummy));
+			}
+			c = Chunk{i + 1, i + 1, off, off, static_cast<uint32_t>(words), static_cast<uint32_t>(words), 0};
+		}
+		ctx->wordOff[nent] = static_cast<uint32_t>(words);
+	}
+	const int nchunks = static_cast<int>(chunks.size());
+	back = nchunks;  // no worker is running yet
+	cutComplete = true;
+	std::unique_ptr<std::atomic<uint32_t>[]> done(new std::atomic<uint32_t>[static_cast<size_t>(nchunks)]);
+	for (int k = 0; k < nchunks; ++k) done[k].store(0, std::memory_order_relaxed);
+	const bool rc = revcomp != 0;
+	auto worker = [&]() {
+		for (int k = claimBack(); k >= 0; k = claimBack()) {
+			Chunk& c = chunks[k];
+			c.bad = pack_range(n, static_cast<uint32_t>(c.s0), static_cast<uint32_t>(c.s1), codes + c.b0, rawTotal - c.b0, rc, hCodes + c.w0, hMask + c.w0, ctx->notX.data() + c.s0);
+			done[k].store(1, std::memory_order_release);
+		}
+	};
+	struct Joiner {
+		std::vector<std::thread> t;
+		~Joiner() { for (auto& th : t) if (th.joinable()) th.join(); }
+	} pool;
+	for (int t = 0; t < nthreads; ++t) pool.t.emplace_back(worker);
+	// ---- this thread: raw chunks onto the bus (bounded depth), packed chunks onto the bus as they finish
+	int packedIssued = nchunks;       // packed chunks packedIssued .. nchunks-1 have been copied
+	auto issuePacked = [&](int k) -> int {
+		const Chunk& c = chunks[k];
+		if (c.w1 > c.w0) {
+			CK(cudaMemcpyAsync(ctx->d_codes.p + c.w0, hCodes + c.w0, static_cast<size_t>(c.w1 - c.w0) * 8, cudaMemcpyHostToDevice, ctx->copyStream));
+			CK(cudaMemcpyAsync(ctx->d_nmask.p + c.w0, hMask + c.w0, static_cast<size_t>(c.w1 - c.w0) * 4, cudaMemcpyHostToDevice, ctx->copyStream));
+		}
+		return 0;
+	};
+	for (;;) {
+		bool progress = false;
+		TRY(pumpRaw(&progress));
+		// the packers work downwards from the end: copy whatever is finished below what has been copied already
+		while (packedIssued > rawIssued && done[packedIssued - 1].load(std::memory_order_acquire)) { TRY(issuePacked(--packedIssued)); progress = true; }
+		if (!claimsOpen && packedIssued == rawIssued) break;
+		if (!progress) std::this_thread::yield();
+	}
+	const int firstPacked = rawIssued;
+	hCodes[ctx->nwords] = hCodes[ctx->nwords + 1] = 0;
+	hMask[ctx->nwords] = hMask[ctx->nwords + 1] = 0xFFFFFFFFu;
+	CK(cudaStreamSynchronize(ctx->stream));  // k_encode may have touched the guard words' neighbours; the guards go last
+	CK(cudaMemcpyAsync(ctx->d_codes.p + ctx->nwords, hCodes + ctx->nwords, 16, cudaMemcpyHostToDevice, ctx->copyStream));
+	CK(cudaMemcpyAsync(ctx->d_nmask.p + ctx->nwords, hMask + ctx->nwords, 8, cudaMemcpyHostToDevice, ctx->copyStream));
+	uint32_t badSeq = 0;
+	for (; rawDone < rawIssued; ++rawDone) fold(rawDone, true);  // the compute stream is idle: every count has landed
+	for (int k = firstPacked; k < nchunks; ++k) {
+		if (chunks[k].bad && !badSeq) badSeq = chunks[k].bad;
+		fold(k, false);
+	}
+	if (overflow) { cudaStreamSynchronize(ctx->copyStream); return ctx->fail("more than 2^31-1 residues: the reference's int totals overflow (Alignment.h:40-41)"); }
+	uint32_t bad = 0;
+	CK(cudaMemcpyAsync(ctx->h_pin + 4, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+	CK(cudaStreamSynchronize(ctx->stream));
+	CK(cudaStreamSynchronize(ctx->copyStream));  // the staging buffer is reused by the next load; the compute stream must see the packed words
+	std::memcpy(&bad, ctx->h_pin + 4, 4);
+	ctx->notXPtr = ctx->notX.data();
+	if (bad && (!badSeq || bad < badSeq)) badSeq = bad;
+	if (badSeq) return ctx->fail("sequence %u holds a code outside 0..4", badSeq);
+	if (ctx->d_raw.cap > (8ull << 30)) ctx->d_raw.release();
+	if (trace) {
+		const auto tEnd = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "xxm load_seqset (hybrid): %d chunks, %d over the bus raw + %d packed by %d host threads, done after %.2f ms\n", nchunks, firstPacked,
+		             nchunks - firstPacked, nthreads, std::chrono::duration<double, std::milli>(tEnd - tStart).count());
+	}
+	ctx->lastLoadRawChunks = firstPacked;
+	ctx->lastLoadChunks = nchunks;
+	return 0;
+}
+
 // a1.  Layout from the lengths, then the packing step where it is cheaper: on the host cores when there are at least
 // kMinPackThreads of them for this GPU (XXM_PACK_THREADS, default min(12, 3/4 of the cores)), else on the device.
 extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp) {
@@ -901,13 +1090,27 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	CKK();
 	const int nthreads = pack_threads_default();
 	constexpr int kMinPackThreads = 6;  // 3 threads pack ~17 GB/s of bases, the bus takes raw bytes at 20-48 GB/s (profiles/README.md)
-	if (nthreads >= kMinPackThreads || rawTotal < (4ull << 20)) {
-		TRY(load_pack_on_host(ctx, nent, n, codes, revcomp, rawTotal, rawTotal < (4ull << 20) ? 0 : nthreads, trace, tStart));
-	} else {
-		TRY(load_pack_on_device(ctx, nent, n, codes, revcomp, rawTotal, trace, tStart));
-	}
+	// XXM_LOAD_PATH=host|device|hybrid overrides the choice (tests, measurements)
+	const char* forced = std::getenv("XXM_LOAD_PATH");
+	const bool small = rawTotal < (4ull << 20);
+	// (the hybrid of both is opt-in: on 1- and 2-GPU boxes, where the bus takes raw bytes at 42-51 GB/s, 3-5 packing threads did not
+	// shorten the load -- profiles/r02_load_paths.json)
+	int path = (nthreads >= kMinPackThreads || small) ? 0 : 1;
+	if (forced && !small) path = !std::strcmp(forced, "host") ? 0 : !std::strcmp(forced, "device") ? 1 : !std::strcmp(forced, "hybrid") ? 2 : path;
+	ctx->lastLoadRawChunks = ctx->lastLoadChunks = 0;
+	if (path == 0) TRY(load_pack_on_host(ctx, nent, n, codes, revcomp, rawTotal, small ? 0 : nthreads, trace, tStart));
+	else if (path == 1) TRY(load_pack_on_device(ctx, nent, n, codes, revcomp, rawTotal, trace, tStart));
+	else TRY(load_pack_hybrid(ctx, nent, n, codes, revcomp, rawTotal, std::max(1, nthreads), trace, tStart));
 	if (ctx->sum_i.size() != static_cast<size_t>(ctx->max_leng) + 1) init_sum_i(ctx->sum_i, ctx->max_leng);
 	ctx->nent = nent;
+	return 0;
+}
+
+// how the last xxm_load_seqset moved the set: chunks that crossed the bus as raw bytes (packed on the device) out of all chunks;
+// 0 of 0 when the whole set was packed on the host cores or on the device
+extern "C" int xxm_last_load_info(const xxm_ctx* ctx, int32_t* rawChunks, int32_t* chunks) {
+	*rawChunks = ctx->lastLoadRawChunks;
+	*chunks = ctx->lastLoadChunks;
 	return 0;
 }
 
