@@ -257,6 +257,8 @@ struct xxm_ctx {
 	DevBuf<uint8_t> d_t8, d_raw;
 	DevBuf<uint32_t> d_pairTab, d_dead, d_scanCounts;
 	DevBuf<uint32_t> d_gapped;      // bins of xxm_count_gapped_kmers
+	DevBuf<uint32_t> d_siteBits;    // one bit per value index: final p-value < 1
+	DevBuf<uint32_t> sweepLong;     // runs whose tail loop goes to the warp-per-run kernel
 	std::vector<uint32_t> h_gapped;
 	std::vector<int> deadKey;   // (load serial, L, column offsets) d_dead was built for
 	uint64_t loadSerial = 0;
@@ -422,7 +424,7 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	// DevBuf members are released explicitly (no destructor: the struct is copied nowhere, but keep it trivial)
 	ctx->d_codes.release(); ctx->d_nmask.release(); ctx->d_wordOff.release(); ctx->d_blk2seq.release(); ctx->d_len.release();
 	ctx->d_rank0.release(); ctx->d_rank1.release(); ctx->d_hit0.release(); for (int k = 0; k < 2; ++k) { ctx->d_ids[k].release(); ctx->d_cls[k].release(); ctx->d_clsOk[k].release(); }
-	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_pack) cudaFreeHost(ctx->h_pack); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_raw.release(); ctx->d_notX.release(); ctx->d_n.release(); ctx->d_dead.release(); ctx->d_gapped.release(); ctx->d_scanCounts.release(); ctx->s_kcls.release(); ctx->d_clsThr.release(); ctx->d_layoutSums.release();
+	ctx->d_stage.release(); if (ctx->h_stage) cudaFreeHost(ctx->h_stage); if (ctx->h_pin) cudaFreeHost(ctx->h_pin); if (ctx->h_pack) cudaFreeHost(ctx->h_pack); if (ctx->h_notX) cudaFreeHost(ctx->h_notX); ctx->d_raw.release(); ctx->d_notX.release(); ctx->d_n.release(); ctx->d_dead.release(); ctx->d_gapped.release(); ctx->d_siteBits.release(); ctx->sweepLong.release(); ctx->d_scanCounts.release(); ctx->s_kcls.release(); ctx->d_clsThr.release(); ctx->d_layoutSums.release();
 	for (cudaEvent_t e : ctx->evPool) cudaEventDestroy(e);
 	if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
 	if (ctx->h_pinXchg) cudaFreeHost(ctx->h_pinXchg); if (ctx->evStage) cudaEventDestroy(ctx->evStage);
@@ -1765,7 +1767,13 @@ extern "C" int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t enrStart,
 		CK(ctx->flag8.ensure(std::max<uint32_t>(1, nc)));
 		CK(ctx->counters.ensure(8));
 		CK(cudaMemsetAsync(ctx->counters.p, 0, 16, ctx->stream));
-		if (nc) {
+		if (nc && V.kind == kFinalTable) {
+			CK(ctx->d_siteBits.ensure(ctx->nval / 32 + 1));
+			k_site_bits<<<cdiv(ctx->nval, 256), 256, 0, ctx->stream>>>(V.finalTab, ctx->nval, ctx->d_siteBits.p);
+			CKK();
+			k_flag_hits_bits<<<cdiv(nc, 256), 256, 0, ctx->stream>>>(ctx->d_siteBits.p, ctx->t_vidx.p, nc, ctx->flag8.p);
+			CKK();
+		} else if (nc) {
 			k_flag_hits<<<cdiv(nc, 256), 256, 0, ctx->stream>>>(V, ctx->t_vidx.p, ctx->t_pos.p, nc, ctx->flag8.p, ctx->counters.p);
 			CKK();
 		}
