@@ -442,3 +442,49 @@ def test_shard_invariance_ragged_12_columns():
             b2.close()
     finally:
         whole.close(); a.close(); b.close()
+
+
+@pytest.mark.parametrize("name,offsets,localization,mops", [
+    ("one_part_span9_localized", [0, 1, 2, 3, 4, 6, 7, 8], True, True),
+    ("one_part_span10_localized_zoops", [0, 1, 2, 3, 5, 6, 8, 9], True, False),
+    ("two_parts_left_span10", [0, 1, 2, 3, 4, 6, 7, 9, 10, 11, 12, 13], False, False),
+    ("two_parts_left_span9_mops", [0, 1, 2, 4, 5, 6, 7, 8, 9, 11], False, True),
+])
+def test_gapped_left_part_beyond_the_pair_table(name, offsets, localization, mops):
+    """A gapped left part that spans 9 or 10 bases: the find kernel works from a pair table over the first 8 bases (a superset of
+    the windows in the table), the expand kernel marks the false hits.  Full scan, lists, subset + recount and the OOPS scan
+    against the oracle."""
+    import oracle_lib as ol
+    import xxmotif_b200 as xb
+    from xxmotif_b200 import hostprep
+    ctx, octx, oset, onm, bg, bgl, n, codes = _setup(4000, 350, 29, False, mops, localization)
+    try:
+        total, _, mxl, _ = ctx.seqset_info()
+        nent = len(n)
+        prof = np.tile(hostprep.TATA_PROFILE, (1, 2))[:, :len(offsets)].copy()
+        prof[:, 8:] = np.array([[55, 20, 15, 10], [15, 50, 15, 20], [20, 20, 10, 50], [10, 10, 60, 20]], dtype=np.float64)[:, :max(0, len(offsets) - 8)]
+        pwm_c, cols_c = hostprep.profile_pwm(prof)
+        first = 5
+        cols = (first + np.asarray(offsets)).astype(np.int32)
+        pwm = np.asarray(pwm_c, dtype=np.float64).reshape(31, 5).copy()
+        src = pwm[cols_c[0]:cols_c[0] + len(offsets)].copy()
+        pwm[:] = 0.0
+        pwm[1:, 1:] = np.log(0.25)
+        for k, c in enumerate(cols):
+            pwm[c] = src[k]
+        enr = (1 - int(cols[0]) + 1, mxl - int(cols[0]) + 1)
+        ctx.reinitialize(pwm, cols, nent, int(total[nent]))
+        tab = ol.Tables(pwm, cols, nent, int(total[nent]), bgl, onm)
+        assert tab.error == 0 and tab.nparts == (2 if len(offsets) > 8 else 1)
+        nb, nbest, mx = ctx.scan_full(nent, enr)
+        octx.scan_full(tab, cols, nent, enr, True)
+        assert (nb, nbest, mx) == (octx.nbSites, octx.nbBestSites, octx.maxSites) and nbest > 500
+        _site_eq("best", ctx.get_sites(xb.LIST_BEST_STARTPOS, xb.ORDER_BY_SCORE), octx.best())
+        _site_eq("sites", ctx.get_sites(xb.LIST_SORTED_SITES, xb.ORDER_AS_IS), octx.sites())
+        ok, nbm, bp, new = ctx.update_pwm_with_best_subset(xb.LIST_SORTED_SITES, pwm, int(cols[0]), nent, False, 0.1)
+        ook, onbm, obp, onew = octx.update_pwm_with_best_subset(0, pwm, cols, nent, 0, False, 0.1)
+        assert (ok, nbm, bp) == (ook, onbm, obp) and (new[5:] == onew[5:]).all()
+        st = ctx.stats()
+        assert st["last_scan_hits"] >= nbest  # the find kernel's hits are a superset of the candidates
+    finally:
+        ctx.close()
