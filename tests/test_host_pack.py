@@ -65,16 +65,18 @@ def test_pack_rejects_bad_code():
         hostprep.pack_seqset(n, codes, True)
 
 
-def test_pack_sse2_path_in_subprocess():
-    """The AVX2 variant is chosen at load time; XXM_PACK_NO_AVX2 forces the SSE2 one, checked in a fresh process."""
+@pytest.mark.parametrize("variant", ["XXM_PACK_NO_AVX512", "XXM_PACK_NO_AVX2"])
+def test_pack_other_simd_paths_in_subprocess(variant):
+    """The widest variant the CPU has (AVX-512 BW, else AVX2, else SSE2) is chosen at load time; XXM_PACK_NO_AVX512 forces the
+    AVX2 one, XXM_PACK_NO_AVX2 the SSE2 one, each checked in a fresh process."""
     import os
     import subprocess
     import sys
-    if os.environ.get("XXM_PACK_NO_AVX2"):
-        pytest.skip("already the SSE2 run")
-    env = dict(os.environ, XXM_PACK_NO_AVX2="1")
+    if os.environ.get("XXM_PACK_NO_AVX2") or os.environ.get("XXM_PACK_NO_AVX512"):
+        pytest.skip("already a forced-variant run")
+    env = dict(os.environ, **{variant: "1"})
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_host_pack.py"), "-q", "-x", "-k", "layout or runs or bad"],
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_host_pack.py"), "-q", "-x", "-k", "layout or runs or bad or threads"],
                        env=env, cwd=root, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
 

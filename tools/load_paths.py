@@ -19,7 +19,10 @@ pinned = torch.from_numpy(codes).pin_memory()
 codes = pinned.numpy()
 ctx = xb.Context(0)
 out = {"what": "xxm_load_seqset wall ms, %d x 1000 bp, pinned input, cpu_count %d" % (nseq, os.cpu_count() or 0), "runs": []}
-for path, threads in (("host", 12), ("host", 6), ("device", 1), ("hybrid", 1), ("hybrid", 2), ("hybrid", 3), ("hybrid", 4), ("hybrid", 5), ("host", 3)):
+cases = [("host", 12), ("host", 6), ("device", 1), ("hybrid", 1), ("hybrid", 2), ("hybrid", 3), ("hybrid", 4), ("hybrid", 5), ("host", 3)]
+if len(sys.argv) > 2:
+    cases = [(c.split(":")[0], int(c.split(":")[1])) for c in sys.argv[2:]]
+for path, threads in cases:
     os.environ["XXM_LOAD_PATH"] = path
     os.environ["XXM_PACK_THREADS"] = str(threads)
     best = 1e9

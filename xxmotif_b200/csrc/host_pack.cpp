@@ -129,6 +129,55 @@ __attribute__((target("avx2"))) void pack_blocks_avx2(const uint8_t* r, uint32_t
 	*bad |= static_cast<uint32_t>(_mm256_movemask_epi8(badv));
 }
 const bool g_haveAvx2 = __builtin_cpu_supports("avx2") && std::getenv("XXM_PACK_NO_AVX2") == nullptr;
+
+// 512-bit registers, 64 bases (two words) per step, chosen at run time when the CPU has AVX-512 BW: the N mask of 64 bases IS the
+// compare mask (no movemask), the four 2-bit codes of a byte group are folded by two multiply-adds (b0 + 4 b1, then + 16 (b2 + 4 b3))
+// and a truncating move; the tail of a sequence is a masked load, so nothing is read beyond the sequence.
+template <bool kStream>
+__attribute__((target("avx512f,avx512bw,avx512vl,popcnt,sse4.1"))) void pack_blocks_avx512(const uint8_t* r, uint32_t n0, uint64_t* c, uint32_t* m, uint64_t* nN, uint32_t* bad) {
+	const __m512i zero = _mm512_setzero_si512(), one = _mm512_set1_epi8(1), three = _mm512_set1_epi8(3), four = _mm512_set1_epi8(4);
+	const __m512i mul4 = _mm512_set1_epi16(0x0401), mul16 = _mm512_set1_epi32(0x00100001);
+	const uint32_t nwords = (n0 + 31) / 32;
+	uint64_t ncount = 0;
+	__mmask64 badm = 0;
+	uint32_t w = 0;
+	for (uint64_t off = 0; off < n0; off += 64, w += 2) {
+		const uint64_t rem = n0 - off;
+		__m512i v;
+		if (rem >= 64) {
+			_mm_prefetch(reinterpret_cast<const char*>(r + off + 1024), _MM_HINT_T0);
+			v = _mm512_loadu_si512(reinterpret_cast<const void*>(r + off));
+		} else {
+			v = _mm512_maskz_loadu_epi8((1ull << rem) - 1ull, reinterpret_cast<const void*>(r + off));  // beyond the sequence: reads as N
+		}
+		const __mmask64 z = _mm512_cmpeq_epi8_mask(v, zero);
+		badm |= _mm512_cmpgt_epu8_mask(v, four);
+		ncount += static_cast<uint64_t>(__builtin_popcountll(static_cast<unsigned long long>(z)));
+		const __m512i x = _mm512_and_si512(_mm512_subs_epu8(v, one), three);
+		const __m512i y = _mm512_madd_epi16(_mm512_maddubs_epi16(x, mul4), mul16);
+		const __m128i packed = _mm512_cvtepi32_epi8(y);  // 16 bytes: code words w and w + 1
+		const uint64_t zm = static_cast<uint64_t>(z);
+		const long long c0 = _mm_cvtsi128_si64(packed), c1 = _mm_extract_epi64(packed, 1);
+		const bool two = w + 2 <= nwords;  // else: an odd last word
+		if (kStream) {
+			_mm_stream_si64(reinterpret_cast<long long*>(c + w), c0);
+			_mm_stream_si32(reinterpret_cast<int*>(m + w), static_cast<int>(static_cast<uint32_t>(zm)));
+			if (two) {
+				_mm_stream_si64(reinterpret_cast<long long*>(c + w + 1), c1);
+				_mm_stream_si32(reinterpret_cast<int*>(m + w + 1), static_cast<int>(static_cast<uint32_t>(zm >> 32)));
+			}
+		} else {
+			c[w] = static_cast<uint64_t>(c0);
+			m[w] = static_cast<uint32_t>(zm);
+			if (two) { c[w + 1] = static_cast<uint64_t>(c1); m[w + 1] = static_cast<uint32_t>(zm >> 32); }
+		}
+	}
+	const uint64_t padded = static_cast<uint64_t>((n0 + 63) / 64) * 64 - n0;  // positions beyond the sequence counted as N above
+	*nN += ncount - padded;
+	if (badm) *bad |= 1u;
+}
+const bool g_haveAvx512 = __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl") && std::getenv("XXM_PACK_NO_AVX512") == nullptr &&
+                          std::getenv("XXM_PACK_NO_AVX2") == nullptr;
 #endif
 
 // order of the 32 two-bit groups of x reversed
@@ -154,7 +203,23 @@ uint32_t pack_sequence(const uint8_t* raw, uint32_t n0, bool revcomp, uint64_t* 
 	const uint32_t fwdWords = fullBlocks + (tail ? 1u : 0u);
 	PackAcc A;
 #if defined(XXM_HAVE_AVX2_DISPATCH)
-	if (g_haveAvx2 && (tail == 0 || canOverread)) {
+	if (g_haveAvx512) {
+		uint64_t nN = 0;
+		uint32_t b = 0;
+		if (revcomp) {
+			pack_blocks_avx512<false>(raw, n0, codes, nmask, &nN, &b);  // the reverse strand reads these words back
+			A.nN = nN + (tail ? 32u - tail : 0u);  // the common code below takes the padding of the tail word off again
+			A.bad = b;
+		} else {
+			pack_blocks_avx512<true>(raw, n0, codes, nmask, &nN, &b);
+			for (uint64_t k = fwdWords; k < words; ++k) {
+				_mm_stream_si64(reinterpret_cast<long long*>(codes + k), 0);
+				_mm_stream_si32(reinterpret_cast<int*>(nmask + k), -1);
+			}
+			if (b) *bad = true;
+			return n0 - static_cast<uint32_t>(nN);
+		}
+	} else if (g_haveAvx2 && (tail == 0 || canOverread)) {
 		if (revcomp) {
 			pack_blocks_avx2<false>(raw, fullBlocks, tail, codes, nmask, &A.nN, &A.bad);  // the reverse strand reads these words back
 		} else {
