@@ -283,6 +283,12 @@ def time_workload(ctx, w, n, codes, neg, ref, steps, peak):
 
     run(3, False)
     ctx.step_phases(reset=True)
+    if os.environ.get("XXM_TRACE"):  # per-call wall times of the timed steps only (the dump clears what the warm-up collected)
+        sys.stderr.write("---- warm-up calls\n")
+        sys.stderr.flush()
+        ctx.L.xxm_trace_dump()
+        sys.stderr.write("---- timed steps\n")
+        sys.stderr.flush()
     import torch
     torch.cuda.synchronize()
     l0 = ctx.stats()["launches"]

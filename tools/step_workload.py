@@ -26,6 +26,9 @@ def main():
     t0 = time.perf_counter()
     r = bench.time_workload(ctx, wl, n, codes, neg, ref, steps, 6556.5)
     print(name, nseq, "ms/step %.3f" % r["ms_per_step"], "value %.3e" % r["value"], r["scan"], r["host_phases_us"], "total %.1f s" % (time.perf_counter() - t0))
+    if os.environ.get("XXM_TRACE"):
+        from xxmotif_b200 import capi
+        capi.load_library().xxm_trace_dump()
     ctx.close()
 
 
