@@ -586,7 +586,7 @@ def _ours(a):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
-                "kernel": "full scan = k_scan5 (find, dead windows cleared, per-chunk counts) + k_tile_scan + k_expand6 (ordered site records)", "kernel_ms": avg_ms,
+                "kernel": "full scan = k_scan5 (find, dead windows cleared, per-chunk counts) + k_tile_scan + %s (ordered site records)" % ("k_expand6" if os.environ.get("XXM_SCAN_GEN") == "6" else "k_expand7"), "kernel_ms": avg_ms,
                 "find_ms": sum(find_ms) / len(find_ms), "expand_ms": avg_ms - sum(find_ms) / len(find_ms), "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback 6.65 TB/s",
                 "algorithmic_bytes": "0.375 B per base (sum of sequence lengths) + 12 B per hit = %.1f MB per scan" % (alg_bytes / 1e6), "step_share": avg_ms / ms_per_step,
                 # the same figure against the nominal 8 TB/s, and in the reference's own representation (1 B per base)

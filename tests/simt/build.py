@@ -1,0 +1,43 @@
+"""TEST INFRASTRUCTURE ONLY: compiles the product's kernel SOURCES for the SIMT emulator (simt_emu.h).
+
+The only rewrite of the sources is textual and mechanical: `extern __shared__` -> `extern` (the harness defines the arrays) and
+`__shared__` -> `static` (one block runs at a time).  Everything else -- intrinsics, collectives, launch geometry -- is the
+kernel's own code, compiled by g++ against the emulator's stand-in for <cuda_runtime.h>."""
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "xxmotif_b200", "csrc")
+BUILD = os.path.join(HERE, "build")
+KERNEL_HEADERS = ["xxm_device.cuh", "xxm_kernels.cuh", "xxm_scan4.cuh", "xxm_scan5.cuh", "xxm_scan6.cuh", "xxm_scan7.cuh"]
+
+
+def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp")):
+    os.makedirs(BUILD, exist_ok=True)
+    newest = 0.0
+    for h in KERNEL_HEADERS:
+        src = os.path.join(CSRC, h)
+        text = re.sub(r"extern __shared__ (__align__\(\d+\) )?", "extern ", open(src).read()).replace("__shared__", "static")
+        dst = os.path.join(BUILD, h)
+        if not os.path.exists(dst) or open(dst).read() != text:
+            with open(dst, "w") as fh:
+                fh.write(text)
+        newest = max(newest, os.path.getmtime(dst))
+    exe = os.path.join(BUILD, target)
+    deps = [os.path.join(HERE, target + ".cpp"), os.path.join(HERE, "simt_emu.h")] + [os.path.join(CSRC, s) for s in extra_sources]
+    newest = max([newest] + [os.path.getmtime(d) for d in deps])
+    if os.path.exists(exe) and os.path.getmtime(exe) >= newest:
+        return exe
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable",
+           "-I", BUILD, "-I", os.path.join(HERE, "shim"), "-I", CSRC, os.path.join(HERE, target + ".cpp")]
+    cmd += [os.path.join(CSRC, s) for s in extra_sources] + ["-o", exe, "-lpthread"]
+    subprocess.check_call(cmd)
+    return exe
+
+
+if __name__ == "__main__":
+    import sys
+    exe = build()
+    sys.exit(subprocess.call([exe] + sys.argv[1:]))

@@ -1,0 +1,39 @@
+"""The full-scan kernels themselves -- k_dead_mask, k_scan5 (find, both mask orders), k_tile_scan, k_expand6 and k_expand7,
+compiled from their CUDA sources (xxmotif_b200/csrc/*.cuh) for the SIMT emulator of tests/simt/ -- against a brute-force
+enumeration of the reference's window loop (StartPosUpdater-inl.h:70-140, table membership branch_and_bound-inl.h:386-392):
+bit-exact (sequence, position, class) records in scan order.  Runs without a GPU; the emulator is test infrastructure only
+(nothing under xxmotif_b200/ includes it, and libxxmotif_gpu.so has no CPU path)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "simt"))
+import build as simt_build  # noqa: E402
+
+CASES = ["tile_scan", "uniform_1kb", "ragged_N", "revcomp_ragged", "dense_lowcomplexity", "gapped_6cols", "five_columns", "tiny", "every_warp_dense",
+         "ten_tiles_uniform", "one_word_sequences", "small_capacity"]
+
+
+@pytest.fixture(scope="module")
+def exe():
+    return simt_build.build()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_scan_kernels_under_emulator(exe, case):
+    r = subprocess.run([exe, case], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
+
+
+def test_product_does_not_reference_the_emulator():
+    """the emulator hooks in the kernel sources are compile-time (#ifdef XXM_SIMT_EMU) and the library is built without them"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mk = open(os.path.join(root, "xxmotif_b200", "csrc", "Makefile")).read()
+    assert "XXM_SIMT_EMU" not in mk and "simt" not in mk
+    for dirpath, _, files in os.walk(os.path.join(root, "xxmotif_b200")):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".inc", ".h", ".cuh")):
+                assert "simt_emu.h" not in open(os.path.join(dirpath, f), errors="ignore").read(), f

@@ -8,7 +8,7 @@ timeout 300 python bench.py --impl reference > gpurun_out/${R}_bench_reference.j
 # every launch of a short bench command (steps, one e2e load + step, the whole refinement run)
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/${R}_launches_bench_steps2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-matrix --e2e-steps 1 > gpurun_out/ncu_bench.log 2>&1
 # one launch of each kernel of a step, full set
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_scan5|k_tile_scan|k_expand6|k_select_cls_fwd|k_count_pwm3" -s 10 -c 5 -o gpurun_out/${R}_step_kernels python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-refine-run --no-matrix --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_scan5|k_tile_scan|k_expand7|k_select_cls_fwd|k_count_pwm3" -s 10 -c 5 -o gpurun_out/${R}_step_kernels python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-refine-run --no-matrix --e2e-steps 1 > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 ncu -i gpurun_out/${R}_step_kernels.ncu-rep --page raw --csv > gpurun_out/${R}_ncu_full_step_kernels_raw.csv
 ncu -i gpurun_out/${R}_step_kernels.ncu-rep --page details > gpurun_out/${R}_ncu_full_step_kernels_details.txt

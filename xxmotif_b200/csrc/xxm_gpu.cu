@@ -32,6 +32,7 @@
 #include "xxm_scan4.cuh"
 #include "xxm_scan5.cuh"
 #include "xxm_scan6.cuh"
+#include "xxm_scan7.cuh"
 #include "xxm_tables_device.cuh"
 #include "pair_table.h"
 #include "nccl_dyn.h"
@@ -272,6 +273,7 @@ struct xxm_ctx {
 	std::vector<uint32_t> h_pairIds, h_pairTab;
 	bool pairOK = false;           // the pair table represents the left table exactly: k_scan5, else k_scan4
 	bool forceGenericScan = false; // tests: always take the generic find kernel
+	int scanGen = 7;               // 7: window-order masks + k_expand7 (xxm_scan7.cuh); 6: even/odd masks + k_expand6
 	DevBuf<uint64_t> d_rawOff, d_layoutSums;
 	DevBuf<int32_t> d_notX, d_n;
 	std::vector<int32_t> notX;  // residues that are not N, per sequence (host_pack.h)
@@ -395,7 +397,8 @@ extern "C" int xxm_create(int device, xxm_ctx** out) {
 		return 1;
 	}
 	// opt-in shared-memory sizes are per DEVICE, not per process: set them for the device of every new context
-	if (cudaFuncSetAttribute(k_scan5, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairTabWords * 4) != cudaSuccess ||
+	if (cudaFuncSetAttribute(k_scan5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairTabWords * 4) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_scan5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairTabWords * 4) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_scan4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 32 * 1024) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_scan4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 16) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_scan4<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100) != cudaSuccess ||
@@ -410,6 +413,8 @@ extern "C" int xxm_create(int device, xxm_ctx** out) {
 	ctx->opt.maxSeqCount = 1000;
 	ctx->opt.overrepCorrection = 1.05;
 	ctx->forceGenericScan = std::getenv("XXM_FORCE_GENERIC_SCAN") != nullptr;  // tests: exercise k_scan4 on every model
+	// XXM_SCAN_GEN=6: the previous generation of the pair-table scan (even/odd masks + k_expand6), kept for A/B timing and tests
+	if (const char* g = std::getenv("XXM_SCAN_GEN")) ctx->scanGen = (std::atoi(g) == 6) ? 6 : 7;
 	*out = ctx;
 	return 0;
 }

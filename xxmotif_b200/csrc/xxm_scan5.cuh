@@ -35,13 +35,25 @@ __device__ __forceinline__ uint32_t pair_lookup(const uint32_t (&r)[5], const ui
 	return *reinterpret_cast<const uint32_t*>(tab + (t & 0x1FF80u));  // tab already points at this lane's column
 }
 
+// prmt.b32 in its default mode: nibble n of the selector picks byte (n & 7) of {b, a}; bit 3 of the nibble replicates the sign of
+// that byte instead.  (__byte_perm documents only the three low bits of a nibble, hence the PTX; XXM_SIMT_EMU: tests/simt.)
+template <uint32_t kSel>
+__device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b) {
+#ifdef XXM_SIMT_EMU
+	return emu::prmt(a, b, kSel);
+#else
+	uint32_t u;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(u) : "r"(a), "r"(b), "n"(kSel));
+	return u;
+#endif
+}
+
 template <int S>
 __device__ __forceinline__ uint32_t gather_flags(uint32_t acc, uint32_t tLo, uint32_t tHi) {
 	// bytes 3 / 1 of a T word hold the sums of its even / odd window; bit 7 of a sum is the hit flag.  PRMT with bit 3 of a
 	// selector nibble set replicates the sign of the selected byte: U = [odd(lo), odd(hi), even(lo), even(hi)], every byte
 	// 0x00 or 0xFF, and one and-or picks bit S of every byte
-	uint32_t u;
-	asm("prmt.b32 %0, %1, %2, 0xFBD9;" : "=r"(u) : "r"(tLo), "r"(tHi));
+	const uint32_t u = prmt_sx<0xFBD9>(tLo, tHi);
 	return acc | (u & (0x01010101u << S));
 }
 
@@ -61,8 +73,34 @@ __device__ __forceinline__ uint32_t scan5_word(const uint32_t (&e)[34]) {
 	return acc;
 }
 
+// The same 32 flags in WINDOW order (bit n = window n of the word), for the seventh-generation expand kernel, which then needs
+// no even/odd -> window conversion (13 instructions per word there against 3 here).  Windows 8B + s, B = 0..3, share bit s of
+// their bytes; pair p (windows 2p, 2p + 1) sits in T word p.  For s' = 0..3 one PRMT gathers the four flags of pairs s', s' + 4
+// into accA -- the even windows at bit 2s' of bytes 0 / 1 (their final place), the odd ones at bit 2s' + 1 of bytes 2 / 3 (two
+// bytes too high) -- and one those of pairs s' + 8, s' + 12 into accB -- even windows in bytes 2 / 3 (final), odd ones in bytes
+// 0 / 1 (two bytes too low); two byte permutes at the end put the odd windows in place.
+template <int S>
+__device__ __forceinline__ void gather_flags_nat(uint32_t& accA, uint32_t& accB, uint32_t t0, uint32_t t4, uint32_t t8, uint32_t t12) {
+	accA |= prmt_sx<0xD9FB>(t0, t4) & ((0x00000101u << (2 * S)) | (0x01010000u << (2 * S + 1)));
+	accB |= prmt_sx<0xFBD9>(t8, t12) & ((0x01010000u << (2 * S)) | (0x00000101u << (2 * S + 1)));
+}
+
+template <int G>
+__device__ __forceinline__ uint32_t scan5_word_nat(const uint32_t (&e)[34]) {
+	uint32_t accA = 0, accB = 0;
+#define XXM_T(j) (e[(j)] + (e[(j) + 2] << 8))
+	gather_flags_nat<0>(accA, accB, XXM_T(G + 0), XXM_T(G + 4), XXM_T(G + 8), XXM_T(G + 12));
+	gather_flags_nat<1>(accA, accB, XXM_T(G + 1), XXM_T(G + 5), XXM_T(G + 9), XXM_T(G + 13));
+	gather_flags_nat<2>(accA, accB, XXM_T(G + 2), XXM_T(G + 6), XXM_T(G + 10), XXM_T(G + 14));
+	gather_flags_nat<3>(accA, accB, XXM_T(G + 3), XXM_T(G + 7), XXM_T(G + 11), XXM_T(G + 15));
+#undef XXM_T
+	return __byte_perm(accA, accB, 0x7610) | __byte_perm(accA, accB, 0x5432);
+}
+
 // dead: windows that cannot be a site whatever the PWM (k_dead_mask, xxm_scan6.cuh), cleared here so that the masks are
 // final; chunkCount[c] = hits of the warp's 64 words, tileCount[c / 16] += the same (one atomic per chunk).
+// kNatural: masks (and the dead-window masks read) in window order instead of even/odd order.
+template <bool kNatural>
 __global__ void __launch_bounds__(kScan5Threads, 1) k_scan5(const uint64_t* __restrict__ codes, const uint32_t* __restrict__ pairTab,
                                                            const uint32_t* __restrict__ dead, uint32_t* __restrict__ hitmask,
                                                            uint32_t* __restrict__ chunkCount, uint32_t* __restrict__ tileCount, uint32_t scanWords) {
@@ -106,7 +144,7 @@ __global__ void __launch_bounds__(kScan5Threads, 1) k_scan5(const uint64_t* __re
 		e[24] = pair_lookup<24>(r, tab); e[25] = pair_lookup<25>(r, tab); e[26] = pair_lookup<26>(r, tab); e[27] = pair_lookup<27>(r, tab);
 		e[28] = pair_lookup<28>(r, tab); e[29] = pair_lookup<29>(r, tab); e[30] = pair_lookup<30>(r, tab); e[31] = pair_lookup<31>(r, tab);
 		e[32] = pair_lookup<32>(r, tab); e[33] = pair_lookup<33>(r, tab);
-		uint32_t h0 = scan5_word<0>(e), h1 = scan5_word<16>(e);
+		uint32_t h0 = kNatural ? scan5_word_nat<0>(e) : scan5_word<0>(e), h1 = kNatural ? scan5_word_nat<16>(e) : scan5_word<16>(e);
 		uint32_t cnt = 0;
 		if (w < scanWords) {
 			h0 &= ~k.d.x;
@@ -144,7 +182,18 @@ __device__ __forceinline__ uint32_t eo_to_natural(uint32_t m) {
 // One step of the hit extraction for one word, branch free: if r != 0, clear its highest set bit j, move the shared-memory
 // cursor back by one 16-bit slot and store tagk + j there; if r == 0 nothing happens (bfind gives 0xFFFFFFFF, the shift
 // clamps to 0, the store and the cursor update are predicated off).
-__device__ __forceinline__ void pop_msb(uint32_t& r, uint32_t& cursor, uint32_t tagk) {
+#ifdef XXM_SIMT_EMU
+using smem_addr_t = uintptr_t;  // the emulator's "shared memory" lives in the host address space
+__device__ __forceinline__ void pop_msb(uint32_t& r, smem_addr_t& cursor, uint32_t tagk) {
+	if (r == 0) return;
+	const int j = 31 - __builtin_clz(r);
+	r ^= 1u << j;
+	cursor -= 2;
+	*reinterpret_cast<uint16_t*>(cursor) = static_cast<uint16_t>(tagk + static_cast<uint32_t>(j));
+}
+#else
+using smem_addr_t = uint32_t;
+__device__ __forceinline__ void pop_msb(uint32_t& r, smem_addr_t& cursor, uint32_t tagk) {
 	asm volatile(
 		"{\n"
 		".reg .pred p;\n"
@@ -163,6 +212,7 @@ __device__ __forceinline__ void pop_msb(uint32_t& r, uint32_t& cursor, uint32_t 
 		: "r"(tagk)
 		: "memory");
 }
+#endif
 
 constexpr int kExpand5Threads = 256;
 constexpr int kExpand5Queue = 4096;
@@ -297,10 +347,10 @@ __global__ void __launch_bounds__(kExpand5Threads) k_expand5(SeqStream S, Model 
 		// the four words of the thread in lock step, highest window first, every word filling its queue range backwards: the
 		// trip count of a warp is the largest hit count of any of its 128 words
 		uint32_t r0 = h[0], r1 = h[1], r2 = h[2], r3 = h[3];
-		uint32_t q0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_q + myOff)) + 2u * __popc(r0);  // one past the last slot of word 0
-		uint32_t q1 = q0 + 2u * __popc(r1);
-		uint32_t q2 = q1 + 2u * __popc(r2);
-		uint32_t q3 = q2 + 2u * __popc(r3);
+		smem_addr_t q0 = static_cast<smem_addr_t>(__cvta_generic_to_shared(s_q + myOff)) + 2u * __popc(r0);  // one past the last slot of word 0
+		smem_addr_t q1 = q0 + 2u * __popc(r1);
+		smem_addr_t q2 = q1 + 2u * __popc(r2);
+		smem_addr_t q3 = q2 + 2u * __popc(r3);
 		const uint32_t tag = static_cast<uint32_t>(4 * tid) << 5;
 		while (r0 | r1 | r2 | r3) {
 			pop_msb(r0, q0, tag);

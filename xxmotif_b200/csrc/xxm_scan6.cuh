@@ -38,7 +38,8 @@ struct DeadCols {
 	int coloff[32];
 };
 
-// dead[w] (even/odd order): window j of word w has an N under a match column.  Words [0, nwords + 8).
+// dead[w] (even/odd order, or window order with kNatural): window j of word w has an N under a match column.  Words [0, nwords + 8).
+template <bool kNatural>
 __global__ void k_dead_mask(const uint32_t* __restrict__ nmask, uint32_t nwords, DeadCols C, uint32_t* __restrict__ dead) {
 	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
 	if (w >= nwords + 8) return;
@@ -55,7 +56,7 @@ __global__ void k_dead_mask(const uint32_t* __restrict__ nmask, uint32_t nwords,
 	} else {
 		for (int c = 1; c < C.L; ++c) x |= mm >> C.coloff[c];
 	}
-	dead[w] = natural_to_eo(static_cast<uint32_t>(x));
+	dead[w] = kNatural ? static_cast<uint32_t>(x) : natural_to_eo(static_cast<uint32_t>(x));
 }
 
 // exclusive prefix over the tile counts.  Block b owns tiles [1024 b, 1024 b + 1024): it adds up everything before them
@@ -199,22 +200,28 @@ __global__ void __launch_bounds__(kExpand6Threads, 6) k_expand6(SeqStream S, Mod
 	uint32_t* pseq = io.oseq + base;
 	uint32_t* ppos = io.opos + base;
 	uint32_t* pvid = io.ovidx + base;
+#ifndef XXM_SIMT_EMU
 	asm volatile("" : "+l"(pseq), "+l"(ppos), "+l"(pvid));  // keep the three bases in registers: one IMAD.WIDE per store instead of 64-bit adds per record
+#endif
 	auto emit = [&](const HitRec& rec, uint32_t q) {
 		if (q < room) {
+#ifdef XXM_SIMT_EMU
+			pseq[q] = rec.seq; ppos[q] = rec.pos; pvid[q] = rec.v;
+#else
 			asm volatile("st.global.u32 [%0], %1;" ::"l"(pseq + q), "r"(rec.seq) : "memory");
 			asm volatile("st.global.u32 [%0], %1;" ::"l"(ppos + q), "r"(rec.pos) : "memory");
 			asm volatile("st.global.u32 [%0], %1;" ::"l"(pvid + q), "r"(rec.v) : "memory");
+#endif
 		}
 	};
 	if (mine <= static_cast<uint32_t>(kWarpQueue)) {
 		// the four words of the lane in lock step, highest window first, every word filling its queue range backwards: the
 		// trip count of the warp is the largest hit count of any of its 128 words
 		uint32_t r0 = h[0], r1 = h[1], r2 = h[2], r3 = h[3];
-		uint32_t q0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_q + myOff)) + 2u * __popc(r0);  // one past the last slot of word 0
-		uint32_t q1 = q0 + 2u * __popc(r1);
-		uint32_t q2 = q1 + 2u * __popc(r2);
-		uint32_t q3 = q2 + 2u * __popc(r3);
+		smem_addr_t q0 = static_cast<smem_addr_t>(__cvta_generic_to_shared(s_q + myOff)) + 2u * __popc(r0);  // one past the last slot of word 0
+		smem_addr_t q1 = q0 + 2u * __popc(r1);
+		smem_addr_t q2 = q1 + 2u * __popc(r2);
+		smem_addr_t q3 = q2 + 2u * __popc(r3);
 		const uint32_t tag = static_cast<uint32_t>(4 * lane) << 5;
 		while (r0 | r1 | r2 | r3) {
 			pop_msb(r0, q0, tag);
