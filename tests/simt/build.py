@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "xxmotif_b200", "csrc")
 BUILD = os.path.join(HERE, "build")
-KERNEL_HEADERS = ["xxm_device.cuh", "xxm_kernels.cuh", "xxm_scan4.cuh", "xxm_scan5.cuh", "xxm_scan6.cuh", "xxm_scan7.cuh"]
+KERNEL_HEADERS = ["xxm_device.cuh", "xxm_kernels.cuh", "xxm_scan4.cuh", "xxm_scan5.cuh", "xxm_scan6.cuh", "xxm_scan7.cuh", "xxm_select2.cuh", "xxm_select3.cuh",
+                  "xxm_select4.cuh"]
 
 
 def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp")):
@@ -39,5 +40,8 @@ def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp")):
 
 if __name__ == "__main__":
     import sys
-    exe = build()
-    sys.exit(subprocess.call([exe] + sys.argv[1:]))
+    target = "scan_emu"
+    args = sys.argv[1:]
+    if args and args[0] in ("scan_emu", "step_emu"):
+        target, args = args[0], args[1:]
+    sys.exit(subprocess.call([build(target)] + args))

@@ -1,0 +1,192 @@
+// TEST INFRASTRUCTURE ONLY (see simt_emu.h): the two kernels that follow the scan in a refinement step, from their CUDA sources
+// under the SIMT emulator:
+//   k_select_cls_fwd (xxm_select3.cuh)  updateMultOcc on class indices        vs the reference's greedy, StartPosUtils.h:12-28
+//   k_count_pwm3     (xxm_select2.cuh)  30-column context counts of the sites vs Motif::updateCounts, refinementPhase/Motif.cpp:617-672
+// on seeded candidate lists (clustered positions, ties of float-rounded p-values, N residues, sites at both sequence ends).
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "cuda_runtime.h"  // tests/simt/shim -> simt_emu.h
+
+#include "xxm_kernels.cuh"
+#include "xxm_select2.cuh"
+#include "xxm_select3.cuh"
+
+#include "host_pack.h"
+
+namespace xxm {
+alignas(16) uint8_t smem3[1 << 16];
+alignas(16) uint8_t smemM[1 << 16];
+uint32_t s_hist[1 << 14];
+uint32_t s_hs[1 << 14];
+}  // namespace xxm
+
+using namespace xxm;
+
+namespace {
+
+struct Case {
+	std::string name;
+	int nseq, lenLo, lenHi;
+	double hitFrac;   // candidates per window
+	int span;         // motif length (overlap distance)
+	uint32_t nval;    // score classes
+	uint32_t nSite;   // classes [0, nSite) are sites
+	double nFrac;
+	uint32_t seed;
+};
+
+int run_case(const Case& c) {
+	std::mt19937 rng(c.seed);
+	// ---- sequences
+	std::vector<int32_t> n(c.nseq);
+	for (auto& v : n) v = c.lenLo + static_cast<int>(rng() % static_cast<uint32_t>(c.lenHi - c.lenLo + 1));
+	uint64_t tot = 0;
+	for (int v : n) tot += static_cast<uint64_t>(v);
+	std::vector<uint8_t> raw(tot + 64);
+	for (uint64_t i = 0; i < tot; ++i) raw[i] = static_cast<uint8_t>((rng() % 1000 < c.nFrac * 1000) ? 0 : 1 + rng() % 4);
+	std::vector<uint32_t> wordOff(c.nseq + 1);
+	uint64_t w = 0;
+	bool uniform = true;
+	for (int i = 0; i < c.nseq; ++i) { wordOff[i] = static_cast<uint32_t>(w); w += stored_words(static_cast<uint32_t>(n[i]), false); uniform = uniform && n[i] == n[0]; }
+	wordOff[c.nseq] = static_cast<uint32_t>(w);
+	std::vector<uint64_t> codes(w + 2, 0ull);
+	std::vector<uint32_t> nmask(w + 2, 0xFFFFFFFFu);
+	std::vector<int32_t> notX(c.nseq);
+	if (pack_range(n.data(), 0, static_cast<uint32_t>(c.nseq), raw.data(), tot, false, codes.data(), nmask.data(), notX.data())) return 2;
+	SeqStream S{};
+	S.codes = codes.data(); S.nmask = nmask.data(); S.wordOff = wordOff.data(); S.len = n.data(); S.nwords = static_cast<uint32_t>(w); S.nent = c.nseq;
+	S.uniformWps = uniform ? wordOff[1] - wordOff[0] : 0; S.uniformLen = uniform ? n[0] : 0;
+	// ---- candidates in scan order: clustered (a hit raises the chance of a hit two positions later, like TATATA)
+	std::vector<uint32_t> seq, pos, vidx;
+	for (int q = 0; q < c.nseq; ++q) {
+		int boost = 0;
+		for (int p = 1; p + c.span - 1 <= n[q]; ++p) {
+			const double pr = c.hitFrac * (boost > 0 ? 12.0 : 1.0);
+			if (boost > 0) --boost;
+			if ((rng() % 100000) < pr * 100000) {
+				seq.push_back(static_cast<uint32_t>(q) + 1);
+				pos.push_back(static_cast<uint32_t>(p));
+				// mostly weak classes, sometimes a class that is not a site, sometimes "none"
+				uint32_t v = static_cast<uint32_t>(std::min<double>(c.nval - 1, std::abs(std::normal_distribution<double>(0.6 * c.nval, 0.3 * c.nval)(rng))));
+				if (rng() % 50 == 0) v = kNone;
+				vidx.push_back(v);
+				boost = 6;
+			}
+		}
+	}
+	const uint32_t ncand = static_cast<uint32_t>(seq.size());
+	// ---- a finalPval table that is non-decreasing in the class index, with neighbours that round to the same float
+	std::vector<double> fin(c.nval);
+	double v = 1e-9;
+	for (uint32_t k = 0; k < c.nval; ++k) {
+		v *= (rng() % 4 == 0) ? (1.0 + 1e-9) : (1.0 + (rng() % 1000) / 900.0);  // some steps are below float resolution
+		fin[k] = (k < c.nSite) ? std::min(v, 0.999999) : 1.0;
+	}
+	for (uint32_t k = 1; k < c.nval; ++k) fin[k] = std::max(fin[k], fin[k - 1]);
+	std::vector<uint16_t> thr(c.nval);
+	for (uint32_t k = 0; k < c.nval; ++k) {
+		const double f = static_cast<double>(static_cast<float>(fin[k]));
+		thr[k] = static_cast<uint16_t>(std::lower_bound(fin.begin(), fin.end(), f) - fin.begin());  // stage_class_order, xxm_gpu.cu
+	}
+	const uint32_t nSite = static_cast<uint32_t>(std::lower_bound(fin.begin(), fin.end(), 1.0) - fin.begin());
+	// ---- the reference's greedy (forward rule only): StartPosUtils.h:12-28, called for windows with finalPval < 1
+	std::vector<uint8_t> wantKeep(ncand, 0);
+	{
+		std::vector<uint32_t> kept;  // indices of kept entries
+		for (uint32_t i = 0; i < ncand; ++i) {
+			if (vidx[i] == kNone || vidx[i] >= c.nval) continue;
+			const double pv = fin[vidx[i]];
+			if (!(pv < 1.0)) continue;
+			if (!kept.empty()) {
+				const uint32_t l = kept.back();
+				if (seq[l] == seq[i] && pos[l] + static_cast<uint32_t>(c.span) >= pos[i]) {
+					if (static_cast<double>(static_cast<float>(fin[vidx[l]])) <= pv) continue;
+					kept.pop_back();
+				}
+			}
+			kept.push_back(i);
+		}
+		for (uint32_t i : kept) wantKeep[i] = 1;
+	}
+	// ---- the kernel
+	std::vector<uint8_t> keep(ncand + 16, 0xEE);
+	std::vector<uint16_t> kcls(ncand + 16, 0xEEEE);
+	std::vector<uint32_t> hist(c.nval, 0u), counters(8, 0u);
+	SelectClsIO f{};
+	f.seq = seq.data(); f.pos = pos.data(); f.vidx = vidx.data(); f.n = ncand; f.nDev = nullptr; f.length = c.span;
+	f.clsThr = thr.data(); f.nSite = nSite; f.nval = c.nval; f.keep = keep.data(); f.kcls = kcls.data(); f.counters = counters.data(); f.hist = hist.data();
+	const unsigned grid = std::max(1u, std::min(3u, (ncand + 256 * kSelChunk - 1) / (256 * kSelChunk)));
+	emu::launch(grid, 32 * kSel3Warps, [&] { k_select_cls_fwd(f); });
+	int bad = 0;
+	uint32_t nkept = 0;
+	std::vector<uint32_t> wantHist(c.nval, 0u);
+	for (uint32_t i = 0; i < ncand; ++i) {
+		if (wantKeep[i]) { ++nkept; ++wantHist[vidx[i]]; }
+		const uint16_t wc = wantKeep[i] ? static_cast<uint16_t>(vidx[i]) : static_cast<uint16_t>(0xFFFF);
+		if (keep[i] != wantKeep[i] || kcls[i] != wc) {
+			if (!bad) std::fprintf(stderr, "FAIL %s: entry %u (seq %u pos %u cls %u): keep %u kcls %u, expected %u %u\n", c.name.c_str(), i, seq[i], pos[i], vidx[i], keep[i], kcls[i], wantKeep[i], wc);
+			++bad;
+		}
+	}
+	if (counters[0] != nkept) { std::fprintf(stderr, "FAIL %s: %u kept sites counted, expected %u\n", c.name.c_str(), counters[0], nkept); ++bad; }
+	if (hist != wantHist) { std::fprintf(stderr, "FAIL %s: class histogram differs\n", c.name.c_str()); ++bad; }
+	// ---- recount: sites with class <= maxClass
+	const uint32_t maxClass = nSite / 2;
+	const int firstColumn = 12, shift = 0;
+	std::vector<unsigned long long> counts(31 * 5, 0ull), wantCounts(31 * 5, 0ull);
+	for (uint32_t i = 0; i < ncand; ++i) {
+		if (!wantKeep[i] || vidx[i] > maxClass) continue;
+		const int q = static_cast<int>(seq[i]) - 1;
+		const int g0 = static_cast<int>(pos[i]) + shift - firstColumn;  // 0-based offset of PWM column 1 inside the sequence
+		for (int j = 1; j <= 30; ++j) {
+			const int p = g0 + j - 1;
+			if (p < 0 || p >= n[q]) continue;
+			const uint32_t ww = wordOff[q] + static_cast<uint32_t>(p >> 5);
+			if ((nmask[ww] >> (p & 31)) & 1u) continue;
+			const uint32_t b = static_cast<uint32_t>(codes[ww] >> (2 * (p & 31))) & 3u;
+			++wantCounts[j * 5 + 1 + b];
+			++wantCounts[j * 5];
+		}
+	}
+	CountIO io{};
+	io.seq = seq.data(); io.pos = pos.data(); io.shift = shift; io.keep = keep.data(); io.n = ncand; io.kcls = kcls.data(); io.maxClass = maxClass;
+	io.firstColumn = firstColumn; io.counts = counts.data();
+	emu::launch(2, 256, [&] { k_count_pwm3(S, io); });
+	if (counts != wantCounts) {
+		std::fprintf(stderr, "FAIL %s: PWM counts differ\n", c.name.c_str());
+		++bad;
+	}
+	std::printf("%-20s %7u candidates, %6u kept, %3u classes (%u sites): %s\n", c.name.c_str(), ncand, nkept, c.nval, nSite, bad ? "DIFFERENT" : "identical");
+	return bad ? 1 : 0;
+}
+
+}  // namespace
+
+int main(int argc, char** argv) {
+	std::vector<Case> cases = {
+		{"clustered_uniform", 60, 1000, 1000, 0.02, 8, 300, 280, 0.0, 1},
+		{"ragged_short", 400, 8, 120, 0.06, 8, 50, 40, 0.02, 2},
+		{"long_motif", 40, 600, 900, 0.03, 26, 523, 500, 0.0, 3},
+		{"all_sites_dense", 20, 400, 400, 0.3, 8, 20, 20, 0.0, 4},
+		{"few_sites", 30, 500, 500, 0.05, 12, 200, 3, 0.01, 5},
+		{"tiny", 1, 9, 9, 0.5, 8, 4, 4, 0.0, 6},
+	};
+	int failed = 0, ran = 0;
+	for (const Case& c : cases) {
+		if (argc > 1) {
+			bool sel = false;
+			for (int i = 1; i < argc; ++i) sel = sel || c.name == argv[i];
+			if (!sel) continue;
+		}
+		failed += run_case(c) ? 1 : 0;
+		++ran;
+	}
+	std::printf("%d runs, %d failed\n", ran, failed);
+	return failed ? 1 : (ran ? 0 : 3);
+}

@@ -1,4 +1,4 @@
-"""The full-scan kernels themselves -- k_dead_mask, k_scan5 (find, both mask orders), k_tile_scan, k_expand6 and k_expand7,
+"""The kernels of a refinement step themselves -- k_dead_mask, k_scan5 (find, both mask orders), k_tile_scan, k_expand6 and k_expand7,
 compiled from their CUDA sources (xxmotif_b200/csrc/*.cuh) for the SIMT emulator of tests/simt/ -- against a brute-force
 enumeration of the reference's window loop (StartPosUpdater-inl.h:70-140, table membership branch_and_bound-inl.h:386-392):
 bit-exact (sequence, position, class) records in scan order.  Runs without a GPU; the emulator is test infrastructure only
@@ -16,9 +16,25 @@ CASES = ["tile_scan", "uniform_1kb", "ragged_N", "revcomp_ragged", "dense_lowcom
          "ten_tiles_uniform", "one_word_sequences", "small_capacity"]
 
 
+STEP_CASES = ["clustered_uniform", "ragged_short", "long_motif", "all_sites_dense", "few_sites", "tiny"]
+
+
 @pytest.fixture(scope="module")
 def exe():
     return simt_build.build()
+
+
+@pytest.fixture(scope="module")
+def step_exe():
+    return simt_build.build("step_emu", extra_sources=("host_pack.cpp",))
+
+
+@pytest.mark.parametrize("case", STEP_CASES)
+def test_select_and_count_kernels_under_emulator(step_exe, case):
+    """k_select_cls_fwd vs the reference's updateMultOcc greedy (StartPosUtils.h:12-28), k_count_pwm3 vs a column-by-column count"""
+    r = subprocess.run([step_exe, case], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
 
 
 @pytest.mark.parametrize("case", CASES)
