@@ -46,6 +46,7 @@ struct Case {
 	double keepFrac;      // fraction of all k-mers in the table (hit density)
 	bool lowComplexity;   // TATATA... stretches: dense hits, exercises the dense-warp path of the expand kernel
 	uint32_t seed;
+	int scanSeqs = 0;     // > 0: only the first scanSeqs sequences are scanned (posSetSize < nent: a negative set follows)
 };
 
 struct Rec { uint32_t seq, pos, v; };
@@ -153,7 +154,8 @@ Table make_table(const Case& c) {
 std::vector<Rec> brute_force(const Case& c, const Set& s, const Table& t) {
 	std::vector<Rec> out;
 	const int span = c.coloff.back() + 1;
-	for (int q = 0; q < c.nseq; ++q) {
+	const int nscan = c.scanSeqs > 0 ? c.scanSeqs : c.nseq;
+	for (int q = 0; q < nscan; ++q) {
 		const uint32_t w0 = s.wordOff[q];
 		const int n = s.len[q];
 		auto base = [&](int p, int& isN) {  // stored position p (0-based) of sequence q, from the packed stream
@@ -200,7 +202,7 @@ Result run_scan(const Case& c, const Set& s, const Table& t, int generation, uns
 		std::fprintf(stderr, "%s: the pair table cannot represent this table\n", c.name.c_str());
 		std::exit(2);
 	}
-	const uint32_t scanWords = s.wordOff[c.nseq];
+	const uint32_t scanWords = s.wordOff[c.scanSeqs > 0 ? c.scanSeqs : c.nseq];
 	const uint32_t ntiles = std::max<uint32_t>(1, (scanWords + kTileWords - 1) / kTileWords);
 	std::vector<uint32_t> dead(static_cast<size_t>(s.nwords) + 8, 0xDEADBEEFu), hitmask(static_cast<size_t>(scanWords) + 8, 0xDEADBEEFu);
 	std::vector<uint32_t> counts(static_cast<size_t>(ntiles) * (kChunksPerTile + 1), 0u);
@@ -291,6 +293,8 @@ int main(int argc, char** argv) {
 		{"ten_tiles_uniform", 320, 1000, 1000, 0.0, false, c8, 0.02, false, 11},
 		{"one_word_sequences", 300, 1, 31, 0.05, false, {0, 1, 2, 3}, 0.3, false, 8},
 		{"small_capacity", 40, 500, 500, 0.0, false, c8, 0.05, false, 9},
+		{"positive_set_prefix_ragged", 200, 20, 400, 0.01, false, c8, 0.04, false, 12, 77},
+		{"positive_set_prefix_uniform", 90, 300, 300, 0.0, false, c8, 0.04, false, 13, 31},
 	};
 	int failed = 0, ran = 0;
 	if (argc <= 1 || std::string(argv[1]) == "tile_scan") {

@@ -13,7 +13,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "sim
 import build as simt_build  # noqa: E402
 
 CASES = ["tile_scan", "uniform_1kb", "ragged_N", "revcomp_ragged", "dense_lowcomplexity", "gapped_6cols", "five_columns", "tiny", "every_warp_dense",
-         "ten_tiles_uniform", "one_word_sequences", "small_capacity"]
+         "ten_tiles_uniform", "one_word_sequences", "small_capacity", "positive_set_prefix_ragged", "positive_set_prefix_uniform"]
 
 
 STEP_CASES = ["clustered_uniform", "ragged_short", "long_motif", "all_sites_dense", "few_sites", "tiny"]

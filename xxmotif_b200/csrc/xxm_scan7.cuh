@@ -47,6 +47,9 @@ template <bool kFast, bool kUniform>
 __global__ void __launch_bounds__(kExpand7Threads, 6) k_expand7(SeqStream S, Model M, Expand6IO io) {
 	__shared__ __align__(16) uint64_t s_codesAll[kExpand7Warps][kE7WarpWords + 2];
 	__shared__ uint16_t s_qAll[kExpand7Warps][kE7Queue];
+	// ragged sets only: (sequence, position of window 0) of every word of the warp -- a lane looks its first word up once
+	// (find_seq: two or three dependent global loads) and walks on from there, instead of one look-up per hit in the resolve loop
+	__shared__ __align__(16) uint2 s_originAll[kUniform ? 1 : kExpand7Warps][kUniform ? 1 : kE7WarpWords];
 	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
 	const uint32_t tile = blockIdx.x;
 	uint64_t* s_codes = s_codesAll[wid];
@@ -87,6 +90,22 @@ __global__ void __launch_bounds__(kExpand7Threads, 6) k_expand7(SeqStream S, Mod
 	*reinterpret_cast<uint4*>(s_codes + 4 * lane) = ca;
 	*reinterpret_cast<uint4*>(s_codes + 4 * lane + 2) = cb;
 	if (lane == 0) s_codes[kE7WarpWords] = ctail;
+	uint2* s_origin = s_originAll[kUniform ? 0 : wid];
+	if (!kUniform && w0 < io.scanWords) {  // (words from scanWords on hold no hits)
+		uint32_t sq = find_seq(S, w0);
+		uint32_t next = S.wordOff[sq + 1];
+		uint32_t r = w0 - S.wordOff[sq];
+		uint2 org[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			org[k] = make_uint2(sq + 1, r * 32 + 1);
+			const uint32_t w = w0 + k + 1;
+			if (w == next && w < io.scanWords) { ++sq; r = 0; next = S.wordOff[sq + 1]; }  // (sequence sq + 1 starts at w < wordOff[nseq]: it exists)
+			else ++r;
+		}
+		*reinterpret_cast<uint4*>(s_origin + 4 * lane) = make_uint4(org[0].x, org[0].y, org[1].x, org[1].y);
+		*reinterpret_cast<uint4*>(s_origin + 4 * lane + 2) = make_uint4(org[2].x, org[2].y, org[3].x, org[3].y);
+	}
 	const uint32_t p0 = __popc(h[0]), p1 = __popc(h[1]), p2 = __popc(h[2]), p3 = __popc(h[3]);
 	const uint32_t cnt = p0 + p1 + p2 + p3;
 	uint32_t incl = cnt;
@@ -120,18 +139,20 @@ __global__ void __launch_bounds__(kExpand7Threads, 6) k_expand7(SeqStream S, Mod
 		} else {
 			v = eval_window(M, s_codes[wi], s_codes[wi + 1], 0u, 0u, static_cast<int>(j));  // N windows are already gone
 		}
-		uint32_t sq, r;  // sequence (0-based) and word inside it
+		uint32_t seq1, pos;  // sequence and position, both 1-based
 		if (kUniform) {
-			sq = __umulhi(w, magic);  // magic = floor(2^32 / wps): at most one too small
-			r = w - sq * wps;
+			uint32_t sq = __umulhi(w, magic);  // magic = floor(2^32 / wps): at most one too small
+			uint32_t r = w - sq * wps;         // word inside the sequence
 			if (r >= wps) { r -= wps; ++sq; }
+			seq1 = sq + 1;
+			pos = r * 32 + j + 1;
 		} else {
-			sq = find_seq(S, w);
-			r = w - S.wordOff[sq];
+			const uint2 org = s_origin[wi];
+			seq1 = org.x;
+			pos = org.y + j;
 		}
-		const uint32_t pos = r * 32 + j + 1;
 #ifdef XXM_SIMT_EMU
-		if (qr < roomL) { pseq[qr] = sq + 1; ppos[qr] = pos; pvid[qr] = v; }
+		if (qr < roomL) { pseq[qr] = seq1; ppos[qr] = pos; pvid[qr] = v; }
 #else
 		// three predicated stores, every address one multiply-add from its base (written in C the loop carries three 64-bit
 		// pointers along and branches around the stores)
@@ -146,7 +167,7 @@ __global__ void __launch_bounds__(kExpand7Threads, 6) k_expand7(SeqStream S, Mod
 			"@p st.global.u32 [a], %5;\n"
 			"@p st.global.u32 [b], %6;\n"
 			"@p st.global.u32 [c], %7;\n"
-			"}" ::"l"(pseq), "l"(ppos), "l"(pvid), "r"(qr), "r"(roomL), "r"(sq + 1), "r"(pos), "r"(v)
+			"}" ::"l"(pseq), "l"(ppos), "l"(pvid), "r"(qr), "r"(roomL), "r"(seq1), "r"(pos), "r"(v)
 			: "memory");
 #endif
 	};
