@@ -166,6 +166,103 @@ int run_case(const Case& c) {
 	return bad ? 1 : 0;
 }
 
+// k_eval_select_zoops (the fused re-score of a candidate list, xxm_kernels.cuh) against fill_elongSites_with_possible_startPositions'
+// ZOOPS branch (StartPosUpdater-inl.h:167-203): window evaluation per candidate, then per sequence the first candidate whose
+// finalPval is below the float-stored best so far
+int run_zoops_case(const std::string& name, int nseq, int lenLo, int lenHi, double candFrac, int shift, double nFrac, uint32_t seed) {
+	std::mt19937 rng(seed);
+	std::vector<int32_t> n(nseq);
+	for (auto& v : n) v = lenLo + static_cast<int>(rng() % static_cast<uint32_t>(lenHi - lenLo + 1));
+	uint64_t tot = 0;
+	for (int v : n) tot += static_cast<uint64_t>(v);
+	std::vector<uint8_t> raw(tot + 64);
+	for (uint64_t i = 0; i < tot; ++i) raw[i] = static_cast<uint8_t>((rng() % 1000 < nFrac * 1000) ? 0 : 1 + rng() % 4);
+	std::vector<uint32_t> wordOff(nseq + 1);
+	uint64_t w = 0;
+	bool uniform = true;
+	for (int i = 0; i < nseq; ++i) { wordOff[i] = static_cast<uint32_t>(w); w += stored_words(static_cast<uint32_t>(n[i]), false); uniform = uniform && n[i] == n[0]; }
+	wordOff[nseq] = static_cast<uint32_t>(w);
+	std::vector<uint64_t> codes(w + 2, 0ull);
+	std::vector<uint32_t> nmask(w + 2, 0xFFFFFFFFu);
+	std::vector<int32_t> notX(nseq);
+	if (pack_range(n.data(), 0, static_cast<uint32_t>(nseq), raw.data(), tot, false, codes.data(), nmask.data(), notX.data())) return 2;
+	SeqStream S{};
+	S.codes = codes.data(); S.nmask = nmask.data(); S.wordOff = wordOff.data(); S.len = n.data(); S.nwords = static_cast<uint32_t>(w); S.nent = nseq;
+	S.uniformWps = uniform ? wordOff[1] - wordOff[0] : 0; S.uniformLen = uniform ? n[0] : 0;
+	// a 7-column table: half of the k-mers, classes by a random additive score
+	const int L = 7;
+	int sc[8][4];
+	for (int k = 0; k < L; ++k) for (int a = 0; a < 4; ++a) sc[k][a] = static_cast<int>(rng() % 1000);
+	const uint32_t N = 1u << (2 * L);
+	std::vector<std::pair<int, uint32_t>> all(N);
+	for (uint32_t id = 0; id < N; ++id) { int v = 0; for (int k = 0; k < L; ++k) v += sc[k][(id >> (2 * k)) & 3u]; all[id] = {-(v / 40), id}; }
+	std::sort(all.begin(), all.end());
+	std::vector<uint32_t> rank(N, 0u);
+	uint32_t cls = 0;
+	for (size_t i = 0; i < N / 2; ++i) { if (i && all[i].first != all[i - 1].first) ++cls; rank[all[i].second] = cls + 1; }
+	const uint32_t nval = cls + 1;
+	std::vector<double> fin(nval), pS(nval, 0.5);
+	double v = 1e-7;
+	for (uint32_t k = 0; k < nval; ++k) { v *= (rng() % 3 == 0) ? (1.0 + 2e-9) : 1.4; fin[k] = (k + 3 < nval) ? std::min(v, 0.99) : 1.0; }
+	Model M{};
+	M.L = L; M.maxk = 8; M.nparts = 1; M.span = L; M.contiguous = 1; M.len0 = L;
+	for (int k = 0; k < L; ++k) M.coloff[k] = k;
+	M.rank0 = rank.data();
+	Values V{};
+	V.pS = pS.data(); V.finalTab = fin.data(); V.kind = kFinalTable;
+	// candidates in (sequence, position) order
+	std::vector<uint32_t> seq, pos;
+	for (int q = 0; q < nseq; ++q)
+		for (int p = 1; p <= n[q]; ++p)
+			if ((rng() % 100000) < candFrac * 100000) { seq.push_back(static_cast<uint32_t>(q) + 1); pos.push_back(static_cast<uint32_t>(p)); }
+	const uint32_t nc = static_cast<uint32_t>(seq.size());
+	// expectation
+	std::vector<uint32_t> wantV(nc, kNone), wantIdx(nseq, kNone);
+	std::vector<float> wantScore(nseq, 1.0f);
+	uint32_t wantFilled = 0;
+	for (uint32_t i = 0; i < nc; ++i) {
+		const int q = static_cast<int>(seq[i]) - 1, p = static_cast<int>(pos[i]) + shift;
+		if (p >= 1 && p + L - 1 <= n[q]) {
+			uint32_t id = 0;
+			bool dead = false;
+			for (int k = 0; k < L; ++k) {
+				const int o = p - 1 + k;
+				const uint32_t ww = wordOff[q] + static_cast<uint32_t>(o >> 5);
+				if ((nmask[ww] >> (o & 31)) & 1u) dead = true;
+				id |= (static_cast<uint32_t>(codes[ww] >> (2 * (o & 31))) & 3u) << (2 * k);
+			}
+			if (!dead && rank[id]) wantV[i] = rank[id] - 1;
+		}
+		if (wantV[i] == kNone) continue;
+		const double f = fin[wantV[i]];
+		if (f < static_cast<double>(wantScore[q])) {
+			if (wantIdx[q] == kNone) ++wantFilled;
+			wantIdx[q] = i;
+			wantScore[q] = static_cast<float>(f);
+		}
+	}
+	std::vector<uint32_t> vidx(nc + 1, 0xABABABABu), slotIdx(nseq, kNone), counters(8, 0u);
+	std::vector<float> slotScore(nseq, 1.0f);
+	SlotIO io{};
+	io.seq = seq.data(); io.pos = pos.data(); io.vidx = nullptr; io.n = nc; io.shift = shift; io.slotIdx = slotIdx.data(); io.slotScore = slotScore.data(); io.counters = counters.data();
+	emu::launch((nc + kZoopsTile - 1) / kZoopsTile, 256, [&] { k_eval_select_zoops(S, M, V, io, vidx.data()); });
+	int bad = 0;
+	for (uint32_t i = 0; i < nc && !bad; ++i)
+		if (vidx[i] != wantV[i]) { std::fprintf(stderr, "FAIL %s: candidate %u value index %u, expected %u\n", name.c_str(), i, vidx[i], wantV[i]); ++bad; }
+	if (slotIdx != wantIdx || slotScore != wantScore) { std::fprintf(stderr, "FAIL %s: slots differ\n", name.c_str()); ++bad; }
+	if (counters[0] != wantFilled) { std::fprintf(stderr, "FAIL %s: %u slots filled, expected %u\n", name.c_str(), counters[0], wantFilled); ++bad; }
+	// the unfused pair must agree as well
+	std::vector<uint32_t> vidx2(nc + 1, 0u), slotIdx2(nseq, kNone), counters2(8, 0u);
+	std::vector<float> slotScore2(nseq, 1.0f);
+	emu::launch((nc + 255) / 256, 256, [&] { k_eval_list(S, M, seq.data(), pos.data(), nc, shift, vidx2.data()); });
+	SlotIO io2 = io;
+	io2.vidx = vidx2.data(); io2.slotIdx = slotIdx2.data(); io2.slotScore = slotScore2.data(); io2.counters = counters2.data();
+	emu::launch((nc + kZoopsTile - 1) / kZoopsTile, 256, [&] { k_select_zoops(V, io2); });
+	if (slotIdx2 != wantIdx || slotScore2 != wantScore || counters2[0] != wantFilled) { std::fprintf(stderr, "FAIL %s: the two-kernel path differs\n", name.c_str()); ++bad; }
+	std::printf("%-20s %7u candidates, %6u of %d slots filled, shift %+d: %s\n", name.c_str(), nc, wantFilled, nseq, shift, bad ? "DIFFERENT" : "identical");
+	return bad ? 1 : 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -185,6 +282,18 @@ int main(int argc, char** argv) {
 			if (!sel) continue;
 		}
 		failed += run_case(c) ? 1 : 0;
+		++ran;
+	}
+	struct Z { const char* name; int nseq, lenLo, lenHi; double frac; int shift; double nFrac; uint32_t seed; };
+	const Z zs[] = {{"zoops_uniform", 300, 200, 200, 0.08, 0, 0.0, 11}, {"zoops_ragged_shift", 500, 10, 300, 0.1, -2, 0.02, 12}, {"zoops_long_runs", 6, 3000, 5000, 0.5, 1, 0.0, 13},
+	                {"zoops_sparse", 2000, 50, 50, 0.01, 2, 0.0, 14}};
+	for (const Z& z : zs) {
+		if (argc > 1) {
+			bool sel = false;
+			for (int i = 1; i < argc; ++i) sel = sel || std::string(z.name) == argv[i];
+			if (!sel) continue;
+		}
+		failed += run_zoops_case(z.name, z.nseq, z.lenLo, z.lenHi, z.frac, z.shift, z.nFrac, z.seed) ? 1 : 0;
 		++ran;
 	}
 	std::printf("%d runs, %d failed\n", ran, failed);

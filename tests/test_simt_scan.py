@@ -16,7 +16,8 @@ CASES = ["tile_scan", "uniform_1kb", "ragged_N", "revcomp_ragged", "dense_lowcom
          "ten_tiles_uniform", "one_word_sequences", "small_capacity", "positive_set_prefix_ragged", "positive_set_prefix_uniform"]
 
 
-STEP_CASES = ["clustered_uniform", "ragged_short", "long_motif", "all_sites_dense", "few_sites", "tiny"]
+STEP_CASES = ["clustered_uniform", "ragged_short", "long_motif", "all_sites_dense", "few_sites", "tiny", "zoops_uniform", "zoops_ragged_shift", "zoops_long_runs",
+              "zoops_sparse"]
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +32,9 @@ def step_exe():
 
 @pytest.mark.parametrize("case", STEP_CASES)
 def test_select_and_count_kernels_under_emulator(step_exe, case):
-    """k_select_cls_fwd vs the reference's updateMultOcc greedy (StartPosUtils.h:12-28), k_count_pwm3 vs a column-by-column count"""
+    """k_select_cls_fwd vs the reference's updateMultOcc greedy (StartPosUtils.h:12-28), k_count_pwm3 vs a column-by-column count;
+    zoops_*: the fused re-score kernel k_eval_select_zoops (and the k_eval_list + k_select_zoops pair) vs the ZOOPS branch of
+    fill_elongSites_with_possible_startPositions (StartPosUpdater-inl.h:167-203)"""
     r = subprocess.run([step_exe, case], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout

@@ -190,21 +190,23 @@ __global__ void k_scatter_mode(const double* __restrict__ vals, const uint32_t* 
 // evaluation of explicit windows (re-score of a candidate list, a motif's own sites, per-site p-values):
 // the calculatePval part of fill_elongSites_with_possible_startPositions (StartPosUpdater-inl.h:167-190).
 // ---------------------------------------------------------------------------------------------------------------
+// value index of the window that starts at position pos1 + shift (1-based) of sequence seq1 (1-based), or kNone
+__device__ __forceinline__ uint32_t eval_entry(const SeqStream& S, const Model& M, uint32_t seq1, uint32_t pos1, int shift) {
+	const uint32_t s = seq1 - 1;
+	const int p = static_cast<int>(pos1) + shift;
+	// (sets of one length: no gathers from the per-sequence arrays)
+	const int len = S.uniformWps ? S.uniformLen : S.len[s];
+	if (p < 1 || p + M.span - 1 > len) return kNone;  // :181
+	const uint32_t g = static_cast<uint32_t>(p - 1);
+	const uint32_t w = (S.uniformWps ? s * S.uniformWps : S.wordOff[s]) + (g >> 5);
+	return eval_window(M, S.codes[w], S.codes[w + 1], S.nmask[w], S.nmask[w + 1], g & 31);
+}
+
 __global__ void k_eval_list(SeqStream S, Model M, const uint32_t* __restrict__ seq, const uint32_t* __restrict__ pos, uint32_t n, int shift,
                             uint32_t* __restrict__ vidx) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	const uint32_t s = seq[i] - 1;
-	const int p = static_cast<int>(pos[i]) + shift;
-	uint32_t v = kNone;
-	// (sets of one length: no gathers from the per-sequence arrays)
-	const int len = S.uniformWps ? S.uniformLen : S.len[s];
-	if (p >= 1 && p + M.span - 1 <= len) {  // :181
-		const uint32_t g = static_cast<uint32_t>(p - 1);
-		const uint32_t w = (S.uniformWps ? s * S.uniformWps : S.wordOff[s]) + (g >> 5);
-		v = eval_window(M, S.codes[w], S.codes[w + 1], S.nmask[w], S.nmask[w + 1], g & 31);
-	}
-	vidx[i] = v;
+	vidx[i] = eval_entry(S, M, seq[i], pos[i], shift);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -376,6 +378,87 @@ __global__ void __launch_bounds__(256) k_select_zoops(Values V, SlotIO io) {
 		if (j == static_cast<uint32_t>(kZoopsTile)) {
 			for (uint32_t g = base + kZoopsTile; g < io.n && io.seq[g] == sq; ++g) {
 				const uint32_t v = io.vidx[g];
+				if (v == kNone) continue;
+				const double f = final_of(V, v, g, needPos ? static_cast<int>(io.pos[g]) + io.shift : 0);
+				if (f < static_cast<double>(slot)) { slot = static_cast<float>(f); idx = g; }
+			}
+		}
+		if (idx != kNone) {
+			io.slotIdx[sq - 1] = idx;
+			io.slotScore[sq - 1] = slot;
+			++filled;
+		}
+	}
+	filled = __reduce_add_sync(0xFFFFFFFFu, filled);
+	if (lane == 0 && filled) atomicAdd(&io.counters[0], filled);
+}
+// The re-score of a candidate list in ONE pass for models whose values need nothing between evaluation and selection (one
+// p-value table, table-valued finalPval): k_eval_list + k_select_zoops fused -- the value index of an entry is computed while its
+// tile is staged, written for the list's later readers, and never read back (12 B per candidate less traffic, one launch less;
+// SURVEY 8(f) row 2, the per-variant half).
+__global__ void __launch_bounds__(256) k_eval_select_zoops(SeqStream S, Model M, Values V, SlotIO io, uint32_t* __restrict__ vidxOut) {
+	__shared__ double s_f[kZoopsTile];
+	__shared__ uint32_t s_seq[kZoopsTile];
+	const uint32_t base = blockIdx.x * kZoopsTile;
+	const bool needPos = V.kind != kFinalTable && V.kind != kFinalPerCand;
+#pragma unroll
+	for (int k = 0; k < kZoopsTile / 256; ++k) {
+		const uint32_t r = k * 256 + threadIdx.x, i = base + r;
+		uint32_t sq = 0;      // (sequence numbers start at 1)
+		double f = 2.0;       // never below a slot score
+		if (i < io.n) {
+			sq = io.seq[i];
+			const uint32_t ps = io.pos[i];
+			const uint32_t v = eval_entry(S, M, sq, ps, io.shift);
+			vidxOut[i] = v;
+			if (v != kNone) f = final_of(V, v, i, needPos ? static_cast<int>(ps) + io.shift : 0);
+		}
+		s_seq[r] = sq;
+		s_f[r] = f;
+	}
+	__syncthreads();
+	// the heads of the runs that start in this tile, compacted: every walking warp has all its lanes busy
+	__shared__ uint16_t s_head[kZoopsTile];
+	__shared__ uint32_t s_wsum[8];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	uint32_t hm = 0;  // bit k: entry 4 * tid + k is the head of a run
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const uint32_t r = 4 * threadIdx.x + k, i = base + r;
+		if (i >= io.n) break;
+		const uint32_t prev = r ? s_seq[r - 1] : (i ? io.seq[i - 1] : 0u);
+		if (s_seq[r] != prev) hm |= 1u << k;
+	}
+	const uint32_t cnt = __popc(hm);
+	uint32_t incl = cnt;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+		if (lane >= d) incl += t;
+	}
+	if (lane == 31) s_wsum[wid] = incl;
+	__syncthreads();
+	uint32_t off = incl - cnt, nheads = 0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) { if (k < wid) off += s_wsum[k]; nheads += s_wsum[k]; }
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+		if ((hm >> k) & 1u) s_head[off++] = static_cast<uint16_t>(4 * threadIdx.x + k);
+	__syncthreads();
+	uint32_t filled = 0;
+	for (uint32_t h = threadIdx.x; h < nheads; h += 256) {
+		const uint32_t r = s_head[h];
+		const uint32_t sq = s_seq[r];
+		float slot = 1.0f;
+		uint32_t idx = kNone;
+		uint32_t j = r;
+		for (; j < static_cast<uint32_t>(kZoopsTile) && s_seq[j] == sq; ++j) {
+			const double f = s_f[j];
+			if (f < static_cast<double>(slot)) { slot = static_cast<float>(f); idx = base + j; }
+		}
+		if (j == static_cast<uint32_t>(kZoopsTile)) {
+			for (uint32_t g = base + kZoopsTile; g < io.n && io.seq[g] == sq; ++g) {
+				const uint32_t v = eval_entry(S, M, sq, io.pos[g], io.shift);  // (the block that owns entry g writes its value index)
 				if (v == kNone) continue;
 				const double f = final_of(V, v, g, needPos ? static_cast<int>(io.pos[g]) + io.shift : 0);
 				if (f < static_cast<double>(slot)) { slot = static_cast<float>(f); idx = g; }
