@@ -166,7 +166,7 @@ int run_case(const Case& c) {
 	return bad ? 1 : 0;
 }
 
-// k_eval_select_zoops (the fused re-score of a candidate list, xxm_kernels.cuh) against fill_elongSites_with_possible_startPositions'
+// k_eval_list + k_select_zoops (the re-score of a candidate list, xxm_kernels.cuh) against fill_elongSites_with_possible_startPositions'
 // ZOOPS branch (StartPosUpdater-inl.h:167-203): window evaluation per candidate, then per sequence the first candidate whose
 // finalPval is below the float-stored best so far
 int run_zoops_case(const std::string& name, int nseq, int lenLo, int lenHi, double candFrac, int shift, double nFrac, uint32_t seed) {
@@ -241,24 +241,19 @@ int run_zoops_case(const std::string& name, int nseq, int lenLo, int lenHi, doub
 			wantScore[q] = static_cast<float>(f);
 		}
 	}
-	std::vector<uint32_t> vidx(nc + 1, 0xABABABABu), slotIdx(nseq, kNone), counters(8, 0u);
-	std::vector<float> slotScore(nseq, 1.0f);
-	SlotIO io{};
-	io.seq = seq.data(); io.pos = pos.data(); io.vidx = nullptr; io.n = nc; io.shift = shift; io.slotIdx = slotIdx.data(); io.slotScore = slotScore.data(); io.counters = counters.data();
-	emu::launch((nc + kZoopsTile - 1) / kZoopsTile, 256, [&] { k_eval_select_zoops(S, M, V, io, vidx.data()); });
 	int bad = 0;
-	for (uint32_t i = 0; i < nc && !bad; ++i)
-		if (vidx[i] != wantV[i]) { std::fprintf(stderr, "FAIL %s: candidate %u value index %u, expected %u\n", name.c_str(), i, vidx[i], wantV[i]); ++bad; }
-	if (slotIdx != wantIdx || slotScore != wantScore) { std::fprintf(stderr, "FAIL %s: slots differ\n", name.c_str()); ++bad; }
-	if (counters[0] != wantFilled) { std::fprintf(stderr, "FAIL %s: %u slots filled, expected %u\n", name.c_str(), counters[0], wantFilled); ++bad; }
-	// the unfused pair must agree as well
+	// k_eval_list, then k_select_zoops on its value indices
 	std::vector<uint32_t> vidx2(nc + 1, 0u), slotIdx2(nseq, kNone), counters2(8, 0u);
 	std::vector<float> slotScore2(nseq, 1.0f);
 	emu::launch((nc + 255) / 256, 256, [&] { k_eval_list(S, M, seq.data(), pos.data(), nc, shift, vidx2.data()); });
-	SlotIO io2 = io;
+	SlotIO io2{};
+	io2.seq = seq.data(); io2.pos = pos.data(); io2.n = nc; io2.shift = shift;
 	io2.vidx = vidx2.data(); io2.slotIdx = slotIdx2.data(); io2.slotScore = slotScore2.data(); io2.counters = counters2.data();
 	emu::launch((nc + kZoopsTile - 1) / kZoopsTile, 256, [&] { k_select_zoops(V, io2); });
-	if (slotIdx2 != wantIdx || slotScore2 != wantScore || counters2[0] != wantFilled) { std::fprintf(stderr, "FAIL %s: the two-kernel path differs\n", name.c_str()); ++bad; }
+	for (uint32_t i = 0; i < nc && !bad; ++i)
+		if (vidx2[i] != wantV[i]) { std::fprintf(stderr, "FAIL %s: candidate %u value index %u, expected %u\n", name.c_str(), i, vidx2[i], wantV[i]); ++bad; }
+	if (slotIdx2 != wantIdx || slotScore2 != wantScore) { std::fprintf(stderr, "FAIL %s: slots differ\n", name.c_str()); ++bad; }
+	if (counters2[0] != wantFilled) { std::fprintf(stderr, "FAIL %s: %u slots filled, expected %u\n", name.c_str(), counters2[0], wantFilled); ++bad; }
 	std::printf("%-20s %7u candidates, %6u of %d slots filled, shift %+d: %s\n", name.c_str(), nc, wantFilled, nseq, shift, bad ? "DIFFERENT" : "identical");
 	return bad ? 1 : 0;
 }

@@ -33,7 +33,7 @@ def step_exe():
 @pytest.mark.parametrize("case", STEP_CASES)
 def test_select_and_count_kernels_under_emulator(step_exe, case):
     """k_select_cls_fwd vs the reference's updateMultOcc greedy (StartPosUtils.h:12-28), k_count_pwm3 vs a column-by-column count;
-    zoops_*: the fused re-score kernel k_eval_select_zoops (and the k_eval_list + k_select_zoops pair) vs the ZOOPS branch of
+    zoops_*: the re-score kernels k_eval_list + k_select_zoops vs the ZOOPS branch of
     fill_elongSites_with_possible_startPositions (StartPosUpdater-inl.h:167-203)"""
     r = subprocess.run([step_exe, case], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr

@@ -1691,10 +1691,8 @@ static int select_mops(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const
 	return 0;
 }
 
-// vidxOut != nullptr: the value indices are not there yet -- k_eval_select_zoops computes them on the way and writes them to
-// vidxOut (ordered lists of one-table models whose finalPval is table valued)
 static int select_slots(xxm_ctx* ctx, const Values& V, const uint32_t* seq, const uint32_t* pos, const uint32_t* vidx, uint32_t n, int shift, bool ordered,
-                        uint32_t nslots, DevBuf<uint32_t>& sIdx, DevBuf<float>& sScore, uint32_t* nFilled, uint32_t* vidxOut = nullptr) {
+                        uint32_t nslots, DevBuf<uint32_t>& sIdx, DevBuf<float>& sScore, uint32_t* nFilled) {
 	CK(sIdx.ensure(std::max<uint32_t>(1, nslots)));
 	CK(sScore.ensure(std::max<uint32_t>(1, nslots)));
 	CK(ctx->counters.ensure(8));
@@ -1708,8 +1706,7 @@ static int select_slots(xxm_ctx* ctx, const Values& V, const uint32_t* seq, cons
 		SlotIO io{};
 		io.seq = seq; io.pos = pos; io.vidx = vidx; io.n = n; io.shift = shift;
 		io.slotIdx = sIdx.p; io.slotScore = sScore.p; io.counters = ctx->counters.p;
-		if (vidxOut) k_eval_select_zoops<<<cdiv(n, static_cast<uint32_t>(kZoopsTile)), 256, 0, ctx->stream>>>(ctx->S, ctx->M, V, io, vidxOut);
-		else if (ordered) k_select_zoops<<<cdiv(n, static_cast<uint32_t>(kZoopsTile)), 256, 0, ctx->stream>>>(V, io);
+		if (ordered) k_select_zoops<<<cdiv(n, static_cast<uint32_t>(kZoopsTile)), 256, 0, ctx->stream>>>(V, io);
 		else k_select_zoops_serial<<<1, 32, 0, ctx->stream>>>(V, io);
 		CKK();
 		CK(cudaMemcpyAsync(nFilled, ctx->counters.p, 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -392,87 +392,6 @@ __global__ void __launch_bounds__(256) k_select_zoops(Values V, SlotIO io) {
 	filled = __reduce_add_sync(0xFFFFFFFFu, filled);
 	if (lane == 0 && filled) atomicAdd(&io.counters[0], filled);
 }
-// The re-score of a candidate list in ONE pass for models whose values need nothing between evaluation and selection (one
-// p-value table, table-valued finalPval): k_eval_list + k_select_zoops fused -- the value index of an entry is computed while its
-// tile is staged, written for the list's later readers, and never read back (12 B per candidate less traffic, one launch less;
-// SURVEY 8(f) row 2, the per-variant half).
-__global__ void __launch_bounds__(256) k_eval_select_zoops(SeqStream S, Model M, Values V, SlotIO io, uint32_t* __restrict__ vidxOut) {
-	__shared__ double s_f[kZoopsTile];
-	__shared__ uint32_t s_seq[kZoopsTile];
-	const uint32_t base = blockIdx.x * kZoopsTile;
-	const bool needPos = V.kind != kFinalTable && V.kind != kFinalPerCand;
-#pragma unroll
-	for (int k = 0; k < kZoopsTile / 256; ++k) {
-		const uint32_t r = k * 256 + threadIdx.x, i = base + r;
-		uint32_t sq = 0;      // (sequence numbers start at 1)
-		double f = 2.0;       // never below a slot score
-		if (i < io.n) {
-			sq = io.seq[i];
-			const uint32_t ps = io.pos[i];
-			const uint32_t v = eval_entry(S, M, sq, ps, io.shift);
-			vidxOut[i] = v;
-			if (v != kNone) f = final_of(V, v, i, needPos ? static_cast<int>(ps) + io.shift : 0);
-		}
-		s_seq[r] = sq;
-		s_f[r] = f;
-	}
-	__syncthreads();
-	// the heads of the runs that start in this tile, compacted: every walking warp has all its lanes busy
-	__shared__ uint16_t s_head[kZoopsTile];
-	__shared__ uint32_t s_wsum[8];
-	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	uint32_t hm = 0;  // bit k: entry 4 * tid + k is the head of a run
-#pragma unroll
-	for (int k = 0; k < 4; ++k) {
-		const uint32_t r = 4 * threadIdx.x + k, i = base + r;
-		if (i >= io.n) break;
-		const uint32_t prev = r ? s_seq[r - 1] : (i ? io.seq[i - 1] : 0u);
-		if (s_seq[r] != prev) hm |= 1u << k;
-	}
-	const uint32_t cnt = __popc(hm);
-	uint32_t incl = cnt;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
-		const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-		if (lane >= d) incl += t;
-	}
-	if (lane == 31) s_wsum[wid] = incl;
-	__syncthreads();
-	uint32_t off = incl - cnt, nheads = 0;
-#pragma unroll
-	for (int k = 0; k < 8; ++k) { if (k < wid) off += s_wsum[k]; nheads += s_wsum[k]; }
-#pragma unroll
-	for (int k = 0; k < 4; ++k)
-		if ((hm >> k) & 1u) s_head[off++] = static_cast<uint16_t>(4 * threadIdx.x + k);
-	__syncthreads();
-	uint32_t filled = 0;
-	for (uint32_t h = threadIdx.x; h < nheads; h += 256) {
-		const uint32_t r = s_head[h];
-		const uint32_t sq = s_seq[r];
-		float slot = 1.0f;
-		uint32_t idx = kNone;
-		uint32_t j = r;
-		for (; j < static_cast<uint32_t>(kZoopsTile) && s_seq[j] == sq; ++j) {
-			const double f = s_f[j];
-			if (f < static_cast<double>(slot)) { slot = static_cast<float>(f); idx = base + j; }
-		}
-		if (j == static_cast<uint32_t>(kZoopsTile)) {
-			for (uint32_t g = base + kZoopsTile; g < io.n && io.seq[g] == sq; ++g) {
-				const uint32_t v = eval_entry(S, M, sq, io.pos[g], io.shift);  // (the block that owns entry g writes its value index)
-				if (v == kNone) continue;
-				const double f = final_of(V, v, g, needPos ? static_cast<int>(io.pos[g]) + io.shift : 0);
-				if (f < static_cast<double>(slot)) { slot = static_cast<float>(f); idx = g; }
-			}
-		}
-		if (idx != kNone) {
-			io.slotIdx[sq - 1] = idx;
-			io.slotScore[sq - 1] = slot;
-			++filled;
-		}
-	}
-	filled = __reduce_add_sync(0xFFFFFFFFu, filled);
-	if (lane == 0 && filled) atomicAdd(&io.counters[0], filled);
-}
 __global__ void k_select_zoops_serial(Values V, SlotIO io) {
 	if (blockIdx.x == 0 && threadIdx.x == 0) zoops_walk(V, io, 0, io.n);
 }

@@ -19,7 +19,9 @@
 // Tried here and dropped after counting SASS instructions against the hit statistics of the bench workload (2-3 % of the
 // windows, clustered: 0.6-1 hits per word, half of the words empty, ~6 in the fullest of 128): compacting the non-empty words of
 // a warp and popping one word per lane (2 passes x 5.5 trips x 9 instructions + 44 to build the list + 30 per pass to set up)
-// costs what the lock-step loop costs (6 trips x 32).
+// costs what the lock-step loop costs (6 trips x 32).  Measured and dropped: for ragged sets, per-word (sequence, position) origins in
+// shared memory -- a lane resolves its first word once and walks on -- instead of one find_seq per hit: 0.333 ms per scan against
+// 0.321 ms (profiles/r02c_ab_ragged.txt); the look-ups of neighbouring hits hit the same cache lines anyway.
 // Same inputs (final masks, chunk counts, tile offsets), same records, same order as k_expand6: globally ordered by
 // (sequence, position), the reference's scan order (StartPosUpdater-inl.h:70-140).
 #pragma once
@@ -47,9 +49,6 @@ template <bool kFast, bool kUniform>
 __global__ void __launch_bounds__(kExpand7Threads, 6) k_expand7(SeqStream S, Model M, Expand6IO io) {
 	__shared__ __align__(16) uint64_t s_codesAll[kExpand7Warps][kE7WarpWords + 2];
 	__shared__ uint16_t s_qAll[kExpand7Warps][kE7Queue];
-	// ragged sets only: (sequence, position of window 0) of every word of the warp -- a lane looks its first word up once
-	// (find_seq: two or three dependent global loads) and walks on from there, instead of one look-up per hit in the resolve loop
-	__shared__ __align__(16) uint2 s_originAll[kUniform ? 1 : kExpand7Warps][kUniform ? 1 : kE7WarpWords];
 	const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
 	const uint32_t tile = blockIdx.x;
 	uint64_t* s_codes = s_codesAll[wid];
@@ -90,22 +89,6 @@ __global__ void __launch_bounds__(kExpand7Threads, 6) k_expand7(SeqStream S, Mod
 	*reinterpret_cast<uint4*>(s_codes + 4 * lane) = ca;
 	*reinterpret_cast<uint4*>(s_codes + 4 * lane + 2) = cb;
 	if (lane == 0) s_codes[kE7WarpWords] = ctail;
-	uint2* s_origin = s_originAll[kUniform ? 0 : wid];
-	if (!kUniform && w0 < io.scanWords) {  // (words from scanWords on hold no hits)
-		uint32_t sq = find_seq(S, w0);
-		uint32_t next = S.wordOff[sq + 1];
-		uint32_t r = w0 - S.wordOff[sq];
-		uint2 org[4];
-#pragma unroll
-		for (int k = 0; k < 4; ++k) {
-			org[k] = make_uint2(sq + 1, r * 32 + 1);
-			const uint32_t w = w0 + k + 1;
-			if (w == next && w < io.scanWords) { ++sq; r = 0; next = S.wordOff[sq + 1]; }  // (sequence sq + 1 starts at w < wordOff[nseq]: it exists)
-			else ++r;
-		}
-		*reinterpret_cast<uint4*>(s_origin + 4 * lane) = make_uint4(org[0].x, org[0].y, org[1].x, org[1].y);
-		*reinterpret_cast<uint4*>(s_origin + 4 * lane + 2) = make_uint4(org[2].x, org[2].y, org[3].x, org[3].y);
-	}
 	const uint32_t p0 = __popc(h[0]), p1 = __popc(h[1]), p2 = __popc(h[2]), p3 = __popc(h[3]);
 	const uint32_t cnt = p0 + p1 + p2 + p3;
 	uint32_t incl = cnt;
@@ -147,9 +130,9 @@ __global__ void __launch_bounds__(kExpand7Threads, 6) k_expand7(SeqStream S, Mod
 			seq1 = sq + 1;
 			pos = r * 32 + j + 1;
 		} else {
-			const uint2 org = s_origin[wi];
-			seq1 = org.x;
-			pos = org.y + j;
+			const uint32_t sq = find_seq(S, w);
+			seq1 = sq + 1;
+			pos = (w - S.wordOff[sq]) * 32 + j + 1;
 		}
 #ifdef XXM_SIMT_EMU
 		if (qr < roomL) { pseq[qr] = seq1; ppos[qr] = pos; pvid[qr] = v; }
