@@ -21,7 +21,10 @@
 // a warp and popping one word per lane (2 passes x 5.5 trips x 9 instructions + 44 to build the list + 30 per pass to set up)
 // costs what the lock-step loop costs (6 trips x 32).  Measured and dropped: for ragged sets, per-word (sequence, position) origins in
 // shared memory -- a lane resolves its first word once and walks on -- instead of one find_seq per hit: 0.333 ms per scan against
-// 0.321 ms (profiles/r02c_ab_ragged.txt); the look-ups of neighbouring hits hit the same cache lines anyway.
+// 0.321 ms (profiles/r02c_ab_ragged.txt); the look-ups of neighbouring hits hit the same cache lines anyway.  Also measured and
+// dropped: one lock-step trip, then the words with more than one hit compacted and finished one per lane (~60 instructions per
+// warp fewer on paper, 150.2 us against 148.1 us on the clock: 8 KB more shared memory per CTA, two more warp barriers); 5 or 8
+// resident CTAs per SM instead of 6 (148.4 / 152.3 us).
 // Same inputs (final masks, chunk counts, tile offsets), same records, same order as k_expand6: globally ordered by
 // (sequence, position), the reference's scan order (StartPosUpdater-inl.h:70-140).
 #pragma once
