@@ -24,6 +24,7 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __noinline__
 #define __align__(n) __attribute__((aligned(n)))
 
 struct uint3 { unsigned x, y, z; };

@@ -16,11 +16,13 @@
 #include "xxm_kernels.cuh"
 #include "xxm_select2.cuh"
 #include "xxm_select3.cuh"
+#include "xxm_select4.cuh"
 
 #include "host_pack.h"
 
 namespace xxm {
 alignas(16) uint8_t smem3[1 << 16];
+alignas(16) uint8_t smem4[1 << 16];
 alignas(16) uint8_t smemM[1 << 16];
 uint32_t s_hist[1 << 14];
 uint32_t s_hs[1 << 14];
@@ -258,6 +260,101 @@ int run_zoops_case(const std::string& name, int nseq, int lenLo, int lenHi, doub
 	return bad ? 1 : 0;
 }
 
+// k_select_cls_rc (xxm_select4.cuh: forward rule + one monotone cursor into the frozen forward list) against the reference's
+// updateMultOcc with Global::revcomp, literally (StartPosUtils.h:12-65: the look-back walk over the kept array and the removal of
+// the loser from its middle), on doubled sequences (stored length 2 n0 + 1) with candidates on both strands
+int run_rc_case(const std::string& name, int nseq, int n0Lo, int n0Hi, double hitFrac, int span, uint32_t nval, uint32_t nSiteWant, uint32_t seed) {
+	std::mt19937 rng(seed);
+	std::vector<int32_t> len(nseq);
+	for (auto& v : len) v = 2 * (n0Lo + static_cast<int>(rng() % static_cast<uint32_t>(n0Hi - n0Lo + 1))) + 1;
+	bool uniform = true;
+	for (int v : len) uniform = uniform && v == len[0];
+	SeqStream S{};
+	S.len = len.data(); S.nent = nseq; S.uniformLen = uniform ? len[0] : 0; S.uniformWps = uniform ? 1u : 0u;
+	std::vector<uint32_t> seq, pos, vidx;
+	for (int q = 0; q < nseq; ++q) {
+		const int n0 = (len[q] - 1) / 2;
+		int boost = 0;
+		for (int p = 1; p + span - 1 <= len[q]; ++p) {
+			if (p + span - 1 > n0 && p <= n0 + 1) continue;  // windows over the separator never are candidates (N under a column)
+			const double pr = hitFrac * (boost > 0 ? 10.0 : 1.0);
+			if (boost > 0) --boost;
+			if ((rng() % 100000) < pr * 100000) {
+				seq.push_back(static_cast<uint32_t>(q) + 1);
+				pos.push_back(static_cast<uint32_t>(p));
+				uint32_t v = rng() % nval;
+				if (rng() % 40 == 0) v = kNone;
+				vidx.push_back(v);
+				boost = 5;
+			}
+		}
+	}
+	const uint32_t nc = static_cast<uint32_t>(seq.size());
+	std::vector<double> fin(nval);
+	double v = 1e-9;
+	for (uint32_t k = 0; k < nval; ++k) { v *= (rng() % 4 == 0) ? (1.0 + 1e-9) : 1.3; fin[k] = (k < nSiteWant) ? std::min(v, 0.999999) : 1.0; }
+	for (uint32_t k = 1; k < nval; ++k) fin[k] = std::max(fin[k], fin[k - 1]);
+	std::vector<uint16_t> thr(nval);
+	for (uint32_t k = 0; k < nval; ++k) thr[k] = static_cast<uint16_t>(std::lower_bound(fin.begin(), fin.end(), static_cast<double>(static_cast<float>(fin[k]))) - fin.begin());
+	const uint32_t nSite = static_cast<uint32_t>(std::lower_bound(fin.begin(), fin.end(), 1.0) - fin.begin());
+	// ---- the reference, literally
+	struct Site { int32_t sequence, startPos; float score; uint32_t idx; };
+	std::vector<uint8_t> wantKeep(nc, 0);
+	{
+		std::vector<Site> sites(nc + 1);
+		int counter = 0;
+		for (uint32_t i = 0; i < nc; ++i) {
+			if (vidx[i] == kNone) continue;
+			const double pVal = fin[vidx[i]];
+			if (!(pVal < 1.0)) continue;
+			const int32_t sq = static_cast<int32_t>(seq[i]), ps = static_cast<int32_t>(pos[i]);
+			const int length = span;
+			bool take = true;
+			if (counter > 0 && sites[counter - 1].sequence == sq && sites[counter - 1].startPos + length >= ps) {
+				if (static_cast<double>(sites[counter - 1].score) <= pVal) take = false;
+				else counter--;
+			}
+			if (take && ps > length / 2) {
+				int back = 1;
+				const int revPos = len[sq - 1] - length + 2 - ps;
+				while (counter - back >= 0 && sites[counter - back].sequence == sq && sites[counter - back].startPos > revPos + length - 1) back++;
+				if (counter - back >= 0 && sites[counter - back].sequence == sq && sites[counter - back].startPos >= revPos - length + 1) {
+					if (static_cast<double>(sites[counter - back].score) <= pVal) take = false;
+					else {
+						while (back > 1) { sites[counter - back] = sites[counter - back + 1]; back--; }
+						counter--;
+					}
+				}
+			}
+			if (!take) continue;
+			sites[counter++] = Site{sq, ps, static_cast<float>(pVal), i};
+		}
+		for (int k = 0; k < counter; ++k) wantKeep[sites[k].idx] = 1;
+	}
+	std::vector<uint8_t> keep(nc + 16, 0xEE);
+	std::vector<uint16_t> kcls(nc + 16, 0xEEEE);
+	std::vector<uint32_t> hist(nval, 0u), counters(8, 0u), stk(nc + 16, 0u);
+	SelectRcIO io{};
+	io.seq = seq.data(); io.pos = pos.data(); io.vidx = vidx.data(); io.n = nc; io.nDev = nullptr; io.length = span; io.clsThr = thr.data(); io.nSite = nSite; io.nval = nval;
+	io.stk = stk.data(); io.keep = keep.data(); io.kcls = kcls.data(); io.counters = counters.data(); io.hist = hist.data();
+	emu::launch(std::max(1u, std::min(3u, (nc + kSel4Tile - 1) / kSel4Tile)), kSel4Threads, [&] { k_select_cls_rc(S, io); });
+	int bad = 0;
+	uint32_t nkept = 0;
+	std::vector<uint32_t> wantHist(nval, 0u);
+	for (uint32_t i = 0; i < nc; ++i) {
+		if (wantKeep[i]) { ++nkept; ++wantHist[vidx[i]]; }
+		const uint16_t wc = wantKeep[i] ? static_cast<uint16_t>(vidx[i]) : static_cast<uint16_t>(0xFFFF);
+		if (keep[i] != wantKeep[i] || kcls[i] != wc) {
+			if (!bad) std::fprintf(stderr, "FAIL %s: entry %u (seq %u pos %u cls %u): keep %u kcls %u, expected %u %u\n", name.c_str(), i, seq[i], pos[i], vidx[i], keep[i], kcls[i], wantKeep[i], wc);
+			++bad;
+		}
+	}
+	if (counters[0] != nkept) { std::fprintf(stderr, "FAIL %s: %u kept sites counted, expected %u\n", name.c_str(), counters[0], nkept); ++bad; }
+	if (hist != wantHist) { std::fprintf(stderr, "FAIL %s: class histogram differs\n", name.c_str()); ++bad; }
+	std::printf("%-20s %7u candidates on both strands, %6u kept, span %d: %s\n", name.c_str(), nc, nkept, span, bad ? "DIFFERENT" : "identical");
+	return bad ? 1 : 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -289,6 +386,18 @@ int main(int argc, char** argv) {
 			if (!sel) continue;
 		}
 		failed += run_zoops_case(z.name, z.nseq, z.lenLo, z.lenHi, z.frac, z.shift, z.nFrac, z.seed) ? 1 : 0;
+		++ran;
+	}
+	struct Rc { const char* name; int nseq, n0Lo, n0Hi; double frac; int span; uint32_t nval, nSite, seed; };
+	const Rc rcs[] = {{"rc_uniform", 200, 250, 250, 0.03, 8, 120, 110, 21}, {"rc_ragged", 300, 20, 400, 0.05, 8, 60, 50, 22}, {"rc_long_motif", 80, 300, 600, 0.04, 21, 300, 290, 23},
+	                  {"rc_long_sequences", 5, 3000, 6000, 0.05, 10, 40, 40, 24}, {"rc_palindromic_dense", 60, 100, 100, 0.4, 6, 12, 12, 25}};
+	for (const Rc& z : rcs) {
+		if (argc > 1) {
+			bool sel = false;
+			for (int i = 1; i < argc; ++i) sel = sel || std::string(z.name) == argv[i];
+			if (!sel) continue;
+		}
+		failed += run_rc_case(z.name, z.nseq, z.n0Lo, z.n0Hi, z.frac, z.span, z.nval, z.nSite, z.seed) ? 1 : 0;
 		++ran;
 	}
 	std::printf("%d runs, %d failed\n", ran, failed);
