@@ -10,10 +10,7 @@
 namespace xxm {
 namespace {
 
-struct Leaf {
-	int32_t score;
-	uint32_t id;
-};
+using Leaf = BgProbCache::LeafRec;  // { int32_t score; uint32_t id; }
 
 // 3 bits per character, first character most significant (UngappedKmer.h:21-31)
 inline int packed_kmer(const uint8_t* s, int len) {
@@ -24,7 +21,8 @@ inline int packed_kmer(const uint8_t* s, int len) {
 
 class Builder {
 public:
-	Builder(PvalueTables& t, const NullModelView& nm) : t_(t), nm_(nm) {}
+	Builder(PvalueTables& t, const NullModelView& nm, BgProbCache* cache = nullptr)
+		: t_(t), nm_(nm), cache_(cache), leaves_(cache ? cache->leaves : ownLeaves_), tmp_(cache ? cache->sorted : ownTmp_) {}
 
 	// one call of set_kmer_to_Pvalue_hash (branch_and_bound-inl.h:462-577) for match columns [start, stop] (1-based)
 	void build_part(int part, int start, int stop, int threshold, bool collectPrefixes, int gapOffset) {
@@ -39,6 +37,18 @@ public:
 		TablePart& P = t_.part[part];
 		P.len = len_;
 		const size_t n = leaves_.size();
+		// the cache serves the rolled-index case of background_probability (left part, ungapped, longer than the model's context)
+		double* memo = nullptr;
+		if (cache_ && part_ == 0 && !collect_ && ungapped_ && len_ > nm_.order + 1 && len_ <= 8) {
+			BgProbCache& C = *cache_;
+			if (C.order != nm_.order || C.rprobs != nm_.rprobs || C.rconds != nm_.rconds) {
+				C.clear();
+				C.order = nm_.order; C.rprobs = nm_.rprobs; C.rconds = nm_.rconds;
+			}
+			std::vector<double>& v = C.p[len_];
+			if (v.size() != (static_cast<size_t>(1) << (2 * len_))) v.assign(static_cast<size_t>(1) << (2 * len_), std::nan(""));
+			memo = v.data();
+		}
 		P.ids.resize(n); P.cls.resize(n);
 		if (collect_) P.prob.resize(n);
 		P.classScore.clear(); P.classCount.clear(); P.classPval.clear();
@@ -49,7 +59,13 @@ public:
 			while (j < n && leaves_[j].score == leaves_[i].score) ++j;
 			const uint32_t c = static_cast<uint32_t>(P.classScore.size());
 			for (size_t k = i; k < j; ++k) {
-				const double p = background_probability(leaves_[k].id);
+				double p;
+				if (memo) {
+					p = memo[leaves_[k].id];
+					if (p != p) { p = background_probability(leaves_[k].id); memo[leaves_[k].id] = p; }
+				} else {
+					p = background_probability(leaves_[k].id);
+				}
 				if (collect_) P.prob[k] = p;
 				cumulative += p;
 				P.ids[k] = leaves_[k].id;
@@ -263,13 +279,16 @@ private:
 
 	PvalueTables& t_;
 	const NullModelView& nm_;
+	BgProbCache* cache_ = nullptr;
 	int part_ = 0, start_ = 1, len_ = 0, T_ = 0, gapOffset_ = 0;
 	bool collect_ = false, ungapped_ = false;
 	int row_[34][5];
 	int col_[34];
 	double sw_[34][5];
 	double smax_[36];
-	std::vector<Leaf> leaves_, tmp_;
+	std::vector<Leaf> ownLeaves_, ownTmp_;
+	std::vector<Leaf>& leaves_;  // the cache's scratch when there is one
+	std::vector<Leaf>& tmp_;
 	std::vector<int> prefixes_;
 	std::vector<int> prefixLen_;
 	std::unordered_map<int, float> rightCond_;
@@ -341,8 +360,8 @@ void part_plan(const PvalueTables& t, int len, PartPlan& P) {
 }
 
 void build_pvalue_tables(const double* pwm, const int32_t* cols, int ncols, int64_t posSetSize, int64_t totalPositions, const double* bgLog,
-                         const NullModelView& nm, PvalueTables& t) {
-	Builder b(t, nm);
+                         const NullModelView& nm, PvalueTables& t, BgProbCache* cache) {
+	Builder b(t, nm, cache);
 	model_header_impl(pwm, cols, ncols, posSetSize, totalPositions, bgLog, t, b.t_lin_);
 	if (t.nparts == 1) {
 		b.build_part(0, 1, t.L, 0, false, 0);

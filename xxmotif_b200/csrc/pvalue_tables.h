@@ -54,7 +54,22 @@ struct PartPlan {
 void model_header(const double* pwm31x5, const int32_t* cols, int ncols, int64_t posSetSize, int64_t totalPositions, const double* bgLog5, PvalueTables& out);
 void part_plan(const PvalueTables& t, int len, PartPlan& out);
 
+// Background probabilities of ungapped left k-mers under ONE null model, kept across the table builds of a refinement run:
+// calculate_kmer_probability (branch_and_bound-inl.h:54-100) depends on the k-mer and the model only, and successive PWMs
+// enumerate largely the same k-mers, so after the first few builds a leaf costs one table read instead of len dependent
+// multiplications.  A value is stored exactly as computed (no re-association), so cached and fresh builds are bit-identical.
+// The owner must call clear() whenever the null model changes (xxm_set_background); the key below guards against the rest.
+struct BgProbCache {
+	int order = -1;
+	const float *rprobs = nullptr, *rconds = nullptr;
+	std::vector<double> p[9];  // p[len]: [4^len], NaN = not computed yet (the column variants of a refinement run alternate between lengths)
+	void clear() { order = -1; rprobs = rconds = nullptr; for (auto& v : p) v.clear(); }
+	// scratch of the enumeration (leaves and their sorted copy), kept so that a build does not start from empty vectors
+	struct LeafRec { int32_t score; uint32_t id; };
+	std::vector<LeafRec> leaves, sorted;
+};
+
 void build_pvalue_tables(const double* pwm31x5, const int32_t* cols, int ncols, int64_t posSetSize, int64_t totalPositions,
-                         const double* bgLog5, const NullModelView& nm, PvalueTables& out);
+                         const double* bgLog5, const NullModelView& nm, PvalueTables& out, BgProbCache* cache = nullptr);
 
 }  // namespace xxm

@@ -180,6 +180,7 @@ struct xxm_ctx {
 	NullModelView nm;
 	std::vector<float> rprobs, rconds;
 	PvalueTables tab;
+	BgProbCache bgCache;          // background probabilities of left k-mers under the current null model (cleared by xxm_set_background)
 	bool haveModel = false;
 	uint64_t modelSerial = 0;
 	int modelPosSetSize = 0;
@@ -1142,6 +1143,7 @@ extern "C" int xxm_set_background(xxm_ctx* ctx, int32_t order, const float* rpro
 	ctx->nm.order = order;
 	ctx->nm.rprobs = ctx->rprobs.data();
 	ctx->nm.rconds = ctx->rconds.data();
+	ctx->bgCache.clear();  // background probabilities of k-mers under the previous model
 	ctx->nmOnDevice = false;
 	ctx->haveModel = false;
 	return 0;
@@ -1302,18 +1304,18 @@ static int reinitialize_impl(xxm_ctx* ctx, const double* pwm, const int32_t* col
 		// a sharded set: the thresholds of the tables follow the WHOLE set (branch_and_bound-inl.h:186-187, :417)
 		TRY(shard_sync(ctx));
 		if (posSetSize != ctx->nent) return ctx->fail("with a communicator attached every call refers to the whole sharded set: posSetSize must be the rank's sequence count");
-		build_pvalue_tables(pwm, cols, ncols, ctx->G.nent, ctx->G.total, ctx->opt.bgLog, ctx->nm, ctx->tab);
+		build_pvalue_tables(pwm, cols, ncols, ctx->G.nent, ctx->G.total, ctx->opt.bgLog, ctx->nm, ctx->tab, &ctx->bgCache);
 	} else if (ctx->G.external) {
 		// the caller runs the exchange itself (split-phase entry points) and has told us the counts of the whole set
 		if (ctx->G.loadSerial != ctx->loadSerial) return ctx->fail("xxm_set_global_counts must be repeated after xxm_load_seqset");
 		if (posSetSize != ctx->nent) return ctx->fail("with global counts set every call refers to the whole sharded set: posSetSize must be the rank's sequence count");
-		build_pvalue_tables(pwm, cols, ncols, ctx->G.nent, ctx->G.total, ctx->opt.bgLog, ctx->nm, ctx->tab);
+		build_pvalue_tables(pwm, cols, ncols, ctx->G.nent, ctx->G.total, ctx->opt.bgLog, ctx->nm, ctx->tab, &ctx->bgCache);
 	} else if (ncols <= 8 && std::getenv("XXM_DEVICE_TABLES")) {
 		// the enumeration, the stable sort and the cumulative class p-values on the device
 		model_header(pwm, cols, ncols, posSetSize, totalPositions, ctx->opt.bgLog, ctx->tab);
 		if (ctx->tab.error == 0) TRY(device_build_part0(ctx, ctx->tab, nullptr));
 	} else
-	build_pvalue_tables(pwm, cols, ncols, posSetSize, totalPositions, ctx->opt.bgLog, ctx->nm, ctx->tab);
+	build_pvalue_tables(pwm, cols, ncols, posSetSize, totalPositions, ctx->opt.bgLog, ctx->nm, ctx->tab, &ctx->bgCache);
 	const PvalueTables& T = ctx->tab;
 	if (T.error == 1) return ctx->fail("gapped motif with >8 match columns and a left part spanning >10 positions: reference behaviour undefined");
 	if (T.error == 2) return ctx->fail("PWM column not normalised (the reference asserts, branch_and_bound-inl.h:223)");
