@@ -23,7 +23,7 @@ bool build_pair_table(const uint32_t* ids, size_t nids, const int* coloff, int l
 	const int nR = len0 - nL;
 	const uint32_t rowsN = 1u << (2 * nL), colsN = 1u << (2 * nR);
 	// membership matrix over (left match columns) x (right match columns)
-	std::vector<Row256> R(rowsN);
+	Row256 R[256];  // (on the stack: this runs once per refinement step)
 	for (size_t i = 0; i < nids; ++i) R[ids[i] & (rowsN - 1)].set(ids[i] >> (2 * nL));
 	int pc[256];
 	int theta[256];
@@ -48,7 +48,7 @@ bool build_pair_table(const uint32_t* ids, size_t nids, const int* coloff, int l
 	for (int c = 1; c <= 256; ++c) levelOf[c] = present[c] ? ++m : 0;
 	if (m > 127) return false;
 	// nestedness: the row of size-level k must be exactly {y : theta[y] <= that size}
-	std::vector<Row256> S(static_cast<size_t>(m) + 1);
+	Row256 S[129];
 	for (uint32_t y = 0; y < colsN; ++y)
 		if (theta[y] <= 256) S[levelOf[theta[y]]].set(y);
 	for (int k = 2; k <= m; ++k) S[k] |= S[k - 1];
