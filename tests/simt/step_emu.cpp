@@ -4,6 +4,7 @@
 //   k_count_pwm3     (xxm_select2.cuh)  30-column context counts of the sites vs Motif::updateCounts, refinementPhase/Motif.cpp:617-672
 // on seeded candidate lists (clustered positions, ties of float-rounded p-values, N residues, sites at both sequence ends).
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -355,6 +356,38 @@ int run_rc_case(const std::string& name, int nseq, int n0Lo, int n0Hi, double hi
 	return bad ? 1 : 0;
 }
 
+// the stable LSD radix sort of (float-score bits, index) pairs (k_rs_hist, k_scan_block_sums / k_scan_sums / k_scan_apply, k_rs_scatter;
+// sortSitesByScore, StartPosUtils.h:68-70 -- glibc's qsort is a merge sort, i.e. stable) against std::stable_sort
+int run_sort_case(const std::string& name, uint32_t n, uint32_t distinct, uint32_t seed) {
+	std::mt19937 rng(seed);
+	std::vector<uint32_t> keys(n), vals(n);
+	std::vector<float> pool(distinct);
+	for (auto& f : pool) f = std::ldexp(static_cast<float>((rng() % 100000) + 1) / 100000.0f, -static_cast<int>(rng() % 40));
+	for (uint32_t i = 0; i < n; ++i) { const float f = pool[rng() % distinct]; std::memcpy(&keys[i], &f, 4); vals[i] = i; }
+	std::vector<uint32_t> order(n);
+	for (uint32_t i = 0; i < n; ++i) order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+	const uint32_t nchunks = (n + kSortChunk - 1) / kSortChunk;
+	std::vector<uint32_t> ka = keys, va = vals, kb(n), vb(n), hist(256u * nchunks), sums((256u * nchunks + 1023) / 1024 + 1);
+	uint32_t *pa = ka.data(), *qa = va.data(), *pb = kb.data(), *qb = vb.data();
+	for (int pass = 0; pass < 4; ++pass) {
+		const int shift = 8 * pass;
+		emu::launch(nchunks, 256, [&] { k_rs_hist(pa, n, shift, hist.data(), nchunks); });
+		const uint32_t nh = 256u * nchunks, nbk = (nh + 1023) / 1024;
+		emu::launch(nbk, 256, [&] { k_scan_block_sums(hist.data(), nh, sums.data()); });
+		emu::launch(1, 1024, [&] { k_scan_sums(sums.data(), nbk); });
+		emu::launch(nbk, 256, [&] { k_scan_apply(hist.data(), nh, sums.data()); });
+		emu::launch(nchunks, kSortWarps * 32, [&] { k_rs_scatter(pa, qa, n, shift, hist.data(), nchunks, pb, qb); });
+		std::swap(pa, pb);
+		std::swap(qa, qb);
+	}
+	int bad = 0;
+	for (uint32_t i = 0; i < n && !bad; ++i)
+		if (qa[i] != order[i] || pa[i] != keys[order[i]]) { std::fprintf(stderr, "FAIL %s: rank %u holds entry %u, expected %u\n", name.c_str(), i, qa[i], order[i]); ++bad; }
+	std::printf("%-20s %7u keys, %5u distinct scores, %u chunks: %s\n", name.c_str(), n, distinct, nchunks, bad ? "DIFFERENT" : "identical");
+	return bad;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -398,6 +431,17 @@ int main(int argc, char** argv) {
 			if (!sel) continue;
 		}
 		failed += run_rc_case(z.name, z.nseq, z.n0Lo, z.n0Hi, z.frac, z.span, z.nval, z.nSite, z.seed) ? 1 : 0;
+		++ran;
+	}
+	struct So { const char* name; uint32_t n, distinct, seed; };
+	const So sos[] = {{"sort_two", 2, 2, 31}, {"sort_one_chunk", 1500, 40, 32}, {"sort_ties", 9000, 3, 33}, {"sort_many_chunks", 70000, 5000, 34}};
+	for (const So& z : sos) {
+		if (argc > 1) {
+			bool sel = false;
+			for (int i = 1; i < argc; ++i) sel = sel || std::string(z.name) == argv[i];
+			if (!sel) continue;
+		}
+		failed += run_sort_case(z.name, z.n, z.distinct, z.seed) ? 1 : 0;
 		++ran;
 	}
 	std::printf("%d runs, %d failed\n", ran, failed);

@@ -17,7 +17,8 @@ CASES = ["tile_scan", "uniform_1kb", "ragged_N", "revcomp_ragged", "dense_lowcom
 
 
 STEP_CASES = ["clustered_uniform", "ragged_short", "long_motif", "all_sites_dense", "few_sites", "tiny", "zoops_uniform", "zoops_ragged_shift", "zoops_long_runs",
-              "zoops_sparse", "rc_uniform", "rc_ragged", "rc_long_motif", "rc_long_sequences", "rc_palindromic_dense"]
+              "zoops_sparse", "rc_uniform", "rc_ragged", "rc_long_motif", "rc_long_sequences", "rc_palindromic_dense", "sort_two", "sort_one_chunk", "sort_ties",
+              "sort_many_chunks"]
 
 
 @pytest.fixture(scope="module")
@@ -35,7 +36,8 @@ def test_select_and_count_kernels_under_emulator(step_exe, case):
     """k_select_cls_fwd vs the reference's updateMultOcc greedy (StartPosUtils.h:12-28), k_count_pwm3 vs a column-by-column count;
     zoops_*: the re-score kernels k_eval_list + k_select_zoops vs the ZOOPS branch of
     fill_elongSites_with_possible_startPositions (StartPosUpdater-inl.h:167-203); rc_*: k_select_cls_rc (forward rule + one cursor into
-    the frozen forward list) vs the reference's updateMultOcc with --revcomp, literally (the look-back walk, StartPosUtils.h:29-58)"""
+    the frozen forward list) vs the reference's updateMultOcc with --revcomp, literally (the look-back walk, StartPosUtils.h:29-58);
+    sort_*: the stable radix sort of (score bits, index) pairs vs std::stable_sort"""
     r = subprocess.run([step_exe, case], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
