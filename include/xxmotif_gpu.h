@@ -344,6 +344,9 @@ int xxm_check_guards(xxm_ctx* ctx, int32_t* checked, int32_t* damaged);
 /* with XXM_TRACE set in the environment the library sums the wall time of every C-ABI call (and of named sections inside
  * some of them) per name; xxm_trace_dump prints the table to stderr and clears it (xxm_destroy does the same) */
 int xxm_trace_dump(void);
+/* XXM_SCAN_GEN=6 in the environment (read by xxm_create) selects the previous generation of the pair-table scan kernels
+ * (even/odd hit masks + k_expand6) instead of the default (window-order masks + k_expand7); both give the same site lists --
+ * it exists for A/B timing and for the parity tests of the older kernels */
 /* the CUDA stream the context launches on, as a cudaStream_t cast to void* (for external event timing) */
 void* xxm_stream(const xxm_ctx* ctx);
 
