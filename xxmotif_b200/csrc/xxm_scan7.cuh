@@ -37,17 +37,6 @@ constexpr int kExpand7Warps = kExpand7Threads / 32;
 constexpr int kE7WarpWords = kTileWords / kExpand7Warps;  // 128: four words per lane
 constexpr int kE7Queue = 512;                             // queue entries per warp and round
 
-// index of the highest set bit (x != 0)
-__device__ __forceinline__ uint32_t bfind32(uint32_t x) {
-#ifdef XXM_SIMT_EMU
-	return 31u - static_cast<uint32_t>(__builtin_clz(x));
-#else
-	uint32_t j;
-	asm("bfind.u32 %0, %1;" : "=r"(j) : "r"(x));
-	return j;
-#endif
-}
-
 template <bool kFast, bool kUniform>
 __global__ void __launch_bounds__(kExpand7Threads, 6) k_expand7(SeqStream S, Model M, Expand6IO io) {
 	__shared__ __align__(16) uint64_t s_codesAll[kExpand7Warps][kE7WarpWords + 2];
