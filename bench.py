@@ -422,7 +422,10 @@ def _ours(a):
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     # packing threads of xxm_load_seqset (the e2e leg): the ranks of one box share its cores
-    pack_threads = max(1, min(12, (3 * (os.cpu_count() or 1)) // (4 * max(1, world))))
+    # (a rank with 12 or more cores to itself leaves two of them to its own thread and the driver's: 14 packers on the 16-core box
+    # load 1 GB in 14.0-14.5 ms, 12 in 14.6-14.8 ms, 16 in 15.1 ms -- profiles/r02b_load_paths_hybrid_threads.txt, r02_load_paths.json)
+    per_rank = (os.cpu_count() or 1) // max(1, world)
+    pack_threads = max(1, min(14, per_rank - 2)) if per_rank >= 12 else max(1, (3 * per_rank) // 4)
     os.environ.setdefault("XXM_PACK_THREADS", str(pack_threads))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
