@@ -64,7 +64,7 @@ int xxm_set_options(xxm_ctx* ctx, const xxm_options* opt);
  * (seqset.cpp:128-178) + calculateSequenceFeatures (seqset.cpp:21-36).
  * n[i], codes: the sequences BEFORE createRevcomp, codes 0=N,1=A,2=C,3=G,4=T concatenated without separators.
  * The set is packed once (2-bit codes + 1-bit N mask, reverse strand included when revcomp != 0) and then stays resident in
- * HBM.  With at least 6 packing threads (XXM_PACK_THREADS, default min(12, 3/4 of the host cores)) the host cores pack it
+ * HBM.  With at least 6 packing threads (XXM_PACK_THREADS, default: cores - 2 up to 14 on hosts with 12 or more cores, else 3/4 of them) the host cores pack it
  * chunk by chunk while earlier chunks are on the bus, so 0.375 bytes per stored base cross PCIe; with fewer, the raw bytes
  * are copied and packed on the device.  total[]/avgLength[] follow the
  * reference's arithmetic, quirks included. */

@@ -1009,7 +1009,7 @@ static int load_pack_hybrid(xxm_ctx* ctx, int32_t nent, const int32_t* n, const 
 }
 
 // a1.  Layout from the lengths, then the packing step where it is cheaper: on the host cores when there are at least
-// kMinPackThreads of them for this GPU (XXM_PACK_THREADS, default min(12, 3/4 of the cores)), else on the device.
+// kMinPackThreads of them for this GPU (XXM_PACK_THREADS, default: cores - 2 up to 14 on hosts with 12 or more cores, else 3/4 of the cores), else on the device.
 extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, const uint8_t* codes, int32_t revcomp) {
 	XXM_NVTX("xxm_load_seqset");
 	CK(cudaSetDevice(ctx->device));
