@@ -605,7 +605,11 @@ static int load_pack_on_host(xxm_ctx* ctx, int32_t nent, const int32_t* n, const
 	uint32_t* const hMask = reinterpret_cast<uint32_t*>(ctx->h_pack + ctx->h_packCap * 8);
 	ctx->notX.resize(nent);
 	// ---- chunks of whole sequences: cut by this thread (which owns wordOff / len), packed by the workers, copied in order
-	constexpr uint64_t kChunkBytes = 8ull << 20;
+	// (the workers take chunks as they come, so the load ends up to one chunk's packing time after the ideal, while every chunk
+	// costs two copy calls: 1M x 1 kb with 14 threads loads in 13.2-13.4 ms with 3-4 MB chunks, 13.5-13.7 ms with 8 MB, 14.1 ms with
+	// 2 MB, 17.9 ms with 1 MB -- profiles/r02e_pack_chunk_size.txt; XXM_PACK_CHUNK_KB overrides it for measurements)
+	uint64_t kChunkBytes = 4ull << 20;
+	if (const char* e = std::getenv("XXM_PACK_CHUNK_KB")) kChunkBytes = std::max<uint64_t>(64ull << 10, static_cast<uint64_t>(std::atoll(e)) << 10);
 	struct Chunk { int s0, s1; uint64_t b0; uint32_t w0, w1; uint32_t bad; };
 	const size_t maxChunks = static_cast<size_t>(rawTotal / kChunkBytes) + 2;
 	std::vector<Chunk> chunks(maxChunks);
