@@ -561,7 +561,7 @@ def _ours(a):
         fr = raw_chunks / all_chunks
         h2d = int(fr * codes.size + (1 - fr) * 12 * packed_words + 4 * nent + 64 * 1024)
         d2h = int(job.last_d2h_bytes + fr * 4 * nent)
-        how = ("%s host threads pack 4 MB chunks from the back of the set while raw chunks from the front cross the bus and are packed on the device: "
+        how = ("%s host threads pack 8 MB chunks from the back of the set while raw chunks from the front cross the bus and are packed on the device: "
                "%d of %d chunks went raw in the last step" % (os.environ["XXM_PACK_THREADS"], raw_chunks, all_chunks))
     elif host_pack:
         h2d = int(12 * packed_words + 4 * nent + 64 * 1024)   # packed stream (8 B codes + 4 B N mask per 32 bases) + lengths + the per-model tables of the step
