@@ -204,6 +204,27 @@ int xxm_optimize_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* p);
 int xxm_maximize_motif_length(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* p, int32_t lengthCorrection, int32_t* noChange);
 int xxm_iterate_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* p, int32_t* rounds);
 
+/* ---- several motifs at once on one GPU ("batch motifs ... so small inputs still fill the GPU") ----
+ * MotifContainer::iterate (MotifContainer.cpp:216-270) refines its motifs one after the other, and nothing the loop body
+ * touches is shared between them (the singletons' buffers are scratch, IterateMotif::elongPWM is rewritten by iteration 0
+ * of every column variant before iteration 1 reads it, Iterate_Motif.cpp:78-86).  On the sets of configs 1-3 and 5 one
+ * motif's kernels occupy a fraction of a B200 and its host thread spends as long building tables as the device scanning.
+ * xxm_share_seqset makes ctx a VIEW of owner: it reads owner's packed stream, per-sequence arrays, options and NullModel
+ * tables (nothing is copied on the device) and keeps its own stream, model, tables and site lists.  Both contexts must be
+ * on one device; owner must hold a loaded, unsharded set and may not reload it, change its background or be destroyed
+ * while views exist (xxm_load_seqset / xxm_set_background fail, xxm_view_count says how many).  A view becomes an
+ * ordinary context again by loading its own set.  xxm_view_create = xxm_create on owner's device + xxm_share_seqset.
+ * xxm_iterate_motifs runs xxm_iterate_motif for nmotifs motifs on nctx contexts of one set (ctxs[0] and its views, or any
+ * contexts holding the same set), one host thread per context, motifs handed out in order as contexts fall free; every
+ * motif's result is bit-identical to a serial xxm_iterate_motif (each runs start to end on one context).  params holds
+ * nparams = 1 (all motifs) or nmotifs entries; rounds[nmotifs] as in xxm_iterate_motif.  Returns 0, or the first non-zero
+ * code of a motif (*failed = its index, text in xxm_last_error of the context that ran it = ctxs[*failedCtx]). */
+int xxm_share_seqset(xxm_ctx* ctx, xxm_ctx* owner);
+int xxm_view_create(xxm_ctx* owner, xxm_ctx** out);
+int xxm_view_count(const xxm_ctx* ctx);
+int xxm_iterate_motifs(xxm_ctx* const* ctxs, int32_t nctx, xxm_motif* motifs, int32_t nmotifs, const xxm_refine_params* params, int32_t nparams,
+                       int32_t* rounds, int32_t* failed, int32_t* failedCtx);
+
 /* ---- a8/a9 split in phases, for a sequence set sharded over several GPUs (one context per GPU) ---------
  * The reference chooses the optimal subset over ALL sites (getBestSubset) and recounts the PWM from them.  With shards,
  * each context reports the run-length histogram of its float site scores (xxm_score_runs, ascending, score 1 excluded);

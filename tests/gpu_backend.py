@@ -6,9 +6,14 @@ from backends import tables_dump_dense
 
 
 class GpuBackend:
-    def __init__(self, ti, device=0):
+    def __init__(self, ti, device=0, ctx=None):
         self.ti = ti
         t = ti.t
+        if ctx is not None:  # a context that already holds the trace's set, options and background (a view, refine.make_view)
+            self.ctx = ctx
+            self.nent = ctx.nent
+            self.max_leng = int(t["in.pos.max_leng"][0])
+            return
         self.ctx = xb.Context(device)
         self.ctx.set_options(mops=ti.mops, oops=ti.oops, localization=ti.localization, bg=ti.bg, bgLog=ti.bgLog,
                              maxMotifsPerSequence=int(t["cfg.maxMotifsPerSequence"][0]), maxSeqCount=int(t["cfg.maxSeqCount"][0]),

@@ -159,19 +159,24 @@ double order_statistics_pvalue(LogSum& ls, int64_t motifNb, int64_t N, double p)
 
 float fast_log(float x) {
 	if (x != x) return x;
-	static float lg2[1025];
-	static float diff[1025];
-	static bool initialized = false;
-	if (!initialized) {
-		float prev = 0.0f;
-		lg2[0] = 0.0f;
-		for (int i = 1; i <= 1024; ++i) {
-			lg2[i] = std::log(static_cast<float>(1024 + i)) * 1.442695041f - 10.0f;  // float overload, as in the reference
-			diff[i - 1] = (lg2[i] - prev) * 1.2352E-4f;
-			prev = lg2[i];
+	// (a function-local static object: initialised once, thread-safely -- contexts may be driven from several host threads)
+	struct Tables {
+		float lg2[1025];
+		float diff[1025];
+		Tables() {
+			float prev = 0.0f;
+			lg2[0] = 0.0f;
+			diff[1024] = 0.0f;
+			for (int i = 1; i <= 1024; ++i) {
+				lg2[i] = std::log(static_cast<float>(1024 + i)) * 1.442695041f - 10.0f;  // float overload, as in the reference
+				diff[i - 1] = (lg2[i] - prev) * 1.2352E-4f;
+				prev = lg2[i];
+			}
 		}
-		initialized = true;
-	}
+	};
+	static const Tables tb;
+	const float* lg2 = tb.lg2;
+	const float* diff = tb.diff;
 	int32_t bits;
 	std::memcpy(&bits, &x, 4);
 	const int32_t a = ((bits & 0x7F800000) >> 23) - 0x7f;

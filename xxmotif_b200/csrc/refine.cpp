@@ -7,9 +7,11 @@
 #include "../../include/xxmotif_gpu.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -208,4 +210,52 @@ extern "C" int xxm_iterate_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_pa
 		for (size_t i = 0; i < n; ++i) { m->siteSeq[i] = static_cast<int32_t>(a[i] >> 32); m->sitePos[i] = static_cast<int32_t>(static_cast<uint32_t>(a[i]) ^ 0x80000000u); }
 	}
 	return 0;
+}
+
+// The motifs of MotifContainer::iterate (MotifContainer.cpp:216-270), several at a time: one host thread per context, every
+// thread takes the next motif that nobody has taken (the list is in the caller's order, so with one context this is the
+// reference's loop).  A motif runs from start to end on one context: its result does not depend on the others.
+extern "C" int xxm_iterate_motifs(xxm_ctx* const* ctxs, int32_t nctx, xxm_motif* motifs, int32_t nmotifs, const xxm_refine_params* params, int32_t nparams,
+                                  int32_t* rounds, int32_t* failed, int32_t* failedCtx) {
+	if (failed) *failed = -1;
+	if (failedCtx) *failedCtx = -1;
+	if (nctx < 1 || nmotifs < 0 || !ctxs || (nmotifs && (!motifs || !params || !rounds))) return 1;
+	if (nparams != 1 && nparams != nmotifs) return 1;
+	for (int32_t i = 0; i < nctx; ++i) {
+		if (!ctxs[i]) return 1;
+		for (int32_t j = 0; j < i; ++j)
+			if (ctxs[j] == ctxs[i]) return 1;  // two threads on one context
+	}
+	std::atomic<int32_t> next{0};
+	std::atomic<int32_t> firstBad{-1};
+	std::vector<int32_t> code(static_cast<size_t>(nctx), 0), badMotif(static_cast<size_t>(nctx), -1);
+	auto work = [&](int32_t c) {
+		for (;;) {
+			if (firstBad.load(std::memory_order_relaxed) >= 0) return;  // a motif failed: nobody starts another one
+			const int32_t i = next.fetch_add(1);
+			if (i >= nmotifs) return;
+			const int rc = xxm_iterate_motif(ctxs[c], &motifs[i], &params[nparams == 1 ? 0 : i], &rounds[i]);
+			if (rc) {
+				code[static_cast<size_t>(c)] = rc;
+				badMotif[static_cast<size_t>(c)] = i;
+				int32_t none = -1;
+				firstBad.compare_exchange_strong(none, c);
+				return;
+			}
+		}
+	};
+	const int32_t nthreads = std::min(nctx, std::max<int32_t>(1, nmotifs));
+	std::vector<std::thread> pool;
+	pool.reserve(static_cast<size_t>(nthreads));
+	for (int32_t c = 1; c < nthreads; ++c) pool.emplace_back(work, c);
+	work(0);  // the caller's thread drives the first context
+	for (std::thread& t : pool) t.join();
+	// report the failure with the smallest motif index (several contexts may have failed before they saw the flag)
+	int32_t bad = -1;
+	for (int32_t c = 0; c < nctx; ++c)
+		if (code[static_cast<size_t>(c)] && (bad < 0 || badMotif[static_cast<size_t>(c)] < badMotif[static_cast<size_t>(bad)])) bad = c;
+	if (bad < 0) return 0;
+	if (failed) *failed = badMotif[static_cast<size_t>(bad)];
+	if (failedCtx) *failedCtx = bad;
+	return code[static_cast<size_t>(bad)];
 }

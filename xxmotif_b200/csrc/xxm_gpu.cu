@@ -47,12 +47,16 @@ struct CallTimes {
 	struct E { const char* name; uint64_t n; double us; };
 	std::vector<E> e;
 	bool on = std::getenv("XXM_TRACE") != nullptr;
+	std::mutex mu;  // contexts may be driven from several host threads (xxm_multi, xxm_iterate_motifs)
 	void add(const char* name, double us) {
+		std::lock_guard<std::mutex> g(mu);
 		for (E& x : e) if (x.name == name) { x.n++; x.us += us; return; }
 		e.push_back(E{name, 1, us});
 	}
 	void print() {
-		if (!on || e.empty()) return;
+		if (!on) return;
+		std::lock_guard<std::mutex> g(mu);
+		if (e.empty()) return;
 		std::sort(e.begin(), e.end(), [](const E& a, const E& b) { return a.us > b.us; });
 		for (const E& x : e) std::fprintf(stderr, "xxm calls: %-36s n=%6llu total %10.1f us  avg %9.1f us\n", x.name, static_cast<unsigned long long>(x.n), x.us, x.us / x.n);
 		e.clear();
@@ -93,8 +97,10 @@ constexpr size_t kGuardBytes = 256;
 struct GuardRegistry {
 	bool on = std::getenv("XXM_DEBUG_GUARDS") != nullptr;
 	std::vector<std::pair<void*, size_t>> bufs;  // (device pointer, user bytes)
-	void add(void* p, size_t bytes) { bufs.emplace_back(p, bytes); }
+	std::mutex mu;
+	void add(void* p, size_t bytes) { std::lock_guard<std::mutex> g(mu); bufs.emplace_back(p, bytes); }
 	void remove(void* p) {
+		std::lock_guard<std::mutex> g(mu);
 		for (size_t i = 0; i < bufs.size(); ++i)
 			if (bufs[i].first == p) { bufs[i] = bufs.back(); bufs.pop_back(); return; }
 	}
@@ -105,6 +111,12 @@ template <typename T>
 struct DevBuf {
 	T* p = nullptr;
 	size_t cap = 0;
+	bool borrowed = false;  // p belongs to another context (xxm_share_seqset): never written through, never freed here
+	DevBuf() = default;
+	DevBuf(const DevBuf&) = delete;
+	DevBuf& operator=(const DevBuf&) = delete;
+	~DevBuf() { release(); }  // (xxm_destroy releases the buffers with the device current; this only catches what it does not name)
+	void borrow(const DevBuf& o) { release(); p = o.p; cap = o.cap; borrowed = true; }
 	cudaError_t ensure(size_t n) {
 		if (n <= cap) return cudaSuccess;
 		release();
@@ -120,9 +132,10 @@ struct DevBuf {
 		return e;
 	}
 	void release() {
-		if (p) { if (g_guards.on) g_guards.remove(p); cudaFree(p); }
+		if (p && !borrowed) { if (g_guards.on) g_guards.remove(p); cudaFree(p); }
 		p = nullptr;
 		cap = 0;
+		borrowed = false;
 	}
 };
 
@@ -175,6 +188,10 @@ struct xxm_ctx {
 	DevBuf<uint32_t> d_nmask, d_wordOff, d_blk2seq;
 	DevBuf<int32_t> d_len;
 	SeqStream S{};
+	// several contexts of one device on one resident set (xxm_share_seqset): a view borrows the five read-only buffers above and
+	// the NullModel tables of its owner; the owner counts its views and refuses to reload or be re-modelled while any exist
+	xxm_ctx* seqOwner = nullptr;
+	std::atomic<int> views{0};
 
 	// ---- background + model
 	NullModelView nm;
@@ -335,6 +352,7 @@ struct xxm_ctx {
 
 static inline uint32_t cdiv(uint64_t a, uint32_t b) { return static_cast<uint32_t>((a + b - 1) / b); }
 static int stage_scan(xxm_ctx* ctx);  // xxm_gpu_scan5.inc
+static void drop_shared_seqset(xxm_ctx* ctx);
 
 #define NCK(call)                                                                                              \
 	do {                                                                                                       \
@@ -420,6 +438,20 @@ extern "C" int xxm_create(int device, xxm_ctx** out) {
 	return 0;
 }
 
+// a view lets go of its owner's set (before it loads its own, adopts another one, or dies)
+static void drop_shared_seqset(xxm_ctx* ctx) {
+	if (!ctx->seqOwner) return;
+	ctx->d_codes.release(); ctx->d_nmask.release(); ctx->d_wordOff.release(); ctx->d_blk2seq.release(); ctx->d_len.release();
+	std::memset(&ctx->S, 0, sizeof ctx->S);
+	ctx->nm = NullModelView();
+	ctx->bgCache.clear();
+	ctx->nmOnDevice = false;
+	ctx->nent = 0;
+	ctx->haveModel = false;
+	ctx->seqOwner->views.fetch_sub(1);
+	ctx->seqOwner = nullptr;
+}
+
 extern "C" int xxm_comm_destroy(xxm_ctx* ctx);
 extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	if (!ctx) return;
@@ -427,6 +459,9 @@ extern "C" void xxm_destroy(xxm_ctx* ctx) {
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
 	xxm_comm_destroy(ctx);
+	drop_shared_seqset(ctx);
+	if (ctx->views.load() > 0)
+		std::fprintf(stderr, "libxxmotif_gpu: xxm_destroy of a context whose sequence set is still shared by %d view(s): destroy the views first\n", ctx->views.load());
 	// DevBuf members are released explicitly (no destructor: the struct is copied nowhere, but keep it trivial)
 	ctx->d_codes.release(); ctx->d_nmask.release(); ctx->d_wordOff.release(); ctx->d_blk2seq.release(); ctx->d_len.release();
 	ctx->d_rank0.release(); ctx->d_rank1.release(); ctx->d_hit0.release(); for (int k = 0; k < 2; ++k) { ctx->d_ids[k].release(); ctx->d_cls[k].release(); ctx->d_clsOk[k].release(); }
@@ -1018,6 +1053,9 @@ extern "C" int xxm_load_seqset(xxm_ctx* ctx, int32_t nent, const int32_t* n, con
 	XXM_NVTX("xxm_load_seqset");
 	CK(cudaSetDevice(ctx->device));
 	if (nent <= 0) return ctx->fail("empty sequence set");
+	if (ctx->views.load() > 0) return ctx->fail("xxm_load_seqset: %d view(s) share this context's set (xxm_share_seqset); destroy or re-point them first", ctx->views.load());
+	CK(cudaStreamSynchronize(ctx->stream));
+	drop_shared_seqset(ctx);  // a view that loads its own set stops being one (it must never write through borrowed pointers)
 	static const bool trace = std::getenv("XXM_TRACE") != nullptr;
 	const auto tStart = std::chrono::steady_clock::now();
 	// whatever happens below, the previous set is gone: a failed load must not leave a valid-looking model over a partly
@@ -1141,6 +1179,7 @@ extern "C" int xxm_seqset_info(const xxm_ctx* ctx, int32_t* total, double* avgLe
 extern "C" int xxm_set_background(xxm_ctx* ctx, int32_t order, const float* rprobs, const float* rconds) {
 	XXM_NVTX("xxm_set_background");
 	if (order < 0 || order > 9) return ctx->fail("background order %d not supported", order);
+	if (ctx->views.load() > 0) return ctx->fail("xxm_set_background: %d view(s) read this context's NullModel tables (xxm_share_seqset)", ctx->views.load());
 	const size_t n = static_cast<size_t>(1) << (3 * (order + 1));
 	ctx->rprobs.assign(rprobs, rprobs + n);
 	ctx->rconds.assign(rconds, rconds + n);
@@ -1876,3 +1915,4 @@ static int scan_full_finish(xxm_ctx* ctx, int32_t* nbSites, int32_t* nbBestSites
 #include "xxm_gpu_part6.inc"
 #include "xxm_gpu_part8.inc"
 #include "xxm_gpu_part9.inc"
+#include "xxm_gpu_part10.inc"

@@ -6,7 +6,8 @@ import numpy as np
 
 from . import capi
 
-EXTRA_EXPORTS = ["xxm_optimize_motif", "xxm_maximize_motif_length", "xxm_iterate_motif"]
+EXTRA_EXPORTS = ["xxm_optimize_motif", "xxm_maximize_motif_length", "xxm_iterate_motif", "xxm_iterate_motifs", "xxm_share_seqset", "xxm_view_create",
+                 "xxm_view_count"]
 
 
 class XxmMotif(C.Structure):
@@ -32,6 +33,14 @@ def _lib():
         L.xxm_maximize_motif_length.argtypes = [vp, P(XxmMotif), P(XxmRefineParams), i32, P(i32)]
         L.xxm_iterate_motif.restype = i32
         L.xxm_iterate_motif.argtypes = [vp, P(XxmMotif), P(XxmRefineParams), P(i32)]
+        L.xxm_iterate_motifs.restype = i32
+        L.xxm_iterate_motifs.argtypes = [P(vp), i32, P(XxmMotif), i32, P(XxmRefineParams), i32, P(i32), P(i32), P(i32)]
+        L.xxm_share_seqset.restype = i32
+        L.xxm_share_seqset.argtypes = [vp, vp]
+        L.xxm_view_create.restype = i32
+        L.xxm_view_create.argtypes = [vp, P(vp)]
+        L.xxm_view_count.restype = i32
+        L.xxm_view_count.argtypes = [vp]
         L._refine_ready = True
     return L
 
@@ -96,3 +105,50 @@ class Refiner:
         r = C.c_int32(0)
         self.ctx._ck(_lib().xxm_iterate_motif(self.ctx.h, C.byref(motif.m), C.byref(self.p), C.byref(r)))
         return r.value
+
+
+def make_view(owner):
+    """A new context on the owner's GPU that reads the owner's resident set, options and NullModel tables and has its own stream,
+    model and site lists (xxm_view_create).  Close the views before the owner."""
+    L = _lib()
+    h = C.c_void_p()
+    if L.xxm_view_create(owner.h, C.byref(h)):
+        raise capi.XxmError(L.xxm_last_error(None).decode())
+    v = capi.Context.__new__(capi.Context)
+    v.L, v.h, v.nent, v.ncols = L, h, owner.nent, 0
+    return v
+
+
+def share_seqset(ctx, owner):
+    """xxm_share_seqset: an existing context becomes a view of owner's set."""
+    ctx._ck(_lib().xxm_share_seqset(ctx.h, owner.h))
+    ctx.nent = owner.nent
+
+
+def view_count(ctx):
+    return int(_lib().xxm_view_count(ctx.h))
+
+
+def iterate_motifs(ctxs, motifs, params):
+    """xxm_iterate_motifs: the motifs of MotifContainer::iterate several at a time, one host thread per context (an owner and its
+    views).  motifs: list of Motif, updated in place; params: one Refiner (its switches are used for every motif).  Returns
+    the rounds of every motif."""
+    L = _lib()
+    n = len(motifs)
+    arr = (XxmMotif * max(1, n))()
+    for i, m in enumerate(motifs):
+        C.memmove(C.byref(arr[i]), C.byref(m.m), C.sizeof(XxmMotif))  # (the site arrays stay the Motif objects' own: only pointers move)
+    hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    rounds = (C.c_int32 * max(1, n))()
+    bad, badCtx = C.c_int32(-1), C.c_int32(-1)
+    p = XxmRefineParams()
+    C.memmove(C.byref(p), C.byref(params.p), C.sizeof(XxmRefineParams))
+    p.elongPWM = None
+    rc = L.xxm_iterate_motifs(hs, len(ctxs), arr, n, C.byref(p), 1, rounds, C.byref(bad), C.byref(badCtx))
+    for i, m in enumerate(motifs):
+        C.memmove(C.byref(m.m), C.byref(arr[i]), C.sizeof(XxmMotif))
+    if rc:
+        who = ctxs[badCtx.value] if 0 <= badCtx.value < len(ctxs) else None
+        msg = L.xxm_last_error(who.h).decode() if who is not None else "invalid arguments"
+        raise capi.XxmError("motif %d: %s" % (bad.value, msg))
+    return [int(rounds[i]) for i in range(n)]
