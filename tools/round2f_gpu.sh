@@ -12,3 +12,6 @@ echo "views rc=$?" | tee -a $O/r02f_status.txt
 echo "motif_batch rc=$?" | tee -a $O/r02f_status.txt
 tail -3 $O/r02f_pytest_parity.log $O/r02f_pytest_views.log
 cat $O/r02f_motif_batch.json
+( time timeout 25 python tools/motif_batch.py --shapes cfg2 --contexts 8 --motifs 16 ) > $O/r02f_motif_batch_8ctx.json 2> $O/r02f_motif_batch_8ctx.err
+echo "motif_batch8 rc=$?" | tee -a $O/r02f_status.txt
+cat $O/r02f_motif_batch_8ctx.json
