@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--matrix-only", default="", help="comma-separated workload names for the `configs` array")
     ap.add_argument("--matrix-steps", type=int, default=10)
     ap.add_argument("--refine-sample-seqs", type=int, default=30000)
+    ap.add_argument("--no-motif-batch", action="store_true", help="skip the `motif_batch` object (several motifs at once on the small sets)")
     return ap.parse_args()
 
 
@@ -685,6 +686,17 @@ def _ours(a):
         del codes, pinned
         out["configs"] = matrix_lines(ctx, a, peak, main_entry)
     ctx.close()
+    # ---- SURVEY 8(f) row 2, "batch motifs": 16 start models refined one after the other (the reference's loop) and four at a time
+    # on views of one resident set, on the small sets of configs 1 and 2.  A separate process with its own limit (tools/motif_batch.py):
+    # whatever happens there cannot cost the line above its numbers.
+    if world == 1 and not a.no_motif_batch:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "motif_batch.py"), "--shapes", "cfg1,cfg2", "--contexts", "4", "--motifs", "16"],
+                               capture_output=True, text=True, timeout=120)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            out["motif_batch"] = json.loads(lines[-1]) if lines else {"failed": "rc %d: %s" % (r.returncode, r.stderr.strip()[-300:])}
+        except Exception as ex:
+            out["motif_batch"] = {"failed": str(ex)}
     if dist:
         dist.destroy_process_group()
     return out, rank
