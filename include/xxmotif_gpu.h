@@ -219,6 +219,17 @@ int xxm_iterate_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* p, in
  * motif's result is bit-identical to a serial xxm_iterate_motif (each runs start to end on one context).  params holds
  * nparams = 1 (all motifs) or nmotifs entries; rounds[nmotifs] as in xxm_iterate_motif.  Returns 0, or the first non-zero
  * code of a motif (*failed = its index, text in xxm_last_error of the context that ran it = ctxs[*failedCtx]). */
+/* The column variants of ONE motif several at a time (the other half of that row: "batch the <= 11 column variants x 3 inner
+ * iterations of maximizeMotifLength").  A variant depends on the motif's PWM, its columns and the candidate list of the motif's
+ * last full scan, and on no other variant (iteration 0 rewrites elongPWM in all 30 columns before iteration 1 reads it, or the
+ * variant is dropped, Iterate_Motif.cpp:73-90); only the choice among them is sequential (:103) and is made once all are known.
+ * xxm_share_candidates lends a view the (sequence, position) arrays of its owner's bestStartPos until the owner scans again;
+ * xxm_maximize_motif_length_on / xxm_iterate_motif_on take ctxs[0] = the context that holds the motif's scan and nctx - 1 views
+ * of it, one host thread per context, variants handed out in loop order; nctx = 1 is xxm_maximize_motif_length / _iterate_motif.
+ * Results are bit-identical to the one-context calls (return 3 = internal inconsistency, never seen). */
+int xxm_share_candidates(xxm_ctx* ctx, xxm_ctx* owner);
+int xxm_maximize_motif_length_on(xxm_ctx* const* ctxs, int32_t nctx, xxm_motif* m, const xxm_refine_params* p, int32_t lengthCorrection, int32_t* noChange);
+int xxm_iterate_motif_on(xxm_ctx* const* ctxs, int32_t nctx, xxm_motif* m, const xxm_refine_params* p, int32_t* rounds);
 int xxm_share_seqset(xxm_ctx* ctx, xxm_ctx* owner);
 int xxm_view_create(xxm_ctx* owner, xxm_ctx** out);
 int xxm_view_count(const xxm_ctx* ctx);

@@ -19,6 +19,7 @@ struct xxm_ctx {
 	std::atomic<int> violations{0};
 	uint64_t model = 0;      // hash of the last reinitialize
 	uint64_t list = 0;       // hash of the last re-score / scan
+	uint64_t cand = 0;       // candidate list of the last full scan (bestStartPos), or the one borrowed from the owner
 	uint64_t kept = 0;       // list set aside by xxm_elong_keep
 	int calls = 0;
 	int failOnModel = -1;    // xxm_reinitialize fails when the PWM carries this marker
@@ -58,12 +59,14 @@ int xxm_reinitialize(xxm_ctx* ctx, const double* pwm, const int32_t* cols, int32
 int xxm_scan_full(xxm_ctx* ctx, int32_t posSetSize, int32_t, int32_t, int32_t* nb, int32_t* nbest, int32_t* mx) {
 	Enter e(ctx);
 	ctx->list = mix(ctx->model, 1);
+	ctx->cand = mix(ctx->model, 77);
 	*nb = static_cast<int32_t>(ctx->list % 1000) + 1; *nbest = *nb * 2; *mx = posSetSize;
 	return 0;
 }
 int xxm_rescore(xxm_ctx* ctx, int32_t firstMotifColumn, int32_t posSetSize, int32_t, int32_t, int32_t, int32_t* nb, int32_t* mx) {
 	Enter e(ctx);
-	ctx->list = mix(ctx->model, 1000 + firstMotifColumn);
+	if (!ctx->cand) { ctx->err = "no candidate list"; return 1; }
+	ctx->list = mix(mix(ctx->model, 1000 + firstMotifColumn), ctx->cand);
 	*nb = static_cast<int32_t>(ctx->list % 1000) + 1; *mx = posSetSize;
 	return 0;
 }
@@ -80,6 +83,13 @@ int xxm_update_pwm_with_best_subset(xxm_ctx* ctx, int32_t which, double* pwm, in
 		for (int a = 0; a < 4; ++a) { w[a] = 1.0 + static_cast<double>(mix(h, c * 4 + a) % 97); s += w[a]; }
 		for (int a = 0; a < 4; ++a) pwm[c * 5 + 1 + a] = std::log(w[a] / s);
 	}
+	return 0;
+}
+int xxm_share_candidates(xxm_ctx* ctx, xxm_ctx* owner) {
+	Enter e(ctx);
+	if (owner->inside.load() != 0) ctx->violations.fetch_add(1);  // the owner must be idle while its list is lent
+	ctx->cand = owner->cand;
+	ctx->kept = 0;
 	return 0;
 }
 int xxm_elong_keep(xxm_ctx* ctx) { Enter e(ctx); ctx->kept = ctx->list; return 0; }
@@ -192,6 +202,52 @@ int main() {
 		int untouched = 0;
 		for (int i = victim + 1; i < nmotifs; ++i) untouched += rounds[i] == -1;
 		if (untouched < nmotifs - victim - 1 - nctx) { std::printf("failure case: %d motifs started after the failure\n", nmotifs - victim - 1 - untouched); ++bad; }
+	}
+	// the column variants of one motif spread over 2..5 contexts: the same motif as the serial loop, every time
+	for (int nctx = 2; nctx <= 5; ++nctx) {
+		std::vector<xxm_ctx> ctxs(nctx);
+		std::vector<xxm_ctx*> ptr(nctx);
+		for (int i = 0; i < nctx; ++i) ptr[i] = &ctxs[i];
+		for (int i = 0; i < nmotifs; ++i) {
+			Holder h;
+			h.init(i);
+			int32_t r = -1;
+			const int rc = xxm_iterate_motif_on(ptr.data(), nctx, &h.m, &P, &r);
+			if (rc || r != roundsSerial[i] || !h.same(serial[i])) { std::printf("variants on %d contexts: motif %d differs (rc %d)\n", nctx, i, rc); ++bad; }
+		}
+		int used = 0;
+		for (int i = 0; i < nctx; ++i) {
+			if (ctxs[i].violations.load()) { std::printf("variants on %d contexts: context %d entered by two threads\n", nctx, i); ++bad; }
+			used += ctxs[i].calls > 0;
+		}
+		if (used != nctx) { std::printf("variants on %d contexts: only %d worked\n", nctx, used); ++bad; }
+	}
+	// ... also without length correction (one variant) and with a failing table build
+	{
+		xxm_ctx a, b;
+		xxm_ctx* ptr[2] = {&a, &b};
+		xxm_refine_params Q = P;
+		Q.maximizeMotifLength = 0;
+		xxm_ctx c;
+		for (int i = 0; i < 5; ++i) {
+			Holder h1, h2;
+			h1.init(i); h2.init(i);
+			int32_t r1 = -1, r2 = -1;
+			if (xxm_iterate_motif(&c, &h1.m, &Q, &r1) || xxm_iterate_motif_on(ptr, 2, &h2.m, &Q, &r2) || r1 != r2 || !h1.same(h2)) { std::printf("one-variant case: motif %d differs\n", i); ++bad; }
+		}
+		a.failOnModel = b.failOnModel = 3;
+		Holder h;
+		h.init(3);
+		int32_t r = -1;
+		if (xxm_iterate_motif_on(ptr, 2, &h.m, &P, &r) != 1) { std::printf("failing table build not reported\n"); ++bad; }
+		// elongPWM carries 0 in its unused entry [0][0]: with this marker the build of iteration 1 fails INSIDE a variant, on some context
+		a.failOnModel = b.failOnModel = 0;
+		Holder g;
+		g.init(4);
+		if (xxm_iterate_motif_on(ptr, 2, &g.m, &P, &r) != 1 || (std::string(xxm_last_error(&a)) != "stand-in failure" && std::string(xxm_last_error(&b)) != "stand-in failure")) {
+			std::printf("failing variant not reported\n");
+			++bad;
+		}
 	}
 	std::printf("refine batch: %d motifs on 1..6 contexts, %d problems\n", nmotifs, bad);
 	return bad ? 1 : 0;

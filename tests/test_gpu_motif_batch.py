@@ -106,3 +106,46 @@ def test_iterate_motifs_equals_the_serial_loop(mops, revcomp):
         for v in views:
             v.close()
         owner.close()
+
+
+def _golden_all():
+    from conftest import golden_names
+    return golden_names()
+
+
+@pytest.mark.parametrize("name", _golden_all())
+def test_refine_callers_with_variants_on_views(golden, name):
+    """maximizeMotifLength / the per-motif loop with the column variants spread over the context and two views
+    (xxm_maximize_motif_length_on, xxm_iterate_motif_on) against the reference's own runs of those functions (stages E, F of the
+    golden traces): bit-exact, like the one-context calls in test_gpu_refine.py."""
+    from gpu_backend import GpuBackend
+    from test_gpu_refine import _cmp_motif
+    from xxmotif_b200 import localization, refine
+    t = golden(name)
+    ti = TraceInputs(t)
+    be = GpuBackend(ti)
+    views = []
+    try:
+        views = [refine.make_view(be.ctx) for _ in range(2)]
+        pss = int(t["m0.posSetSize"][0])
+        m = refine.Motif(t["m0.pwm"], t["m0.cols"], pss, enr=t["m0.enrich"], siteSeq=t["m0.sites.seq"], sitePos=t["m0.sites.pos"],
+                         pval=float(t["m0.pval"][0]), posPval=float(t["m0.posPval"][0]))
+        R = refine.Refiner(be.ctx, totalPositions=int(ti.total[pss]), revcomp=ti.revcomp, localization=ti.localization,
+                           maximizeMotifLength=int(t["cfg.maximizeMotifLength"][0]), minMatchPositions=int(t["cfg.minMatchPositions"][0]),
+                           maxMatchPositions=int(t["cfg.maxMatchPositions"][0]), pseudo=ti.pseudo, neff_pwm=float(t["cfg.neff_pwm"][0]))
+        R.optimize_motif(m)
+        assert np.array_equal(m.pwm[5:], t["opt1.pwm_out"][5:])
+        if ti.localization:
+            cols = m.cols
+            e = localization.update_enriched_region(be.ctx, int(cols[0]), int(cols[-1] - cols[0] + 1), m.enr)
+            for i in range(3):
+                m.m.enr[i] = e[i]
+        R.maximize_motif_length_on(m, views)
+        _cmp_motif("maxlen on views", m, t, "maxlen")
+        rounds = R.iterate_motif(m, views=views)
+        assert rounds >= 1
+        _cmp_motif("converged on views", m, t, "converged")
+    finally:
+        for v in views:
+            v.close()
+        be.ctx.close()

@@ -69,6 +69,32 @@ int set_positional_pval(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* P) 
 	return 0;
 }
 
+// the end of maximizeMotifLength (Iterate_Motif.cpp:129-148): the winning variant becomes the motif, re-centred in the 30 columns
+int finish_maximize(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* P, const Cols& bestElongation, double bestPval, const std::vector<double>& bestElong,
+                    const std::vector<int32_t>& realSeq, const std::vector<int32_t>& realPos) {
+	m->pval = bestPval;
+	set_cols(m, bestElongation);
+	const int newFirst = (XXM_PWM_LENGTH - bestElongation.span()) / 2 + 1;
+	const int offset = newFirst - bestElongation.front();
+	if (static_cast<int32_t>(realSeq.size()) > m->siteCap) return 2;
+	m->nsites = static_cast<int32_t>(realSeq.size());
+	for (int32_t i = 0; i < m->nsites; ++i) { m->siteSeq[i] = realSeq[i]; m->sitePos[i] = realPos[i] - offset; }
+	for (int32_t col : bestElongation.c)
+		for (int a = 1; a <= 4; ++a) m->pwm[col * 5 + a] = bestElong[col * 5 + a];
+	if (offset != 0) {  // Motif::offset, Motif.h:648-673
+		m->enr[0] -= offset; m->enr[1] -= offset; m->enr[2] -= offset;
+		if (offset > 0) {
+			for (auto it = bestElongation.c.rbegin(); it != bestElongation.c.rend(); ++it)
+				for (int a = 1; a <= 4; ++a) m->pwm[(*it + offset) * 5 + a] = m->pwm[*it * 5 + a];
+		} else {
+			for (int32_t col : bestElongation.c)
+				for (int a = 1; a <= 4; ++a) m->pwm[(col + offset) * 5 + a] = m->pwm[col * 5 + a];
+		}
+		for (int32_t i = 0; i < m->ncols; ++i) m->cols[i] += offset;
+	}
+	return set_positional_pval(ctx, m, P);
+}
+
 }  // namespace
 
 extern "C" int xxm_optimize_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* P) {
@@ -142,30 +168,149 @@ extern "C" int xxm_maximize_motif_length(xxm_ctx* ctx, xxm_motif* m, const xxm_r
 		realPos.resize(static_cast<size_t>(n));
 		m->worstScore = worst;
 	}
-	m->pval = bestPval;
-	set_cols(m, bestElongation);
-	const int newFirst = (XXM_PWM_LENGTH - bestElongation.span()) / 2 + 1;
-	const int offset = newFirst - bestElongation.front();
-	if (static_cast<int32_t>(realSeq.size()) > m->siteCap) return 2;
-	m->nsites = static_cast<int32_t>(realSeq.size());
-	for (int32_t i = 0; i < m->nsites; ++i) { m->siteSeq[i] = realSeq[i]; m->sitePos[i] = realPos[i] - offset; }
-	for (int32_t col : bestElongation.c)
-		for (int a = 1; a <= 4; ++a) m->pwm[col * 5 + a] = bestElong[col * 5 + a];
-	if (offset != 0) {  // Motif::offset, Motif.h:648-673
-		m->enr[0] -= offset; m->enr[1] -= offset; m->enr[2] -= offset;
-		if (offset > 0) {
-			for (auto it = bestElongation.c.rbegin(); it != bestElongation.c.rend(); ++it)
-				for (int a = 1; a <= 4; ++a) m->pwm[(*it + offset) * 5 + a] = m->pwm[*it * 5 + a];
-		} else {
-			for (int32_t col : bestElongation.c)
-				for (int a = 1; a <= 4; ++a) m->pwm[(col + offset) * 5 + a] = m->pwm[col * 5 + a];
-		}
-		for (int32_t i = 0; i < m->ncols; ++i) m->cols[i] += offset;
-	}
-	return set_positional_pval(ctx, m, P);
+	return finish_maximize(ctx, m, P, bestElongation, bestPval, bestElong, realSeq, realPos);
 }
 
-extern "C" int xxm_iterate_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* P, int32_t* rounds) {
+// ---- the column variants of one motif several at a time (variant half) ---------------------------------------
+// One variant = the three inner iterations of Iterate_Motif.cpp:73-90 under its column set.  Iteration 0 reads the motif's PWM,
+// iterations 1 and 2 read elongPWM -- which iteration 0 has just rewritten in all 30 columns (updatePWM_OOL recounts every column,
+// Motif.cpp:617-651), or the variant is dropped (motifNb stays 0, :88).  So a variant depends on the motif's PWM, its columns and
+// the candidate list of the last full scan, and on no other variant; only the CHOICE among them (strict <, in loop order, :103)
+// is sequential, and it is made after all of them are known.
+namespace {
+
+struct VariantJob {
+	int front = 0, back = 0;
+	Cols cols;
+	// results
+	int32_t motifNb = 0;
+	double overrepPval = 1e100;
+	bool updated = false;          // some iteration rewrote elongPWM
+	std::vector<double> elong;     // elongPWM as this variant leaves it
+	int ctxIndex = -1;
+	int rc = 0;
+};
+
+int evaluate_variant(xxm_ctx* ctx, const xxm_motif* m, int firstMotifColumn, const xxm_refine_params* P, const std::vector<double>& elongIn, VariantJob& J) {
+	J.elong = elongIn;
+	for (int iter = 0; iter < 3; ++iter) {
+		const double* pwm = (iter == 0) ? m->pwm : J.elong.data();
+		if (xxm_reinitialize(ctx, pwm, J.cols.c.data(), static_cast<int32_t>(J.cols.c.size()), m->posSetSize, P->totalPositions)) return 1;
+		int32_t nb = 0, mx = 0;
+		if (xxm_rescore(ctx, firstMotifColumn, m->posSetSize, m->enr[1], m->enr[2], 0, &nb, &mx)) return 1;
+		int32_t upd = 0, nbOut = 0;
+		double pvOut = 0;
+		std::vector<double> work(J.elong);
+		if (xxm_update_pwm_with_best_subset(ctx, XXM_LIST_SORTED_SITES_ELONG, work.data(), J.cols.front(), m->posSetSize, iter == 0, P->pseudo, &upd, &nbOut, &pvOut))
+			return 1;
+		if (upd) { J.elong = work; J.motifNb = nbOut; J.overrepPval = pvOut; J.updated = true; }
+		if (J.motifNb == 0) break;
+	}
+	return 0;
+}
+
+}  // namespace
+
+extern "C" int xxm_maximize_motif_length_on(xxm_ctx* const* ctxs, int32_t nctx, xxm_motif* m, const xxm_refine_params* P, int32_t lengthCorrection,
+                                            int32_t* noChangeOut) {
+	if (nctx < 1 || !ctxs || !ctxs[0]) return 1;
+	if (nctx == 1) return xxm_maximize_motif_length(ctxs[0], m, P, lengthCorrection, noChangeOut);
+	xxm_ctx* owner = ctxs[0];
+	const Cols motifCols = cols_of(m);
+	std::vector<double> elong0(31 * 5, 0.0);
+	if (P->elongPWM) std::memcpy(elong0.data(), P->elongPWM, sizeof(double) * 31 * 5);
+	// the variants in the order of the reference's loops
+	std::vector<VariantJob> jobs;
+	const int lo = lengthCorrection ? -2 : 0, hi = lengthCorrection ? 2 : 0;
+	for (int front = lo; front <= hi; ++front)
+		for (int back = lo; back <= hi; ++back) {
+			VariantJob J;
+			if (!variant_columns(motifCols, front, back, P->minMatchPositions, P->maxMatchPositions, J.cols)) continue;
+			J.front = front; J.back = back;
+			jobs.push_back(std::move(J));
+		}
+	const int32_t nwork = std::min<int32_t>(nctx, std::max<int32_t>(1, static_cast<int32_t>(jobs.size())));
+	for (int32_t c = 1; c < nwork; ++c)
+		if (xxm_share_candidates(ctxs[c], owner)) return 1;
+	// every context takes the next variant nobody has taken (so its own variants come in loop order) and sets the list of its best
+	// one so far aside, by the reference's rule
+	std::atomic<int> next{0};
+	std::atomic<bool> stop{false};
+	std::vector<int> localBest(static_cast<size_t>(nwork), -1);
+	auto work = [&](int32_t c) {
+		double best = DBL_MAX;
+		for (;;) {
+			if (stop.load(std::memory_order_relaxed)) return;
+			const int i = next.fetch_add(1);
+			if (i >= static_cast<int>(jobs.size())) return;
+			VariantJob& J = jobs[static_cast<size_t>(i)];
+			J.ctxIndex = c;
+			J.rc = evaluate_variant(ctxs[c], m, motifCols.front(), P, elong0, J);
+			if (J.rc) { stop.store(true); return; }
+			if (J.motifNb == 0) continue;
+			const double newPval = J.overrepPval + J.cols.span() * std::log(P->neff_pwm);
+			if (newPval < best) {
+				best = newPval;
+				localBest[static_cast<size_t>(c)] = i;
+				if (xxm_elong_keep(ctxs[c])) { J.rc = 1; stop.store(true); return; }
+			}
+		}
+	};
+	{
+		std::vector<std::thread> pool;
+		pool.reserve(static_cast<size_t>(nwork));
+		for (int32_t c = 1; c < nwork; ++c) pool.emplace_back(work, c);
+		work(0);
+		for (std::thread& t : pool) t.join();
+	}
+	for (const VariantJob& J : jobs)
+		if (J.rc) return J.rc;
+	// the reference's choice, in loop order
+	int bestMotifNb = 0, winner = -1;
+	bool noChange = false;
+	double bestPval = DBL_MAX;
+	std::vector<double> elong(elong0), bestElong(31 * 5, 0.0);
+	for (size_t i = 0; i < jobs.size(); ++i) {
+		const VariantJob& J = jobs[i];
+		if (J.updated) elong = J.elong;  // elongPWM as the serial loop would hold it after this variant
+		if (J.motifNb == 0) continue;
+		const double newPval = J.overrepPval + J.cols.span() * std::log(P->neff_pwm);  // calculate_log_bonferonni, utils.h:39-56
+		if (newPval < bestPval) {
+			bestPval = newPval;
+			bestMotifNb = J.motifNb;
+			winner = static_cast<int>(i);
+			noChange = (J.front == 0 && J.back == 0);
+			for (int32_t col : J.cols.c)
+				for (int a = 1; a <= 4; ++a) bestElong[col * 5 + a] = J.elong[col * 5 + a];
+		}
+	}
+	if (P->elongPWM) std::memcpy(P->elongPWM, elong.data(), sizeof(double) * 31 * 5);
+	*noChangeOut = noChange;
+	if (bestMotifNb == 0) return 0;
+	const VariantJob& W = jobs[static_cast<size_t>(winner)];
+	xxm_ctx* wctx = ctxs[W.ctxIndex];
+	// the overall winner is also the best of the context that evaluated it (smallest p-value, earliest in loop order among equals),
+	// so its list is the one that context has kept
+	if (localBest[static_cast<size_t>(W.ctxIndex)] != winner) return 3;
+	const Cols& bestElongation = W.cols;
+	std::vector<int32_t> realSeq(static_cast<size_t>(bestMotifNb), 0), realPos(static_cast<size_t>(bestMotifNb), 0);
+	{
+		int32_t n = 0;
+		double worst = 1;
+		if (xxm_startposlist_from_kept(wctx, bestMotifNb, bestElongation.front(), realSeq.data(), realPos.data(), bestMotifNb, &n, &worst)) return 1;
+		realSeq.resize(static_cast<size_t>(n));
+		realPos.resize(static_cast<size_t>(n));
+		m->worstScore = worst;
+	}
+	return finish_maximize(owner, m, P, bestElongation, bestPval, bestElong, realSeq, realPos);
+}
+
+extern "C" int xxm_iterate_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_params* P, int32_t* rounds) { return xxm_iterate_motif_on(&ctx, 1, m, P, rounds); }
+
+// the per-motif loop on ctxs[0]; with nctx > 1 the column variants of maximizeMotifLength are spread over ctxs[0] and its views
+extern "C" int xxm_iterate_motif_on(xxm_ctx* const* ctxs, int32_t nctx, xxm_motif* m, const xxm_refine_params* P, int32_t* rounds) {
+	if (nctx < 1 || !ctxs || !ctxs[0]) return 1;
+	xxm_ctx* ctx = ctxs[0];
 	double oldPval = 1000, bestPval = 1000;
 	int loop = 1;
 	*rounds = 0;
@@ -181,7 +326,7 @@ extern "C" int xxm_iterate_motif(xxm_ctx* ctx, xxm_motif* m, const xxm_refine_pa
 			if (xxm_update_enriched_region(ctx, c.front(), c.span(), m->enr)) return 1;
 		}
 		int32_t noChange = 0;
-		rc = xxm_maximize_motif_length(ctx, m, &Q, P->maximizeMotifLength, &noChange);
+		rc = xxm_maximize_motif_length_on(ctxs, nctx, m, &Q, P->maximizeMotifLength, &noChange);
 		if (rc) return rc;
 		bestPval = m->pval;
 		++*rounds;

@@ -7,7 +7,7 @@ import numpy as np
 from . import capi
 
 EXTRA_EXPORTS = ["xxm_optimize_motif", "xxm_maximize_motif_length", "xxm_iterate_motif", "xxm_iterate_motifs", "xxm_share_seqset", "xxm_view_create",
-                 "xxm_view_count"]
+                 "xxm_view_count", "xxm_share_candidates", "xxm_maximize_motif_length_on", "xxm_iterate_motif_on"]
 
 
 class XxmMotif(C.Structure):
@@ -41,6 +41,12 @@ def _lib():
         L.xxm_view_create.argtypes = [vp, P(vp)]
         L.xxm_view_count.restype = i32
         L.xxm_view_count.argtypes = [vp]
+        L.xxm_share_candidates.restype = i32
+        L.xxm_share_candidates.argtypes = [vp, vp]
+        L.xxm_maximize_motif_length_on.restype = i32
+        L.xxm_maximize_motif_length_on.argtypes = [P(vp), i32, P(XxmMotif), P(XxmRefineParams), i32, P(i32)]
+        L.xxm_iterate_motif_on.restype = i32
+        L.xxm_iterate_motif_on.argtypes = [P(vp), i32, P(XxmMotif), P(XxmRefineParams), P(i32)]
         L._refine_ready = True
     return L
 
@@ -101,10 +107,31 @@ class Refiner:
         self.ctx._ck(_lib().xxm_maximize_motif_length(self.ctx.h, C.byref(motif.m), C.byref(self.p), lc, C.byref(nc)))
         return bool(nc.value)
 
-    def iterate_motif(self, motif):
+    def iterate_motif(self, motif, views=()):
+        """the per-motif loop of MotifContainer::iterate; views (refine.make_view of this context): the column variants of
+        maximizeMotifLength are spread over this context and the views (xxm_iterate_motif_on), same result"""
         r = C.c_int32(0)
-        self.ctx._ck(_lib().xxm_iterate_motif(self.ctx.h, C.byref(motif.m), C.byref(self.p), C.byref(r)))
+        if not views:
+            self.ctx._ck(_lib().xxm_iterate_motif(self.ctx.h, C.byref(motif.m), C.byref(self.p), C.byref(r)))
+            return r.value
+        ctxs = [self.ctx] + list(views)
+        hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        rc = _lib().xxm_iterate_motif_on(hs, len(ctxs), C.byref(motif.m), C.byref(self.p), C.byref(r))
+        if rc:
+            msgs = [c.L.xxm_last_error(c.h).decode() for c in ctxs]
+            raise capi.XxmError("xxm_iterate_motif_on: rc %d: %s" % (rc, "; ".join(x for x in msgs if x) or "no message"))
         return r.value
+
+    def maximize_motif_length_on(self, motif, views, lengthCorrection=None):
+        nc = C.c_int32(0)
+        lc = self.p.maximizeMotifLength if lengthCorrection is None else int(lengthCorrection)
+        ctxs = [self.ctx] + list(views)
+        hs = (C.c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        rc = _lib().xxm_maximize_motif_length_on(hs, len(ctxs), C.byref(motif.m), C.byref(self.p), lc, C.byref(nc))
+        if rc:
+            msgs = [c.L.xxm_last_error(c.h).decode() for c in ctxs]
+            raise capi.XxmError("xxm_maximize_motif_length_on: rc %d: %s" % (rc, "; ".join(x for x in msgs if x) or "no message"))
+        return bool(nc.value)
 
 
 def make_view(owner):
