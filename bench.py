@@ -697,6 +697,20 @@ def _ours(a):
             out["motif_batch"] = json.loads(lines[-1]) if lines else {"failed": "rc %d: %s" % (r.returncode, r.stderr.strip()[-300:])}
         except Exception as ex:
             out["motif_batch"] = {"failed": str(ex)}
+    # ---- the other half of that row: the column variants of maximizeMotifLength of the ONE jump-start motif spread over the
+    # context and its views (xxm_iterate_motif_on), on the bench's own set size -- again in a process of its own
+    if world == 1 and not a.no_motif_batch and not a.no_refine_run:
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "variant_batch.py"), "--sizes", str(a.nseq), "--seqlen", str(a.seqlen),
+                                "--contexts", "1,2,4"], capture_output=True, text=True, timeout=180)
+            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            vb = json.loads(lines[-1]) if lines else {"failed": "rc %d: %s" % (r.returncode, r.stderr.strip()[-300:])}
+        except Exception as ex:
+            vb = {"failed": str(ex)}
+        if isinstance(out.get("refine_run"), dict):
+            out["refine_run"]["variants_on_views"] = vb
+        else:
+            out["variants_on_views"] = vb
     if dist:
         dist.destroy_process_group()
     return out, rank
