@@ -396,6 +396,22 @@ def parity_nranks(ctx, dist, rank, world, local):
     return res
 
 
+def tool_json(argv, timeout):
+    """Run one of tools/*.py in a process of its own and return the last JSON object it printed, or {"failed": why}: a side
+    measurement that crashes, hangs or prints nothing must not cost the bench line its numbers."""
+    try:
+        r = subprocess.run([sys.executable] + list(argv), capture_output=True, text=True, timeout=timeout)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if not lines:
+            return {"failed": "rc %d: %s" % (r.returncode, (r.stderr or "").strip()[-300:])}
+        res = json.loads(lines[-1])
+        if r.returncode:
+            res["rc"] = r.returncode
+        return res
+    except Exception as ex:
+        return {"failed": "%s: %s" % (type(ex).__name__, ex)}
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------------------------
@@ -690,23 +706,11 @@ def _ours(a):
     # on views of one resident set, on the small sets of configs 1 and 2.  A separate process with its own limit (tools/motif_batch.py):
     # whatever happens there cannot cost the line above its numbers.
     if world == 1 and not a.no_motif_batch:
-        try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "motif_batch.py"), "--shapes", "cfg1,cfg2", "--contexts", "4", "--motifs", "16"],
-                               capture_output=True, text=True, timeout=120)
-            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            out["motif_batch"] = json.loads(lines[-1]) if lines else {"failed": "rc %d: %s" % (r.returncode, r.stderr.strip()[-300:])}
-        except Exception as ex:
-            out["motif_batch"] = {"failed": str(ex)}
+        out["motif_batch"] = tool_json([os.path.join(ROOT, "tools", "motif_batch.py"), "--shapes", "cfg1,cfg2", "--contexts", "4", "--motifs", "16"], 120)
     # ---- the other half of that row: the column variants of maximizeMotifLength of the ONE jump-start motif spread over the
     # context and its views (xxm_iterate_motif_on), on the bench's own set size -- again in a process of its own
     if world == 1 and not a.no_motif_batch and not a.no_refine_run:
-        try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "variant_batch.py"), "--sizes", str(a.nseq), "--seqlen", str(a.seqlen),
-                                "--contexts", "1,2,4"], capture_output=True, text=True, timeout=180)
-            lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            vb = json.loads(lines[-1]) if lines else {"failed": "rc %d: %s" % (r.returncode, r.stderr.strip()[-300:])}
-        except Exception as ex:
-            vb = {"failed": str(ex)}
+        vb = tool_json([os.path.join(ROOT, "tools", "variant_batch.py"), "--sizes", str(a.nseq), "--seqlen", str(a.seqlen), "--contexts", "1,2,4"], 180)
         if isinstance(out.get("refine_run"), dict):
             out["refine_run"]["variants_on_views"] = vb
         else:

@@ -149,3 +149,35 @@ def test_many_runs_sweep_matches_literal_sweep():
     K3, bp3, _ = sharded.choose_subset(scores[:1500], counts[:1500], int(counts[:1500].sum()), nb * 10, maxSites)
     K4, bp4 = capi.host_best_subset(np.repeat(scores[:1500], counts[:1500]), seq[:int(counts[:1500].sum())], nb, maxSites, nb)
     assert (K3, bp3) == (K4, bp4)
+
+
+def test_bench_side_measurements_cannot_take_the_line_down(tmp_path):
+    """bench.tool_json: a tool that prints a JSON line, one that fails without printing, one that hangs, one that prints garbage"""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    ok = tmp_path / "ok.py"
+    ok.write_text("print('noise')\nprint('{\"a\": 1}')\nprint('{\"ok\": true, \"v\": [1, 2]}')\n")
+    assert bench.tool_json([str(ok)], 30) == {"ok": True, "v": [1, 2]}
+    bad = tmp_path / "bad.py"
+    bad.write_text("import sys\nsys.stderr.write('no CUDA device')\nsys.exit(4)\n")
+    r = bench.tool_json([str(bad)], 30)
+    assert "failed" in r and "rc 4" in r["failed"] and "no CUDA device" in r["failed"]
+    hang = tmp_path / "hang.py"
+    hang.write_text("import time\ntime.sleep(60)\n")
+    r = bench.tool_json([str(hang)], 1)
+    assert "failed" in r and "Timeout" in r["failed"]
+    junk = tmp_path / "junk.py"
+    junk.write_text("print('{not json')\n")
+    assert "failed" in bench.tool_json([str(junk)], 30)
+    half = tmp_path / "half.py"
+    half.write_text("import sys\nprint('{\"ok\": false}')\nsys.exit(3)\n")
+    assert bench.tool_json([str(half)], 30) == {"ok": False, "rc": 3}
+    # the two tools themselves, in a container without a GPU: they fail loudly, bench keeps going
+    r = bench.tool_json([os.path.join(root, "tools", "motif_batch.py"), "--shapes", "cfg1", "--contexts", "2", "--motifs", "2"], 120)
+    import torch
+    if not torch.cuda.is_available():
+        assert "failed" in r and "no CUDA device" in r["failed"]
