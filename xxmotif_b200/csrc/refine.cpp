@@ -259,7 +259,9 @@ extern "C" int xxm_maximize_motif_length_on(xxm_ctx* const* ctxs, int32_t nctx, 
 	{
 		std::vector<std::thread> pool;
 		pool.reserve(static_cast<size_t>(nwork));
-		for (int32_t c = 1; c < nwork; ++c) pool.emplace_back(work, c);
+		try {
+			for (int32_t c = 1; c < nwork; ++c) pool.emplace_back(work, c);
+		} catch (...) {}  // no more threads to be had: the contexts that did start share the variants
 		work(0);
 		for (std::thread& t : pool) t.join();
 	}
@@ -392,7 +394,9 @@ extern "C" int xxm_iterate_motifs(xxm_ctx* const* ctxs, int32_t nctx, xxm_motif*
 	const int32_t nthreads = std::min(nctx, std::max<int32_t>(1, nmotifs));
 	std::vector<std::thread> pool;
 	pool.reserve(static_cast<size_t>(nthreads));
-	for (int32_t c = 1; c < nthreads; ++c) pool.emplace_back(work, c);
+	try {
+		for (int32_t c = 1; c < nthreads; ++c) pool.emplace_back(work, c);
+	} catch (...) {}  // no more threads to be had: the contexts that did start share the motifs
 	work(0);  // the caller's thread drives the first context
 	for (std::thread& t : pool) t.join();
 	// report the failure with the smallest motif index (several contexts may have failed before they saw the flag)
