@@ -847,6 +847,20 @@ void xo_ctx_free(xo_ctx* c) {
 	free(c->sortedSites); free(c->sortedSites_elong); free(c->bestStartPos); free(c->tmp);
 	free(c->motifsPerSequenceCount); free(c);
 }
+/* test plumbing without a counterpart in the reference (its singletons exist once): a second context on the SAME set takes over the
+ * candidate list of another one -- bestStartPos with its count, and sortedSites, whose sequences fill_startPosList_with_elongSites
+ * counts (StartPosUpdater.cpp:128) -- and a list saved earlier is put back as sortedSites_elong */
+int64_t xo_ctx_cap(const xo_ctx* c) { return c->cap; }
+void xo_ctx_copy_candidates(xo_ctx* dst, const xo_ctx* src) {
+	const int64_t n = dst->cap < src->cap ? dst->cap : src->cap;
+	memcpy(dst->bestStartPos, src->bestStartPos, (size_t) n * sizeof(xo_site));
+	memcpy(dst->sortedSites, src->sortedSites, (size_t) n * sizeof(xo_site));
+	dst->nbBestSites = src->nbBestSites;
+}
+void xo_ctx_set_elong(xo_ctx* c, const xo_site* sites, int64_t n) {
+	if (n > c->cap) n = c->cap;
+	memcpy(c->sortedSites_elong, sites, (size_t) n * sizeof(xo_site));
+}
 const xo_site* xo_ctx_best(const xo_ctx* c) { return c->bestStartPos; }
 const xo_site* xo_ctx_sites(const xo_ctx* c) { return c->sortedSites; }
 const xo_site* xo_ctx_elong(const xo_ctx* c) { return c->sortedSites_elong; }

@@ -91,6 +91,10 @@ double xo_tables_lookup_window(const xo_tables*, const uint8_t* window); /* get_
 /* ---- scan / select layer (StartPosUpdater*, pValCalculation.*) ---- */
 xo_ctx* xo_ctx_new(const xo_seqset*, const xo_config*);
 void xo_ctx_free(xo_ctx*);
+/* test plumbing (no counterpart in the reference): several contexts on one set, see xxm_oracle.c */
+int64_t xo_ctx_cap(const xo_ctx*);
+void xo_ctx_copy_candidates(xo_ctx* dst, const xo_ctx* src);
+void xo_ctx_set_elong(xo_ctx*, const xo_site* sites, int64_t n);
 const xo_site* xo_ctx_best(const xo_ctx*);         /* bestStartPos */
 const xo_site* xo_ctx_sites(const xo_ctx*);        /* sortedSites */
 const xo_site* xo_ctx_elong(const xo_ctx*);        /* sortedSites_elong */
