@@ -15,7 +15,9 @@ KERNEL_HEADERS = ["xxm_device.cuh", "xxm_kernels.cuh", "xxm_scan4.cuh", "xxm_sca
                   "xxm_select4.cuh"]
 
 
-def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp")):
+def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp"), sanitize=False):
+    """sanitize: AddressSanitizer + UBSan over the emulated kernels -- every load and store of a kernel into the harness' "device"
+    buffers (sized like the library's) and its `__shared__` arrays is bounds-checked, a memcheck without a GPU"""
     os.makedirs(BUILD, exist_ok=True)
     newest = 0.0
     for h in KERNEL_HEADERS:
@@ -26,12 +28,12 @@ def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp")):
             with open(dst, "w") as fh:
                 fh.write(text)
         newest = max(newest, os.path.getmtime(dst))
-    exe = os.path.join(BUILD, target)
+    exe = os.path.join(BUILD, target + ("_asan" if sanitize else ""))
     deps = [os.path.join(HERE, target + ".cpp"), os.path.join(HERE, "simt_emu.h")] + [os.path.join(CSRC, s) for s in extra_sources]
     newest = max([newest] + [os.path.getmtime(d) for d in deps])
     if os.path.exists(exe) and os.path.getmtime(exe) >= newest:
         return exe
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable",
+    cmd = ["g++", "-std=c++17", "-O1", "-g"] + (["-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if sanitize else []) + ["-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable",
            "-I", BUILD, "-I", os.path.join(HERE, "shim"), "-I", CSRC, os.path.join(HERE, target + ".cpp")]
     cmd += [os.path.join(CSRC, s) for s in extra_sources] + ["-o", exe, "-lpthread"]
     subprocess.check_call(cmd)

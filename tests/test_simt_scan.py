@@ -50,6 +50,30 @@ def test_scan_kernels_under_emulator(exe, case):
     assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
 
 
+ASAN_ENV = dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0:detect_leaks=0", UBSAN_OPTIONS="print_stacktrace=1:halt_on_error=1")
+
+
+@pytest.mark.parametrize("target,extra,cases", [
+    ("scan_emu", ("host_pack.cpp", "pair_table.cpp"), ["ragged_N", "revcomp_ragged", "gapped_6cols", "one_word_sequences", "small_capacity", "positive_set_prefix_ragged"]),
+    ("step_emu", ("host_pack.cpp",), ["ragged_short", "all_sites_dense", "zoops_ragged_shift", "rc_ragged", "rc_long_sequences", "sort_many_chunks"]),
+])
+def test_kernels_under_address_sanitizer(target, extra, cases):
+    """The same kernels with every access bounds-checked (AddressSanitizer + UBSan over the emulated run; compute-sanitizer is closed on
+    the GPU pool, profiles/r02_compute_sanitizer_closed.txt).  The harness' buffers have the library's sizes (stream + 2 guard words,
+    record arrays of exactly the capacity passed to the kernel + 1).  The full list of 33 cases: profiles/r02h_emulator_asan.txt."""
+    try:
+        exe = simt_build.build(target, extra_sources=extra, sanitize=True)
+    except subprocess.CalledProcessError:
+        pytest.skip("no sanitizer runtime in this toolchain")
+    for case in cases:
+        r = subprocess.run([exe, case], capture_output=True, text=True, timeout=900, env=ASAN_ENV)
+        if r.returncode and "Shadow memory range interleaves" in r.stderr:
+            pytest.skip("AddressSanitizer cannot map its shadow memory here")
+        assert r.returncode == 0, case + "\n" + r.stdout[-2000:] + r.stderr[-4000:]
+        assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, case + "\n" + r.stderr[-4000:]
+        assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
+
+
 def test_product_does_not_reference_the_emulator():
     """the emulator hooks in the kernel sources are compile-time (#ifdef XXM_SIMT_EMU) and the library is built without them"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
