@@ -15,9 +15,13 @@ KERNEL_HEADERS = ["xxm_device.cuh", "xxm_kernels.cuh", "xxm_scan4.cuh", "xxm_sca
                   "xxm_select4.cuh"]
 
 
-def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp"), sanitize=False):
-    """sanitize: AddressSanitizer + UBSan over the emulated kernels -- every load and store of a kernel into the harness' "device"
-    buffers (sized like the library's) and its `__shared__` arrays is bounds-checked, a memcheck without a GPU"""
+def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp"), sanitize=False, kernel_dir=None):
+    """sanitize=True / "address": AddressSanitizer + UBSan over the emulated kernels -- every load and store of a kernel into the
+    harness' "device" buffers (sized like the library's) and its `__shared__` arrays is bounds-checked, a memcheck without a GPU.
+    sanitize="thread": ThreadSanitizer with one fiber per CUDA thread (simt_emu.h) -- accesses of one block to the same address
+    that no barrier or warp fence orders are reported, a racecheck without a GPU; "thread-strict": only __syncthreads and
+    __syncwarp order memory, the other *_sync collectives do not (what the CUDA programming guide promises).
+    kernel_dir: take the rewritten kernel headers from there instead of BUILD (mutation controls)."""
     os.makedirs(BUILD, exist_ok=True)
     newest = 0.0
     for h in KERNEL_HEADERS:
@@ -28,13 +32,16 @@ def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp"), 
             with open(dst, "w") as fh:
                 fh.write(text)
         newest = max(newest, os.path.getmtime(dst))
-    exe = os.path.join(BUILD, target + ("_asan" if sanitize else ""))
+    mode = "address" if sanitize is True else (sanitize or "")
+    exe = os.path.join(BUILD, target + {"": "", "address": "_asan", "thread": "_tsan", "thread-strict": "_tsan_strict"}[mode] + ("_mut" if kernel_dir else ""))
     deps = [os.path.join(HERE, target + ".cpp"), os.path.join(HERE, "simt_emu.h")] + [os.path.join(CSRC, s) for s in extra_sources]
     newest = max([newest] + [os.path.getmtime(d) for d in deps])
-    if os.path.exists(exe) and os.path.getmtime(exe) >= newest:
+    if os.path.exists(exe) and os.path.getmtime(exe) >= newest and not kernel_dir:
         return exe
-    cmd = ["g++", "-std=c++17", "-O1", "-g"] + (["-fsanitize=address,undefined", "-fno-omit-frame-pointer"] if sanitize else []) + ["-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable",
-           "-I", BUILD, "-I", os.path.join(HERE, "shim"), "-I", CSRC, os.path.join(HERE, target + ".cpp")]
+    flags = {"": [], "address": ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"], "thread": ["-fsanitize=thread", "-fno-omit-frame-pointer"],
+             "thread-strict": ["-fsanitize=thread", "-fno-omit-frame-pointer", "-DXXM_EMU_STRICT_SHFL"]}[mode]
+    cmd = ["g++", "-std=c++17", "-O1", "-g"] + flags + ["-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable",
+           "-I", kernel_dir or BUILD, "-I", os.path.join(HERE, "shim"), "-I", HERE, "-I", CSRC, os.path.join(HERE, target + ".cpp")]
     cmd += [os.path.join(CSRC, s) for s in extra_sources] + ["-o", exe, "-lpthread"]
     subprocess.check_call(cmd)
     return exe

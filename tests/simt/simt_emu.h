@@ -19,6 +19,34 @@
 #include <vector>
 
 #define XXM_SIMT_EMU 1
+
+// ---- race detection (build.py sanitize="thread"): every CUDA thread is a ThreadSanitizer fiber.  Switching fibers creates NO
+// happens-before edge; the edges are the ones the programming model gives -- __syncthreads among the threads of a block, __syncwarp
+// (and, unless XXM_EMU_STRICT_SHFL is defined, the other *_sync collectives) among the lanes named in the mask, launch order on the
+// stream, atomics -- so two accesses of one block to the same shared or global address with a write among them and no such edge
+// between them are reported with both source lines: what `compute-sanitizer --tool racecheck` reports, without a GPU.  Blocks of a
+// grid run one after another on the same `static` arrays that stand in for __shared__, so consecutive blocks are ordered
+// (races BETWEEN blocks are out of scope, as they are for racecheck).  The emulator's own bookkeeping is not instrumented.
+#if defined(__SANITIZE_THREAD__)
+#define XXM_EMU_TSAN 1
+extern "C" {
+void* __tsan_get_current_fiber(void);
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void* fiber);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+void __tsan_acquire(void* addr);
+void __tsan_release(void* addr);
+}
+#define EMU_NOTSAN __attribute__((no_sanitize("thread")))
+#define EMU_TSAN_SWITCH(f) __tsan_switch_to_fiber((f), 1u /* no synchronisation */)
+#define EMU_TSAN_ACQUIRE(p) __tsan_acquire(static_cast<void*>(p))
+#define EMU_TSAN_RELEASE(p) __tsan_release(static_cast<void*>(p))
+#else
+#define EMU_NOTSAN
+#define EMU_TSAN_SWITCH(f) ((void) 0)
+#define EMU_TSAN_ACQUIRE(p) ((void) 0)
+#define EMU_TSAN_RELEASE(p) ((void) 0)
+#endif
 #define __global__
 #define __device__
 #define __host__
@@ -53,6 +81,7 @@ constexpr size_t kStackBytes = 256 * 1024;
 struct Fiber {
 	ucontext_t ctx;
 	void* stack = nullptr;
+	void* tsan = nullptr;  // ThreadSanitizer's view of this CUDA thread
 	bool done = false;
 };
 
@@ -62,12 +91,19 @@ struct WarpState {
 	uint32_t arrived = 0;
 	uint32_t readers = 0;
 	bool ready = false;
+	char hb = 0;  // carries the happens-before edge of this warp's collectives
 };
 
 struct BlockState {
 	std::vector<Fiber> fib;
 	std::vector<WarpState> warp;
 	ucontext_t sched;
+	void* schedTsan = nullptr;
+	// addresses that carry the happens-before edges of __syncthreads / of block and launch order.  A block's threads acquire
+	// chain[b & 1] when they start and release into chain[(b + 1) & 1] when they end: the next block (and the host) sees them, the
+	// threads of the SAME block that start later do not
+	char barObj = 0, chain[2] = {0, 0};
+	unsigned block = 0;
 	int cur = 0;
 	int alive = 0;
 	int barCount = 0;
@@ -80,9 +116,12 @@ struct BlockState {
 
 inline BlockState* B = nullptr;
 
-inline void yield() { swapcontext(&B->fib[B->cur].ctx, &B->sched); }
+EMU_NOTSAN inline void yield() {
+	EMU_TSAN_SWITCH(B->schedTsan);
+	swapcontext(&B->fib[B->cur].ctx, &B->sched);
+}
 
-inline void release_barrier_if_complete() {
+EMU_NOTSAN inline void release_barrier_if_complete() {
 	if (B->barCount > 0 && B->barCount == B->alive) {
 		B->barCount = 0;
 		++B->barGen;
@@ -91,32 +130,40 @@ inline void release_barrier_if_complete() {
 	}
 }
 
-inline void fiber_entry() {
-	B->body();
-	B->fib[B->cur].done = true;
-	--B->alive;
-	++B->progress;
+EMU_NOTSAN inline void fiber_entry() {
+	EMU_TSAN_ACQUIRE(&B->chain[B->block & 1u]);  // after the host code before the launch and after the previous blocks
+	BlockState* const b = B;
+	Fiber* const self = &b->fib[b->cur];
+	b->body();
+	self->done = true;
+	--b->alive;
+	++b->progress;
 	release_barrier_if_complete();  // exited threads do not take part in later barriers
-	swapcontext(&B->fib[B->cur].ctx, &B->sched);
+	EMU_TSAN_RELEASE(&b->chain[(b->block + 1u) & 1u]);  // (nothing below touches instrumented memory)
+	EMU_TSAN_SWITCH(b->schedTsan);
+	swapcontext(&self->ctx, &b->sched);
 }
 
-inline void syncthreads() {
+EMU_NOTSAN inline void syncthreads() {
 	const uint64_t g = B->barGen;
+	EMU_TSAN_RELEASE(&B->barObj);
 	++B->barCount;
 	release_barrier_if_complete();
 	while (B->barGen == g) yield();
+	EMU_TSAN_ACQUIRE(&B->barObj);
 }
 
 // every lane of `mask` deposits v; returns once all have, with the 32 deposited values in out[]
-inline void exchange(uint32_t mask, uint64_t v, uint64_t* out) {
+EMU_NOTSAN inline void exchange(uint32_t mask, uint64_t v, uint64_t* out, bool orders = true) {
 	const int t = B->cur, lane = t & 31;
 	WarpState& W = B->warp[t >> 5];
+	if (orders) EMU_TSAN_RELEASE(&W.hb);
 	if (!((mask >> lane) & 1u)) { std::fprintf(stderr, "simt_emu: lane %d calls a collective whose mask %08x does not name it\n", lane, mask); std::abort(); }
 	while (W.ready) yield();  // the previous collective of this warp is still being read
 	W.val[lane] = v;
 	W.arrived |= 1u << lane;
 	if (W.arrived == mask) {
-		std::memcpy(W.snap, W.val, sizeof(W.val));
+		for (int l = 0; l < 32; ++l) W.snap[l] = W.val[l];
 		W.ready = true;
 		W.readers = mask;
 		W.arrived = 0;
@@ -127,17 +174,24 @@ inline void exchange(uint32_t mask, uint64_t v, uint64_t* out) {
 		std::abort();
 	}
 	while (!W.ready || !((W.readers >> lane) & 1u)) yield();
-	std::memcpy(out, W.snap, sizeof(W.snap));
+	for (int l = 0; l < 32; ++l) out[l] = W.snap[l];
 	W.readers &= ~(1u << lane);
 	if (W.readers == 0) { W.ready = false; ++B->progress; }
+	if (orders) EMU_TSAN_ACQUIRE(&W.hb);
 }
+// __syncwarp orders memory among the named lanes; the CUDA programming guide does not promise that of the other *_sync collectives
+#ifdef XXM_EMU_STRICT_SHFL
+constexpr bool kShflOrders = false;
+#else
+constexpr bool kShflOrders = true;
+#endif
 
 struct LaunchStats { uint64_t collectives, barriers; };
 inline LaunchStats lastLaunch{0, 0};
 
 // runs body() once per CUDA thread of a grid x block launch (1-D)
 template <class F>
-void launch(unsigned grid, unsigned block, F&& body) {
+EMU_NOTSAN void launch(unsigned grid, unsigned block, F&& body) {
 	BlockState st;
 	B = &st;
 	gridDim = dim3(grid);
@@ -145,9 +199,16 @@ void launch(unsigned grid, unsigned block, F&& body) {
 	st.fib.resize(block);
 	st.warp.resize((block + 31) / 32);
 	for (auto& f : st.fib) f.stack = std::malloc(kStackBytes);
+#ifdef XXM_EMU_TSAN
+	st.schedTsan = __tsan_get_current_fiber();
+	for (auto& f : st.fib) f.tsan = __tsan_create_fiber(0);
+#endif
 	st.body = body;
+	EMU_TSAN_RELEASE(&st.chain[0]);  // what the host wrote before the launch is visible to every thread of the grid
+	EMU_TSAN_RELEASE(&st.chain[1]);
 	for (unsigned b = 0; b < grid; ++b) {
 		blockIdx = uint3{b, 0, 0};
+		st.block = b;
 		st.alive = static_cast<int>(block);
 		st.barCount = 0;
 		for (auto& w : st.warp) { w.arrived = 0; w.readers = 0; w.ready = false; }
@@ -166,6 +227,7 @@ void launch(unsigned grid, unsigned block, F&& body) {
 				if (st.fib[t].done) continue;
 				st.cur = static_cast<int>(t);
 				threadIdx = uint3{t, 0, 0};
+				EMU_TSAN_SWITCH(st.fib[t].tsan);
 				swapcontext(&st.sched, &st.fib[t].ctx);
 			}
 			if (st.progress == before && st.alive > 0) {
@@ -174,7 +236,12 @@ void launch(unsigned grid, unsigned block, F&& body) {
 			}
 		}
 	}
+	EMU_TSAN_ACQUIRE(&st.chain[0]);  // ... and what the grid wrote is visible to the host code after the launch
+	EMU_TSAN_ACQUIRE(&st.chain[1]);
 	lastLaunch = LaunchStats{st.collectives, st.barriers};
+#ifdef XXM_EMU_TSAN
+	for (auto& f : st.fib) __tsan_destroy_fiber(f.tsan);
+#endif
 	for (auto& f : st.fib) std::free(f.stack);
 	B = nullptr;
 }
@@ -211,11 +278,11 @@ inline uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 
 // ---- barriers and warp collectives
 inline void __syncthreads() { emu::syncthreads(); }
-inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { uint64_t o[32]; emu::exchange(mask, 0, o); }
+inline void __syncwarp(unsigned mask = 0xFFFFFFFFu) { uint64_t o[32]; emu::exchange(mask, 0, o, true); }
 template <class T>
 inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
 	uint64_t o[32];
-	emu::exchange(mask, emu::to_bits(v), o);
+	emu::exchange(mask, emu::to_bits(v), o, emu::kShflOrders);
 	const int lane = emu::lane_id();
 	const int base = lane & ~(width - 1);
 	return emu::from_bits<T>(o[base + (src & (width - 1))]);
@@ -223,7 +290,7 @@ inline T __shfl_sync(unsigned mask, T v, int src, int width = 32) {
 template <class T>
 inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32) {
 	uint64_t o[32];
-	emu::exchange(mask, emu::to_bits(v), o);
+	emu::exchange(mask, emu::to_bits(v), o, emu::kShflOrders);
 	const int lane = emu::lane_id();
 	const int base = lane & ~(width - 1);
 	const int src = lane - static_cast<int>(d);
@@ -232,7 +299,7 @@ inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32) {
 template <class T>
 inline T __shfl_down_sync(unsigned mask, T v, unsigned d, int width = 32) {
 	uint64_t o[32];
-	emu::exchange(mask, emu::to_bits(v), o);
+	emu::exchange(mask, emu::to_bits(v), o, emu::kShflOrders);
 	const int lane = emu::lane_id();
 	const int base = lane & ~(width - 1);
 	const int src = lane + static_cast<int>(d);
@@ -242,12 +309,12 @@ template <class T>
 inline T __shfl_xor_sync(unsigned mask, T v, int d, int width = 32) {
 	(void) width;
 	uint64_t o[32];
-	emu::exchange(mask, emu::to_bits(v), o);
+	emu::exchange(mask, emu::to_bits(v), o, emu::kShflOrders);
 	return emu::from_bits<T>(o[emu::lane_id() ^ d]);
 }
 inline unsigned __ballot_sync(unsigned mask, int pred) {
 	uint64_t o[32];
-	emu::exchange(mask, pred ? 1u : 0u, o);
+	emu::exchange(mask, pred ? 1u : 0u, o, emu::kShflOrders);
 	unsigned r = 0;
 	for (int l = 0; l < 32; ++l)
 		if (((mask >> l) & 1u) && o[l]) r |= 1u << l;
@@ -257,7 +324,7 @@ inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred
 inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) == mask; }
 inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
 	uint64_t o[32];
-	emu::exchange(mask, v, o);
+	emu::exchange(mask, v, o, emu::kShflOrders);
 	unsigned r = 0;
 	for (int l = 0; l < 32; ++l)
 		if ((mask >> l) & 1u) r += static_cast<unsigned>(o[l]);
@@ -265,7 +332,7 @@ inline unsigned __reduce_add_sync(unsigned mask, unsigned v) {
 }
 inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
 	uint64_t o[32];
-	emu::exchange(mask, v, o);
+	emu::exchange(mask, v, o, emu::kShflOrders);
 	unsigned r = 0;
 	for (int l = 0; l < 32; ++l)
 		if (((mask >> l) & 1u) && static_cast<unsigned>(o[l]) > r) r = static_cast<unsigned>(o[l]);
@@ -273,7 +340,7 @@ inline unsigned __reduce_max_sync(unsigned mask, unsigned v) {
 }
 inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
 	uint64_t o[32];
-	emu::exchange(mask, v, o);
+	emu::exchange(mask, v, o, emu::kShflOrders);
 	unsigned r = 0;
 	for (int l = 0; l < 32; ++l)
 		if ((mask >> l) & 1u) r |= static_cast<unsigned>(o[l]);
@@ -282,7 +349,7 @@ inline unsigned __reduce_or_sync(unsigned mask, unsigned v) {
 template <class T>
 inline unsigned __match_any_sync(unsigned mask, T v) {
 	uint64_t o[32];
-	emu::exchange(mask, emu::to_bits(v), o);
+	emu::exchange(mask, emu::to_bits(v), o, emu::kShflOrders);
 	unsigned r = 0;
 	const uint64_t mine = emu::to_bits(v);
 	for (int l = 0; l < 32; ++l)
@@ -314,7 +381,27 @@ inline unsigned __float_as_uint(float f) { return emu::to_bits(f) & 0xFFFFFFFFu;
 inline float __uint_as_float(unsigned u) { return emu::from_bits<float>(u); }
 inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
 
-// ---- atomics (one OS thread: plain read-modify-write)
+// ---- atomics (one OS thread: plain read-modify-write; under ThreadSanitizer real relaxed atomics, so that they do not count as races)
+#ifdef XXM_EMU_TSAN
+template <class T, class U>
+inline T atomicAdd(T* p, U v) { return __atomic_fetch_add(p, static_cast<T>(v), __ATOMIC_RELAXED); }
+template <class T, class U>
+inline T atomicOr(T* p, U v) { return __atomic_fetch_or(p, static_cast<T>(v), __ATOMIC_RELAXED); }
+template <class T, class U>
+inline T atomicMax(T* p, U v) {
+	T o = __atomic_load_n(p, __ATOMIC_RELAXED);
+	while (static_cast<T>(v) > o && !__atomic_compare_exchange_n(p, &o, static_cast<T>(v), false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+	return o;
+}
+template <class T, class U>
+inline T atomicExch(T* p, U v) { return __atomic_exchange_n(p, static_cast<T>(v), __ATOMIC_RELAXED); }
+template <class T, class U, class V>
+inline T atomicCAS(T* p, U cmp, V v) {
+	T o = static_cast<T>(cmp);
+	__atomic_compare_exchange_n(p, &o, static_cast<T>(v), false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+	return o;
+}
+#else
 template <class T, class U>
 inline T atomicAdd(T* p, U v) { const T o = *p; *p = static_cast<T>(o + static_cast<T>(v)); return o; }
 template <class T, class U>
@@ -325,6 +412,7 @@ template <class T, class U>
 inline T atomicExch(T* p, U v) { const T o = *p; *p = static_cast<T>(v); return o; }
 template <class T, class U, class V>
 inline T atomicCAS(T* p, U cmp, V v) { const T o = *p; if (o == static_cast<T>(cmp)) *p = static_cast<T>(v); return o; }
+#endif
 
 // ---- CUDA's global min / max overloads
 template <class T>

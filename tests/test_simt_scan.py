@@ -74,6 +74,72 @@ def test_kernels_under_address_sanitizer(target, extra, cases):
         assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
 
 
+TSAN_ENV = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=66")
+
+
+def _tsan_run(exe, case):
+    r = subprocess.run([exe, case], capture_output=True, text=True, timeout=900, env=TSAN_ENV)
+    if r.returncode and "FATAL: ThreadSanitizer" in r.stderr:
+        pytest.skip("ThreadSanitizer cannot start here: " + r.stderr.strip().splitlines()[0])
+    return r, r.stderr.count("WARNING: ThreadSanitizer: data race")
+
+
+def test_race_detector_controls():
+    """the emulator's racecheck (ThreadSanitizer, one fiber per CUDA thread, edges only where the programming model gives them) on
+    kernels with a known hazard and their repaired twins (tests/simt/race_control.cpp)"""
+    try:
+        lenient = simt_build.build("race_control", extra_sources=(), sanitize="thread")
+        strict = simt_build.build("race_control", extra_sources=(), sanitize="thread-strict")
+    except subprocess.CalledProcessError:
+        pytest.skip("no ThreadSanitizer runtime in this toolchain")
+    expect = {"warp_racy": (True, True), "warp_synced": (False, False), "block_racy": (True, True), "block_synced": (False, False),
+              "shfl": (False, True), "atomics": (False, False)}  # (reported by the default model, by the strict one)
+    for case, (a, b) in expect.items():
+        for exe, want in ((lenient, a), (strict, b)):
+            r, n = _tsan_run(exe, case)
+            assert (n > 0) == want, (case, exe, n, r.stderr[-3000:])
+            assert " done" in r.stdout
+
+
+@pytest.mark.parametrize("target,extra,cases", [
+    ("scan_emu", ("host_pack.cpp", "pair_table.cpp"), ["uniform_1kb", "ragged_N", "revcomp_ragged", "every_warp_dense", "small_capacity", "positive_set_prefix_ragged"]),
+    ("step_emu", ("host_pack.cpp",), ["clustered_uniform", "all_sites_dense", "zoops_ragged_shift", "rc_ragged", "rc_long_sequences", "sort_many_chunks"]),
+])
+def test_kernels_under_race_detector(target, extra, cases):
+    """The kernels of a step under the STRICT model (only __syncthreads and __syncwarp order memory): no two accesses of a block to
+    one shared or global address with a write among them and no fence between them.  All 33 cases, both models:
+    profiles/r02h_emulator_tsan.txt."""
+    try:
+        exe = simt_build.build(target, extra_sources=extra, sanitize="thread-strict")
+    except subprocess.CalledProcessError:
+        pytest.skip("no ThreadSanitizer runtime in this toolchain")
+    for case in cases:
+        r, n = _tsan_run(exe, case)
+        assert n == 0 and r.returncode == 0, case + "\n" + r.stderr[-6000:]
+        assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
+
+
+def test_race_detector_sees_a_removed_fence(tmp_path):
+    """mutation control on a product kernel: k_expand7 without the __syncwarp between filling the hit queue and reading it"""
+    import re
+    import shutil
+    simt_build.build("scan_emu")  # refreshes the rewritten headers
+    mut = tmp_path / "mut"
+    shutil.copytree(simt_build.BUILD, mut, ignore=shutil.ignore_patterns("*_emu*", "race_control*"))
+    f = mut / "xxm_scan7.cuh"
+    text = f.read_text()
+    # the fence right after the lock-step extraction loop (the sparse path every case takes)
+    m = re.search(r"pop_msb\(r3, q3, tag \+ 96\);\s*\}\s*__syncwarp\(\);", text)
+    assert m, "k_expand7 changed: update the mutation"
+    f.write_text(text[:m.start()] + m.group(0).replace("__syncwarp();", "/* fence removed */") + text[m.end():])
+    try:
+        exe = simt_build.build("scan_emu", sanitize="thread", kernel_dir=str(mut))
+    except subprocess.CalledProcessError:
+        pytest.skip("no ThreadSanitizer runtime in this toolchain")
+    r, n = _tsan_run(exe, "uniform_1kb")
+    assert n > 0 and "xxm_scan7.cuh" in r.stderr, r.stderr[-3000:]
+
+
 def test_product_does_not_reference_the_emulator():
     """the emulator hooks in the kernel sources are compile-time (#ifdef XXM_SIMT_EMU) and the library is built without them"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
