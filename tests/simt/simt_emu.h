@@ -361,6 +361,7 @@ inline unsigned __match_any_sync(unsigned mask, T v) {
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 inline int __clz(int x) { return x ? __builtin_clz(static_cast<unsigned>(x)) : 32; }
 inline unsigned __brev(unsigned x) {
 	unsigned r = 0;

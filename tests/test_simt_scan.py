@@ -140,6 +140,27 @@ def test_race_detector_sees_a_removed_fence(tmp_path):
     assert n > 0 and "xxm_scan7.cuh" in r.stderr, r.stderr[-3000:]
 
 
+@pytest.mark.parametrize("mode", [False, "address", "thread-strict"])
+def test_histogram_kernels_under_emulator(mode):
+    """k_kmer_hist (all three bin layouts: private bins without atomics, lane-replicated bins, plain bins in two passes) and
+    k_gapped_hist (contiguous and gapped patterns, a prefix of the set, the first-half rule of palindromic seeds under --revcomp)
+    against position-by-position counts over the raw sequences -- plain, bounds-checked, and under the strict race model"""
+    try:
+        exe = simt_build.build("hist_emu", extra_sources=("host_pack.cpp",), sanitize=mode)
+    except subprocess.CalledProcessError:
+        if mode:
+            pytest.skip("no sanitizer runtime in this toolchain")
+        raise
+    env = dict(ASAN_ENV, TSAN_OPTIONS=TSAN_ENV["TSAN_OPTIONS"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    if r.returncode and ("FATAL: ThreadSanitizer" in r.stderr or "Shadow memory range interleaves" in r.stderr):
+        pytest.skip("the sanitizer cannot start here")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
+    for mark in ("ERROR: AddressSanitizer", "runtime error", "WARNING: ThreadSanitizer"):
+        assert mark not in r.stderr, r.stderr[-4000:]
+
+
 def test_product_does_not_reference_the_emulator():
     """the emulator hooks in the kernel sources are compile-time (#ifdef XXM_SIMT_EMU) and the library is built without them"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
