@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "xxmotif_b200", "csrc")
 BUILD = os.path.join(HERE, "build")
 KERNEL_HEADERS = ["xxm_device.cuh", "xxm_kernels.cuh", "xxm_scan4.cuh", "xxm_scan5.cuh", "xxm_scan6.cuh", "xxm_scan7.cuh", "xxm_select2.cuh", "xxm_select3.cuh",
-                  "xxm_select4.cuh", "xxm_kmerhist.cuh", "xxm_gappedhist.cuh"]
+                  "xxm_select4.cuh", "xxm_kmerhist.cuh", "xxm_gappedhist.cuh", "xxm_tables_device.cuh"]
 
 
 def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp"), sanitize=False, kernel_dir=None):
@@ -40,7 +40,7 @@ def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp"), 
         return exe
     flags = {"": [], "address": ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"], "thread": ["-fsanitize=thread", "-fno-omit-frame-pointer"],
              "thread-strict": ["-fsanitize=thread", "-fno-omit-frame-pointer", "-DXXM_EMU_STRICT_SHFL"]}[mode]
-    cmd = ["g++", "-std=c++17", "-O1", "-g"] + flags + ["-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable",
+    cmd = ["g++", "-std=c++17", "-O1", "-g"] + flags + ["-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-maybe-uninitialized",
            "-I", kernel_dir or BUILD, "-I", os.path.join(HERE, "shim"), "-I", HERE, "-I", CSRC, os.path.join(HERE, target + ".cpp")]
     cmd += [os.path.join(CSRC, s) for s in extra_sources] + ["-o", exe, "-lpthread"]
     subprocess.check_call(cmd)

@@ -378,6 +378,7 @@ inline double __dmul_rn(double a, double b) { return a * b; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+inline int __double2int_rz(double a) { return static_cast<int>(a); }
 inline unsigned __float_as_uint(float f) { return emu::to_bits(f) & 0xFFFFFFFFu; }
 inline float __uint_as_float(unsigned u) { return emu::from_bits<float>(u); }
 inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }

@@ -161,6 +161,29 @@ def test_histogram_kernels_under_emulator(mode):
         assert mark not in r.stderr, r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("mode,cases", [(False, []), ("address", ["five_columns", "gapped_six", "ties_seven", "one_column"]),
+                                        ("thread-strict", ["five_columns", "gapped_six", "ties_seven", "one_column"])])
+def test_device_table_build_under_emulator(mode, cases):
+    """k_tab_count + k_tile_scan + k_tab_leaves + k_tab_rank + k_tab_accumulate, launched as the library launches
+    them, against the product's host build (ids, classes, integer scores, class sizes, cumulative FP64 class p-values: bit for bit) for
+    5..8 columns, gap columns, null-model orders 0..4 and PWMs whose k-mers tie in score -- plain (all 10 cases), bounds-checked and
+    under the strict race model (4 cases; all 10: profiles/r02h_emulator_tsan.txt)"""
+    try:
+        exe = simt_build.build("tables_emu", extra_sources=("pvalue_tables.cpp", "background_model.cpp"), sanitize=mode)
+    except subprocess.CalledProcessError:
+        if mode:
+            pytest.skip("no sanitizer runtime in this toolchain")
+        raise
+    env = dict(ASAN_ENV, TSAN_OPTIONS=TSAN_ENV["TSAN_OPTIONS"])
+    r = subprocess.run([exe] + cases, capture_output=True, text=True, timeout=900, env=env)
+    if r.returncode and ("FATAL: ThreadSanitizer" in r.stderr or "Shadow memory range interleaves" in r.stderr):
+        pytest.skip("the sanitizer cannot start here")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
+    for mark in ("ERROR: AddressSanitizer", "runtime error", "WARNING: ThreadSanitizer"):
+        assert mark not in r.stderr, r.stderr[-4000:]
+
+
 def test_product_does_not_reference_the_emulator():
     """the emulator hooks in the kernel sources are compile-time (#ifdef XXM_SIMT_EMU) and the library is built without them"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
