@@ -184,6 +184,27 @@ def test_device_table_build_under_emulator(mode, cases):
         assert mark not in r.stderr, r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("mode", [False, "address", "thread-strict"])
+def test_memo_evaluation_under_emulator(mode):
+    """k_memo_eval_list (the convolution over the left score classes for motifs with more than 8 match columns; the kernel bisects where
+    the reference walks its class pointer down) against the reference's loop written out literally (branch_and_bound-inl.h:425-449,
+    binarySearch :337-357), FP64 bit for bit, class arrays in shared and in global memory -- plain, bounds-checked, strict race model"""
+    try:
+        exe = simt_build.build("memo_emu", extra_sources=(), sanitize=mode)
+    except subprocess.CalledProcessError:
+        if mode:
+            pytest.skip("no sanitizer runtime in this toolchain")
+        raise
+    env = dict(ASAN_ENV, TSAN_OPTIONS=TSAN_ENV["TSAN_OPTIONS"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    if r.returncode and ("FATAL: ThreadSanitizer" in r.stderr or "Shadow memory range interleaves" in r.stderr):
+        pytest.skip("the sanitizer cannot start here")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
+    for mark in ("ERROR: AddressSanitizer", "runtime error", "WARNING: ThreadSanitizer"):
+        assert mark not in r.stderr, r.stderr[-4000:]
+
+
 def test_product_does_not_reference_the_emulator():
     """the emulator hooks in the kernel sources are compile-time (#ifdef XXM_SIMT_EMU) and the library is built without them"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
