@@ -5,6 +5,9 @@
 // counts taken position by position from the raw sequences.  Under build.py's sanitizers the same runs are a memcheck and a
 // racecheck of these kernels (the bins of k_kmer_hist's private layout are read-modify-written WITHOUT atomics by design).
 //
+// Also k_logodds_hist (a14: the forward / reverse-complement log-odds histogram of Output::printScoreDistribution), against the same sums
+// taken window by window.
+//
 // usage: hist_emu [case ...]; exit code 0 = every case identical
 #include <algorithm>
 #include <cstdint>
@@ -16,6 +19,7 @@
 
 #include "cuda_runtime.h"  // tests/simt/shim -> simt_emu.h
 
+#include "xxm_kernels.cuh"   // k_logodds_hist
 #include "xxm_kmerhist.cuh"
 #include "xxm_gappedhist.cuh"
 
@@ -25,6 +29,8 @@ namespace xxm {
 // dynamic shared memory of the two kernels (block-scope `extern` after the rewrite of `extern __shared__`)
 uint32_t s_bins[56 * 1024];
 uint32_t s_gbins[1 << 14];
+alignas(16) uint8_t smemM[1 << 16];  // (kernels of xxm_kernels.cuh that are not launched here)
+uint32_t s_hs[1 << 14];
 }  // namespace xxm
 
 using namespace xxm;
@@ -173,6 +179,52 @@ int run_gapped(const Case& c, const Set& s, const std::vector<int>& offset, bool
 	return same ? 0 : 1;
 }
 
+// ---- k_logodds_hist (a14: Output::printScoreDistribution, output.cpp:1050-1064 with calculateMatrixScore_logOdds, Motif.h:584-599):
+// per start position, the number of sequences whose window scores above the threshold under the PWM and under its reverse complement
+int run_logodds(const Case& c, const Set& s, const std::vector<int>& coloff, int nseqScan, uint32_t seed) {
+	std::mt19937 rng(seed);
+	std::uniform_real_distribution<double> U(-2.5, 1.5);
+	HistModel H{};
+	H.ncols = static_cast<int>(coloff.size());
+	H.span = coloff.back() + 1;
+	for (int k = 0; k < H.ncols; ++k) {
+		H.coloff[k] = coloff[static_cast<size_t>(k)];
+		H.lodF[k][0] = H.lodB[k][0] = std::log(1.0 / 1000) + std::log(2.0);  // the N penalty (Motif.h:592)
+		for (int a = 1; a <= 4; ++a) { H.lodF[k][a] = U(rng); H.lodB[k][a] = U(rng); }
+	}
+	H.thrF = 0.3 * H.ncols * 0.5; H.thrB = -0.2;
+	int maxLen = 0;
+	for (int i = 0; i < nseqScan; ++i) maxLen = std::max(maxLen, s.len[static_cast<size_t>(i)]);
+	const int npos = std::max(1, maxLen - H.span + 1 - 3);  // a few positions short of the longest sequence: the kernel must stop at npos
+	std::vector<unsigned int> wantF(static_cast<size_t>(npos), 0u), wantB(wantF), gotF(wantF), gotB(wantF);
+	for (int i = 0; i < nseqScan; ++i) {
+		const auto& q = s.seq[static_cast<size_t>(i)];
+		const int n = static_cast<int>(q.size());
+		for (int pos = 1; pos <= n - H.span + 1 && pos <= npos; ++pos) {
+			double f = 0, b = 0;
+			for (int k = 0; k < H.ncols; ++k) {
+				const int a = q[static_cast<size_t>(pos - 1 + H.coloff[k])];
+				f = f + H.lodF[k][a];
+				b = b + H.lodB[k][a];
+			}
+			if (f > H.thrF) wantF[static_cast<size_t>(pos - 1)]++;
+			if (b > H.thrB) wantB[static_cast<size_t>(pos - 1)]++;
+		}
+	}
+	SeqStream S{};
+	S.codes = s.codes.data(); S.nmask = s.nmask.data(); S.wordOff = s.wordOff.data(); S.len = s.len.data(); S.blk2seq = s.blk2seq.data();
+	S.nwords = s.nwords; S.nent = static_cast<int32_t>(s.n.size());
+	const uint32_t scanWords = s.wordOff[static_cast<size_t>(nseqScan)];
+	emu::launch((scanWords + 255) / 256, 256, [&] { k_logodds_hist(S, H, scanWords, gotF.data(), gotB.data(), npos); });
+	const bool same = wantF == gotF && wantB == gotB;
+	unsigned long long tf = 0, tb = 0;
+	for (unsigned v : gotF) tf += v;
+	for (unsigned v : gotB) tb += v;
+	std::printf("%-22s k_logodds_hist %d columns span %d, %d sequences, %d positions: %llu / %llu windows above the thresholds  %s\n", c.name.c_str(), H.ncols, H.span,
+	            nseqScan, npos, tf, tb, same ? "identical" : "DIFFERENT");
+	return same ? 0 : 1;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -194,6 +246,8 @@ int main(int argc, char** argv) {
 		failed += run_gapped(c, s, {0, 1, 4, 5, 9}, false, c.nseq, 3); ++runs;
 		failed += run_gapped(c, s, {0, 2, 3, 11, 12, 20}, false, std::max(1, c.nseq / 2), 2); ++runs;
 		if (c.revcomp) { failed += run_gapped(c, s, {0, 1, 2, 8, 9, 10}, true, c.nseq, 2); ++runs; }  // palindromic seeds: first half of the doubled sequence
+		failed += run_logodds(c, s, {0, 1, 2, 3, 4, 5, 6, 7}, c.nseq, c.seed + 100); ++runs;
+		failed += run_logodds(c, s, {0, 1, 3, 4, 5, 9, 10, 12, 13, 14, 15, 20}, std::max(1, c.nseq - 3), c.seed + 200); ++runs;
 	}
 	std::printf("%d runs, %d failed\n", runs, failed);
 	return failed ? 1 : 0;

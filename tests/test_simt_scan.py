@@ -142,9 +142,10 @@ def test_race_detector_sees_a_removed_fence(tmp_path):
 
 @pytest.mark.parametrize("mode", [False, "address", "thread-strict"])
 def test_histogram_kernels_under_emulator(mode):
-    """k_kmer_hist (all three bin layouts: private bins without atomics, lane-replicated bins, plain bins in two passes) and
-    k_gapped_hist (contiguous and gapped patterns, a prefix of the set, the first-half rule of palindromic seeds under --revcomp)
-    against position-by-position counts over the raw sequences -- plain, bounds-checked, and under the strict race model"""
+    """k_kmer_hist (all three bin layouts: private bins without atomics, lane-replicated bins, plain bins in two passes),
+    k_gapped_hist (contiguous and gapped patterns, a prefix of the set, the first-half rule of palindromic seeds under --revcomp) and
+    k_logodds_hist (a14; contiguous and gapped columns, N penalty, a position limit below the longest sequence) against
+    position-by-position counts over the raw sequences -- plain, bounds-checked, and under the strict race model"""
     try:
         exe = simt_build.build("hist_emu", extra_sources=("host_pack.cpp",), sanitize=mode)
     except subprocess.CalledProcessError:
