@@ -206,6 +206,28 @@ def test_memo_evaluation_under_emulator(mode):
         assert mark not in r.stderr, r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("mode", [False, "address", "thread-strict"])
+def test_generic_find_kernel_under_emulator(mode):
+    """k_build_t9 + k_scan4<true/false> -- the find kernel of every model the pair table cannot represent (left parts spanning more
+    than 8 bases, two-part models, localization) -- staged and launched as the library does, against the definition of a scan
+    candidate taken window by window (no N in a match column, left k-mer in the table): exact and projected table entries, bitmap in
+    shared and in global memory, --revcomp, one-word sequences, several blocks -- plain, bounds-checked, strict race model"""
+    try:
+        exe = simt_build.build("scan4_emu", extra_sources=("host_pack.cpp",), sanitize=mode)
+    except subprocess.CalledProcessError:
+        if mode:
+            pytest.skip("no sanitizer runtime in this toolchain")
+        raise
+    env = dict(ASAN_ENV, TSAN_OPTIONS=TSAN_ENV["TSAN_OPTIONS"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    if r.returncode and ("FATAL: ThreadSanitizer" in r.stderr or "Shadow memory range interleaves" in r.stderr):
+        pytest.skip("the sanitizer cannot start here")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
+    for mark in ("ERROR: AddressSanitizer", "runtime error", "WARNING: ThreadSanitizer"):
+        assert mark not in r.stderr, r.stderr[-4000:]
+
+
 def test_product_does_not_reference_the_emulator():
     """the emulator hooks in the kernel sources are compile-time (#ifdef XXM_SIMT_EMU) and the library is built without them"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
