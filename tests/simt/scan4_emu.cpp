@@ -3,7 +3,11 @@
 // from the CUDA SOURCES under the SIMT emulator, staged as stage_t9 / launch_scan4 stage and launch it (xxm_gpu_scan4.inc), against
 // the definition of a scan candidate taken window by window from the raw sequences: no N in any match column
 // (branch_and_bound-inl.h:388) and the left k-mer in the table (:390-392).  Exact and projected table entries, bitmap in shared and
-// in global memory, --revcomp, N runs, one-word sequences.  Under build.py's sanitizers a memcheck and a racecheck.
+// in global memory, --revcomp, N runs, one-word sequences.  Then the generic EXPAND kernel k_expand5<true/false> (xxm_scan5.cuh: hit masks
+// -> ordered (sequence, position, value index) records through a decoupled look-back over the tiles; the value index is the class of
+// the left k-mer or, for two-part models, the memo slot of the window's integer score, kNone where the right table or the product
+// test rejects the window, branch_and_bound-inl.h:399-423) against the same records taken window by window; record arrays of exactly
+// the number of records.  Under build.py's sanitizers a memcheck and a racecheck.
 //
 // usage: scan4_emu [case ...]; exit code 0 = every case identical
 #include <algorithm>
@@ -18,11 +22,13 @@
 
 #include "xxm_kernels.cuh"
 #include "xxm_scan4.cuh"
+#include "xxm_scan5.cuh"  // k_expand5
 
 #include "host_pack.h"
 
 namespace xxm {
 alignas(16) uint8_t smem4[65536 + 65536];
+alignas(16) uint8_t smem5[kPairTabWords * 4];
 alignas(16) uint8_t smemM[1 << 16];
 uint32_t s_hs[1 << 14];
 }  // namespace xxm
@@ -170,7 +176,102 @@ int run(const Case& c) {
 	const bool same = want == hitmask;
 	std::printf("%-24s %d columns (left %d, span %d), table %zu of %zu, bitmap in %s memory, exact offsets %u, grid %u: %llu candidates over %u words  %s\n",
 	            c.name.c_str(), L, c.len0, M.span, ids.size(), size, smemBm ? "shared" : "global", exact, grid, cand, scanWords, same ? "identical" : "DIFFERENT");
-	return same ? 0 : 1;
+	if (!same) return 1;
+
+	// ---- the generic expand on those masks
+	const int len1 = L - c.len0;
+	const uint32_t nclass0 = 50, nclass1 = 70;
+	std::vector<uint32_t> rank0(size, 0u);
+	for (size_t i = 0; i < ids.size(); ++i) rank0[ids[i]] = static_cast<uint32_t>(i % nclass0) + 1;
+	std::vector<uint32_t> rank1;
+	std::vector<double> cpval0(nclass0), cpval1(nclass1);
+	std::uniform_real_distribution<double> U(1e-6, 1e-2);
+	for (double& v : cpval0) v = U(rng);
+	for (double& v : cpval1) v = U(rng);
+	const uint32_t memoCap = 1u << 14;
+	std::vector<int32_t> memoKey(memoCap, kMemoEmpty);
+	uint32_t memoOverflow = 0;
+	M.rank0 = rank0.data(); M.cpval0 = cpval0.data(); M.nclass0 = static_cast<int>(nclass0);
+	M.len1 = len1;
+	M.contiguous = (M.span == L) ? 1 : 0;
+	if (len1 > 0) {
+		rank1.assign(static_cast<size_t>(1) << (2 * len1), 0u);
+		for (size_t id = 0; id < rank1.size(); ++id)
+			if (rng() % 3) rank1[id] = static_cast<uint32_t>(rng() % nclass1) + 1;  // two thirds of the right k-mers are in the right table
+		M.rank1 = rank1.data(); M.cpval1 = cpval1.data(); M.nclass1 = static_cast<int>(nclass1);
+		M.pruneThr = 2.5e-5;  // about half of the products pass
+		std::uniform_real_distribution<double> Lo(-1.5, 1.0);
+		for (int k = 0; k < L; ++k)
+			for (int a = 0; a < 4; ++a) M.logodds[k][a] = Lo(rng);
+		M.memoKey = memoKey.data(); M.memoCap = memoCap; M.memoOverflow = &memoOverflow;
+	}
+	// the records the reference's loop would make of the candidates, in scan order
+	struct Want { uint32_t seq, pos; bool none; uint32_t v; int32_t s; };
+	std::vector<Want> recs;
+	for (int i = 0; i < c.nseq; ++i) {
+		const auto& q = s.seq[i];
+		const int n = static_cast<int>(q.size());
+		for (int p0 = 0; p0 < n; ++p0) {
+			if (!((want[s.wordOff[i] + static_cast<uint32_t>(p0 / 32)] >> (p0 % 32)) & 1u)) continue;
+			uint32_t id0 = 0, id1 = 0;
+			for (int k = 0; k < c.len0; ++k) id0 |= static_cast<uint32_t>(q[p0 + c.coloff[k]] - 1) << (2 * k);
+			for (int k = c.len0; k < L; ++k) id1 |= static_cast<uint32_t>(q[p0 + c.coloff[k]] - 1) << (2 * (k - c.len0));
+			Want w{static_cast<uint32_t>(i + 1), static_cast<uint32_t>(p0 + 1), false, rank0[id0] - 1, 0};
+			if (len1 > 0) {
+				const uint32_t r0 = rank0[id0], r1 = rank1[id1];
+				if (r1 == 0 || cpval0[r0 - 1] * cpval1[r1 - 1] > M.pruneThr) w.none = true;
+				else {
+					double score = 0;
+					for (int k = 0; k < L; ++k) score = score + M.logodds[k][q[p0 + c.coloff[k]] - 1];
+					w.s = static_cast<int32_t>(score * 1e6 - 1.0);
+				}
+			}
+			recs.push_back(w);
+		}
+	}
+	const uint32_t nrec = static_cast<uint32_t>(recs.size());
+	const uint32_t ntiles = (scanWords + kTileWords - 1) / kTileWords;
+	std::vector<uint64_t> status(static_cast<size_t>(ntiles) + 1, 0ull), gstatus(static_cast<size_t>(ntiles) / 32 + 2, 0ull);
+	uint32_t ticket = 0;
+	uint64_t total = ~0ull;
+	const uint32_t nval = len1 > 0 ? memoCap : nclass0;
+	std::vector<double> pS(nval);
+	for (double& v : pS) v = U(rng);
+	Values V{};
+	V.pS = pS.data(); V.kind = kFinalTable;
+	int bad = 0;
+	for (uint32_t cap : {nrec, nrec > 8 ? nrec - 5 : nrec}) {  // exactly enough room, and five records too few (they must be dropped, not written)
+		std::vector<uint32_t> oseq(std::max(1u, cap), 0xABABABABu), opos(oseq), ovidx(oseq);
+		std::vector<float> oscore(std::max(1u, cap), -1.f);
+		std::fill(status.begin(), status.end(), 0ull);
+		std::fill(gstatus.begin(), gstatus.end(), 0ull);
+		std::fill(memoKey.begin(), memoKey.end(), kMemoEmpty);
+		Expand5IO io{};
+		io.hitmask = hitmask.data(); io.scanWords = scanWords; io.eoFormat = 0; io.wantScore = 1;
+		io.oseq = oseq.data(); io.opos = opos.data(); io.ovidx = ovidx.data(); io.oscore = oscore.data();
+		io.cap = cap; io.status = status.data(); io.gstatus = gstatus.data(); io.ticket = &ticket; io.total = &total; io.ntiles = ntiles;
+		io.wpsMagic = 0;
+		const bool fast = M.nparts == 1 && M.contiguous;
+		emu::launch(ntiles, kExpand5Threads, [&] {
+			if (fast) k_expand5<true>(S, M, V, io);
+			else k_expand5<false>(S, M, V, io);
+		});
+		bool ok = total == nrec && memoOverflow == 0;
+		for (uint32_t k = 0; ok && k < std::min(cap, nrec); ++k) {
+			const Want& w = recs[k];
+			ok = oseq[k] == w.seq && opos[k] == w.pos;
+			if (!ok) break;
+			if (w.none) ok = ovidx[k] == kNone && oscore[k] == 1.0f;
+			else if (len1 > 0) ok = ovidx[k] < memoCap && memoKey[ovidx[k]] == w.s && oscore[k] == static_cast<float>(pS[ovidx[k]]);
+			else ok = ovidx[k] == w.v && oscore[k] == static_cast<float>(pS[w.v]);
+		}
+		unsigned none = 0;
+		for (const Want& w : recs) none += w.none;
+		std::printf("%-24s k_expand5<%s> %u tiles, capacity %u: %u records (%u without a value)  %s\n", c.name.c_str(), fast ? "true" : "false", ntiles, cap, nrec, none,
+		            ok ? "identical" : "DIFFERENT");
+		bad += ok ? 0 : 1;
+	}
+	return bad;
 }
 
 }  // namespace
@@ -186,6 +287,9 @@ int main(int argc, char** argv) {
 		{"five_columns_dense", 40, 1, 90, 0.08, false, {0, 1, 2, 3, 4}, 5, 0.30, 57},
 		{"one_word_sequences", 70, 1, 31, 0.05, true, {0, 1, 3, 4, 5, 6}, 6, 0.20, 58},
 		{"several_blocks_gapped", 150, 100, 700, 0.02, false, {0, 1, 2, 3, 5, 6, 7, 9}, 8, 0.02, 59},
+		{"dense_tiles", 90, 300, 500, 0.01, false, {0, 1, 2, 3, 4}, 5, 0.50, 60},              // more hits per tile than the queue holds
+		{"dense_tiles_gapped", 70, 300, 500, 0.01, false, {0, 1, 3, 4, 6}, 5, 0.45, 61},
+		{"forty_tiles", 1300, 900, 1100, 0.002, false, {0, 1, 2, 3, 4, 5, 7, 8}, 8, 0.004, 62},  // the look-back crosses a group of 32 tiles
 	};
 	int runs = 0, failed = 0;
 	for (const Case& c : cases) {

@@ -211,7 +211,10 @@ def test_generic_find_kernel_under_emulator(mode):
     """k_build_t9 + k_scan4<true/false> -- the find kernel of every model the pair table cannot represent (left parts spanning more
     than 8 bases, two-part models, localization) -- staged and launched as the library does, against the definition of a scan
     candidate taken window by window (no N in a match column, left k-mer in the table): exact and projected table entries, bitmap in
-    shared and in global memory, --revcomp, one-word sequences, several blocks -- plain, bounds-checked, strict race model"""
+    shared and in global memory, --revcomp, one-word sequences, several blocks; then k_expand5<true/false> on those masks -- ordered
+    (sequence, position, value index) records incl. the memo slots and rejections of two-part models, tiles with more hits than the
+    queue holds, a look-back across 42 tiles, record arrays of exactly the right size and five records short -- plain, bounds-checked,
+    strict race model"""
     try:
         exe = simt_build.build("scan4_emu", extra_sources=("host_pack.cpp",), sanitize=mode)
     except subprocess.CalledProcessError:
