@@ -262,6 +262,94 @@ int run_zoops_case(const std::string& name, int nseq, int lenLo, int lenHi, doub
 }
 
 // k_select_cls_rc (xxm_select4.cuh: forward rule + one monotone cursor into the frozen forward list) against the reference's
+// k_select_mops_fwd (xxm_select2.cuh): updateMultOcc's forward rule on FLOAT-valued lists -- what two-part models, localization and
+// re-scored lists take (the finalPval is not a monotone function of a class index there) -- against the reference's greedy,
+// StartPosUtils.h:12-28, literally.  kind 0: finalPval from a table over the value index (any order); 1: the localized MOPS formula
+// from pS and the positional prior (pValCalculation.h:79); 2: one finalPval per candidate.
+int run_fwd_generic_case(const std::string& name, int nseq, int lenLo, int lenHi, double hitFrac, int span, uint32_t nval, int kind, int shift, uint32_t seed) {
+	std::mt19937 rng(seed);
+	std::vector<int32_t> n(nseq);
+	int maxLen = 0;
+	for (auto& v : n) { v = lenLo + static_cast<int>(rng() % static_cast<uint32_t>(lenHi - lenLo + 1)); maxLen = std::max(maxLen, v); }
+	std::vector<uint32_t> seq, pos, vidx;
+	for (int q = 0; q < nseq; ++q) {
+		int boost = 0;
+		for (int p = std::max(1, 1 - shift); p + span - 1 <= n[q]; ++p) {
+			const double pr = hitFrac * (boost > 0 ? 12.0 : 1.0);
+			if (boost > 0) --boost;
+			if ((rng() % 100000) < pr * 100000) {
+				seq.push_back(static_cast<uint32_t>(q) + 1);
+				pos.push_back(static_cast<uint32_t>(p));
+				vidx.push_back((rng() % 40 == 0) ? kNone : static_cast<uint32_t>(rng() % nval));
+				boost = 6;
+			}
+		}
+	}
+	const uint32_t ncand = static_cast<uint32_t>(seq.size());
+	std::uniform_real_distribution<double> U(0.0, 1.0);
+	std::vector<double> pS(nval), finTab(nval), posProb(static_cast<size_t>(maxLen) + 8 + static_cast<size_t>(std::abs(shift))), perCand(std::max(1u, ncand));
+	for (uint32_t k = 0; k < nval; ++k) {
+		pS[k] = (rng() % 9 == 0) ? 1.0 : std::pow(U(rng), 6);         // 1.0: not a site
+		finTab[k] = (rng() % 7 == 0) ? 1.0 : std::pow(U(rng), 5);      // in no particular order; a few values repeat (ties keep the earlier site)
+		if (k && rng() % 5 == 0) finTab[k] = finTab[k - 1];
+	}
+	for (double& v : posProb) v = 0.05 + 0.95 * U(rng);
+	for (double& v : perCand) v = (rng() % 6 == 0) ? 1.0 : std::pow(U(rng), 4);
+	Values V{};
+	V.pS = pS.data(); V.finalTab = finTab.data(); V.posProb = posProb.data(); V.perCand = perCand.data();
+	V.kind = kind == 0 ? kFinalTable : kind == 1 ? kFinalLocMops : kFinalPerCand;
+	// ---- the reference's greedy: the incoming double finalPval against the float score stored with the kept site
+	std::vector<double> fin(std::max(1u, ncand), 1.0);
+	for (uint32_t i = 0; i < ncand; ++i)
+		if (vidx[i] != kNone) fin[i] = final_of(V, vidx[i], i, static_cast<int>(pos[i]) + shift);
+	std::vector<uint8_t> wantKeep(std::max(1u, ncand), 0);
+	{
+		std::vector<uint32_t> kept;
+		for (uint32_t i = 0; i < ncand; ++i) {
+			if (!(fin[i] < 1.0)) continue;
+			if (!kept.empty()) {
+				const uint32_t l = kept.back();
+				if (seq[l] == seq[i] && pos[l] + static_cast<uint32_t>(span) >= pos[i]) {
+					if (static_cast<double>(static_cast<float>(fin[l])) <= fin[i]) continue;
+					kept.pop_back();
+				}
+			}
+			kept.push_back(i);
+		}
+		for (uint32_t i : kept) wantKeep[i] = 1;
+	}
+	// ---- the kernel: arrays of exactly n entries, histogram in shared memory and (a second launch) in global memory
+	int bad = 0;
+	for (int smemHist = 1; smemHist >= 0; --smemHist) {
+		std::vector<uint8_t> keep(std::max(1u, ncand), 0xEE);
+		std::vector<float> kscore(std::max(1u, ncand), -5.f);
+		std::vector<uint16_t> kcls(std::max(1u, ncand), 0xEEEE);
+		std::vector<uint32_t> hist(nval, 0u), counters(8, 0u);
+		SelectFwdIO f{};
+		f.seq = seq.data(); f.pos = pos.data(); f.vidx = vidx.data(); f.n = ncand; f.nDev = nullptr; f.length = span; f.shift = shift;
+		f.kscore = kscore.data(); f.keep = keep.data(); f.counters = counters.data();
+		const bool wantHist = kind == 0;
+		if (wantHist) { f.hist = hist.data(); f.nval = nval; f.smemHist = smemHist; f.kcls = kcls.data(); }
+		const unsigned grid = std::max(1u, std::min(3u, (ncand + 256 * kSelChunk - 1) / (256 * kSelChunk)));
+		emu::launch(grid, 256, [&] { k_select_mops_fwd(V, f); });
+		uint32_t nkept = 0, wrong = 0;
+		std::vector<uint32_t> wantHistV(nval, 0u);
+		for (uint32_t i = 0; i < ncand; ++i) {
+			if (wantKeep[i]) { ++nkept; if (wantHist) ++wantHistV[vidx[i]]; }
+			const float ws = static_cast<float>(fin[i]);
+			bool ok = keep[i] == wantKeep[i] && !std::memcmp(&kscore[i], &ws, 4);
+			if (wantHist) ok = ok && kcls[i] == (wantKeep[i] ? static_cast<uint16_t>(vidx[i]) : static_cast<uint16_t>(0xFFFF));
+			wrong += ok ? 0 : 1;
+		}
+		const bool same = wrong == 0 && counters[0] == nkept && (!wantHist || hist == wantHistV);
+		std::printf("%-22s k_select_mops_fwd kind %d%s: %u candidates, %u kept, span %d, shift %d  %s\n", name.c_str(), kind,
+		            wantHist ? (smemHist ? ", histogram in shared memory" : ", histogram in global memory") : "", ncand, nkept, span, shift, same ? "identical" : "DIFFERENT");
+		bad += same ? 0 : 1;
+		if (!wantHist) break;
+	}
+	return bad;
+}
+
 // updateMultOcc with Global::revcomp, literally (StartPosUtils.h:12-65: the look-back walk over the kept array and the removal of
 // the loser from its middle), on doubled sequences (stored length 2 n0 + 1) with candidates on both strands
 int run_rc_case(const std::string& name, int nseq, int n0Lo, int n0Hi, double hitFrac, int span, uint32_t nval, uint32_t nSiteWant, uint32_t seed) {
@@ -419,6 +507,19 @@ int main(int argc, char** argv) {
 			if (!sel) continue;
 		}
 		failed += run_zoops_case(z.name, z.nseq, z.lenLo, z.lenHi, z.frac, z.shift, z.nFrac, z.seed) ? 1 : 0;
+		++ran;
+	}
+	struct Ge { const char* name; int nseq, lenLo, lenHi; double frac; int span; uint32_t nval; int kind, shift; uint32_t seed; };
+	const Ge ges[] = {{"gen_table_clustered", 120, 300, 300, 0.04, 8, 300, 0, 0, 41}, {"gen_table_ragged_long", 200, 12, 500, 0.06, 21, 4000, 0, 0, 42},
+	                  {"gen_localized", 150, 100, 400, 0.05, 12, 700, 1, 0, 43}, {"gen_localized_shift", 90, 200, 350, 0.08, 9, 120, 1, -2, 44},
+	                  {"gen_per_candidate", 100, 50, 600, 0.05, 17, 50, 2, 1, 45}, {"gen_dense", 10, 700, 700, 0.4, 6, 25, 0, 0, 46}, {"gen_tiny", 1, 10, 10, 0.6, 8, 5, 2, 0, 47}};
+	for (const Ge& z : ges) {
+		if (argc > 1) {
+			bool sel = false;
+			for (int i = 1; i < argc; ++i) sel = sel || std::string(z.name) == argv[i];
+			if (!sel) continue;
+		}
+		failed += run_fwd_generic_case(z.name, z.nseq, z.lenLo, z.lenHi, z.frac, z.span, z.nval, z.kind, z.shift, z.seed) ? 1 : 0;
 		++ran;
 	}
 	struct Rc { const char* name; int nseq, n0Lo, n0Hi; double frac; int span; uint32_t nval, nSite, seed; };
