@@ -5,7 +5,8 @@
 // counts taken position by position from the raw sequences.  Under build.py's sanitizers the same runs are a memcheck and a
 // racecheck of these kernels (the bins of k_kmer_hist's private layout are read-modify-written WITHOUT atomics by design).
 //
-// Also k_logodds_hist (a14: the forward / reverse-complement log-odds histogram of Output::printScoreDistribution), against the same sums
+// Also k_encode (a1 on the device: the packing kernel of the load path for hosts with few cores, against the host packing) and
+// k_logodds_hist (a14: the forward / reverse-complement log-odds histogram of Output::printScoreDistribution), against the same sums
 // taken window by window.
 //
 // usage: hist_emu [case ...]; exit code 0 = every case identical
@@ -225,6 +226,32 @@ int run_logodds(const Case& c, const Set& s, const std::vector<int>& coloff, int
 	return same ? 0 : 1;
 }
 
+// ---- k_encode (a1 on the device: raw codes -> packed stream with the reverse strand generated on the fly, createRevcomp,
+// seqset.cpp:128-178; the load path of hosts with few cores per GPU) against the host packing (host_pack.cpp), word for word
+int run_encode(const Case& c, const Set& s) {
+	uint64_t tot = 0;
+	std::vector<uint64_t> rawOff(s.n.size() + 1, 0);
+	for (size_t i = 0; i < s.n.size(); ++i) { rawOff[i] = tot; tot += static_cast<uint64_t>(s.n[i]); }
+	rawOff[s.n.size()] = tot;
+	const std::vector<uint8_t> raw(s.raw.begin(), s.raw.begin() + static_cast<std::ptrdiff_t>(tot));  // exactly the residues: no slack to over-read into
+	std::vector<uint64_t> codes(static_cast<size_t>(s.nwords) + 2, 0x5555555555555555ull);
+	std::vector<uint32_t> nmask(static_cast<size_t>(s.nwords) + 2, 0x12345678u);
+	SeqStream S{};
+	S.wordOff = s.wordOff.data(); S.len = s.len.data(); S.blk2seq = s.blk2seq.data(); S.nwords = s.nwords; S.nent = static_cast<int32_t>(s.n.size());
+	// three chunks of whole words, the last one with the two guard words (load_pack_on_device, xxm_gpu.cu)
+	const uint32_t cut1 = s.nwords / 3, cut2 = 2 * (s.nwords / 3) + 1;
+	const uint32_t bounds[4] = {0, cut1, std::min(cut2, s.nwords), s.nwords + 2};
+	for (int k = 0; k < 3; ++k) {
+		const uint32_t w0 = bounds[k], w1 = bounds[k + 1];
+		if (w1 <= w0) continue;
+		emu::launch((w1 - w0 + 255) / 256, 256, [&] { k_encode(raw.data(), rawOff.data(), S, w0, w1, codes.data(), nmask.data(), c.revcomp ? 1 : 0); });
+	}
+	const bool same = codes == s.codes && nmask == s.nmask;
+	std::printf("%-22s k_encode%s: %u words + 2 guard words in 3 chunks vs the host packing  %s\n", c.name.c_str(), c.revcomp ? " --revcomp" : "", s.nwords,
+	            same ? "identical" : "DIFFERENT");
+	return same ? 0 : 1;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -233,6 +260,7 @@ int main(int argc, char** argv) {
 		{"ragged_N", 40, 5, 260, 0.06, false, 12},
 		{"revcomp_ragged_N", 30, 9, 180, 0.04, true, 13},
 		{"short_sequences", 60, 1, 40, 0.10, false, 14},
+		{"revcomp_short", 50, 1, 70, 0.08, true, 15},
 	};
 	int runs = 0, failed = 0;
 	for (const Case& c : cases) {
@@ -246,6 +274,7 @@ int main(int argc, char** argv) {
 		failed += run_gapped(c, s, {0, 1, 4, 5, 9}, false, c.nseq, 3); ++runs;
 		failed += run_gapped(c, s, {0, 2, 3, 11, 12, 20}, false, std::max(1, c.nseq / 2), 2); ++runs;
 		if (c.revcomp) { failed += run_gapped(c, s, {0, 1, 2, 8, 9, 10}, true, c.nseq, 2); ++runs; }  // palindromic seeds: first half of the doubled sequence
+		failed += run_encode(c, s); ++runs;
 		failed += run_logodds(c, s, {0, 1, 2, 3, 4, 5, 6, 7}, c.nseq, c.seed + 100); ++runs;
 		failed += run_logodds(c, s, {0, 1, 3, 4, 5, 9, 10, 12, 13, 14, 15, 20}, std::max(1, c.nseq - 3), c.seed + 200); ++runs;
 	}

@@ -148,7 +148,8 @@ def test_histogram_kernels_under_emulator(mode):
     """k_kmer_hist (all three bin layouts: private bins without atomics, lane-replicated bins, plain bins in two passes),
     k_gapped_hist (contiguous and gapped patterns, a prefix of the set, the first-half rule of palindromic seeds under --revcomp) and
     k_logodds_hist (a14; contiguous and gapped columns, N penalty, a position limit below the longest sequence) against
-    position-by-position counts over the raw sequences -- plain, bounds-checked, and under the strict race model"""
+    position-by-position counts over the raw sequences, and k_encode (a1: the device packing incl. createRevcomp) against the host
+    packing word for word -- plain, bounds-checked, and under the strict race model"""
     try:
         exe = simt_build.build("hist_emu", extra_sources=("host_pack.cpp",), sanitize=mode)
     except subprocess.CalledProcessError:
