@@ -15,6 +15,9 @@
 #include "cuda_runtime.h"  // tests/simt/shim -> simt_emu.h
 
 #include "xxm_kernels.cuh"
+#include "xxm_scan4.cuh"
+#include "xxm_scan5.cuh"
+#include "xxm_scan6.cuh"  // k_tile_scan
 #include "xxm_select2.cuh"
 #include "xxm_select3.cuh"
 #include "xxm_select4.cuh"
@@ -23,7 +26,8 @@
 
 namespace xxm {
 alignas(16) uint8_t smem3[1 << 16];
-alignas(16) uint8_t smem4[1 << 16];
+alignas(16) uint8_t smem4[65536 + 65536];
+alignas(16) uint8_t smem5[kPairTabWords * 4];
 alignas(16) uint8_t smemM[1 << 16];
 uint32_t s_hist[1 << 14];
 uint32_t s_hs[1 << 14];
@@ -350,6 +354,54 @@ int run_fwd_generic_case(const std::string& name, int nseq, int lenLo, int lenHi
 	return bad;
 }
 
+// ordered compaction (k_cmp_count + k_tile_scan + k_cmp_scatter, xxm_kernels.cuh): the selected elements of a (sequence, position,
+// value index) list, in order -- selected by a flag byte, or as the heads of the runs of equal keys of a sorted key array --
+// against std::copy_if; output arrays of exactly the number selected
+int run_compact_case(const std::string& name, uint32_t n, double frac, bool runHeads, uint32_t seed) {
+	std::mt19937 rng(seed);
+	std::vector<uint32_t> seq(n), pos(n), vidx(n), keys(n);
+	std::vector<uint8_t> flag(n);
+	uint32_t key = 5;
+	for (uint32_t i = 0; i < n; ++i) {
+		seq[i] = 1 + i / 7; pos[i] = rng(); vidx[i] = rng() % 1000;
+		flag[i] = ((rng() % 100000) < frac * 100000) ? static_cast<uint8_t>(1 + rng() % 3) : 0;  // any non-zero byte selects
+		if ((rng() % 100000) < frac * 100000) key += 1 + rng() % 9;
+		keys[i] = key;
+	}
+	std::vector<uint32_t> wSeq, wPos, wVidx, wIdx;
+	for (uint32_t i = 0; i < n; ++i) {
+		const bool sel = runHeads ? (i == 0 || keys[i] != keys[i - 1]) : flag[i] != 0;
+		if (sel) { wSeq.push_back(seq[i]); wPos.push_back(pos[i]); wVidx.push_back(vidx[i]); wIdx.push_back(i); }
+	}
+	const uint32_t ntiles = (n + kCmpTile - 1) / kCmpTile;
+	std::vector<uint32_t> tileCount(ntiles, 0xDEADu);
+	std::vector<uint64_t> tileOff(static_cast<size_t>(ntiles) + 2, ~0ull);
+	uint64_t total = ~0ull;
+	CompactIO io{};
+	io.seq = seq.data(); io.pos = pos.data(); io.vidx = vidx.data(); io.flag = runHeads ? nullptr : flag.data(); io.keys = runHeads ? keys.data() : nullptr; io.n = n;
+	io.tileCount = tileCount.data(); io.tileOff = tileOff.data();
+	emu::launch(ntiles, 256, [&] { k_cmp_count(io); });
+	emu::launch((ntiles + 1023) / 1024, 1024, [&] { k_tile_scan(tileCount.data(), ntiles, tileOff.data(), &total); });
+	const size_t m = wIdx.size();
+	std::vector<uint32_t> oseq(std::max<size_t>(1, m), 0xABu), opos(oseq), ovidx(oseq), oidx(oseq);
+	io.oseq = oseq.data(); io.opos = opos.data(); io.ovidx = ovidx.data(); io.oidx = oidx.data();
+	bool same = total == m;
+	if (same) {
+		emu::launch(ntiles, 256, [&] { k_cmp_scatter(io); });
+		oseq.resize(m); opos.resize(m); ovidx.resize(m); oidx.resize(m);
+		same = oseq == wSeq && opos == wPos && ovidx == wVidx && oidx == wIdx;
+		// only the index array (what the run-length encoding of the subset choice asks for)
+		std::vector<uint32_t> only(std::max<size_t>(1, m), 0xCDu);
+		io.oseq = io.opos = io.ovidx = nullptr; io.oidx = only.data();
+		emu::launch(ntiles, 256, [&] { k_cmp_scatter(io); });
+		only.resize(m);
+		same = same && only == wIdx;
+	}
+	std::printf("%-22s k_cmp_count + k_tile_scan + k_cmp_scatter (%s): %zu of %u elements over %u tiles  %s\n", name.c_str(), runHeads ? "run heads" : "flags", m, n, ntiles,
+	            same ? "identical" : "DIFFERENT");
+	return same ? 0 : 1;
+}
+
 // updateMultOcc with Global::revcomp, literally (StartPosUtils.h:12-65: the look-back walk over the kept array and the removal of
 // the loser from its middle), on doubled sequences (stored length 2 n0 + 1) with candidates on both strands
 int run_rc_case(const std::string& name, int nseq, int n0Lo, int n0Hi, double hitFrac, int span, uint32_t nval, uint32_t nSiteWant, uint32_t seed) {
@@ -520,6 +572,18 @@ int main(int argc, char** argv) {
 			if (!sel) continue;
 		}
 		failed += run_fwd_generic_case(z.name, z.nseq, z.lenLo, z.lenHi, z.frac, z.span, z.nval, z.kind, z.shift, z.seed) ? 1 : 0;
+		++ran;
+	}
+	struct Cm { const char* name; uint32_t n; double frac; bool heads; uint32_t seed; };
+	const Cm cms[] = {{"cmp_flags_sparse", 9000, 0.02, false, 51}, {"cmp_flags_dense", 6151, 0.7, false, 52}, {"cmp_run_heads", 12345, 0.1, true, 53}, {"cmp_one", 1, 1.0, false, 54},
+	                  {"cmp_none_selected", 3000, 0.0, false, 55}, {"cmp_all_one_run", 2049, 0.0, true, 56}};
+	for (const Cm& z : cms) {
+		if (argc > 1) {
+			bool sel = false;
+			for (int i = 1; i < argc; ++i) sel = sel || std::string(z.name) == argv[i];
+			if (!sel) continue;
+		}
+		failed += run_compact_case(z.name, z.n, z.frac, z.heads, z.seed) ? 1 : 0;
 		++ran;
 	}
 	struct Rc { const char* name; int nseq, n0Lo, n0Hi; double frac; int span; uint32_t nval, nSite, seed; };

@@ -18,7 +18,8 @@ CASES = ["tile_scan", "uniform_1kb", "ragged_N", "revcomp_ragged", "dense_lowcom
 
 STEP_CASES = ["clustered_uniform", "ragged_short", "long_motif", "all_sites_dense", "few_sites", "tiny", "zoops_uniform", "zoops_ragged_shift", "zoops_long_runs",
               "zoops_sparse", "rc_uniform", "rc_ragged", "rc_long_motif", "rc_long_sequences", "rc_palindromic_dense", "sort_two", "sort_one_chunk", "sort_ties",
-              "sort_many_chunks", "gen_table_clustered", "gen_table_ragged_long", "gen_localized", "gen_localized_shift", "gen_per_candidate", "gen_dense", "gen_tiny"]
+              "sort_many_chunks", "gen_table_clustered", "gen_table_ragged_long", "gen_localized", "gen_localized_shift", "gen_per_candidate", "gen_dense", "gen_tiny",
+              "cmp_flags_sparse", "cmp_flags_dense", "cmp_run_heads", "cmp_one", "cmp_none_selected", "cmp_all_one_run"]
 
 
 @pytest.fixture(scope="module")
@@ -38,7 +39,8 @@ def test_select_and_count_kernels_under_emulator(step_exe, case):
     fill_elongSites_with_possible_startPositions (StartPosUpdater-inl.h:167-203); rc_*: k_select_cls_rc (forward rule + one cursor into
     the frozen forward list) vs the reference's updateMultOcc with --revcomp, literally (the look-back walk, StartPosUtils.h:29-58);
     sort_*: the stable radix sort of (score bits, index) pairs vs std::stable_sort; gen_*: k_select_mops_fwd (the forward rule on float-valued
-    lists: finalPval from a table in any order, from the localized MOPS formula, per candidate) vs the same greedy"""
+    lists: finalPval from a table in any order, from the localized MOPS formula, per candidate) vs the same greedy; cmp_*: the ordered
+    compaction k_cmp_count + k_tile_scan + k_cmp_scatter (by flag byte, by run heads of sorted keys) vs std::copy_if"""
     r = subprocess.run([step_exe, case], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
@@ -57,7 +59,7 @@ ASAN_ENV = dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0:detect
 @pytest.mark.parametrize("target,extra,cases", [
     ("scan_emu", ("host_pack.cpp", "pair_table.cpp"), ["ragged_N", "revcomp_ragged", "gapped_6cols", "one_word_sequences", "small_capacity", "positive_set_prefix_ragged"]),
     ("step_emu", ("host_pack.cpp",), ["ragged_short", "all_sites_dense", "zoops_ragged_shift", "rc_ragged", "rc_long_sequences", "sort_many_chunks", "gen_table_clustered",
-                                   "gen_localized_shift", "gen_per_candidate"]),
+                                   "gen_localized_shift", "gen_per_candidate", "cmp_flags_dense", "cmp_run_heads", "cmp_one"]),
 ])
 def test_kernels_under_address_sanitizer(target, extra, cases):
     """The same kernels with every access bounds-checked (AddressSanitizer + UBSan over the emulated run; compute-sanitizer is closed on
@@ -106,7 +108,7 @@ def test_race_detector_controls():
 @pytest.mark.parametrize("target,extra,cases", [
     ("scan_emu", ("host_pack.cpp", "pair_table.cpp"), ["uniform_1kb", "ragged_N", "revcomp_ragged", "every_warp_dense", "small_capacity", "positive_set_prefix_ragged"]),
     ("step_emu", ("host_pack.cpp",), ["clustered_uniform", "all_sites_dense", "zoops_ragged_shift", "rc_ragged", "rc_long_sequences", "sort_many_chunks", "gen_table_clustered",
-                                   "gen_localized_shift", "gen_per_candidate"]),
+                                   "gen_localized_shift", "gen_per_candidate", "cmp_flags_dense", "cmp_run_heads", "cmp_one"]),
 ])
 def test_kernels_under_race_detector(target, extra, cases):
     """The kernels of a step under the STRICT model (only __syncthreads and __syncwarp order memory): no two accesses of a block to
