@@ -169,6 +169,59 @@ int run_case(const Case& c) {
 		std::fprintf(stderr, "FAIL %s: PWM counts differ\n", c.name.c_str());
 		++bad;
 	}
+	// ---- k_count_pwm2 (the count kernel of float-valued lists, ZOOPS slots and explicit index lists; the chosen entries are parked in a
+	// per-warp buffer and counted 32 at a time with ballots) on the same sites, in its three ways of choosing
+	{
+		auto expected = [&](const std::vector<uint32_t>& chosen) {
+			std::vector<unsigned long long> wc(31 * 5, 0ull);
+			for (uint32_t i : chosen) {
+				const int q = static_cast<int>(seq[i]) - 1;
+				const int g0 = static_cast<int>(pos[i]) + shift - firstColumn;
+				for (int j = 1; j <= 30; ++j) {
+					const int p = g0 + j - 1;
+					if (p < 0 || p >= n[q]) continue;
+					const uint32_t ww = wordOff[q] + static_cast<uint32_t>(p >> 5);
+					if ((nmask[ww] >> (p & 31)) & 1u) continue;
+					++wc[j * 5 + 1 + (static_cast<uint32_t>(codes[ww] >> (2 * (p & 31))) & 3u)];
+					++wc[j * 5];
+				}
+			}
+			wc[0] = chosen.size();  // row 0 is unused by the PWM and carries the number of chosen sites
+			return wc;
+		};
+		std::vector<float> kscore(ncand + 16, 2.f);
+		for (uint32_t i = 0; i < ncand; ++i)
+			if (vidx[i] != kNone && vidx[i] < c.nval) kscore[i] = static_cast<float>(fin[vidx[i]]);
+		const float thr = static_cast<float>(fin[maxClass]);
+		std::vector<uint32_t> byScore, slotIdx, slotChosen;
+		for (uint32_t i = 0; i < ncand; ++i)
+			if (wantKeep[i] && kscore[i] <= thr) byScore.push_back(i);
+		auto run2 = [&](const char* how, CountIO io2, const std::vector<uint32_t>& chosen) {
+			std::vector<unsigned long long> got(31 * 5, 0ull);
+			io2.seq = seq.data(); io2.pos = pos.data(); io2.shift = shift; io2.firstColumn = firstColumn; io2.counts = got.data();
+			emu::launch(2, 256, [&] { k_count_pwm2(S, io2); });
+			if (got != expected(chosen)) { std::fprintf(stderr, "FAIL %s: k_count_pwm2 (%s) differs\n", c.name.c_str(), how); ++bad; }
+		};
+		CountIO a{};  // kept entries with float score <= thr
+		a.keep = keep.data(); a.kscore = kscore.data(); a.n = ncand; a.thr = thr;
+		run2("keep flags + float scores", a, byScore);
+		std::vector<uint32_t> idx(byScore.rbegin(), byScore.rend());  // an explicit list, in another order
+		CountIO b{};
+		b.idx = idx.data(); b.n = static_cast<uint32_t>(idx.size());
+		if (b.n) run2("index list", b, idx);
+		std::vector<float> slotScore;  // ZOOPS: one slot per sequence, the first kept entry of the sequence if any
+		for (int q = 0, i = 0; q < c.nseq; ++q) {
+			uint32_t pick = kNone;
+			for (; i < static_cast<int>(ncand) && static_cast<int>(seq[i]) - 1 == q; ++i)
+				if (pick == kNone && wantKeep[i]) pick = static_cast<uint32_t>(i);
+			slotIdx.push_back(pick);
+			slotScore.push_back(pick == kNone ? 1.f : kscore[pick]);
+			if (pick != kNone && kscore[pick] <= thr) slotChosen.push_back(pick);
+		}
+		CountIO z{};
+		z.slotIdx = slotIdx.data(); z.slotScore = slotScore.data(); z.n = static_cast<uint32_t>(slotIdx.size()); z.thr = thr;
+		run2("ZOOPS slots", z, slotChosen);
+	}
 	std::printf("%-20s %7u candidates, %6u kept, %3u classes (%u sites): %s\n", c.name.c_str(), ncand, nkept, c.nval, nSite, bad ? "DIFFERENT" : "identical");
 	return bad ? 1 : 0;
 }

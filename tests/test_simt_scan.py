@@ -34,7 +34,8 @@ def step_exe():
 
 @pytest.mark.parametrize("case", STEP_CASES)
 def test_select_and_count_kernels_under_emulator(step_exe, case):
-    """k_select_cls_fwd vs the reference's updateMultOcc greedy (StartPosUtils.h:12-28), k_count_pwm3 vs a column-by-column count;
+    """k_select_cls_fwd vs the reference's updateMultOcc greedy (StartPosUtils.h:12-28), k_count_pwm3 and k_count_pwm2 (keep flags + float
+    scores, index list, ZOOPS slots) vs a column-by-column count;
     zoops_*: the re-score kernels k_eval_list + k_select_zoops vs the ZOOPS branch of
     fill_elongSites_with_possible_startPositions (StartPosUpdater-inl.h:167-203); rc_*: k_select_cls_rc (forward rule + one cursor into
     the frozen forward list) vs the reference's updateMultOcc with --revcomp, literally (the look-back walk, StartPosUtils.h:29-58);
