@@ -545,6 +545,41 @@ int run_rc_case(const std::string& name, int nseq, int n0Lo, int n0Hi, double hi
 	}
 	if (counters[0] != nkept) { std::fprintf(stderr, "FAIL %s: %u kept sites counted, expected %u\n", name.c_str(), counters[0], nkept); ++bad; }
 	if (hist != wantHist) { std::fprintf(stderr, "FAIL %s: class histogram differs\n", name.c_str()); ++bad; }
+	// ---- k_select_mops / k_select_mops_serial (xxm_kernels.cuh): the walk itself, one thread per sequence, for float-valued lists with
+	// --revcomp -- the same expectation (the final table here happens to be ordered; the kernels do not use that)
+	{
+		Values V{};
+		V.finalTab = fin.data(); V.pS = fin.data(); V.kind = kFinalTable;
+		uint32_t maxPer = 0;
+		{
+			uint32_t run = 0;
+			for (uint32_t i = 0; i < nc; ++i) {
+				if (i && seq[i] != seq[i - 1]) run = 0;
+				if (wantKeep[i]) maxPer = std::max(maxPer, ++run);
+			}
+		}
+		for (int serial = 0; serial < 2; ++serial) {
+			std::vector<uint8_t> keep2(std::max(1u, nc), 0);
+			std::vector<float> kscore2(std::max(1u, nc), -1.f);
+			std::vector<uint32_t> stk2(std::max(1u, nc), 0u), counters2(8, 0u);
+			SelectIO g{};
+			g.seq = seq.data(); g.pos = pos.data(); g.vidx = vidx.data(); g.n = nc; g.shift = 0; g.length = span; g.revcomp = 1;
+			g.stk = stk2.data(); g.kscore = kscore2.data(); g.keep = keep2.data(); g.counters = counters2.data();
+			if (serial) emu::launch(1, 32, [&] { k_select_mops_serial(S, V, g); });
+			else emu::launch((nc + 255) / 256, 256, [&] { k_select_mops(S, V, g); });
+			uint32_t wrong = 0;
+			for (uint32_t i = 0; i < nc; ++i) {
+				wrong += keep2[i] != wantKeep[i];
+				if (wantKeep[i]) { const float f = static_cast<float>(fin[vidx[i]]); wrong += std::memcmp(&kscore2[i], &f, 4) != 0; }
+			}
+			// (the serial walk treats the whole list as one run: its per-sequence maximum is the total)
+			if (wrong || counters2[0] != nkept || counters2[1] != (serial ? nkept : maxPer)) {
+				std::fprintf(stderr, "FAIL %s: %s: %u entries differ, %u kept (expected %u), max per sequence %u (expected %u)\n", name.c_str(),
+				             serial ? "k_select_mops_serial" : "k_select_mops", wrong, counters2[0], nkept, counters2[1], serial ? nkept : maxPer);
+				++bad;
+			}
+		}
+	}
 	std::printf("%-20s %7u candidates on both strands, %6u kept, span %d: %s\n", name.c_str(), nc, nkept, span, bad ? "DIFFERENT" : "identical");
 	return bad ? 1 : 0;
 }
