@@ -314,11 +314,34 @@ int run_zoops_case(const std::string& name, int nseq, int lenLo, int lenHi, doub
 		if (vidx2[i] != wantV[i]) { std::fprintf(stderr, "FAIL %s: candidate %u value index %u, expected %u\n", name.c_str(), i, vidx2[i], wantV[i]); ++bad; }
 	if (slotIdx2 != wantIdx || slotScore2 != wantScore) { std::fprintf(stderr, "FAIL %s: slots differ\n", name.c_str()); ++bad; }
 	if (counters2[0] != wantFilled) { std::fprintf(stderr, "FAIL %s: %u slots filled, expected %u\n", name.c_str(), counters2[0], wantFilled); ++bad; }
+	// the serial fallback of the same selection (lists that are not ordered by sequence take it)
+	{
+		std::vector<uint32_t> slotIdx3(nseq, kNone), counters3(8, 0u);
+		std::vector<float> slotScore3(nseq, 1.0f);
+		SlotIO io3 = io2;
+		io3.slotIdx = slotIdx3.data(); io3.slotScore = slotScore3.data(); io3.counters = counters3.data();
+		emu::launch(1, 32, [&] { k_select_zoops_serial(V, io3); });
+		if (slotIdx3 != wantIdx || slotScore3 != wantScore || counters3[0] != wantFilled) { std::fprintf(stderr, "FAIL %s: k_select_zoops_serial differs\n", name.c_str()); ++bad; }
+	}
+	// k_hist_slots: the value-index histogram of the filled slots (what the subset choice of a ZOOPS re-score reads), bins in shared
+	// memory, in global memory, and split between the two
+	{
+		uint32_t nval = 1;
+		for (uint32_t i = 0; i < nc; ++i)
+			if (wantV[i] != kNone) nval = std::max(nval, wantV[i] + 1);
+		std::vector<uint32_t> wantHist(nval, 0u);
+		for (int q = 0; q < nseq; ++q)
+			if (wantIdx[q] != kNone) ++wantHist[wantV[wantIdx[q]]];
+		for (uint32_t shared : {nval, 0u, nval / 2}) {
+			std::vector<uint32_t> hist(nval, 0u);
+			emu::launch(2, 256, [&] { k_hist_slots(slotIdx2.data(), vidx2.data(), static_cast<uint32_t>(nseq), hist.data(), shared); });
+			if (hist != wantHist) { std::fprintf(stderr, "FAIL %s: k_hist_slots (%u bins in shared memory) differs\n", name.c_str(), shared); ++bad; }
+		}
+	}
 	std::printf("%-20s %7u candidates, %6u of %d slots filled, shift %+d: %s\n", name.c_str(), nc, wantFilled, nseq, shift, bad ? "DIFFERENT" : "identical");
 	return bad ? 1 : 0;
 }
 
-// k_select_cls_rc (xxm_select4.cuh: forward rule + one monotone cursor into the frozen forward list) against the reference's
 // k_select_mops_fwd (xxm_select2.cuh): updateMultOcc's forward rule on FLOAT-valued lists -- what two-part models, localization and
 // re-scored lists take (the finalPval is not a monotone function of a class index there) -- against the reference's greedy,
 // StartPosUtils.h:12-28, literally.  kind 0: finalPval from a table over the value index (any order); 1: the localized MOPS formula
@@ -455,6 +478,7 @@ int run_compact_case(const std::string& name, uint32_t n, double frac, bool runH
 	return same ? 0 : 1;
 }
 
+// k_select_cls_rc (xxm_select4.cuh: forward rule + one monotone cursor into the frozen forward list) against the reference's
 // updateMultOcc with Global::revcomp, literally (StartPosUtils.h:12-65: the look-back walk over the kept array and the removal of
 // the loser from its middle), on doubled sequences (stored length 2 n0 + 1) with candidates on both strands
 int run_rc_case(const std::string& name, int nseq, int n0Lo, int n0Hi, double hitFrac, int span, uint32_t nval, uint32_t nSiteWant, uint32_t seed) {
