@@ -238,6 +238,27 @@ def test_generic_find_kernel_under_emulator(mode):
         assert mark not in r.stderr, r.stderr[-4000:]
 
 
+@pytest.mark.parametrize("mode", [False, "address", "thread-strict"])
+def test_load_kernels_under_emulator(mode):
+    """a1 on the device: k_seq_layout_sums + k_seq_layout (offsets and stored lengths of 1 .. 5000 sequences, blocks of 1024, --revcomp),
+    k_blk2seq and k_seq_stats (residue counts, a code outside 0..4 flagged; raw array of exactly the residues) against the same
+    quantities sequence by sequence -- plain, bounds-checked, strict race model"""
+    try:
+        exe = simt_build.build("load_emu", extra_sources=(), sanitize=mode)
+    except subprocess.CalledProcessError:
+        if mode:
+            pytest.skip("no sanitizer runtime in this toolchain")
+        raise
+    env = dict(ASAN_ENV, TSAN_OPTIONS=TSAN_ENV["TSAN_OPTIONS"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    if r.returncode and ("FATAL: ThreadSanitizer" in r.stderr or "Shadow memory range interleaves" in r.stderr):
+        pytest.skip("the sanitizer cannot start here")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
+    for mark in ("ERROR: AddressSanitizer", "runtime error", "WARNING: ThreadSanitizer"):
+        assert mark not in r.stderr, r.stderr[-4000:]
+
+
 def test_product_does_not_reference_the_emulator():
     """the emulator hooks in the kernel sources are compile-time (#ifdef XXM_SIMT_EMU) and the library is built without them"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
