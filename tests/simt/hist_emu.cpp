@@ -23,6 +23,7 @@
 #include "xxm_kernels.cuh"   // k_logodds_hist
 #include "xxm_kmerhist.cuh"
 #include "xxm_gappedhist.cuh"
+#include "xxm_region.cuh"    // k_region_hist
 
 #include "host_pack.h"
 
@@ -30,6 +31,7 @@ namespace xxm {
 // dynamic shared memory of the two kernels (block-scope `extern` after the rewrite of `extern __shared__`)
 uint32_t s_bins[56 * 1024];
 uint32_t s_gbins[1 << 14];
+unsigned int s_rh[8192 + 8];
 alignas(16) uint8_t smemM[1 << 16];  // (kernels of xxm_kernels.cuh that are not launched here)
 uint32_t s_hs[1 << 14];
 }  // namespace xxm
@@ -252,6 +254,36 @@ int run_encode(const Case& c, const Set& s) {
 	return same ? 0 : 1;
 }
 
+// ---- k_region_hist (a15: the start-position histogram of Motif::updateEnrichedRegion, Motif.cpp:989-999: candidates with
+// float(pValScore) < 1e-3 inside the search window, reverse-strand positions folded back)
+int run_region(const std::string& name, uint32_t n, int max_leng, bool revcomp, int motifLength, int lo, int hi, uint32_t seed) {
+	std::mt19937 rng(seed);
+	std::vector<uint32_t> pos(n);
+	std::vector<float> score(n);
+	for (uint32_t i = 0; i < n; ++i) {
+		pos[i] = 1 + rng() % static_cast<uint32_t>(max_leng);
+		const int k = static_cast<int>(rng() % 4);
+		score[i] = k == 0 ? 1e-3f : k == 1 ? 9.99e-4f : k == 2 ? 1.0f : 1e-7f;  // 1e-3f as a double is just above 1e-3: not counted
+	}
+	const int nc = max_leng + 2;
+	std::vector<unsigned int> want(static_cast<size_t>(nc) + 1, 0u);
+	for (uint32_t i = 0; i < n; ++i) {
+		if (!(static_cast<double>(score[i]) < 1e-3)) continue;
+		int p = static_cast<int>(pos[i]);
+		if (revcomp && p > max_leng / 2) p = max_leng - (p + motifLength - 1);
+		if (p >= lo && p <= hi && p >= 0 && p <= max_leng) { ++want[static_cast<size_t>(p)]; ++want[static_cast<size_t>(nc)]; }
+	}
+	int bad = 0;
+	for (uint32_t nbs : {static_cast<uint32_t>(nc), 0u, static_cast<uint32_t>(nc) / 2}) {  // bins in shared memory, in global memory, split
+		std::vector<unsigned int> got(static_cast<size_t>(nc) + 1, 0u);
+		emu::launch(3, 256, [&] { k_region_hist(pos.data(), score.data(), n, revcomp ? 1 : 0, max_leng, motifLength, lo, hi, got.data(), got.data() + nc, nbs); });
+		bad += got == want ? 0 : 1;
+	}
+	std::printf("%-22s k_region_hist %u candidates, max_leng %d%s, window [%d, %d]: %u counted  %s\n", name.c_str(), n, max_leng, revcomp ? " --revcomp" : "", lo, hi,
+	            want[static_cast<size_t>(nc)], bad ? "DIFFERENT" : "identical");
+	return bad ? 1 : 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -277,6 +309,15 @@ int main(int argc, char** argv) {
 		failed += run_encode(c, s); ++runs;
 		failed += run_logodds(c, s, {0, 1, 2, 3, 4, 5, 6, 7}, c.nseq, c.seed + 100); ++runs;
 		failed += run_logodds(c, s, {0, 1, 3, 4, 5, 9, 10, 12, 13, 14, 15, 20}, std::max(1, c.nseq - 3), c.seed + 200); ++runs;
+	}
+	struct Rg { const char* name; uint32_t n; int max_leng; bool rc; int motifLength, lo, hi; uint32_t seed; };
+	const Rg rgs[] = {{"region_forward", 5000, 300, false, 8, 120, 220, 81}, {"region_revcomp", 7000, 601, true, 10, -20, 150, 82}, {"region_whole", 900, 50, false, 6, -100, 1000, 83}};
+	for (const Rg& g : rgs) {
+		bool wanted = argc <= 1;
+		for (int i = 1; i < argc; ++i) wanted = wanted || std::string(g.name) == argv[i];
+		if (!wanted) continue;
+		failed += run_region(g.name, g.n, g.max_leng, g.rc, g.motifLength, g.lo, g.hi, g.seed);
+		++runs;
 	}
 	std::printf("%d runs, %d failed\n", runs, failed);
 	return failed ? 1 : 0;
