@@ -40,11 +40,29 @@ def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp"), 
         return exe
     flags = {"": [], "address": ["-fsanitize=address,undefined", "-fno-omit-frame-pointer"], "thread": ["-fsanitize=thread", "-fno-omit-frame-pointer"],
              "thread-strict": ["-fsanitize=thread", "-fno-omit-frame-pointer", "-DXXM_EMU_STRICT_SHFL"]}[mode]
-    cmd = ["g++", "-std=c++17", "-O1", "-g"] + flags + ["-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-maybe-uninitialized",
+    cmd = ["g++", "-std=c++17", "-O1", "-g1"] + flags + ["-ffp-contract=off", "-Wall", "-Wno-unknown-pragmas", "-Wno-unused-function", "-Wno-unused-variable", "-Wno-maybe-uninitialized",
            "-I", kernel_dir or BUILD, "-I", os.path.join(HERE, "shim"), "-I", HERE, "-I", CSRC, os.path.join(HERE, target + ".cpp")]
     cmd += [os.path.join(CSRC, s) for s in extra_sources] + ["-o", exe, "-lpthread"]
     subprocess.check_call(cmd)
     return exe
+
+
+def build_many(jobs, workers=None):
+    """jobs: (target, extra_sources, sanitize) triples, compiled side by side (a fresh tree needs two dozen builds of 5-15 s each);
+    returns {(target, sanitize): exe or the CalledProcessError}"""
+    from concurrent.futures import ThreadPoolExecutor
+    build("race_control", extra_sources=())  # refreshes the rewritten headers once, before the threads start
+    out = {}
+
+    def one(j):
+        try:
+            return j, build(j[0], extra_sources=j[1], sanitize=j[2])
+        except subprocess.CalledProcessError as e:
+            return j, e
+    with ThreadPoolExecutor(max_workers=workers or max(1, min(8, (os.cpu_count() or 2) - 1))) as ex:
+        for j, r in ex.map(one, jobs):
+            out[(j[0], j[2])] = r
+    return out
 
 
 if __name__ == "__main__":

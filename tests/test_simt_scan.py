@@ -22,6 +22,16 @@ STEP_CASES = ["clustered_uniform", "ragged_short", "long_motif", "all_sites_dens
               "cmp_flags_sparse", "cmp_flags_dense", "cmp_run_heads", "cmp_one", "cmp_none_selected", "cmp_all_one_run"]
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _all_binaries():
+    """every harness in every mode this module uses, compiled side by side up front (the tests below then find them built)"""
+    targets = [("scan_emu", ("host_pack.cpp", "pair_table.cpp")), ("step_emu", ("host_pack.cpp",)), ("scan4_emu", ("host_pack.cpp",)), ("hist_emu", ("host_pack.cpp",)),
+               ("tables_emu", ("pvalue_tables.cpp", "background_model.cpp")), ("memo_emu", ()), ("load_emu", ())]
+    jobs = [(t, e, m) for t, e in targets for m in (False, "address", "thread-strict")]
+    jobs += [("race_control", (), "thread"), ("race_control", (), "thread-strict")]
+    simt_build.build_many(jobs)  # a failed sanitizer build is left to the test that needs it (it skips)
+
+
 @pytest.fixture(scope="module")
 def exe():
     return simt_build.build()
