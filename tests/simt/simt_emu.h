@@ -379,6 +379,8 @@ inline double __dadd_rn(double a, double b) { return a + b; }
 inline double __dsub_rn(double a, double b) { return a - b; }
 inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 inline int __double2int_rz(double a) { return static_cast<int>(a); }
+inline long long __double_as_longlong(double a) { return emu::from_bits<long long>(emu::to_bits(a)); }
+inline double __longlong_as_double(long long a) { return emu::from_bits<double>(emu::to_bits(a)); }
 inline unsigned __float_as_uint(float f) { return emu::to_bits(f) & 0xFFFFFFFFu; }
 inline float __uint_as_float(unsigned u) { return emu::from_bits<float>(u); }
 inline size_t __cvta_generic_to_shared(const void* p) { return reinterpret_cast<size_t>(p); }
@@ -393,6 +395,12 @@ template <class T, class U>
 inline T atomicMax(T* p, U v) {
 	T o = __atomic_load_n(p, __ATOMIC_RELAXED);
 	while (static_cast<T>(v) > o && !__atomic_compare_exchange_n(p, &o, static_cast<T>(v), false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+	return o;
+}
+template <class T, class U>
+inline T atomicMin(T* p, U v) {
+	T o = __atomic_load_n(p, __ATOMIC_RELAXED);
+	while (static_cast<T>(v) < o && !__atomic_compare_exchange_n(p, &o, static_cast<T>(v), false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
 	return o;
 }
 template <class T, class U>
@@ -411,10 +419,22 @@ inline T atomicOr(T* p, U v) { const T o = *p; *p = static_cast<T>(o | static_ca
 template <class T, class U>
 inline T atomicMax(T* p, U v) { const T o = *p; if (static_cast<T>(v) > o) *p = static_cast<T>(v); return o; }
 template <class T, class U>
+inline T atomicMin(T* p, U v) { const T o = *p; if (static_cast<T>(v) < o) *p = static_cast<T>(v); return o; }
+template <class T, class U>
 inline T atomicExch(T* p, U v) { const T o = *p; *p = static_cast<T>(v); return o; }
 template <class T, class U, class V>
 inline T atomicCAS(T* p, U cmp, V v) { const T o = *p; if (o == static_cast<T>(cmp)) *p = static_cast<T>(v); return o; }
 #endif
+
+// ---- device libm stand-ins where the host's has side effects the device's does not: glibc's lgamma() writes the global `signgam`
+// (every thread calling it would "race" on that); CUDA's has no such global.  The kernels live in namespace xxm, so an unqualified
+// lgamma() there finds this one first.
+namespace xxm {
+inline double lgamma(double x) {
+	int sign;
+	return ::lgamma_r(x, &sign);
+}
+}  // namespace xxm
 
 // ---- CUDA's global min / max overloads
 template <class T>

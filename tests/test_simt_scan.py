@@ -26,7 +26,7 @@ STEP_CASES = ["clustered_uniform", "ragged_short", "long_motif", "all_sites_dens
 def _all_binaries():
     """every harness in every mode this module uses, compiled side by side up front (the tests below then find them built)"""
     targets = [("scan_emu", ("host_pack.cpp", "pair_table.cpp")), ("step_emu", ("host_pack.cpp",)), ("scan4_emu", ("host_pack.cpp",)), ("hist_emu", ("host_pack.cpp",)),
-               ("tables_emu", ("pvalue_tables.cpp", "background_model.cpp")), ("memo_emu", ()), ("load_emu", ())]
+               ("tables_emu", ("pvalue_tables.cpp", "background_model.cpp")), ("memo_emu", ()), ("load_emu", ()), ("sweep_emu", ("host_stats.cpp",))]
     jobs = [(t, e, m) for t, e in targets for m in (False, "address", "thread-strict")]
     jobs += [("race_control", (), "thread"), ("race_control", (), "thread-strict")]
     simt_build.build_many(jobs)  # a failed sanitizer build is left to the test that needs it (it skips)
@@ -261,6 +261,28 @@ def test_load_kernels_under_emulator(mode):
         raise
     env = dict(ASAN_ENV, TSAN_OPTIONS=TSAN_ENV["TSAN_OPTIONS"])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    if r.returncode and ("FATAL: ThreadSanitizer" in r.stderr or "Shadow memory range interleaves" in r.stderr):
+        pytest.skip("the sanitizer cannot start here")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
+    for mark in ("ERROR: AddressSanitizer", "runtime error", "WARNING: ThreadSanitizer"):
+        assert mark not in r.stderr, r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("mode,cases", [(False, []), ("address", ["limit_binds", "few_runs", "tiny"]), ("thread-strict", ["strong_motif", "few_runs", "tiny"])])
+def test_sweep_prefilter_under_emulator(mode, cases):
+    """a8: the device prefilter of getBestSubset's sweep (k_pack_runs, k_sweep_eval, k_sweep_long, k_sweep_flag, k_sweep_gather with the
+    ordered compaction in between, staged as sorted_score_runs stages them) must hand the exact host sweep (the product's
+    best_subset_from_runs) runs that lead to the SAME subset -- size, log p-value bit for bit, last score -- as all runs do; decided
+    approximations within 1e-9 of the sequential formula (the warp-scan composition of k_sweep_long), the minimum key right"""
+    try:
+        exe = simt_build.build("sweep_emu", extra_sources=("host_stats.cpp",), sanitize=mode)
+    except subprocess.CalledProcessError:
+        if mode:
+            pytest.skip("no sanitizer runtime in this toolchain")
+        raise
+    env = dict(ASAN_ENV, TSAN_OPTIONS=TSAN_ENV["TSAN_OPTIONS"])
+    r = subprocess.run([exe] + cases, capture_output=True, text=True, timeout=900, env=env)
     if r.returncode and ("FATAL: ThreadSanitizer" in r.stderr or "Shadow memory range interleaves" in r.stderr):
         pytest.skip("the sanitizer cannot start here")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
