@@ -26,7 +26,7 @@ STEP_CASES = ["clustered_uniform", "ragged_short", "long_motif", "all_sites_dens
 def _all_binaries():
     """every harness in every mode this module uses, compiled side by side up front (the tests below then find them built)"""
     targets = [("scan_emu", ("host_pack.cpp", "pair_table.cpp")), ("step_emu", ("host_pack.cpp",)), ("scan4_emu", ("host_pack.cpp",)), ("hist_emu", ("host_pack.cpp",)),
-               ("tables_emu", ("pvalue_tables.cpp", "background_model.cpp")), ("memo_emu", ()), ("load_emu", ()), ("sweep_emu", ("host_stats.cpp",))]
+               ("tables_emu", ("pvalue_tables.cpp", "background_model.cpp")), ("memo_emu", ()), ("load_emu", ()), ("sweep_emu", ("host_stats.cpp",)), ("elem_emu", ())]
     jobs = [(t, e, m) for t, e in targets for m in (False, "address", "thread-strict")]
     jobs += [("race_control", (), "thread"), ("race_control", (), "thread-strict")]
     simt_build.build_many(jobs)  # a failed sanitizer build is left to the test that needs it (it skips)
@@ -287,6 +287,26 @@ def test_sweep_prefilter_under_emulator(mode, cases):
         pytest.skip("the sanitizer cannot start here")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "DIFFERENT" not in r.stdout and " 0 failed" in r.stdout, r.stdout
+    for mark in ("ERROR: AddressSanitizer", "runtime error", "WARNING: ThreadSanitizer"):
+        assert mark not in r.stderr, r.stderr[-4000:]
+
+
+@pytest.mark.parametrize("mode", [False, "address", "thread-strict"])
+def test_elementwise_kernels_under_emulator(mode):
+    """the one-thread-per-element kernels (fills, gathers, flags, value conversions under the three kinds of finalPval, site bits, memo
+    bookkeeping, site records, the dense rank table) against the obvious loops, arrays of exactly n elements"""
+    try:
+        exe = simt_build.build("elem_emu", extra_sources=(), sanitize=mode)
+    except subprocess.CalledProcessError:
+        if mode:
+            pytest.skip("no sanitizer runtime in this toolchain")
+        raise
+    env = dict(ASAN_ENV, TSAN_OPTIONS=TSAN_ENV["TSAN_OPTIONS"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    if r.returncode and ("FATAL: ThreadSanitizer" in r.stderr or "Shadow memory range interleaves" in r.stderr):
+        pytest.skip("the sanitizer cannot start here")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "DIFFERENT" not in r.stdout and "0 failed" in r.stdout, r.stdout
     for mark in ("ERROR: AddressSanitizer", "runtime error", "WARNING: ThreadSanitizer"):
         assert mark not in r.stderr, r.stderr[-4000:]
 
