@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "xxmotif_b200", "csrc")
 BUILD = os.path.join(HERE, "build")
 KERNEL_HEADERS = ["xxm_device.cuh", "xxm_kernels.cuh", "xxm_scan4.cuh", "xxm_scan5.cuh", "xxm_scan6.cuh", "xxm_scan7.cuh", "xxm_select2.cuh", "xxm_select3.cuh",
-                  "xxm_select4.cuh", "xxm_kmerhist.cuh", "xxm_gappedhist.cuh", "xxm_tables_device.cuh", "xxm_load.cuh", "xxm_region.cuh", "xxm_sweep.cuh"]
+                  "xxm_select4.cuh", "xxm_kmerhist.cuh", "xxm_gappedhist.cuh", "xxm_tables_device.cuh", "xxm_load.cuh", "xxm_region.cuh", "xxm_sweep.cuh", "xxm_stage.cuh", "xxm_xchg.cuh"]
 
 
 def build(target="scan_emu", extra_sources=("host_pack.cpp", "pair_table.cpp"), sanitize=False, kernel_dir=None):

@@ -14,6 +14,8 @@
 
 #include "xxm_kernels.cuh"
 #include "xxm_sweep.cuh"
+#include "xxm_stage.cuh"  // k_scatter_stage
+#include "xxm_xchg.cuh"   // k_pack_hist
 
 namespace xxm {
 alignas(16) uint8_t smemM[1 << 16];
@@ -183,6 +185,53 @@ int main() {
 			if (clsOk[cls[static_cast<size_t>(i)]]) { wantR[ids[static_cast<size_t>(i)]] = cls[static_cast<size_t>(i)] + 1; wantB[ids[static_cast<size_t>(i)] >> 5] |= 1u << (ids[static_cast<size_t>(i)] & 31); }
 		each(static_cast<uint32_t>(nid), [&] { k_fill_rank(ids.data(), cls.data(), clsOk.data(), nid, rank.data(), bm.data()); });
 		check("k_fill_rank", rank == wantR && bm == wantB);
+	}
+	{  // the scatter half of the batched table staging: segments of a staging buffer to their arrays (word copies where both sides are
+		// aligned, byte copies otherwise), blockIdx.y = segment
+		std::vector<uint8_t> stage(5000);
+		for (auto& b : stage) b = static_cast<uint8_t>(rng());
+		const uint32_t off[4] = {0, 1024, 2051, 4000}, bytes[4] = {1000, 1026, 1500, 1};  // aligned words, aligned with a tail, unaligned source, one byte
+		std::vector<std::vector<uint32_t>> dst(4);
+		UpSegs segs{};
+		for (int k = 0; k < 4; ++k) {
+			dst[k].assign((bytes[k] + 3) / 4 + 1, 0xEEEEEEEEu);
+			segs.dst[k] = (k == 3) ? static_cast<void*>(reinterpret_cast<uint8_t*>(dst[k].data()) + 1) : static_cast<void*>(dst[k].data());  // ... and an unaligned destination
+			segs.off[k] = off[k]; segs.bytes[k] = bytes[k];
+		}
+		for (int k = 0; k < 4; ++k) {  // (the emulator's grid is one-dimensional: one launch per segment, blockIdx.y = k)
+			emu::blockY = static_cast<unsigned>(k);
+			emu::launch(2, 256, [&] { k_scatter_stage(stage.data(), segs); });
+		}
+		emu::blockY = 0;
+		bool ok = true;
+		for (int k = 0; k < 4; ++k) {
+			const uint8_t* d = static_cast<const uint8_t*>(segs.dst[k]);
+			ok = ok && !std::memcmp(d, stage.data() + off[k], bytes[k]) && d[bytes[k]] == 0xEE;  // and not one byte more
+		}
+		check("k_scatter_stage", ok);
+	}
+	{  // the exchange vector of a sharded step: header (two slots taken from the device) + histogram padded to its fixed length
+		bool ok = true;
+		for (uint32_t nv : {1u, 300u, kXchgHist}) {
+			std::vector<uint32_t> hist(nv);
+			for (auto& h : hist) h = rng() % 100000;
+			XchgHead head{};
+			for (uint32_t i = 0; i < kXchgHead; ++i) head.v[i] = 1000 + i;
+			const uint32_t kept = 4242;
+			const unsigned long long tot = 9000, cap = 8000;
+			for (int fromDev = 0; fromDev < 2; ++fromDev) {
+				std::vector<unsigned long long> out(kXchgHead + kXchgHist, ~0ull);
+				emu::launch((kXchgHist + 255) / 256, 256, [&] { k_pack_hist(hist.data(), nv, head, fromDev ? &kept : nullptr, fromDev ? &tot : nullptr, cap, out.data()); });
+				for (uint32_t i = 0; i < kXchgHead; ++i) {
+					unsigned long long w = head.v[i];
+					if (fromDev && i == 5) w = kept;
+					if (fromDev && i == 8) w = 1;  // the list outgrew its arrays
+					ok = ok && out[i] == w;
+				}
+				for (uint32_t i = 0; i < kXchgHist; ++i) ok = ok && out[kXchgHead + i] == (i < nv ? hist[i] : 0ull);
+			}
+		}
+		check("k_pack_hist", ok);
 	}
 	std::printf("%d failed\n", failures);
 	return failures ? 1 : 0;

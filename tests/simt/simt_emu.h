@@ -115,6 +115,7 @@ struct BlockState {
 };
 
 inline BlockState* B = nullptr;
+inline unsigned blockY = 0;  // blockIdx.y of the next launches (the grid itself is one-dimensional: a harness launches once per y)
 
 EMU_NOTSAN inline void yield() {
 	EMU_TSAN_SWITCH(B->schedTsan);
@@ -207,7 +208,7 @@ EMU_NOTSAN void launch(unsigned grid, unsigned block, F&& body) {
 	EMU_TSAN_RELEASE(&st.chain[0]);  // what the host wrote before the launch is visible to every thread of the grid
 	EMU_TSAN_RELEASE(&st.chain[1]);
 	for (unsigned b = 0; b < grid; ++b) {
-		blockIdx = uint3{b, 0, 0};
+		blockIdx = uint3{b, blockY, 0};
 		st.block = b;
 		st.alive = static_cast<int>(block);
 		st.barCount = 0;

@@ -311,6 +311,24 @@ def test_elementwise_kernels_under_emulator(mode):
         assert mark not in r.stderr, r.stderr[-4000:]
 
 
+def test_every_kernel_runs_under_the_emulator():
+    """every __global__ function of the library is launched by one of the harnesses (a new kernel needs a case before it ships)"""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    kernels = set()
+    for f in glob.glob(os.path.join(root, "xxmotif_b200", "csrc", "*")):
+        if f.endswith((".cuh", ".cu", ".inc")):
+            kernels |= set(re.findall(r"__global__\s+void\s+(?:__launch_bounds__\([^)]*\)\s*)?(\w+)", open(f).read()))
+    harness = " ".join(open(f).read() for f in glob.glob(os.path.join(root, "tests", "simt", "*.cpp")))
+    missing = sorted(k for k in kernels if not re.search(r"\b" + k + r"\b", harness))
+    assert len(kernels) >= 60 and not missing, missing
+    # ... and the kernels live in headers (what the emulator can compile), not next to host code
+    for f in glob.glob(os.path.join(root, "xxmotif_b200", "csrc", "*")):
+        if f.endswith((".cu", ".inc")):
+            assert "__global__" not in open(f).read(), f
+
+
 def test_product_does_not_reference_the_emulator():
     """the emulator hooks in the kernel sources are compile-time (#ifdef XXM_SIMT_EMU) and the library is built without them"""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
