@@ -35,3 +35,13 @@ def test_create_fails_loudly_without_gpu():
     with pytest.raises(xb.XxmError) as e:
         xb.Context(0)
     assert "no CUDA device" in str(e.value)
+
+
+def test_header_is_plain_c():
+    """the drop-in boundary is a C ABI: include/xxmotif_gpu.h compiles as C99 and as C++17 on its own (no torch, no CUDA types)"""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "xxmotif_gpu.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+    text = open(hdr).read()
+    assert "torch" not in text and "cuda_runtime" not in text and "#include <cuda" not in text
