@@ -43,5 +43,5 @@ def test_header_is_plain_c():
     hdr = os.path.join(ROOT, "include", "xxmotif_gpu.h")
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr])
     subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
-    text = open(hdr).read()
-    assert "torch" not in text and "cuda_runtime" not in text and "#include <cuda" not in text
+    code = re.sub(r"/\*.*?\*/", "", open(hdr).read(), flags=re.S)  # comments may mention how a caller distributes the NCCL id
+    assert "torch" not in code and "cuda" not in code.lower() and "nccl" not in code.lower()
