@@ -2,7 +2,6 @@
 (SURVEY.md 8(f) row 2).  The refinement itself is GPU-only: tests/test_gpu_motif_batch.py."""
 import ctypes as C
 
-import numpy as np
 
 
 def _call(L, ctx_ptrs, motifs, nmotifs, nparams):
