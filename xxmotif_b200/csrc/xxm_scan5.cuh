@@ -10,7 +10,7 @@
 //                    flag) and 1.5 instructions to gather the flags.  The kernel does not look at N masks and does not
 //                    count; it writes one 32-bit mask per 32 windows in "even/odd" order: bit 16 + t = window 2t,
 //                    bit t = window 2t + 1.
-// expand (k_expand5): one CTA per tile of 1024 words, tiles handed out by ticket.  Stages the tile's codes and N masks in
+// expand (k_expand5): one CTA per tile of 1024 words, tile = block index (see the kernel on dispatch order).  Stages the tile's codes and N masks in
 //                    shared memory (coalesced), brings the masks into window order, clears windows with an N in a match
 //                    column (branch_and_bound-inl.h:388) and words outside the scanned range, counts, obtains the tile's
 //                    global offset by a decoupled look-back over the tile status words (warp-parallel), and resolves the
