@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY (see simt_emu.h): the GENERIC find kernel -- k_build_t9 + k_scan4<true/false> (xxm_scan4.cuh), the one that
-// runs whenever the pair table cannot represent the left table: left parts spanning more than 8 bases, two-part models, localization --
+// runs whenever the pair table cannot represent the left table (stage_pair, xxm_gpu_scan5.inc: gapped left parts beyond 8 bases whose scan
+// must find sites only, tables that are not threshold-shaped, XXM_FORCE_GENERIC_SCAN) --
 // from the CUDA SOURCES under the SIMT emulator, staged as stage_t9 / launch_scan4 stage and launch it (xxm_gpu_scan4.inc), against
 // the definition of a scan candidate taken window by window from the raw sequences: no N in any match column
 // (branch_and_bound-inl.h:388) and the left k-mer in the table (:390-392).  Exact and projected table entries, bitmap in shared and

@@ -225,8 +225,8 @@ def test_memo_evaluation_under_emulator(mode):
 
 @pytest.mark.parametrize("mode", [False, "address", "thread-strict"])
 def test_generic_find_kernel_under_emulator(mode):
-    """k_build_t9 + k_scan4<true/false> -- the find kernel of every model the pair table cannot represent (left parts spanning more
-    than 8 bases, two-part models, localization) -- staged and launched as the library does, against the definition of a scan
+    """k_build_t9 + k_scan4<true/false> -- the find kernel of every model the pair table cannot represent (gapped left parts beyond 8
+    bases whose scan must find sites only, tables that are not threshold-shaped) -- staged and launched as the library does, against the definition of a scan
     candidate taken window by window (no N in a match column, left k-mer in the table): exact and projected table entries, bitmap in
     shared and in global memory, --revcomp, one-word sequences, several blocks; then k_expand5<true/false> on those masks -- ordered
     (sequence, position, value index) records incl. the memo slots and rejections of two-part models, tiles with more hits than the
