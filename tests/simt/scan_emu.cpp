@@ -47,9 +47,34 @@ struct Case {
 	bool lowComplexity;   // TATATA... stretches: dense hits, exercises the dense-warp path of the expand kernel
 	uint32_t seed;
 	int scanSeqs = 0;     // > 0: only the first scanSeqs sequences are scanned (posSetSize < nent: a negative set follows)
+	std::vector<int> rightOff;  // non-empty: a two-part model -- offsets of the match columns beyond the table's (more than 8 match columns)
 };
 
-struct Rec { uint32_t seq, pos, v; };
+// the second part of a two-part model (branch_and_bound-inl.h:399-423): right table, class p-values, product threshold, log-odds
+struct Right {
+	std::vector<uint32_t> rank1;
+	std::vector<double> cpval0, cpval1;
+	double pruneThr = 0;
+	double logodds[32][4];
+};
+Right make_right(const Case& c, uint32_t nclass0) {
+	std::mt19937 rng(c.seed * 104729u + 5u);
+	std::uniform_real_distribution<double> U(1e-6, 1e-2), Lo(-1.5, 1.0);
+	Right r;
+	r.rank1.assign(static_cast<size_t>(1) << (2 * c.rightOff.size()), 0u);
+	const uint32_t nclass1 = 40;
+	for (auto& v : r.rank1)
+		if (rng() % 3) v = static_cast<uint32_t>(rng() % nclass1) + 1;
+	r.cpval0.resize(std::max(1u, nclass0)); r.cpval1.resize(nclass1);
+	for (double& v : r.cpval0) v = U(rng);
+	for (double& v : r.cpval1) v = U(rng);
+	r.pruneThr = 2.5e-5;
+	for (auto& row : r.logodds)
+		for (double& v : row) v = Lo(rng);
+	return r;
+}
+
+struct Rec { uint32_t seq, pos, v; bool none = false; int32_t s = 0; bool twoPart = false; };  // two-part models: v is a memo slot, checked through its key s
 
 struct Set {
 	std::vector<int32_t> n;      // raw lengths
@@ -151,9 +176,9 @@ Table make_table(const Case& c) {
 	return t;
 }
 
-std::vector<Rec> brute_force(const Case& c, const Set& s, const Table& t) {
+std::vector<Rec> brute_force(const Case& c, const Set& s, const Table& t, const Right* R = nullptr) {
 	std::vector<Rec> out;
-	const int span = c.coloff.back() + 1;
+	const int span = (c.rightOff.empty() ? c.coloff.back() : c.rightOff.back()) + 1;
 	const int nscan = c.scanSeqs > 0 ? c.scanSeqs : c.nseq;
 	for (int q = 0; q < nscan; ++q) {
 		const uint32_t w0 = s.wordOff[q];
@@ -172,21 +197,42 @@ std::vector<Rec> brute_force(const Case& c, const Set& s, const Table& t) {
 				if (isN) { dead = true; break; }
 				id |= b << (2 * k);
 			}
+			uint32_t id1 = 0;
+			for (size_t k = 0; k < c.rightOff.size() && !dead; ++k) {  // an N in ANY match column kills the window (:388)
+				int isN = 0;
+				const uint32_t b = base(p + c.rightOff[k], isN);
+				if (isN) dead = true;
+				id1 |= b << (2 * k);
+			}
 			if (dead || !t.rank[id]) continue;
-			out.push_back(Rec{static_cast<uint32_t>(q) + 1, static_cast<uint32_t>(p) + 1, t.rank[id] - 1});
+			Rec rec{static_cast<uint32_t>(q) + 1, static_cast<uint32_t>(p) + 1, t.rank[id] - 1};
+			if (R) {
+				rec.twoPart = true;
+				const uint32_t r0 = t.rank[id], r1 = R->rank1[id1];
+				if (r1 == 0 || R->cpval0[r0 - 1] * R->cpval1[r1 - 1] > R->pruneThr) rec.none = true;
+				else {
+					double score = 0;
+					int isN = 0;
+					for (size_t k = 0; k < c.coloff.size(); ++k) score = score + R->logodds[k][base(p + c.coloff[k], isN)];
+					for (size_t k = 0; k < c.rightOff.size(); ++k) score = score + R->logodds[c.coloff.size() + k][base(p + c.rightOff[k], isN)];
+					rec.s = static_cast<int32_t>(score * 1e6 - 1.0);
+				}
+			}
+			out.push_back(rec);
 		}
 	}
 	return out;
 }
 
 struct Result {
+	std::vector<int32_t> memoKey;
 	std::vector<Rec> recs;
 	uint64_t total = 0;
 	uint64_t collectives = 0;
 };
 
 // generation 6 = k_scan5 (even/odd masks) + k_expand6; generation 7 = k_scan5<natural> + k_expand7
-Result run_scan(const Case& c, const Set& s, const Table& t, int generation, unsigned findGrid, size_t cap) {
+Result run_scan(const Case& c, const Set& s, const Table& t, int generation, unsigned findGrid, size_t cap, const Right* RT = nullptr) {
 	SeqStream S{};
 	S.codes = s.codes.data(); S.nmask = s.nmask.data(); S.wordOff = s.wordOff.data(); S.len = s.len.data(); S.blk2seq = s.blk2seq.data();
 	S.nwords = s.nwords; S.nent = c.nseq; S.uniformWps = s.uniformWps; S.uniformLen = s.uniformLen;
@@ -195,10 +241,24 @@ Result run_scan(const Case& c, const Set& s, const Table& t, int generation, uns
 	M.len0 = M.L; M.len1 = 0;
 	for (int k = 0; k < M.L; ++k) M.coloff[k] = c.coloff[k];
 	M.rank0 = t.rank.data();
+	const int leftCols = M.L;
+	Result R;
+	uint32_t memoOverflow = 0;
+	if (RT) {  // the table covers the left part; the window has L = left + right match columns
+		M.nparts = 2; M.len1 = static_cast<int>(c.rightOff.size()); M.L = leftCols + M.len1;
+		for (int k = 0; k < M.len1; ++k) M.coloff[leftCols + k] = c.rightOff[static_cast<size_t>(k)];
+		M.span = c.rightOff.back() + 1; M.contiguous = (M.span == M.L);
+		M.rank1 = RT->rank1.data(); M.cpval0 = RT->cpval0.data(); M.cpval1 = RT->cpval1.data(); M.pruneThr = RT->pruneThr;
+		M.nclass0 = static_cast<int>(RT->cpval0.size()); M.nclass1 = static_cast<int>(RT->cpval1.size());
+		for (int k = 0; k < M.L; ++k)
+			for (int a = 0; a < 4; ++a) M.logodds[k][a] = RT->logodds[k][a];
+		R.memoKey.assign(1u << 14, kMemoEmpty);
+		M.memoKey = R.memoKey.data(); M.memoCap = 1u << 14; M.memoOverflow = &memoOverflow;
+	}
 	std::vector<uint32_t> pairTab(kPairEntries);
 	int levels = 0;
 	std::vector<int> co(c.coloff);
-	if (!build_pair_table(t.ids.data(), t.ids.size(), co.data(), M.L, pairTab.data(), &levels)) {
+	if (!build_pair_table(t.ids.data(), t.ids.size(), co.data(), leftCols, pairTab.data(), &levels)) {
 		std::fprintf(stderr, "%s: the pair table cannot represent this table\n", c.name.c_str());
 		std::exit(2);
 	}
@@ -211,7 +271,6 @@ Result run_scan(const Case& c, const Set& s, const Table& t, int generation, uns
 	DeadCols C{};
 	C.L = M.L; C.contiguous = M.contiguous;
 	for (int k = 0; k < M.L; ++k) C.coloff[k] = M.coloff[k];
-	Result R;
 	const bool natural = generation >= 7;
 	emu::launch((s.nwords + 8 + 255) / 256, 256, [&] {
 		if (natural) k_dead_mask<true>(s.nmask.data(), s.nwords, C, dead.data());
@@ -250,6 +309,7 @@ Result run_scan(const Case& c, const Set& s, const Table& t, int generation, uns
 	}
 	R.collectives += emu::lastLaunch.collectives;
 	R.total = total;
+	if (memoOverflow) { std::fprintf(stderr, "%s: the memo overflowed\n", c.name.c_str()); std::exit(1); }
 	// nothing may be written behind the capacity
 	if (oseq[cap] != 0xABABABABu || opos[cap] != 0xABABABABu || ovidx[cap] != 0xABABABABu) {
 		std::fprintf(stderr, "%s: generation %d wrote behind the capacity of the record arrays\n", c.name.c_str(), generation);
@@ -268,7 +328,10 @@ bool check(const Case& c, int generation, const std::vector<Rec>& want, const Re
 	}
 	const size_t n = std::min(want.size(), cap);
 	for (size_t i = 0; i < n; ++i) {
-		if (got.recs[i].seq != want[i].seq || got.recs[i].pos != want[i].pos || got.recs[i].v != want[i].v) {
+		bool vOk = got.recs[i].v == want[i].v;
+		if (want[i].twoPart)
+			vOk = want[i].none ? got.recs[i].v == kNone : (got.recs[i].v < got.memoKey.size() && got.memoKey[got.recs[i].v] == want[i].s);
+		if (got.recs[i].seq != want[i].seq || got.recs[i].pos != want[i].pos || !vOk) {
 			std::fprintf(stderr, "FAIL %s gen %d: record %zu is (%u, %u, %u), expected (%u, %u, %u)\n", c.name.c_str(), generation, i, got.recs[i].seq,
 			             got.recs[i].pos, got.recs[i].v, want[i].seq, want[i].pos, want[i].v);
 			return false;
@@ -295,6 +358,11 @@ int main(int argc, char** argv) {
 		{"small_capacity", 40, 500, 500, 0.0, false, c8, 0.05, false, 9},
 		{"positive_set_prefix_ragged", 200, 20, 400, 0.01, false, c8, 0.04, false, 12, 77},
 		{"positive_set_prefix_uniform", 90, 300, 300, 0.0, false, c8, 0.04, false, 13, 31},
+		// two-part models (more than 8 match columns): the pair table finds the left 8, k_expand6/7<false> evaluate both tables, the product
+		// test and the memo slot of the window's integer score
+		{"two_part_twelve", 70, 100, 500, 0.01, false, c8, 0.03, false, 14, 0, {8, 9, 10, 11}},
+		{"two_part_seventeen_rc", 40, 60, 300, 0.01, true, c8, 0.04, false, 15, 0, {8, 9, 10, 11, 12, 13, 14, 15, 16}},
+		{"two_part_gapped_uniform", 50, 400, 400, 0.005, false, {0, 1, 2, 3, 5, 6, 7}, 0.05, false, 16, 0, {9, 10, 12}},
 	};
 	int failed = 0, ran = 0;
 	if (argc <= 1 || std::string(argv[1]) == "tile_scan") {
@@ -322,12 +390,15 @@ int main(int argc, char** argv) {
 		}
 		const Set s = make_set(c);
 		const Table t = make_table(c);
-		const std::vector<Rec> want = brute_force(c, s, t);
+		Right right;
+		const Right* RT = nullptr;
+		if (!c.rightOff.empty()) { right = make_right(c, t.nclass); RT = &right; }
+		const std::vector<Rec> want = brute_force(c, s, t, RT);
 		// "small_capacity": the record arrays hold fewer records than the scan finds (the caller then grows them and repeats)
 		const size_t cap = (c.name == "small_capacity") ? want.size() / 2 + 3 : want.size() + 100;
 		for (int gen : {6, 7}) {
 			for (unsigned grid : {1u, 3u}) {
-				const Result r = run_scan(c, s, t, gen, grid, cap);
+				const Result r = run_scan(c, s, t, gen, grid, cap, RT);
 				const bool ok = check(c, gen, want, r, cap);
 				std::printf("%-22s gen %d find grid %u: %6zu sites over %7u words, %8llu collectives  %s\n", c.name.c_str(), gen, grid, want.size(), s.nwords,
 				            static_cast<unsigned long long>(r.collectives), ok ? "identical" : "DIFFERENT");

@@ -13,7 +13,8 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "sim
 import build as simt_build  # noqa: E402
 
 CASES = ["tile_scan", "uniform_1kb", "ragged_N", "revcomp_ragged", "dense_lowcomplexity", "gapped_6cols", "five_columns", "tiny", "every_warp_dense",
-         "ten_tiles_uniform", "one_word_sequences", "small_capacity", "positive_set_prefix_ragged", "positive_set_prefix_uniform"]
+         "ten_tiles_uniform", "one_word_sequences", "small_capacity", "positive_set_prefix_ragged", "positive_set_prefix_uniform",
+         "two_part_twelve", "two_part_seventeen_rc", "two_part_gapped_uniform"]
 
 
 STEP_CASES = ["clustered_uniform", "ragged_short", "long_motif", "all_sites_dense", "few_sites", "tiny", "zoops_uniform", "zoops_ragged_shift", "zoops_long_runs",
@@ -68,7 +69,8 @@ ASAN_ENV = dict(os.environ, ASAN_OPTIONS="detect_stack_use_after_return=0:detect
 
 
 @pytest.mark.parametrize("target,extra,cases", [
-    ("scan_emu", ("host_pack.cpp", "pair_table.cpp"), ["ragged_N", "revcomp_ragged", "gapped_6cols", "one_word_sequences", "small_capacity", "positive_set_prefix_ragged"]),
+    ("scan_emu", ("host_pack.cpp", "pair_table.cpp"), ["ragged_N", "revcomp_ragged", "gapped_6cols", "one_word_sequences", "small_capacity", "positive_set_prefix_ragged",
+                                                         "two_part_seventeen_rc"]),
     ("step_emu", ("host_pack.cpp",), ["ragged_short", "all_sites_dense", "zoops_ragged_shift", "rc_ragged", "rc_long_sequences", "sort_many_chunks", "gen_table_clustered",
                                    "gen_localized_shift", "gen_per_candidate", "cmp_flags_dense", "cmp_run_heads", "cmp_one"]),
 ])
@@ -117,7 +119,8 @@ def test_race_detector_controls():
 
 
 @pytest.mark.parametrize("target,extra,cases", [
-    ("scan_emu", ("host_pack.cpp", "pair_table.cpp"), ["uniform_1kb", "ragged_N", "revcomp_ragged", "every_warp_dense", "small_capacity", "positive_set_prefix_ragged"]),
+    ("scan_emu", ("host_pack.cpp", "pair_table.cpp"), ["uniform_1kb", "ragged_N", "revcomp_ragged", "every_warp_dense", "small_capacity", "positive_set_prefix_ragged",
+                                                         "two_part_twelve"]),
     ("step_emu", ("host_pack.cpp",), ["clustered_uniform", "all_sites_dense", "zoops_ragged_shift", "rc_ragged", "rc_long_sequences", "sort_many_chunks", "gen_table_clustered",
                                    "gen_localized_shift", "gen_per_candidate", "cmp_flags_dense", "cmp_run_heads", "cmp_one"]),
 ])
