@@ -379,6 +379,10 @@ int xxm_trace_dump(void);
 /* XXM_SCAN_GEN=6 in the environment (read by xxm_create) selects the previous generation of the pair-table scan kernels
  * (even/odd hit masks + k_expand6) instead of the default (window-order masks + k_expand7); both give the same site lists --
  * it exists for A/B timing and for the parity tests of the older kernels */
+/* XXM_EXPAND5_TICKET=1: the expand kernel of the GENERIC scan (k_expand5; only models whose left table the pair table cannot
+ * represent take it) hands its tiles out by ticket instead of by block index, which removes its one assumption about the order in
+ * which blocks become resident.  Same site lists; verified under the SIMT emulator with blocks in reverse order, not yet on a GPU,
+ * hence opt-in. */
 /* the CUDA stream the context launches on, as a cudaStream_t cast to void* (for external event timing) */
 void* xxm_stream(const xxm_ctx* ctx);
 

@@ -241,7 +241,11 @@ int run(const Case& c) {
 	Values V{};
 	V.pS = pS.data(); V.kind = kFinalTable;
 	int bad = 0;
-	for (uint32_t cap : {nrec, nrec > 8 ? nrec - 5 : nrec}) {  // exactly enough room, and five records too few (they must be dropped, not written)
+	// run 0, 1: tile = block index, exactly enough room / five records too few (they must be dropped, not written); run 2, 3: tile = ticket
+	// (kTicket, XXM_EXPAND5_TICKET), blocks in order and in REVERSE order -- the ticket variant must not care in which order blocks start
+	for (int variant = 0; variant < 4; ++variant) {
+		const uint32_t cap = (variant == 1 && nrec > 8) ? nrec - 5 : nrec;
+		const bool ticketed = variant >= 2;
 		std::vector<uint32_t> oseq(std::max(1u, cap), 0xABABABABu), opos(oseq), ovidx(oseq);
 		std::vector<float> oscore(std::max(1u, cap), -1.f);
 		std::fill(status.begin(), status.end(), 0ull);
@@ -253,10 +257,16 @@ int run(const Case& c) {
 		io.cap = cap; io.status = status.data(); io.gstatus = gstatus.data(); io.ticket = &ticket; io.total = &total; io.ntiles = ntiles;
 		io.wpsMagic = 0;
 		const bool fast = M.nparts == 1 && M.contiguous;
+		ticket = 0;
+		emu::reverseBlocks = variant == 3;
 		emu::launch(ntiles, kExpand5Threads, [&] {
-			if (fast) k_expand5<true>(S, M, V, io);
+			if (ticketed) {
+				if (fast) k_expand5<true, true>(S, M, V, io);
+				else k_expand5<false, true>(S, M, V, io);
+			} else if (fast) k_expand5<true>(S, M, V, io);
 			else k_expand5<false>(S, M, V, io);
 		});
+		emu::reverseBlocks = false;
 		bool ok = total == nrec && memoOverflow == 0;
 		for (uint32_t k = 0; ok && k < std::min(cap, nrec); ++k) {
 			const Want& w = recs[k];
@@ -268,8 +278,8 @@ int run(const Case& c) {
 		}
 		unsigned none = 0;
 		for (const Want& w : recs) none += w.none;
-		std::printf("%-24s k_expand5<%s> %u tiles, capacity %u: %u records (%u without a value)  %s\n", c.name.c_str(), fast ? "true" : "false", ntiles, cap, nrec, none,
-		            ok ? "identical" : "DIFFERENT");
+		std::printf("%-24s k_expand5<%s%s> %u tiles%s, capacity %u: %u records (%u without a value)  %s\n", c.name.c_str(), fast ? "true" : "false",
+		            ticketed ? ", ticket" : "", ntiles, variant == 3 ? " in reverse order" : "", cap, nrec, none, ok ? "identical" : "DIFFERENT");
 		bad += ok ? 0 : 1;
 	}
 	return bad;

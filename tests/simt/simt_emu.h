@@ -116,6 +116,7 @@ struct BlockState {
 
 inline BlockState* B = nullptr;
 inline unsigned blockY = 0;  // blockIdx.y of the next launches (the grid itself is one-dimensional: a harness launches once per y)
+inline bool reverseBlocks = false;  // run the blocks of the next launches from the last to the first (a kernel must not care)
 
 EMU_NOTSAN inline void yield() {
 	EMU_TSAN_SWITCH(B->schedTsan);
@@ -207,9 +208,10 @@ EMU_NOTSAN void launch(unsigned grid, unsigned block, F&& body) {
 	st.body = body;
 	EMU_TSAN_RELEASE(&st.chain[0]);  // what the host wrote before the launch is visible to every thread of the grid
 	EMU_TSAN_RELEASE(&st.chain[1]);
-	for (unsigned b = 0; b < grid; ++b) {
+	for (unsigned bi = 0; bi < grid; ++bi) {
+		const unsigned b = reverseBlocks ? grid - 1 - bi : bi;
 		blockIdx = uint3{b, blockY, 0};
-		st.block = b;
+		st.block = bi;  // (execution order: what the happens-before chain between consecutive blocks follows)
 		st.alive = static_cast<int>(block);
 		st.barCount = 0;
 		for (auto& w : st.warp) { w.arrived = 0; w.readers = 0; w.ready = false; }

@@ -264,16 +264,27 @@ __device__ __forceinline__ HitRec expand_hit(const SeqStream& S, const Model& M,
 	return r;
 }
 
-template <bool kFast>
+// kTicket (XXM_EXPAND5_TICKET, off by default): the tile is the block's ticket from an atomic counter instead of its index, so a tile
+// only ever waits for tiles whose blocks have already started -- no assumption about the order in which blocks become resident.
+// Verified under the SIMT emulator with the blocks run in REVERSE order (tests/simt/scan4_emu.cpp); it has not run on a GPU yet,
+// which is why the instantiation that has -- kTicket = false, machine code unchanged -- stays the default.
+template <bool kFast, bool kTicket = false>
 __global__ void __launch_bounds__(kExpand5Threads) k_expand5(SeqStream S, Model M, Values V, Expand5IO io) {
 	__shared__ __align__(16) uint64_t s_codes[kTileWords + 4];
 	__shared__ uint16_t s_q[kExpand5Queue];
 	__shared__ uint32_t s_warp[kExpand5Threads / 32];
 	__shared__ uint64_t s_base;
 	const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-	// tile = block index: like CUB's decoupled look-back this relies on blocks being dispatched in index order (a tile only
-	// ever waits for tiles with smaller indices, which then are resident or done)
-	const uint32_t tile = blockIdx.x;
+	// tile = block index: like CUB's decoupled look-back WITHOUT its ticket this relies on blocks being dispatched in index order (a
+	// tile only ever waits for tiles with smaller indices, which then are resident or done)
+	uint32_t tileOf = blockIdx.x;
+	if constexpr (kTicket) {
+		__shared__ uint32_t s_ticket;
+		if (tid == 0) s_ticket = atomicAdd(io.ticket, 1u);
+		__syncthreads();
+		tileOf = s_ticket;
+	}
+	const uint32_t tile = tileOf;
 	const uint32_t wbase = tile * kTileWords;
 	const uint32_t w0 = wbase + 4 * tid;
 	// ---- all loads of the thread up front: its four hit masks, five N masks, four code words (staged for the expansion)
